@@ -1,0 +1,93 @@
+"""ctypes binding of libadmp_b200.so (the C ABI declared in include/admp_b200.h).
+
+The product path has NO CPU fallback: if the library is missing or no CUDA device is
+present, every compute entry point raises (loudly) instead of computing elsewhere.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libadmp_b200.so')
+
+F64, F32 = 0, 1
+CK_COULOMB, CK_DISP6, CK_DISP8, CK_DISP10 = 1, 6, 8, 10
+
+# scalar block slots (include/admp_b200.h)
+S_E_REAL, S_E_RECIP, S_E_SELF, S_E_PEN = 0, 1, 2, 3
+S_DBOX, S_DNSTAR, S_TK, S_DMSCALE, S_DPSCALE, S_MAXFIELD, S_COUNT = 4, 13, 22, 28, 33, 38, 48
+
+WANT_GRAD, WANT_VIRIAL, WANT_PGRAD, SCF, SCF_HOSTSYNC = 1, 2, 4, 8, 16
+
+EXPORTS = [
+    'admp_last_error', 'admp_version', 'admp_ctx_create', 'admp_ctx_destroy', 'admp_ctx_set_pme',
+    'admp_ctx_set_topology', 'admp_ctx_workspace_bytes', 'admp_ctx_scf_graph_active',
+    'admp_frames_fwd', 'admp_frames_bwd', 'admp_rotate', 'admp_pme_real', 'admp_pme_recip', 'admp_pme_self',
+    'admp_pme_eval', 'admp_disp_eval', 'admp_tt_pair', 'admp_nblist_build',
+]
+
+
+class AdmpLibraryError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library once; raise AdmpLibraryError with build instructions if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AdmpLibraryError(
+            'admp_b200: CUDA library %s is missing. Build it with `python -c "import __graft_entry__ as g; g.build()"` '
+            'or `make -C admp_b200/csrc`. There is no CPU fallback.' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, u32, dbl = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint32, ctypes.c_double
+    lib.admp_last_error.restype = ctypes.c_char_p
+    lib.admp_last_error.argtypes = []
+    lib.admp_version.restype = i32
+    lib.admp_ctx_create.argtypes = [ctypes.POINTER(vp), i32, i32]
+    lib.admp_ctx_destroy.argtypes = [vp]
+    lib.admp_ctx_set_pme.argtypes = [vp, dbl, i32, i32, i32, i32]
+    lib.admp_ctx_set_topology.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    lib.admp_ctx_workspace_bytes.restype = i64
+    lib.admp_ctx_workspace_bytes.argtypes = [vp]
+    lib.admp_ctx_scf_graph_active.argtypes = [vp]
+    lib.admp_frames_fwd.argtypes = [vp] * 8
+    lib.admp_frames_bwd.argtypes = [vp] * 9
+    lib.admp_rotate.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp]
+    lib.admp_pme_real.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, i32, u32, vp, vp, vp, vp, vp, vp]
+    lib.admp_pme_recip.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp, i32, i32, u32, vp, vp, i32, vp, vp]
+    lib.admp_pme_self.argtypes = [vp, vp, vp, vp, vp, u32, vp, vp, vp, vp]
+    lib.admp_pme_eval.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, u32, i32, dbl, vp, vp, vp, vp, vp, vp, vp]
+    lib.admp_disp_eval.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp, i32, u32, vp, vp, vp]
+    lib.admp_tt_pair.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, u32, vp, vp, vp]
+    lib.admp_nblist_build.argtypes = [vp, vp, vp, vp, i32, dbl, vp, i64, vp]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if name not in ('admp_last_error', 'admp_ctx_workspace_bytes'):
+            fn.restype = i32
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise AdmpLibraryError(load().admp_last_error().decode('utf-8', 'replace'))
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise AdmpLibraryError('admp_b200 needs a CUDA device (B200, sm_100a); none is visible and there is no CPU fallback.')
+
+
+def ptr(t):
+    """Device (or host) address of a tensor / None -> NULL."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

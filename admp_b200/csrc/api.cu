@@ -1,0 +1,620 @@
+// C ABI of libadmp_b200.so: context, cuFFT plans, stage entry points and the fused
+// evaluation (energy_pme + optimize_Uind + all adjoints) - see include/admp_b200.h.
+#include <cufft.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+using namespace admp;
+
+static thread_local std::string g_err;
+
+static int fail(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+#define CKFFT(call)                                                                                \
+    do {                                                                                           \
+        cufftResult r_ = (call);                                                                   \
+        if (r_ != CUFFT_SUCCESS) return fail("%s:%d %s -> cufft error %d", __FILE__, __LINE__, #call, (int)r_); \
+    } while (0)
+#define CKLAUNCH() CK(cudaGetLastError())
+
+struct admp_ctx {
+    int device = 0, dtype = ADMP_F64, n_sm = 148;
+    size_t w = 8;
+    double kappa = 0.0;
+    int K[3] = {0, 0, 0};
+    int lmax = 2;
+    int n_atoms = 0;
+    // topology
+    int32_t *axis_type = nullptr, *axis_idx = nullptr, *cov_off = nullptr, *cov_idx = nullptr;
+    int8_t* cov_nb = nullptr;
+    // cell
+    BoxInfo* box = nullptr;
+    // reciprocal space
+    void *mesh = nullptr, *spec = nullptr, *fftwork = nullptr;
+    size_t mesh_bytes = 0, spec_bytes = 0, fftwork_bytes = 0;
+    cufftHandle plan_fwd = 0, plan_inv = 0;
+    bool plans = false;
+    double* bt[3] = {nullptr, nullptr, nullptr};
+    // per-atom workspaces and staged inputs of admp_pme_eval
+    void *M = nullptr, *G = nullptr, *Fscf = nullptr;
+    void *s_pos = nullptr, *s_U = nullptr, *s_pol = nullptr, *s_th = nullptr, *s_mS = nullptr, *s_pS = nullptr, *s_box = nullptr;
+    int32_t* s_pairs = nullptr;
+    int64_t pairs_cap = 0;
+    double* scal = nullptr;
+    int32_t* state = nullptr;
+    int32_t* h_state = nullptr;     // pinned mirror for the host-synchronised loop
+    // SCF graph cache
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    cudaStream_t cap_stream = nullptr;
+    int g_maxiter = -1;
+    double g_thresh = -1.0;
+    uint32_t g_flags = 0;
+    bool graph_failed = false;
+    // neighbour list
+    NbWork nb = {};
+    size_t ws_bytes = 0;
+};
+
+extern "C" const char* admp_last_error(void) { return g_err.c_str(); }
+extern "C" int admp_version(void) { return 100; }
+
+static void drop_graph(admp_ctx* c) {
+    if (c->gexec) cudaGraphExecDestroy(c->gexec);
+    if (c->graph) cudaGraphDestroy(c->graph);
+    c->gexec = nullptr;
+    c->graph = nullptr;
+}
+
+template <typename P> static void dfree(P*& p) {
+    if (p) cudaFree((void*)p);
+    p = nullptr;
+}
+
+extern "C" int admp_ctx_create(admp_ctx** out, int device, int dtype) {
+    if (!out) return fail("admp_ctx_create: null out");
+    if (dtype != ADMP_F64 && dtype != ADMP_F32) return fail("admp_ctx_create: bad dtype %d", dtype);
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail("admp_ctx_create: device %d not present (%d devices)", device, ndev);
+    CK(cudaSetDevice(device));
+    admp_ctx* c = new admp_ctx();
+    c->device = device;
+    c->dtype = dtype;
+    c->w = dtype == ADMP_F64 ? 8 : 4;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    c->n_sm = prop.multiProcessorCount;
+    CK(cudaMalloc(&c->box, sizeof(BoxInfo)));
+    CK(cudaMalloc(&c->scal, sizeof(double) * ADMP_S_COUNT));
+    CK(cudaMalloc(&c->state, sizeof(int32_t) * 8));
+    CK(cudaMalloc(&c->s_mS, 8 * 8));
+    CK(cudaMalloc(&c->s_pS, 8 * 8));
+    CK(cudaMalloc(&c->s_box, 9 * 8));
+    CK(cudaMallocHost(&c->h_state, sizeof(int32_t) * 8));
+    CK(cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking));
+    c->ws_bytes = sizeof(BoxInfo) + sizeof(double) * ADMP_S_COUNT + 256;
+    *out = c;
+    return 0;
+}
+
+static void free_recip(admp_ctx* c) {
+    if (c->plans) { cufftDestroy(c->plan_fwd); cufftDestroy(c->plan_inv); c->plans = false; }
+    c->ws_bytes -= c->mesh_bytes + c->spec_bytes + c->fftwork_bytes;
+    dfree(c->mesh); dfree(c->spec); dfree(c->fftwork);
+    c->mesh_bytes = c->spec_bytes = c->fftwork_bytes = 0;
+    for (int d = 0; d < 3; ++d) dfree(c->bt[d]);
+}
+
+static void free_atoms(admp_ctx* c) {
+    dfree(c->M); dfree(c->G); dfree(c->Fscf); dfree(c->s_pos); dfree(c->s_U); dfree(c->s_pol); dfree(c->s_th);
+    dfree(c->axis_type); dfree(c->axis_idx); dfree(c->cov_off); dfree(c->cov_idx); dfree(c->cov_nb);
+}
+
+extern "C" int admp_ctx_destroy(admp_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    drop_graph(c);
+    free_recip(c);
+    free_atoms(c);
+    dfree(c->s_pairs); dfree(c->box); dfree(c->scal); dfree(c->state); dfree(c->s_mS); dfree(c->s_pS); dfree(c->s_box);
+    dfree(c->nb.cell_of); dfree(c->nb.cell_count); dfree(c->nb.cell_start); dfree(c->nb.sorted); dfree(c->nb.nbr_count); dfree(c->nb.nbr_start);
+    if (c->h_state) cudaFreeHost(c->h_state);
+    if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
+    delete c;
+    return 0;
+}
+
+extern "C" int64_t admp_ctx_workspace_bytes(const admp_ctx* c) { return c ? (int64_t)c->ws_bytes : 0; }
+extern "C" int admp_ctx_scf_graph_active(const admp_ctx* c) { return (c && c->gexec && !c->graph_failed) ? 1 : 0; }
+
+// 1/theta_k^2 per dimension (admp/recip.py:400-408): theta = sum_{m=-2..2} M6(m+3) cos(2 pi m k / K)
+static std::vector<double> theta_inv2(int K, int count) {
+    const double M6[5] = {1.0 / 120, 26.0 / 120, 66.0 / 120, 26.0 / 120, 1.0 / 120};   // M6(1..5)
+    std::vector<double> out(count);
+    for (int i = 0; i < count; ++i) {
+        const int k = (2 * i < K) ? i : i - K;
+        double th = 0.0;
+        for (int m = -2; m <= 2; ++m) th += M6[m + 2] * std::cos(2.0 * M_PI * m * (double)k / (double)K);
+        out[i] = 1.0 / (th * th);
+    }
+    return out;
+}
+
+extern "C" int admp_ctx_set_pme(admp_ctx* c, double kappa, int K1, int K2, int K3, int lmax) {
+    if (!c) return fail("admp_ctx_set_pme: null ctx");
+    if (lmax < 0 || lmax > 2) return fail("l > 2 (beyond quadrupole) not supported");   // admp/multipole.py:111
+    if (K1 < 6 || K2 < 6 || K3 < 6) return fail("admp_ctx_set_pme: mesh %dx%dx%d smaller than the order-6 stencil", K1, K2, K3);
+    if (!(kappa > 0.0)) return fail("admp_ctx_set_pme: kappa must be positive");
+    CK(cudaSetDevice(c->device));
+    c->kappa = kappa;
+    c->lmax = lmax;
+    drop_graph(c);
+    if (c->plans && c->K[0] == K1 && c->K[1] == K2 && c->K[2] == K3) return 0;
+    free_recip(c);
+    c->K[0] = K1; c->K[1] = K2; c->K[2] = K3;
+    const size_t G = (size_t)K1 * K2 * K3, Gh = (size_t)K1 * K2 * (K3 / 2 + 1);
+    c->mesh_bytes = G * c->w;
+    c->spec_bytes = Gh * 2 * c->w;
+    CK(cudaMalloc(&c->mesh, c->mesh_bytes));
+    CK(cudaMalloc(&c->spec, c->spec_bytes));
+    size_t ws1 = 0, ws2 = 0;
+    CKFFT(cufftCreate(&c->plan_fwd));
+    CKFFT(cufftCreate(&c->plan_inv));
+    c->plans = true;
+    CKFFT(cufftSetAutoAllocation(c->plan_fwd, 0));
+    CKFFT(cufftSetAutoAllocation(c->plan_inv, 0));
+    CKFFT(cufftMakePlan3d(c->plan_fwd, K1, K2, K3, c->dtype == ADMP_F64 ? CUFFT_D2Z : CUFFT_R2C, &ws1));
+    CKFFT(cufftMakePlan3d(c->plan_inv, K1, K2, K3, c->dtype == ADMP_F64 ? CUFFT_Z2D : CUFFT_C2R, &ws2));
+    c->fftwork_bytes = ws1 > ws2 ? ws1 : ws2;
+    if (c->fftwork_bytes == 0) c->fftwork_bytes = 256;
+    CK(cudaMalloc(&c->fftwork, c->fftwork_bytes));        // one work area shared by both directions
+    CKFFT(cufftSetWorkArea(c->plan_fwd, c->fftwork));
+    CKFFT(cufftSetWorkArea(c->plan_inv, c->fftwork));
+    const int cnt[3] = {K1, K2, K3 / 2 + 1};
+    for (int d = 0; d < 3; ++d) {
+        std::vector<double> t = theta_inv2(c->K[d], cnt[d]);
+        CK(cudaMalloc(&c->bt[d], sizeof(double) * cnt[d]));
+        CK(cudaMemcpy(c->bt[d], t.data(), sizeof(double) * cnt[d], cudaMemcpyHostToDevice));
+    }
+    c->ws_bytes += c->mesh_bytes + c->spec_bytes + c->fftwork_bytes;
+    return 0;
+}
+
+extern "C" int admp_ctx_set_topology(admp_ctx* c, int n, const int32_t* axis_type, const int32_t* axis_indices,
+                                     const int32_t* cov_offsets, const int32_t* cov_index, const int8_t* cov_nbonds) {
+    if (!c) return fail("admp_ctx_set_topology: null ctx");
+    if (n <= 0) return fail("admp_ctx_set_topology: n_atoms = %d", n);
+    CK(cudaSetDevice(c->device));
+    drop_graph(c);
+    free_atoms(c);
+    c->n_atoms = n;
+    const size_t w = c->w;
+    CK(cudaMalloc(&c->M, (size_t)n * 10 * w));
+    CK(cudaMalloc(&c->G, (size_t)n * 10 * w));
+    CK(cudaMalloc(&c->Fscf, (size_t)n * 3 * w));
+    CK(cudaMalloc(&c->s_pos, (size_t)n * 3 * w));
+    CK(cudaMalloc(&c->s_U, (size_t)n * 3 * w));
+    CK(cudaMalloc(&c->s_pol, (size_t)n * w));
+    CK(cudaMalloc(&c->s_th, (size_t)n * w));
+    if (axis_type && axis_indices) {
+        CK(cudaMalloc(&c->axis_type, sizeof(int32_t) * n));
+        CK(cudaMalloc(&c->axis_idx, sizeof(int32_t) * 3 * n));
+        // anchors a site's axis type does not use may be -1 (admp/parser.py); keep reads in range
+        std::vector<int32_t> ai(axis_indices, axis_indices + 3 * (size_t)n);
+        for (size_t k = 0; k < ai.size(); ++k)
+            if (ai[k] < 0 || ai[k] >= n) ai[k] = (int32_t)(k / 3);
+        for (int a = 0; a < n; ++a) {
+            const int t = axis_type[a];
+            if (t < 0 || t > 5) return fail("admp_ctx_set_topology: axis type %d of atom %d out of range", t, a);
+            const int need = (t == 5) ? 0 : (t == 4) ? 1 : (t == 2 || t == 3) ? 3 : 2;
+            for (int k = 0; k < need; ++k) {
+                const int v = axis_indices[3 * a + k];
+                if (v < 0 || v >= n || v == a) return fail("admp_ctx_set_topology: atom %d (axis type %d) has invalid anchor %d", a, t, v);
+            }
+        }
+        CK(cudaMemcpy(c->axis_type, axis_type, sizeof(int32_t) * n, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->axis_idx, ai.data(), sizeof(int32_t) * 3 * n, cudaMemcpyHostToDevice));
+    }
+    if (cov_offsets && cov_offsets[n] > 0) {
+        if (!cov_index || !cov_nbonds) return fail("admp_ctx_set_topology: covalent CSR incomplete");
+        const int nnz = cov_offsets[n];
+        CK(cudaMalloc(&c->cov_off, sizeof(int32_t) * (n + 1)));
+        CK(cudaMalloc(&c->cov_idx, sizeof(int32_t) * nnz));
+        CK(cudaMalloc(&c->cov_nb, nnz));
+        CK(cudaMemcpy(c->cov_off, cov_offsets, sizeof(int32_t) * (n + 1), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->cov_idx, cov_index, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->cov_nb, cov_nbonds, nnz, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ helpers
+#define DISPATCH(c, fn, ...)                              \
+    do {                                                  \
+        if ((c)->dtype == ADMP_F64) fn<double>(__VA_ARGS__); \
+        else fn<float>(__VA_ARGS__);                      \
+    } while (0)
+
+static int need(admp_ctx* c, bool recip, bool atoms) {
+    if (!c) return fail("null ctx");
+    if (recip && !c->plans) return fail("admp_ctx_set_pme has not been called");
+    if (atoms && c->n_atoms <= 0) return fail("admp_ctx_set_topology has not been called");
+    return 0;
+}
+
+static int fft_fwd(admp_ctx* c, cudaStream_t st) {
+    CKFFT(cufftSetStream(c->plan_fwd, st));
+    if (c->dtype == ADMP_F64) CKFFT(cufftExecD2Z(c->plan_fwd, (cufftDoubleReal*)c->mesh, (cufftDoubleComplex*)c->spec));
+    else CKFFT(cufftExecR2C(c->plan_fwd, (cufftReal*)c->mesh, (cufftComplex*)c->spec));
+    return 0;
+}
+static int fft_inv(admp_ctx* c, cudaStream_t st) {
+    CKFFT(cufftSetStream(c->plan_inv, st));
+    if (c->dtype == ADMP_F64) CKFFT(cufftExecZ2D(c->plan_inv, (cufftDoubleComplex*)c->spec, (cufftDoubleReal*)c->mesh));
+    else CKFFT(cufftExecC2R(c->plan_inv, (cufftComplex*)c->spec, (cufftReal*)c->mesh));
+    return 0;
+}
+
+// spread -> FFT -> influence function (+energy) -> inverse FFT; leaves phi = dE/dmesh in c->mesh
+static int recip_field(admp_ctx* c, cudaStream_t st, const void* pos, const void* M, int cols, int stride, const void* U,
+                       int kind, double* scalars, int want_vir) {
+    CK(cudaMemsetAsync(c->mesh, 0, c->mesh_bytes, st));
+    DISPATCH(c, launch_spread, st, c->n_atoms, c->box, pos, M, cols, stride, U, c->mesh);
+    CKLAUNCH();
+    if (fft_fwd(c, st)) return 1;
+    const size_t nh = (size_t)c->K[0] * c->K[1] * (c->K[2] / 2 + 1);
+    DISPATCH(c, launch_convolve, st, c->box, nh, c->n_sm, c->kappa, kind, c->bt[0], c->bt[1], c->bt[2], c->spec, scalars, want_vir);
+    CKLAUNCH();
+    if (fft_inv(c, st)) return 1;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ stages
+extern "C" int admp_frames_fwd(admp_ctx* c, void* stream, const void* pos, const void* box, const void* Ql, void* M, void* Qg,
+                               void* frames) {
+    if (need(c, false, true)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(c->device));
+    DISPATCH(c, launch_box_setup, st, box, c->box, c->K[0], c->K[1], c->K[2]);
+    DISPATCH(c, launch_frames_fwd, st, c->n_atoms, c->lmax, c->box, pos, c->axis_type, c->axis_idx, Ql, M, Qg, frames);
+    CKLAUNCH();
+    return 0;
+}
+
+extern "C" int admp_frames_bwd(admp_ctx* c, void* stream, const void* pos, const void* box, const void* Ql, const void* G,
+                               void* dQl, void* dpos, double* scalars) {
+    if (need(c, false, true)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(c->device));
+    DISPATCH(c, launch_box_setup, st, box, c->box, c->K[0], c->K[1], c->K[2]);
+    DISPATCH(c, launch_frames_bwd, st, c->n_atoms, c->lmax, c->box, pos, c->axis_type, c->axis_idx, Ql, G, dQl, dpos, scalars, 1);
+    CKLAUNCH();
+    return 0;
+}
+
+extern "C" int admp_rotate(admp_ctx* c, void* stream, int64_t n, int lmax, int to_local, const void* Q, const void* frames, void* out) {
+    if (!c) return fail("null ctx");
+    if (lmax < 0 || lmax > 2) return fail("l > 2 (beyond quadrupole) not supported");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(c->device));
+    DISPATCH(c, launch_rotate, st, n, lmax, to_local, Q, frames, out);
+    CKLAUNCH();
+    return 0;
+}
+
+extern "C" int admp_pme_real(admp_ctx* c, void* stream, const void* pos, const void* box, const int32_t* pairs, int64_t n_rows,
+                             const void* M, const void* U, const void* pol, const void* tholes, const void* mScales,
+                             const void* pScales, int mode, uint32_t flags, void* dpos, void* G, void* F, void* dpol,
+                             void* dtholes, double* scalars) {
+    if (need(c, false, true)) return 1;
+    if (U && (!pol || !tholes || !pScales)) return fail("admp_pme_real: polarizable call needs pol, tholes and pScales");
+    if (mode == 1 && !U) return fail("admp_pme_real: mode 1 (field only) needs U");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(c->device));
+    DISPATCH(c, launch_box_setup, st, box, c->box, c->K[0], c->K[1], c->K[2]);
+    DISPATCH(c, launch_pme_pair, st, n_rows, c->n_atoms, c->box, c->kappa, pos, pairs, c->cov_off, c->cov_idx, c->cov_nb, M, U, pol,
+             tholes, mScales, pScales, mode, flags, dpos, G, F, dpol, dtholes, scalars);
+    CKLAUNCH();
+    return 0;
+}
+
+extern "C" int admp_pme_recip(admp_ctx* c, void* stream, const void* pos, const void* box, const void* M, int M_cols, int M_stride,
+                              const void* U, int kind, int mode, uint32_t flags, void* dpos, void* G, int G_stride, void* F,
+                              double* scalars) {
+    if (need(c, true, true)) return 1;
+    if (M_cols != 1 && M_cols != 10) return fail("admp_pme_recip: M_cols must be 1 or 10");
+    if (kind != ADMP_CK_COULOMB && kind != ADMP_CK_DISP6 && kind != ADMP_CK_DISP8 && kind != ADMP_CK_DISP10)
+        return fail("admp_pme_recip: unknown influence function %d", kind);
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(c->device));
+    DISPATCH(c, launch_box_setup, st, box, c->box, c->K[0], c->K[1], c->K[2]);
+    if (recip_field(c, st, pos, M, M_cols, M_stride, U, kind, scalars, (flags & ADMP_WANT_VIRIAL) ? 1 : 0)) return 1;
+    if (mode == 1 || (flags & ADMP_WANT_GRAD)) {
+        DISPATCH(c, launch_gather, st, c->n_atoms, c->box, pos, M, M_cols, M_stride, U, c->mesh, mode, flags, dpos, G, G_stride, F, scalars);
+        CKLAUNCH();
+    }
+    return 0;
+}
+
+extern "C" int admp_pme_self(admp_ctx* c, void* stream, const void* M, const void* U, const void* pol, uint32_t flags, void* G,
+                             void* F, void* dpol, double* scalars) {
+    if (need(c, false, true)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(c->device));
+    DISPATCH(c, launch_self, st, c->n_atoms, c->kappa, M, U, pol, flags, G, F, dpol, scalars);
+    CKLAUNCH();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ fused evaluation
+// one pass of optimize_Uind's loop body on staged inputs (admp/pme.py:132-138)
+static int scf_body(admp_ctx* c, cudaStream_t st, int maxiter, double thresh, uint32_t flags, cudaGraphConditionalHandle h, int use_h) {
+    launch_scf_rearm(st, c->scal);
+    if (recip_field(c, st, c->s_pos, c->M, 10, 10, c->s_U, ADMP_CK_COULOMB, c->scal, (flags & ADMP_WANT_VIRIAL) ? 1 : 0)) return 1;
+    DISPATCH(c, launch_gather, st, c->n_atoms, c->box, c->s_pos, c->M, 10, 10, c->s_U, c->mesh, 1, 0u, nullptr, nullptr, 10, c->Fscf, c->scal);
+    DISPATCH(c, launch_pme_pair, st, c->pairs_cap, c->n_atoms, c->box, c->kappa, c->s_pos, c->s_pairs, c->cov_off, c->cov_idx, c->cov_nb,
+             c->M, c->s_U, c->s_pol, c->s_th, c->s_mS, c->s_pS, 1, 0u, nullptr, nullptr, c->Fscf, nullptr, nullptr, c->scal);
+    DISPATCH(c, launch_scf_field, st, c->n_atoms, c->kappa, c->M, c->s_U, c->s_pol, c->Fscf, c->scal);
+    launch_scf_decide(st, c->state, c->scal, maxiter, thresh, h, use_h);
+    DISPATCH(c, launch_scf_update, st, c->n_atoms, c->state, c->Fscf, c->s_pol, c->s_U, c->scal);
+    CKLAUNCH();
+    return 0;
+}
+
+// device-resident loop: a CUDA graph whose WHILE node re-runs the body until scf_decide clears it
+static int build_scf_graph(admp_ctx* c, int maxiter, double thresh, uint32_t flags) {
+    drop_graph(c);
+    CK(cudaGraphCreate(&c->graph, 0));
+    cudaGraphConditionalHandle handle;
+    CK(cudaGraphConditionalHandleCreate(&handle, c->graph, 1, cudaGraphCondAssignDefault));
+    cudaGraphNodeParams p = {};
+    p.type = cudaGraphNodeTypeConditional;
+    p.conditional.handle = handle;
+    p.conditional.type = cudaGraphCondTypeWhile;
+    p.conditional.size = 1;
+    cudaGraphNode_t node;
+    CK(cudaGraphAddNode(&node, c->graph, nullptr, 0, &p));
+    cudaGraph_t body = p.conditional.phGraph_out[0];
+    CK(cudaStreamBeginCaptureToGraph(c->cap_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    const int rc = scf_body(c, c->cap_stream, maxiter, thresh, flags, handle, 1);
+    cudaGraph_t got = nullptr;
+    cudaError_t e = cudaStreamEndCapture(c->cap_stream, &got);
+    if (rc) return 1;
+    if (e != cudaSuccess) return fail("scf graph capture failed: %s", cudaGetErrorString(e));
+    CK(cudaGraphInstantiate(&c->gexec, c->graph, 0));
+    c->g_maxiter = maxiter;
+    c->g_thresh = thresh;
+    c->g_flags = flags;
+    return 0;
+}
+
+static int run_scf(admp_ctx* c, cudaStream_t st, int maxiter, double thresh, uint32_t flags) {
+    CK(cudaMemsetAsync(c->state, 0, sizeof(int32_t) * 8, st));
+    const uint32_t gkey = flags & ADMP_WANT_VIRIAL;
+    if (!(flags & ADMP_SCF_HOSTSYNC) && !c->graph_failed) {
+        if (!c->gexec || c->g_maxiter != maxiter || c->g_thresh != thresh || c->g_flags != gkey) {
+            if (build_scf_graph(c, maxiter, thresh, gkey)) {
+                c->graph_failed = true;       // keep the message; fall through to the host-synchronised loop
+                drop_graph(c);
+                cudaGetLastError();
+            }
+        }
+        if (c->gexec) {
+            CK(cudaGraphLaunch(c->gexec, st));
+            return 0;
+        }
+    }
+    // debug / fallback: same kernels, loop condition read back every iteration
+    cudaGraphConditionalHandle none;
+    memset(&none, 0, sizeof(none));
+    for (int it = 0; it <= maxiter; ++it) {
+        if (scf_body(c, st, maxiter, thresh, gkey, none, 0)) return 1;
+        CK(cudaMemcpyAsync(c->h_state, c->state, sizeof(int32_t) * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (!c->h_state[5]) break;
+    }
+    return 0;
+}
+
+static int ensure_pairs(admp_ctx* c, int64_t n_rows) {
+    if (n_rows <= c->pairs_cap) return 0;
+    drop_graph(c);
+    dfree(c->s_pairs);
+    int64_t cap = n_rows + n_rows / 4 + 1024;
+    CK(cudaMalloc(&c->s_pairs, sizeof(int32_t) * 2 * cap));
+    c->pairs_cap = cap;
+    return 0;
+}
+
+extern "C" int admp_pme_eval(admp_ctx* c, void* stream, const void* pos, const void* box, const int32_t* pairs, int64_t n_rows,
+                             const void* Ql, void* U_io, const void* pol, const void* tholes, const void* mScales,
+                             const void* pScales, uint32_t flags, int maxiter, double thresh, double* scalars, void* dpos,
+                             void* dQl, void* F, void* dpol, void* dtholes, int32_t* scf_out) {
+    if (need(c, true, true)) return 1;
+    const bool polz = (pol != nullptr);
+    if (polz && (!tholes || !pScales || !U_io)) return fail("admp_pme_eval: polarizable call needs U, pol, tholes, pScales");
+    if (polz && c->lmax < 1) return fail("admp_pme_eval: lpol with lmax = 0 is not supported (admp/pme.py:224-228 is broken upstream)");
+    if ((flags & ADMP_WANT_GRAD) && (!dpos || !dQl)) return fail("admp_pme_eval: gradient outputs missing");
+    if (!scalars) return fail("admp_pme_eval: scalars missing");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(c->device));
+    const int n = c->n_atoms;
+    const size_t w = c->w;
+    const int nh = (c->lmax + 1) * (c->lmax + 1);
+    if (ensure_pairs(c, n_rows)) return 1;
+    // stage inputs so that the SCF graph only ever sees context-owned addresses
+    CK(cudaMemcpyAsync(c->s_pos, pos, (size_t)n * 3 * w, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(c->s_box, box, 9 * w, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemsetAsync(c->s_pairs, 0, sizeof(int32_t) * 2 * c->pairs_cap, st));        // (0,0) rows are skipped (i<j fails)
+    if (n_rows > 0) CK(cudaMemcpyAsync(c->s_pairs, pairs, sizeof(int32_t) * 2 * n_rows, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(c->s_mS, mScales, 5 * w, cudaMemcpyDeviceToDevice, st));
+    if (polz) {
+        CK(cudaMemcpyAsync(c->s_U, U_io, (size_t)n * 3 * w, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(c->s_pol, pol, (size_t)n * w, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(c->s_th, tholes, (size_t)n * w, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(c->s_pS, pScales, 5 * w, cudaMemcpyDeviceToDevice, st));
+    }
+    CK(cudaMemsetAsync(c->scal, 0, sizeof(double) * ADMP_S_COUNT, st));
+    CK(cudaMemsetAsync(c->G, 0, (size_t)n * 10 * w, st));
+    if (dpos) CK(cudaMemsetAsync(dpos, 0, (size_t)n * 3 * w, st));
+    if (F) CK(cudaMemsetAsync(F, 0, (size_t)n * 3 * w, st));
+    if (dpol) CK(cudaMemsetAsync(dpol, 0, (size_t)n * w, st));
+    if (dtholes) CK(cudaMemsetAsync(dtholes, 0, (size_t)n * w, st));
+    DISPATCH(c, launch_box_setup, st, c->s_box, c->box, c->K[0], c->K[1], c->K[2]);
+    DISPATCH(c, launch_frames_fwd, st, n, c->lmax, c->box, c->s_pos, c->axis_type, c->axis_idx, Ql, c->M, nullptr, nullptr);
+    CKLAUNCH();
+    const int want_vir = (flags & ADMP_WANT_VIRIAL) ? 1 : 0;
+    if (polz && (flags & ADMP_SCF)) {
+        if (run_scf(c, st, maxiter, thresh, flags)) return 1;
+        if (scf_out) CK(cudaMemcpyAsync(scf_out, c->state + 3, sizeof(int32_t) * 2, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(U_io, c->s_U, (size_t)n * 3 * w, cudaMemcpyDeviceToDevice, st));
+    } else {
+        if (recip_field(c, st, c->s_pos, c->M, 10, 10, polz ? c->s_U : nullptr, ADMP_CK_COULOMB, c->scal, want_vir)) return 1;
+    }
+    // final evaluation at fixed U (Hellmann-Feynman, pme.py:83-85): phi of the last pass is still in c->mesh
+    const void* Uf = polz ? c->s_U : nullptr;
+    const uint32_t f = flags & (ADMP_WANT_GRAD | ADMP_WANT_VIRIAL | ADMP_WANT_PGRAD);
+    if (flags & ADMP_WANT_GRAD) {
+        DISPATCH(c, launch_gather, st, n, c->box, c->s_pos, c->M, 10, 10, Uf, c->mesh, 0, f, dpos, c->G, 10, polz ? F : nullptr, c->scal);
+    }
+    DISPATCH(c, launch_pme_pair, st, c->pairs_cap, n, c->box, c->kappa, c->s_pos, c->s_pairs, c->cov_off, c->cov_idx, c->cov_nb, c->M, Uf,
+             polz ? c->s_pol : nullptr, polz ? c->s_th : nullptr, c->s_mS, polz ? c->s_pS : nullptr, 0, f, dpos, c->G, F, dpol, dtholes, c->scal);
+    DISPATCH(c, launch_self, st, n, c->kappa, c->M, Uf, polz ? c->s_pol : nullptr, f, c->G, F, dpol, c->scal);
+    if (flags & ADMP_WANT_GRAD) {
+        DISPATCH(c, launch_frames_bwd, st, n, c->lmax, c->box, c->s_pos, c->axis_type, c->axis_idx, Ql, c->G, dQl, dpos, c->scal, want_vir);
+    }
+    if (want_vir) launch_virial_finalize(st, c->box, c->scal);
+    CKLAUNCH();
+    CK(cudaMemcpyAsync(scalars, c->scal, sizeof(double) * ADMP_S_COUNT, cudaMemcpyDeviceToDevice, st));
+    (void)nh;
+    return 0;
+}
+
+extern "C" int admp_disp_eval(admp_ctx* c, void* stream, const void* pos, const void* box, const int32_t* pairs, int64_t n_rows,
+                              const void* c_list, const void* mScales, int pmax, uint32_t flags, double* scalars, void* dpos,
+                              void* dc) {
+    if (need(c, true, true)) return 1;
+    if (pmax != 6 && pmax != 8 && pmax != 10) return fail("admp_disp_eval: pmax must be 6, 8 or 10");
+    if ((flags & ADMP_WANT_GRAD) && !dpos) return fail("admp_disp_eval: dpos missing");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(c->device));
+    const int n = c->n_atoms;
+    const size_t w = c->w;
+    CK(cudaMemsetAsync(c->scal, 0, sizeof(double) * ADMP_S_COUNT, st));
+    if (dpos) CK(cudaMemsetAsync(dpos, 0, (size_t)n * 3 * w, st));
+    if (dc) CK(cudaMemsetAsync(dc, 0, (size_t)n * 3 * w, st));
+    DISPATCH(c, launch_box_setup, st, box, c->box, c->K[0], c->K[1], c->K[2]);
+    const uint32_t f = flags & (ADMP_WANT_GRAD | ADMP_WANT_VIRIAL | ADMP_WANT_PGRAD);
+    DISPATCH(c, launch_disp_pair, st, n_rows, n, c->box, c->kappa, pmax, pos, pairs, c->cov_off, c->cov_idx, c->cov_nb, c_list, mScales, f,
+             dpos, (f & ADMP_WANT_PGRAD) ? dc : nullptr, c->scal);
+    CKLAUNCH();
+    const int kinds[3] = {ADMP_CK_DISP6, ADMP_CK_DISP8, ADMP_CK_DISP10};
+    for (int p = 0; p < (pmax - 4) / 2; ++p) {
+        const char* col = (const char*)c_list + p * w;
+        if (recip_field(c, st, pos, col, 1, 3, nullptr, kinds[p], c->scal, (f & ADMP_WANT_VIRIAL) ? 1 : 0)) return 1;
+        if (f & (ADMP_WANT_GRAD | ADMP_WANT_PGRAD)) {
+            void* g = ((f & ADMP_WANT_PGRAD) && dc) ? (void*)((char*)dc + p * w) : nullptr;
+            DISPATCH(c, launch_gather, st, n, c->box, pos, col, 1, 3, nullptr, c->mesh, 0, f, (f & ADMP_WANT_GRAD) ? dpos : nullptr, g, 3,
+                     nullptr, c->scal);
+            CKLAUNCH();
+        }
+    }
+    DISPATCH(c, launch_disp_self, st, n, c->kappa, pmax, c_list, f, dc, c->scal);
+    if (f & ADMP_WANT_VIRIAL) launch_virial_finalize(st, c->box, c->scal);
+    CKLAUNCH();
+    CK(cudaMemcpyAsync(scalars, c->scal, sizeof(double) * ADMP_S_COUNT, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+extern "C" int admp_tt_pair(admp_ctx* c, void* stream, const void* pos, const void* box, const int32_t* pairs, int64_t n_rows,
+                            const void* mScales, const void* a, const void* b, const void* q, const void* cc, uint32_t flags,
+                            double* scalars, void* dpos, void* dparams) {
+    if (need(c, false, true)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(c->device));
+    const int n = c->n_atoms;
+    const size_t w = c->w;
+    CK(cudaMemsetAsync(c->scal, 0, sizeof(double) * ADMP_S_COUNT, st));
+    if (dpos) CK(cudaMemsetAsync(dpos, 0, (size_t)n * 3 * w, st));
+    if (dparams) CK(cudaMemsetAsync(dparams, 0, (size_t)n * 4 * w, st));
+    DISPATCH(c, launch_box_setup, st, box, c->box, c->K[0] ? c->K[0] : 6, c->K[1] ? c->K[1] : 6, c->K[2] ? c->K[2] : 6);
+    const uint32_t f = flags & (ADMP_WANT_GRAD | ADMP_WANT_VIRIAL | ADMP_WANT_PGRAD);
+    DISPATCH(c, launch_tt_pair, st, n_rows, n, c->box, pos, pairs, c->cov_off, c->cov_idx, c->cov_nb, mScales, a, b, q, cc, f, dpos,
+             (f & ADMP_WANT_PGRAD) ? dparams : nullptr, c->scal);
+    CKLAUNCH();
+    CK(cudaMemcpyAsync(scalars, c->scal, sizeof(double) * ADMP_S_COUNT, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+extern "C" int admp_nblist_build(admp_ctx* c, void* stream, const void* pos, const void* box, int n, double rc, int32_t* pairs,
+                                 int64_t capacity, int32_t* info) {
+    if (!c) return fail("null ctx");
+    if (n <= 0 || rc <= 0.0) return fail("admp_nblist_build: bad n_atoms / rc");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(c->device));
+    // cell grid from the box lengths: needs the box on the host once (the build is the only
+    // stage whose launch geometry depends on the box)
+    double hb[9];
+    if (c->dtype == ADMP_F64) CK(cudaMemcpyAsync(hb, box, 72, cudaMemcpyDeviceToHost, st));
+    else {
+        float fb[9];
+        CK(cudaMemcpyAsync(fb, box, 36, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (int k = 0; k < 9; ++k) hb[k] = fb[k];
+    }
+    CK(cudaStreamSynchronize(st));
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b)
+            if (a != b && hb[3 * a + b] != 0.0) return fail("admp_nblist_build: orthorhombic boxes only");
+    int nc[3];
+    long long ncell = 1;
+    for (int d = 0; d < 3; ++d) {
+        if (!(hb[4 * d] > 0.0)) return fail("admp_nblist_build: non-positive box length");
+        if (2.0 * rc > hb[4 * d]) return fail("admp_nblist_build: rc exceeds half the box length (minimum image)");
+        int v = (int)std::floor(hb[4 * d] / (rc * (1.0 + 1e-6)));
+        if (v < 1) v = 1;
+        if (v > 512) v = 512;
+        nc[d] = v;
+        ncell *= v;
+    }
+    if (n > c->nb.capacity_atoms) {
+        dfree(c->nb.cell_of); dfree(c->nb.sorted); dfree(c->nb.nbr_count); dfree(c->nb.nbr_start);
+        CK(cudaMalloc(&c->nb.cell_of, sizeof(int32_t) * n));
+        CK(cudaMalloc(&c->nb.sorted, sizeof(int32_t) * n));
+        CK(cudaMalloc(&c->nb.nbr_count, sizeof(int32_t) * (n + 1)));
+        CK(cudaMalloc(&c->nb.nbr_start, sizeof(int32_t) * (n + 1)));
+        c->nb.capacity_atoms = n;
+    }
+    if (ncell > c->nb.capacity_cells) {
+        dfree(c->nb.cell_count); dfree(c->nb.cell_start);
+        CK(cudaMalloc(&c->nb.cell_count, sizeof(int32_t) * (ncell + 1)));
+        CK(cudaMalloc(&c->nb.cell_start, sizeof(int32_t) * (ncell + 1)));
+        c->nb.capacity_cells = (int)ncell;
+    }
+    const int K1 = c->K[0] ? c->K[0] : 6, K2 = c->K[1] ? c->K[1] : 6, K3 = c->K[2] ? c->K[2] : 6;
+    DISPATCH(c, launch_box_setup, st, box, c->box, K1, K2, K3);
+    launch_nblist(st, c->box, pos, c->dtype, n, rc, c->nb, nc[0], nc[1], nc[2], pairs, capacity, info);
+    CKLAUNCH();
+    return 0;
+}

@@ -1,0 +1,72 @@
+// Internal launcher declarations shared by the translation units of libadmp_b200.
+#pragma once
+#include "common.cuh"
+
+namespace admp {
+
+// frames.cu
+template <typename T>
+void launch_frames_fwd(cudaStream_t st, int n, int lmax, const BoxInfo* B, const void* pos, const int32_t* atype,
+                       const int32_t* ai, const void* Ql, void* M, void* Qg, void* Fr);
+template <typename T>
+void launch_frames_bwd(cudaStream_t st, int n, int lmax, const BoxInfo* B, const void* pos, const int32_t* atype,
+                       const int32_t* ai, const void* Ql, const void* G, void* dQl, void* dpos, double* scalars, int want_box);
+
+template <typename T> void launch_rotate(cudaStream_t st, int64_t n, int lmax, int to_local, const void* Q, const void* Fr, void* out);
+
+// pair.cu
+template <typename T>
+void launch_pme_pair(cudaStream_t st, int64_t n_rows, int n_atoms, const BoxInfo* B, double kappa, const void* pos,
+                     const int32_t* pairs, const int32_t* cov_off, const int32_t* cov_idx, const int8_t* cov_nb,
+                     const void* M, const void* U, const void* pol, const void* tholes, const void* mS, const void* pS,
+                     int mode, uint32_t flags, void* dpos, void* G, void* F, void* dpol, void* dth, double* scalars);
+template <typename T>
+void launch_disp_pair(cudaStream_t st, int64_t n_rows, int n_atoms, const BoxInfo* B, double kappa, int pmax, const void* pos,
+                      const int32_t* pairs, const int32_t* cov_off, const int32_t* cov_idx, const int8_t* cov_nb,
+                      const void* c_list, const void* mS, uint32_t flags, void* dpos, void* dc, double* scalars);
+template <typename T>
+void launch_tt_pair(cudaStream_t st, int64_t n_rows, int n_atoms, const BoxInfo* B, const void* pos, const int32_t* pairs,
+                    const int32_t* cov_off, const int32_t* cov_idx, const int8_t* cov_nb, const void* mS, const void* a,
+                    const void* b, const void* q, const void* c, uint32_t flags, void* dpos, void* dparams, double* scalars);
+
+// recip.cu
+template <typename T>
+void launch_spread(cudaStream_t st, int n, const BoxInfo* B, const void* pos, const void* M, int m_cols, int m_stride,
+                   const void* U, void* mesh);
+template <typename T>
+void launch_convolve(cudaStream_t st, const BoxInfo* B, size_t n_half, int n_sm, double kappa, int kind, const double* bt1,
+                     const double* bt2, const double* bt3, void* S, double* scalars, int want_vir);
+template <typename T>
+void launch_gather(cudaStream_t st, int n, const BoxInfo* B, const void* pos, const void* M, int m_cols, int m_stride, const void* U,
+                   const void* phi, int mode, uint32_t flags, void* dpos, void* G, int g_stride, void* F, double* scalars);
+
+// site.cu
+template <typename T> void launch_box_setup(cudaStream_t st, const void* box, BoxInfo* B, int K1, int K2, int K3);
+template <typename T>
+void launch_self(cudaStream_t st, int n, double kappa, const void* M, const void* U, const void* pol, uint32_t flags, void* G,
+                 void* F, void* dpol, double* scalars);
+template <typename T>
+void launch_disp_self(cudaStream_t st, int n, double kappa, int pmax, const void* c_list, uint32_t flags, void* dc, double* scalars);
+template <typename T>
+void launch_scf_field(cudaStream_t st, int n, double kappa, const void* M, const void* U, const void* pol, void* F, double* scalars);
+void launch_scf_decide(cudaStream_t st, int32_t* state, double* scalars, int maxiter, double thresh,
+                       cudaGraphConditionalHandle handle, int use_handle);
+template <typename T>
+void launch_scf_update(cudaStream_t st, int n, const int32_t* state, const void* F, const void* pol, void* U, double* scalars);
+void launch_scf_rearm(cudaStream_t st, double* scalars);
+void launch_virial_finalize(cudaStream_t st, const BoxInfo* B, double* scalars);
+
+// nblist.cu
+struct NbWork {
+    int32_t* cell_of;      // n
+    int32_t* cell_count;   // ncell+1
+    int32_t* cell_start;   // ncell+1
+    int32_t* sorted;       // n
+    int32_t* nbr_count;    // n+1
+    int32_t* nbr_start;    // n+1
+    int capacity_atoms, capacity_cells;
+};
+void launch_nblist(cudaStream_t st, const BoxInfo* B, const void* pos, int dtype, int n, double rc, NbWork& w, int ncx, int ncy,
+                   int ncz, int32_t* pairs, int64_t capacity, int32_t* info);
+
+}  // namespace admp

@@ -1,0 +1,582 @@
+// Real-space pair kernels.
+//
+// pme_pair_kernel replaces admp/pme.py:258-729 (calc_e_perm, calc_e_ind, pme_real_kernel,
+// pme_real) AND everything jax.grad derives from them: one pass over the pair list gives
+// the energy, dE/dr, the image-shift box term, dE/dM (potential / field / field gradient
+// per site), dE/dU, and the scale / Thole / polarizability gradients.
+//
+// Formulation (validated against the oracle's autograd in tests/test_analytic_proto.py):
+// instead of rotating both sites into the reference's quasi-internal frame (two 5x5
+// D-matrix builds per pair), the pair energy is written with rotational invariants of
+// (n = dr/|dr|, mu, Theta, u):
+//   E = A0 qI qJ + A1 (qI dJ - dI qJ) + A2 dI dJ + A3 muI.muJ + A4 (tI qJ + qI tJ)
+//     + A5 (tI dJ - dI tJ) + A6 (muJ.vI - muI.vJ) + A7 tI tJ + A8 vI.vJ + A9 TI:TJ
+//     + B1 (qI pJ - pI qJ) + B2 (pI dJ + pJ dI) + B3 (uI.muJ + uJ.muI)
+//     + B5 (tI pJ - pI tJ) + B6 (uJ.vI - uI.vJ) + C2 pI pJ + C3 uI.uJ
+// with d = mu.n, p = u.n, v = Theta n, t = n.v and radial functions that are linear
+// combinations of the reference's cc..qq_m2 / cud..udud_m1. FP64/FP32 CUDA-core work
+// (erf, exp, rsqrt): no tensor cores, this is not a dense contraction.
+#include "kernels.h"
+
+namespace admp {
+
+template <typename T> struct Radial {
+    T x, X, ri[6];   // ri[i] = DIEL r^-i
+    T b2, b3, b4, db2, db3, db4, kappa, r;
+    __device__ __forceinline__ T dxnX(int n, T xnm1, T xnp1) const { return kappa * ((T)n * xnm1 - 2 * xnp1) * X; }
+};
+
+template <typename T>
+__device__ __forceinline__ void radial_setup(T r, T kappa, Radial<T>& R) {
+    R.r = r; R.kappa = kappa;
+    const T rinv = (T)1 / r;
+    R.ri[0] = (T)ADMP_DIEL;
+#pragma unroll
+    for (int i = 1; i < 6; ++i) R.ri[i] = R.ri[i - 1] * rinv;
+    const T x = kappa * r, x2 = x * x;
+    R.x = x;
+    R.X = (T)(2 / ADMP_SQRT_PI) * exp(-x2);
+    const T b1 = -erf(x);
+    const T x3 = x2 * x, x5 = x3 * x2;
+    R.b2 = b1 + x * R.X;
+    R.b3 = R.b2 + (T)(2.0 / 3) * x3 * R.X;
+    R.b4 = R.b3 + (T)(4.0 / 15) * x5 * R.X;
+    R.db2 = -2 * kappa * x2 * R.X;
+    R.db3 = (T)(-4.0 / 3) * kappa * x2 * x2 * R.X;
+    R.db4 = (T)(-8.0 / 15) * kappa * x3 * x3 * R.X;
+}
+
+// A[0..9] (+ dA/dr, dA/dm) for scale m. With thole factors (t*, s* = dt/d(au)) this same routine
+// yields the halved perm-induced coefficients: pass m*t_x per rank via the "eff" arguments.
+template <typename T, bool DERIV>
+__device__ __forceinline__ void perm_coeffs(const Radial<T>& R, T m, T (&A)[10], T (&dA)[10], T (&mA)[10]) {
+    const T x = R.x, x2 = x * x, x3 = x2 * x, x4 = x2 * x2, x5 = x4 * x, x6 = x3 * x3, x7 = x6 * x, x8 = x4 * x4, X = R.X;
+    const T c23 = (T)(2 / ADMP_SQRT3), s3 = (T)ADMP_SQRT3;
+    const T* ri = R.ri;
+    const T rinv = ri[1] * (T)(1 / ADMP_DIEL);
+    // reference coefficients
+    const T tcc = m + R.b2 - x * X;
+    const T cc = ri[1] * tcc;
+    const T cd = ri[2] * (m + R.b2);
+    const T tdd0 = 3 * (m + R.b3) + x3 * X;
+    const T dd0 = (T)(-2.0 / 3) * ri[3] * tdd0;
+    const T tdd1 = m + R.b3 - (T)(2.0 / 3) * x3 * X;
+    const T dd1 = ri[3] * tdd1;
+    const T cq = ri[3] * (m + R.b3);
+    const T tdq0 = 3 * (m + R.b3) + (T)(4.0 / 3) * x5 * X;
+    const T dq0 = ri[4] * tdq0;
+    const T dq1 = -s3 * ri[4] * (m + R.b3);
+    const T tqq0 = 6 * (m + R.b4) + (T)(4.0 / 45) * (-3 * x5 + 10 * x7) * X;
+    const T qq0 = ri[5] * tqq0;
+    const T tqq1 = 15 * (m + R.b4) + x5 * X;
+    const T qq1 = (T)(-4.0 / 15) * ri[5] * tqq1;
+    const T tqq2 = m + R.b4 - (T)(4.0 / 15) * x5 * X;
+    const T qq2 = ri[5] * tqq2;
+    A[0] = cc; A[1] = cd; A[2] = dd0 - dd1; A[3] = dd1; A[4] = cq; A[5] = dq0 - c23 * dq1; A[6] = c23 * dq1;
+    A[7] = qq0 - (T)(4.0 / 3) * qq1 + (T)(1.0 / 3) * qq2; A[8] = (T)(4.0 / 3) * (qq1 - qq2); A[9] = (T)(2.0 / 3) * qq2;
+    if (DERIV) {
+        const T d1 = R.dxnX(1, (T)1, x2), d3 = R.dxnX(3, x2, x4), d5 = R.dxnX(5, x4, x6), d7 = R.dxnX(7, x6, x8);
+        const T dcc = -rinv * cc + ri[1] * (R.db2 - d1);
+        const T dcd = -2 * rinv * cd + ri[2] * R.db2;
+        const T ddd0 = -3 * rinv * dd0 + (T)(-2.0 / 3) * ri[3] * (3 * R.db3 + d3);
+        const T ddd1 = -3 * rinv * dd1 + ri[3] * (R.db3 - (T)(2.0 / 3) * d3);
+        const T dcq = -3 * rinv * cq + ri[3] * R.db3;
+        const T ddq0 = -4 * rinv * dq0 + ri[4] * (3 * R.db3 + (T)(4.0 / 3) * d5);
+        const T ddq1 = -4 * rinv * dq1 - s3 * ri[4] * R.db3;
+        const T dqq0 = -5 * rinv * qq0 + ri[5] * (6 * R.db4 + (T)(4.0 / 45) * (-3 * d5 + 10 * d7));
+        const T dqq1 = -5 * rinv * qq1 + (T)(-4.0 / 15) * ri[5] * (15 * R.db4 + d5);
+        const T dqq2 = -5 * rinv * qq2 + ri[5] * (R.db4 - (T)(4.0 / 15) * d5);
+        dA[0] = dcc; dA[1] = dcd; dA[2] = ddd0 - ddd1; dA[3] = ddd1; dA[4] = dcq; dA[5] = ddq0 - c23 * ddq1; dA[6] = c23 * ddq1;
+        dA[7] = dqq0 - (T)(4.0 / 3) * dqq1 + (T)(1.0 / 3) * dqq2; dA[8] = (T)(4.0 / 3) * (dqq1 - dqq2); dA[9] = (T)(2.0 / 3) * dqq2;
+        // d/dm of (cc, cd, dd0, dd1, cq, dq0, dq1, qq0, qq1, qq2) = (r1, r2, -2r3, r3, r3, 3r4, -s3 r4, 6r5, -4r5, r5)
+        mA[0] = ri[1]; mA[1] = ri[2]; mA[2] = -3 * ri[3]; mA[3] = ri[3]; mA[4] = ri[3]; mA[5] = 3 * ri[4] + c23 * s3 * ri[4];
+        mA[6] = -c23 * s3 * ri[4]; mA[7] = 6 * ri[5] + (T)(16.0 / 3) * ri[5] + (T)(1.0 / 3) * ri[5];
+        mA[8] = (T)(4.0 / 3) * (-5 * ri[5]); mA[9] = (T)(2.0 / 3) * ri[5];
+    }
+}
+
+// B[0..6] = B1, B2, B3, B5, B6, C2, C3 (admp/pme.py:379-475, halved perm-induced factors)
+template <typename T> struct IndCoef {
+    T B[7], dB[7];        // value, total d/dr
+    T pB[7], aB[7];       // d/dpscale, d/d(au)  (for parameter gradients)
+    T au_a, au_d, da_dth; // d(au)/da, d(au)/d(dmp), da/dthole
+    bool trimmed;
+    T dmp;
+};
+
+template <typename T, bool DERIV>
+__device__ __forceinline__ void ind_coeffs(const Radial<T>& R, T p, T th1, T th2, T pol1, T pol2, IndCoef<T>& C) {
+    const T x = R.x, x2 = x * x, x3 = x2 * x, x4 = x2 * x2, x5 = x4 * x, x6 = x3 * x3, X = R.X;
+    const T c23 = (T)(2 / ADMP_SQRT3), s3 = (T)ADMP_SQRT3;
+    const T* ri = R.ri;
+    const T rinv = ri[1] * (T)(1 / ADMP_DIEL);
+    // Thole width: Fermi switch of admp/pme.py:337-348,411, piecewise constant in pscale (A7)
+    T uarg = (p - (T)1e-3) * (T)1e5;
+    uarg = uarg > (T)80 ? (T)80 : uarg;
+    const T w0 = (T)1 / (exp(uarg) + (T)1);
+    const T a = w0 * (T)ADMP_THOLE_DEFAULT + ((T)1 - w0) * (th1 + th2);
+    C.da_dth = (T)1 - w0;
+    // dmp = trim_val_0((pol1 pol2)^(1/6)), u = trim_val_infty(r/dmp)   (pme.py:413-414,732-735)
+    const double prod = (double)pol1 * (double)pol2;
+    double dmpd = prod < 1e-48 ? 0.0 : pow(prod, 1.0 / 6.0);
+    C.trimmed = dmpd < 1e-8;
+    if (C.trimmed) dmpd = 1e-8;
+    const T dmp = (T)dmpd;
+    C.dmp = dmp;
+    const double ud = (double)R.r / dmpd;
+    const bool clipped = ud >= 1e8;
+    const T u = clipped ? (T)1e8 : (T)ud;
+    const T au = a * u;
+    T tc = 1, td0 = 1, tq0 = 1, tq1 = 1, sc = 0, sd0 = 0, sq0 = 0, sq1 = 0;
+    if (au < (T)50) {                                      // pme.py:418 (expau := 0 beyond)
+        const T e = exp(-au), au2 = au * au, au3 = au2 * au, au4 = au2 * au2;
+        const T base = (T)1 + au + (T)0.5 * au2;
+        tc = (T)1 - e * base;
+        td0 = (T)1 - e * (base + (T)0.25 * au3);
+        tq1 = (T)1 - e * (base + au3 * (T)(1.0 / 6));
+        tq0 = (T)1 - e * (base + au3 * (T)(1.0 / 6) + au4 * (T)(1.0 / 18));
+        sc = e * au2 * (T)0.5;
+        sd0 = e * (au3 - au2) * (T)0.25;
+        sq0 = e * (au4 - au3) * (T)(1.0 / 18);
+        sq1 = e * au3 * (T)(1.0 / 6);
+    }
+    const T au_r = clipped ? (T)0 : a / dmp;
+    C.au_a = u;
+    C.au_d = clipped ? (T)0 : -a * R.r / (dmp * dmp);
+    const T d3 = R.dxnX(3, x2, x4), d5 = R.dxnX(5, x4, x6);
+    // cud/2
+    const T t1 = p * tc + R.b2;
+    const T B1 = ri[2] * t1;
+    // dud0/2, dud1/2
+    const T th0 = 3 * (p * td0 + R.b3) + x3 * X;
+    const T h0 = (T)(-2.0 / 3) * ri[3] * th0;
+    const T th1_ = p * tc + R.b3 - (T)(2.0 / 3) * x3 * X;
+    const T h1 = ri[3] * th1_;
+    // udq0/2, udq1/2
+    const T tq0_ = 3 * (p * tq0 + R.b3) + (T)(4.0 / 3) * x5 * X;
+    const T q0 = ri[4] * tq0_;
+    const T q1 = -s3 * ri[4] * (p * tq1 + R.b3);
+    // udud0, udud1 (uscales = 1, pme.py:470)
+    const T tu0 = 3 * (td0 + R.b3) + x3 * X;
+    const T u0 = (T)(-2.0 / 3) * ri[3] * tu0;
+    const T u1 = ri[3] * (tc + R.b3 - (T)(2.0 / 3) * x3 * X);
+    C.B[0] = B1; C.B[1] = h0 - h1; C.B[2] = h1; C.B[3] = q0 - c23 * q1; C.B[4] = c23 * q1; C.B[5] = u0 - u1; C.B[6] = u1;
+    if (DERIV) {
+        // partial d/dr at fixed au
+        const T dB1 = -2 * rinv * B1 + ri[2] * R.db2;
+        const T dh0 = -3 * rinv * h0 + (T)(-2.0 / 3) * ri[3] * (3 * R.db3 + d3);
+        const T dh1 = -3 * rinv * h1 + ri[3] * (R.db3 - (T)(2.0 / 3) * d3);
+        const T dq0 = -4 * rinv * q0 + ri[4] * (3 * R.db3 + (T)(4.0 / 3) * d5);
+        const T dq1 = -4 * rinv * q1 - s3 * ri[4] * R.db3;
+        const T du0 = -3 * rinv * u0 + (T)(-2.0 / 3) * ri[3] * (3 * R.db3 + d3);
+        const T du1 = -3 * rinv * u1 + ri[3] * (R.db3 - (T)(2.0 / 3) * d3);
+        // d/d(au)
+        const T aB1 = ri[2] * p * sc;
+        const T ah0 = -2 * ri[3] * p * sd0, ah1 = ri[3] * p * sc;
+        const T aq0 = 3 * ri[4] * p * sq0, aq1 = -s3 * ri[4] * p * sq1;
+        const T au0 = -2 * ri[3] * sd0, au1 = ri[3] * sc;
+        C.aB[0] = aB1; C.aB[1] = ah0 - ah1; C.aB[2] = ah1; C.aB[3] = aq0 - c23 * aq1; C.aB[4] = c23 * aq1; C.aB[5] = au0 - au1; C.aB[6] = au1;
+        C.dB[0] = dB1 + C.aB[0] * au_r; C.dB[1] = dh0 - dh1 + C.aB[1] * au_r; C.dB[2] = dh1 + C.aB[2] * au_r;
+        C.dB[3] = dq0 - c23 * dq1 + C.aB[3] * au_r; C.dB[4] = c23 * dq1 + C.aB[4] * au_r;
+        C.dB[5] = du0 - du1 + C.aB[5] * au_r; C.dB[6] = du1 + C.aB[6] * au_r;
+        // d/dpscale
+        const T pB1 = ri[2] * tc, ph0 = -2 * ri[3] * td0, ph1 = ri[3] * tc, pq0 = 3 * ri[4] * tq0, pq1 = -s3 * ri[4] * tq1;
+        C.pB[0] = pB1; C.pB[1] = ph0 - ph1; C.pB[2] = ph1; C.pB[3] = pq0 - c23 * pq1; C.pB[4] = c23 * pq1; C.pB[5] = 0; C.pB[6] = 0;
+    }
+}
+
+template <typename T> __device__ __forceinline__ T dot3(const T* a, const T* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+// v = Theta n for the 6-component symmetric layout (xx,xy,xz,yy,yz,zz)
+template <typename T> __device__ __forceinline__ void symv(const T* t, const T* n, T* v) {
+    v[0] = t[0] * n[0] + t[1] * n[1] + t[2] * n[2];
+    v[1] = t[1] * n[0] + t[3] * n[1] + t[4] * n[2];
+    v[2] = t[2] * n[0] + t[4] * n[1] + t[5] * n[2];
+}
+
+// MODE 0: energy + adjoints. MODE 1: dE/dU only (the SCF field).
+template <typename T, bool POL, int MODE>
+__global__ void __launch_bounds__(128)
+pme_pair_kernel(int64_t n_rows, int n_atoms, const BoxInfo* __restrict__ Bp, T kappa,
+                const T* __restrict__ pos, const int32_t* __restrict__ pairs,
+                const int32_t* __restrict__ cov_off, const int32_t* __restrict__ cov_idx, const int8_t* __restrict__ cov_nb,
+                const T* __restrict__ M, const T* __restrict__ U, const T* __restrict__ pol, const T* __restrict__ tholes,
+                const T* __restrict__ mScales, const T* __restrict__ pScales, uint32_t flags,
+                T* __restrict__ dpos, T* __restrict__ G, T* __restrict__ F, T* __restrict__ dpol, T* __restrict__ dth,
+                double* __restrict__ scalars) {
+    __shared__ double red[10 * 4];
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double acc_e = 0.0;
+    double acc_box[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    double acc_ms[5] = {0, 0, 0, 0, 0}, acc_ps[5] = {0, 0, 0, 0, 0};
+    const bool want_grad = (flags & ADMP_WANT_GRAD) != 0, want_vir = (flags & ADMP_WANT_VIRIAL) != 0,
+               want_pg = (flags & ADMP_WANT_PGRAD) != 0;
+    int i = 0, j = 0;
+    bool live = false;
+    if (p < n_rows) {
+        i = pairs[2 * p]; j = pairs[2 * p + 1];
+        live = (i < j) && (i >= 0) && (j < n_atoms);              // pme.py:671 (padding rows are (N,N))
+    }
+    if (live) {
+        const BoxInfo& B = *Bp;
+        T d[3] = {pos[3 * i] - pos[3 * j], pos[3 * i + 1] - pos[3 * j + 1], pos[3 * i + 2] - pos[3 * j + 2]};
+        T sh[3];
+        min_image(B, d, sh);
+        const T r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+        const T rinv = rsqrt(r2), r = r2 * rinv;
+        const T n[3] = {d[0] * rinv, d[1] * rinv, d[2] * rinv};
+        const int sidx = scale_index(cov_off, cov_idx, cov_nb, i, j);
+        Radial<T> R;
+        radial_setup(r, kappa, R);
+        T mi[10], mj[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) { mi[k] = M[(size_t)i * 10 + k]; mj[k] = M[(size_t)j * 10 + k]; }
+        const T qI = mi[0], qJ = mj[0];
+        const T *muI = mi + 1, *muJ = mj + 1, *TI = mi + 4, *TJ = mj + 4;
+        T vI[3], vJ[3];
+        symv(TI, n, vI); symv(TJ, n, vJ);
+        const T dI = dot3(muI, n), dJ = dot3(muJ, n), tI = dot3(vI, n), tJ = dot3(vJ, n);
+        T uI[3] = {0, 0, 0}, uJ[3] = {0, 0, 0}, pI = 0, pJ = 0;
+        IndCoef<T> C;
+        if (POL) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { uI[k] = U[(size_t)i * 3 + k]; uJ[k] = U[(size_t)j * 3 + k]; }
+            pI = dot3(uI, n); pJ = dot3(uJ, n);
+            ind_coeffs<T, MODE == 0>(R, pScales[sidx], tholes[i], tholes[j], pol[i], pol[j], C);
+        }
+        if (MODE == 1) {
+            // dE/du only
+            const T B1 = C.B[0], B2 = C.B[1], B3 = C.B[2], B5 = C.B[3], B6 = C.B[4], C2 = C.B[5], C3 = C.B[6];
+            const T e_pI = -B1 * qJ + B2 * dJ - B5 * tJ + C2 * pJ;
+            const T e_pJ = B1 * qI + B2 * dI + B5 * tI + C2 * pI;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                atomicAdd(F + (size_t)i * 3 + k, e_pI * n[k] + B3 * muJ[k] - B6 * vJ[k] + C3 * uJ[k]);
+                atomicAdd(F + (size_t)j * 3 + k, e_pJ * n[k] + B3 * muI[k] + B6 * vI[k] + C3 * uI[k]);
+            }
+        } else {
+            T A[10], dA[10], mA[10];
+            perm_coeffs<T, true>(R, mScales[sidx], A, dA, mA);
+            const T mm = dot3(muI, muJ), gJI = dot3(muJ, vI), gIJ = dot3(muI, vJ), vv = dot3(vI, vJ);
+            const T TT = TI[0] * TJ[0] + TI[3] * TJ[3] + TI[5] * TJ[5] + 2 * (TI[1] * TJ[1] + TI[2] * TJ[2] + TI[4] * TJ[4]);
+            const T inv[10] = {qI * qJ, qI * dJ - dI * qJ, dI * dJ, mm, tI * qJ + qI * tJ, tI * dJ - dI * tJ, gJI - gIJ, tI * tJ, vv, TT};
+            T e = 0, dEdr = 0, dm = 0;
+#pragma unroll
+            for (int k = 0; k < 10; ++k) { e += A[k] * inv[k]; dEdr += dA[k] * inv[k]; dm += mA[k] * inv[k]; }
+            T e_dI = -A[1] * qJ + A[2] * dJ - A[5] * tJ, e_dJ = A[1] * qI + A[2] * dI + A[5] * tI;
+            T e_tI = A[4] * qJ + A[5] * dJ + A[7] * tJ, e_tJ = A[4] * qI - A[5] * dI + A[7] * tI;
+            T g_qI = A[0] * qJ + A[1] * dJ + A[4] * tJ, g_qJ = A[0] * qI - A[1] * dI + A[4] * tI;
+            T e_pI = 0, e_pJ = 0;
+            T inv2[7];
+            if (POL) {
+                inv2[0] = qI * pJ - pI * qJ; inv2[1] = pI * dJ + pJ * dI; inv2[2] = dot3(uI, muJ) + dot3(uJ, muI);
+                inv2[3] = tI * pJ - pI * tJ; inv2[4] = dot3(uJ, vI) - dot3(uI, vJ); inv2[5] = pI * pJ; inv2[6] = dot3(uI, uJ);
+#pragma unroll
+                for (int k = 0; k < 7; ++k) { e += C.B[k] * inv2[k]; dEdr += C.dB[k] * inv2[k]; }
+                const T B1 = C.B[0], B2 = C.B[1], B5 = C.B[3], C2 = C.B[5];
+                e_dI += B2 * pJ; e_dJ += B2 * pI; e_tI += B5 * pJ; e_tJ -= B5 * pI; g_qI += B1 * pJ; g_qJ -= B1 * pI;
+                e_pI = -B1 * qJ + B2 * dJ - B5 * tJ + C2 * pJ;
+                e_pJ = B1 * qI + B2 * dI + B5 * tI + C2 * pI;
+            }
+            acc_e = (double)e;
+            if (want_pg) {
+                acc_ms[sidx] = (double)dm;
+                if (POL) {
+                    T dp = 0, da = 0;
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) { dp += C.pB[k] * inv2[k]; da += C.aB[k] * inv2[k]; }
+                    acc_ps[sidx] = (double)dp;
+                    const T e_th = da * C.au_a * C.da_dth;
+                    if (dth != nullptr) { atomicAdd(dth + i, e_th); atomicAdd(dth + j, e_th); }
+                    if (!C.trimmed && dpol != nullptr) {
+                        const T e_dmp = da * C.au_d * C.dmp * (T)(1.0 / 6);
+                        atomicAdd(dpol + i, e_dmp / pol[i]); atomicAdd(dpol + j, e_dmp / pol[j]);
+                    }
+                }
+            }
+            if (want_grad) {
+                const T B3 = POL ? C.B[2] : (T)0, B6 = POL ? C.B[4] : (T)0, C3 = POL ? C.B[6] : (T)0;
+                T TImuJ[3], TJmuI[3], TIvJ[3], TJvI[3];
+                symv(TI, muJ, TImuJ); symv(TJ, muI, TJmuI); symv(TI, vJ, TIvJ); symv(TJ, vI, TJvI);
+                T gn[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    gn[k] = e_dI * muI[k] + e_dJ * muJ[k] + 2 * e_tI * vI[k] + 2 * e_tJ * vJ[k] + A[6] * (TImuJ[k] - TJmuI[k]) + A[8] * (TIvJ[k] + TJvI[k]);
+                if (POL) {
+                    T TIuJ[3], TJuI[3];
+                    symv(TI, uJ, TIuJ); symv(TJ, uI, TJuI);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) gn[k] += e_pI * uI[k] + e_pJ * uJ[k] + B6 * (TIuJ[k] - TJuI[k]);
+                }
+                const T gnn = dot3(gn, n);
+                T fv[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    fv[k] = dEdr * n[k] + (gn[k] - gnn * n[k]) * rinv;
+                    atomicAdd(dpos + (size_t)i * 3 + k, fv[k]);
+                    atomicAdd(dpos + (size_t)j * 3 + k, -fv[k]);
+                }
+                if (want_vir) {
+#pragma unroll
+                    for (int a = 0; a < 3; ++a)
+#pragma unroll
+                        for (int b = 0; b < 3; ++b) acc_box[3 * a + b] = -(double)(sh[a] * fv[b]);
+                }
+                // dE/dM
+                T* Gi = G + (size_t)i * 10;
+                T* Gj = G + (size_t)j * 10;
+                atomicAdd(Gi, g_qI); atomicAdd(Gj, g_qJ);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    atomicAdd(Gi + 1 + k, e_dI * n[k] + A[3] * muJ[k] - A[6] * vJ[k] + B3 * uJ[k]);
+                    atomicAdd(Gj + 1 + k, e_dJ * n[k] + A[3] * muI[k] + A[6] * vI[k] + B3 * uI[k]);
+                }
+                // quadrupole gradient: e_t n n^T + w n^T (symmetrised into the 6-comp layout) + A9 T_other
+                T wI[3], wJ[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    wI[k] = A[6] * muJ[k] + A[8] * vJ[k] + B6 * uJ[k];
+                    wJ[k] = -A[6] * muI[k] + A[8] * vI[k] - B6 * uI[k];
+                }
+                const int ia[6] = {0, 0, 0, 1, 1, 2}, ib[6] = {0, 1, 2, 1, 2, 2};
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    const int a = ia[k], b = ib[k];
+                    const T mult = (a == b) ? (T)1 : (T)2;
+                    T gI = e_tI * n[a] * n[b] * mult + ((a == b) ? wI[a] * n[a] : wI[a] * n[b] + wI[b] * n[a]) + A[9] * TJ[k] * mult;
+                    T gJ = e_tJ * n[a] * n[b] * mult + ((a == b) ? wJ[a] * n[a] : wJ[a] * n[b] + wJ[b] * n[a]) + A[9] * TI[k] * mult;
+                    atomicAdd(Gi + 4 + k, gI);
+                    atomicAdd(Gj + 4 + k, gJ);
+                }
+                if (POL) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        atomicAdd(F + (size_t)i * 3 + k, e_pI * n[k] + B3 * muJ[k] - B6 * vJ[k] + C3 * uJ[k]);
+                        atomicAdd(F + (size_t)j * 3 + k, e_pJ * n[k] + B3 * muI[k] + B6 * vI[k] + C3 * uI[k]);
+                    }
+                }
+            }
+        }
+    }
+    if (MODE == 0) {
+        double v1[1] = {acc_e};
+        block_accumulate<1>(v1, red, scalars + ADMP_S_E_REAL);
+        if (want_vir && want_grad) block_accumulate<9>(acc_box, red, scalars + ADMP_S_DBOX);
+        if (want_pg) {
+            block_accumulate<5>(acc_ms, red, scalars + ADMP_S_DMSCALE);
+            if (POL) block_accumulate<5>(acc_ps, red, scalars + ADMP_S_DPSCALE);
+        }
+    }
+}
+
+template <typename T>
+void launch_pme_pair(cudaStream_t st, int64_t n_rows, int n_atoms, const BoxInfo* B, double kappa, const void* pos,
+                     const int32_t* pairs, const int32_t* cov_off, const int32_t* cov_idx, const int8_t* cov_nb,
+                     const void* M, const void* U, const void* pol, const void* tholes, const void* mS, const void* pS,
+                     int mode, uint32_t flags, void* dpos, void* G, void* F, void* dpol, void* dth, double* scalars) {
+    if (n_rows <= 0) return;
+    const unsigned grid = (unsigned)((n_rows + 127) / 128);
+    const bool polz = (U != nullptr);
+#define ADMP_PAIR_ARGS n_rows, n_atoms, B, (T)kappa, (const T*)pos, pairs, cov_off, cov_idx, cov_nb, (const T*)M, (const T*)U, \
+    (const T*)pol, (const T*)tholes, (const T*)mS, (const T*)pS, flags, (T*)dpos, (T*)G, (T*)F, (T*)dpol, (T*)dth, scalars
+    if (mode == 1) {
+        if (polz) pme_pair_kernel<T, true, 1><<<grid, 128, 0, st>>>(ADMP_PAIR_ARGS);
+    } else if (polz) {
+        pme_pair_kernel<T, true, 0><<<grid, 128, 0, st>>>(ADMP_PAIR_ARGS);
+    } else {
+        pme_pair_kernel<T, false, 0><<<grid, 128, 0, st>>>(ADMP_PAIR_ARGS);
+    }
+#undef ADMP_PAIR_ARGS
+}
+template void launch_pme_pair<double>(cudaStream_t, int64_t, int, const BoxInfo*, double, const void*, const int32_t*, const int32_t*,
+                                      const int32_t*, const int8_t*, const void*, const void*, const void*, const void*, const void*,
+                                      const void*, int, uint32_t, void*, void*, void*, void*, void*, double*);
+template void launch_pme_pair<float>(cudaStream_t, int64_t, int, const BoxInfo*, double, const void*, const int32_t*, const int32_t*,
+                                     const int32_t*, const int8_t*, const void*, const void*, const void*, const void*, const void*,
+                                     const void*, int, uint32_t, void*, void*, void*, void*, void*, double*);
+
+// ------------------------------------------------------------------------------------------
+// Dispersion real space: admp/disp_pme.py:126-251.  E = sum_p (m + g_p(x^2) - 1) ci cj / r^p.
+template <typename T>
+__global__ void __launch_bounds__(128)
+disp_pair_kernel(int64_t n_rows, int n_atoms, const BoxInfo* __restrict__ Bp, T kappa, int pmax,
+                 const T* __restrict__ pos, const int32_t* __restrict__ pairs,
+                 const int32_t* __restrict__ cov_off, const int32_t* __restrict__ cov_idx, const int8_t* __restrict__ cov_nb,
+                 const T* __restrict__ c_list, const T* __restrict__ mScales, uint32_t flags,
+                 T* __restrict__ dpos, T* __restrict__ dc, double* __restrict__ scalars) {
+    __shared__ double red[10 * 4];
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double acc_e = 0.0, acc_box[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, acc_ms[5] = {0, 0, 0, 0, 0};
+    const bool want_grad = (flags & ADMP_WANT_GRAD) != 0, want_vir = (flags & ADMP_WANT_VIRIAL) != 0,
+               want_pg = (flags & ADMP_WANT_PGRAD) != 0;
+    int i = 0, j = 0;
+    bool live = false;
+    if (p < n_rows) { i = pairs[2 * p]; j = pairs[2 * p + 1]; live = (i < j) && (i >= 0) && (j < n_atoms); }
+    if (live) {
+        T d[3] = {pos[3 * i] - pos[3 * j], pos[3 * i + 1] - pos[3 * j + 1], pos[3 * i + 2] - pos[3 * j + 2]};
+        T sh[3];
+        min_image(*Bp, d, sh);
+        const T r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+        const int sidx = scale_index(cov_off, cov_idx, cov_nb, i, j);
+        const T m = mScales[sidx];
+        const T x2 = kappa * kappa * r2, x4 = x2 * x2, ex = exp(-x2);
+        const T ir2 = (T)1 / r2, ir6 = ir2 * ir2 * ir2;
+        // g_p and dg_p/dx2 = -exp(-x2) x2^(p/2-1)/(p/2-1)!
+        const T g6 = ((T)1 + x2 + (T)0.5 * x4) * ex, g8 = g6 + x4 * x2 * (T)(1.0 / 6) * ex, g10 = g8 + x4 * x4 * (T)(1.0 / 24) * ex;
+        const T h6 = -ex * x4 * (T)0.5, h8 = -ex * x4 * x2 * (T)(1.0 / 6), h10 = -ex * x4 * x4 * (T)(1.0 / 24);
+        const T ci[3] = {c_list[(size_t)i * 3], c_list[(size_t)i * 3 + 1], c_list[(size_t)i * 3 + 2]};
+        const T cj[3] = {c_list[(size_t)j * 3], c_list[(size_t)j * 3 + 1], c_list[(size_t)j * 3 + 2]};
+        const T g[3] = {g6, g8, g10}, h[3] = {h6, h8, h10};
+        T irp = ir6, e = 0, dEdr2 = 0, dm = 0;
+        T gci[3] = {0, 0, 0}, gcj[3] = {0, 0, 0};
+        const int np = (pmax - 4) / 2;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (k < np) {
+                const T cc = ci[k] * cj[k], f = (m + g[k] - (T)1);
+                e += f * cc * irp;
+                // d/dr2: h kappa^2 cc irp - (p/2) f cc irp / r2
+                dEdr2 += cc * irp * (h[k] * kappa * kappa - (T)(3 + k) * f * ir2);
+                dm += cc * irp;
+                gci[k] = f * cj[k] * irp; gcj[k] = f * ci[k] * irp;
+            }
+            irp *= ir2;
+        }
+        acc_e = (double)e;
+        if (want_pg) {
+            acc_ms[sidx] = (double)dm;
+            if (dc != nullptr) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { atomicAdd(dc + (size_t)i * 3 + k, gci[k]); atomicAdd(dc + (size_t)j * 3 + k, gcj[k]); }
+            }
+        }
+        if (want_grad) {
+            T fv[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                fv[k] = 2 * dEdr2 * d[k];
+                atomicAdd(dpos + (size_t)i * 3 + k, fv[k]);
+                atomicAdd(dpos + (size_t)j * 3 + k, -fv[k]);
+            }
+            if (want_vir) {
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) acc_box[3 * a + b] = -(double)(sh[a] * fv[b]);
+            }
+        }
+    }
+    double v1[1] = {acc_e};
+    block_accumulate<1>(v1, red, scalars + ADMP_S_E_REAL);
+    if (want_vir && want_grad) block_accumulate<9>(acc_box, red, scalars + ADMP_S_DBOX);
+    if (want_pg) block_accumulate<5>(acc_ms, red, scalars + ADMP_S_DMSCALE);
+}
+
+// Tang-Toennies short-range kernel through the generic pair driver: admp/pairwise.py:45-113.
+template <typename T>
+__global__ void __launch_bounds__(128)
+tt_pair_kernel(int64_t n_rows, int n_atoms, const BoxInfo* __restrict__ Bp, const T* __restrict__ pos,
+               const int32_t* __restrict__ pairs, const int32_t* __restrict__ cov_off, const int32_t* __restrict__ cov_idx,
+               const int8_t* __restrict__ cov_nb, const T* __restrict__ mScales, const T* __restrict__ pa,
+               const T* __restrict__ pb, const T* __restrict__ pq, const T* __restrict__ pc, uint32_t flags,
+               T* __restrict__ dpos, T* __restrict__ dparams, double* __restrict__ scalars) {
+    __shared__ double red[10 * 4];
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double acc_e = 0.0, acc_box[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, acc_ms[5] = {0, 0, 0, 0, 0};
+    const bool want_grad = (flags & ADMP_WANT_GRAD) != 0, want_vir = (flags & ADMP_WANT_VIRIAL) != 0,
+               want_pg = (flags & ADMP_WANT_PGRAD) != 0;
+    int i = 0, j = 0;
+    bool live = false;
+    if (p < n_rows) { i = pairs[2 * p]; j = pairs[2 * p + 1]; live = (i < j) && (i >= 0) && (j < n_atoms); }
+    if (live) {
+        T d[3] = {pos[3 * i] - pos[3 * j], pos[3 * i + 1] - pos[3 * j + 1], pos[3 * i + 2] - pos[3 * j + 2]};
+        T sh[3];
+        min_image(*Bp, d, sh);
+        const T r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+        const T r = sqrt(r2);
+        const int sidx = scale_index(cov_off, cov_idx, cov_nb, i, j);
+        const T m = mScales[sidx];
+        const T ai = pa[i], aj = pa[j], bi = pb[i], bj = pb[j], qi = pq[i], qj = pq[j], ci = pc[i], cj = pc[j];
+        const T a = sqrt(ai * aj), b = sqrt(bi * bj), c = ci * cj, q = qi * qj;
+        const T bohr = (T)1.889726878, ha = (T)2625.5;
+        const T br = b * r * bohr, ex = exp(-br);
+        T poly = 1, term = 1, dpoly = 0;      // poly = sum_{k<=6} br^k/k!, dpoly = sum_{k<=5}
+#pragma unroll
+        for (int k = 1; k <= 6; ++k) { dpoly = poly; term *= br / (T)k; poly += term; }
+        const T ir6 = (T)1 / (r2 * r2 * r2);
+        const T f1 = ha * a * ex;
+        const T f2 = -ha * ex * ((T)1 + br) * q / br;
+        const T f3 = ex * poly * c * ir6;
+        const T e = (f1 + f2 + f3) * m;
+        acc_e = (double)e;
+        // d/d(br) of each term (r-dependence of 1/r^6 handled separately)
+        const T d1 = -f1;
+        // d/dbr [ -e^{-br}(1+br)/br ] = e^{-br} (1 + (1+br)/br^2)
+        const T d2 = ha * ex * q * ((T)1 + ((T)1 + br) / (br * br));
+        const T d3 = ex * c * ir6 * (dpoly - poly);
+        const T dE_dbr = (d1 + d2 + d3) * m;
+        const T dE_dr = dE_dbr * b * bohr - 6 * f3 * m / r;
+        if (want_grad) {
+            T fv[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                fv[k] = dE_dr * d[k] / r;
+                atomicAdd(dpos + (size_t)i * 3 + k, fv[k]);
+                atomicAdd(dpos + (size_t)j * 3 + k, -fv[k]);
+            }
+            if (want_vir) {
+#pragma unroll
+                for (int aa = 0; aa < 3; ++aa)
+#pragma unroll
+                    for (int bb = 0; bb < 3; ++bb) acc_box[3 * aa + bb] = -(double)(sh[aa] * fv[bb]);
+            }
+        }
+        if (want_pg) {
+            acc_ms[sidx] = (double)(f1 + f2 + f3);
+            if (dparams != nullptr) {
+                const size_t n = (size_t)n_atoms;
+                // a = sqrt(ai aj): da/dai = a/(2 ai)
+                const T ea = m * ha * ex;
+                atomicAdd(dparams + i, ea * a / (2 * ai)); atomicAdd(dparams + j, ea * a / (2 * aj));
+                const T eb = dE_dbr * r * bohr;      // dE/db
+                atomicAdd(dparams + n + i, eb * b / (2 * bi)); atomicAdd(dparams + n + j, eb * b / (2 * bj));
+                const T eq = m * (-ha * ex * ((T)1 + br) / br);
+                atomicAdd(dparams + 2 * n + i, eq * qj); atomicAdd(dparams + 2 * n + j, eq * qi);
+                const T ec = m * ex * poly * ir6;
+                atomicAdd(dparams + 3 * n + i, ec * cj); atomicAdd(dparams + 3 * n + j, ec * ci);
+            }
+        }
+    }
+    double v1[1] = {acc_e};
+    block_accumulate<1>(v1, red, scalars + ADMP_S_E_REAL);
+    if (want_vir && want_grad) block_accumulate<9>(acc_box, red, scalars + ADMP_S_DBOX);
+    if (want_pg) block_accumulate<5>(acc_ms, red, scalars + ADMP_S_DMSCALE);
+}
+
+template <typename T>
+void launch_disp_pair(cudaStream_t st, int64_t n_rows, int n_atoms, const BoxInfo* B, double kappa, int pmax, const void* pos,
+                      const int32_t* pairs, const int32_t* cov_off, const int32_t* cov_idx, const int8_t* cov_nb,
+                      const void* c_list, const void* mS, uint32_t flags, void* dpos, void* dc, double* scalars) {
+    if (n_rows <= 0) return;
+    disp_pair_kernel<T><<<(unsigned)((n_rows + 127) / 128), 128, 0, st>>>(n_rows, n_atoms, B, (T)kappa, pmax, (const T*)pos, pairs, cov_off,
+                                                                         cov_idx, cov_nb, (const T*)c_list, (const T*)mS, flags,
+                                                                         (T*)dpos, (T*)dc, scalars);
+}
+template <typename T>
+void launch_tt_pair(cudaStream_t st, int64_t n_rows, int n_atoms, const BoxInfo* B, const void* pos, const int32_t* pairs,
+                    const int32_t* cov_off, const int32_t* cov_idx, const int8_t* cov_nb, const void* mS, const void* a,
+                    const void* b, const void* q, const void* c, uint32_t flags, void* dpos, void* dparams, double* scalars) {
+    if (n_rows <= 0) return;
+    tt_pair_kernel<T><<<(unsigned)((n_rows + 127) / 128), 128, 0, st>>>(n_rows, n_atoms, B, (const T*)pos, pairs, cov_off, cov_idx, cov_nb,
+                                                                       (const T*)mS, (const T*)a, (const T*)b, (const T*)q, (const T*)c,
+                                                                       flags, (T*)dpos, (T*)dparams, scalars);
+}
+template void launch_disp_pair<double>(cudaStream_t, int64_t, int, const BoxInfo*, double, int, const void*, const int32_t*, const int32_t*,
+                                       const int32_t*, const int8_t*, const void*, const void*, uint32_t, void*, void*, double*);
+template void launch_disp_pair<float>(cudaStream_t, int64_t, int, const BoxInfo*, double, int, const void*, const int32_t*, const int32_t*,
+                                      const int32_t*, const int8_t*, const void*, const void*, uint32_t, void*, void*, double*);
+template void launch_tt_pair<double>(cudaStream_t, int64_t, int, const BoxInfo*, const void*, const int32_t*, const int32_t*, const int32_t*,
+                                     const int8_t*, const void*, const void*, const void*, const void*, const void*, uint32_t, void*, void*, double*);
+template void launch_tt_pair<float>(cudaStream_t, int64_t, int, const BoxInfo*, const void*, const int32_t*, const int32_t*, const int32_t*,
+                                    const int8_t*, const void*, const void*, const void*, const void*, const void*, uint32_t, void*, void*, double*);
+
+}  // namespace admp

@@ -1,0 +1,433 @@
+// Reciprocal-space kernels: order-6 B-spline multipole spread, influence-function
+// convolution (+ energy, + k-space virial), and potential / field / field-gradient /
+// force gather. Replaces admp/recip.py:21-431 and what jax.grad derives from it.
+//
+// All three are HBM-bound; algorithmic bytes (w = sizeof(real), G = K1*K2*K3):
+//   spread   : w*G (mesh zero-fill) + Na*(3+n_comp)*w read + 216*Na RMW updates
+//   convolve : 2 * (2w) * (G/2)  (half spectrum read + write, in place)
+//   gather   : min(w*G, 216*w*Na) mesh reads + Na*(n_comp+3)*w
+// The FFTs in between are cuFFT (D2Z/Z2D or R2C/C2R), see api.cu.
+//
+// Fractional formulation (tools/analytic_proto.py, validated vs the oracle):
+//   u_d = m0_d - Nstar[d].r + 3 + s ; w_d^p[k] = d^p M6/du^p at f_d + k
+//   mesh(g) += q W000 + sum_d muf_d W[e_d] + sum_de Tf_de W[e_d+e_e]
+//   muf_d = -sum_c Nstar[d][c] mu_c ; Tf_de = sum_ab Nstar[d][a] Nstar[e][b] T_ab / 3
+#include "kernels.h"
+
+namespace admp {
+
+// w[p*6+k] = d^p/du^p M6(f+k), p = 0..NP-1, by the Cox-de Boor recursion (A23: any stable
+// evaluation is acceptable; the reference's piecewise polynomials recip.py:80-137 agree to 4e-13)
+template <typename T, int NP>
+__device__ __forceinline__ void bspline6(T f, T* __restrict__ w) {
+    T a[8][4];   // a[k+1][o-3] = M_o(f+k), o = 3..6, with zero guards at both ends
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int o = 0; o < 4; ++o) a[k][o] = (T)0;
+    const T m2_0 = f, m2_1 = (T)1 - f;
+    // order 3 from order 2
+    a[1][0] = (T)0.5 * (f * m2_0);
+    a[2][0] = (T)0.5 * ((f + 1) * m2_1 + ((T)2 - f) * m2_0);
+    a[3][0] = (T)0.5 * (((T)1 - f) * m2_1);
+#pragma unroll
+    for (int o = 4; o <= 6; ++o) {
+        const T inv = (T)1 / (T)(o - 1);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            if (k < o) {
+                const T prev_k = (k < o - 1) ? a[k + 1][o - 4] : (T)0;
+                const T prev_km1 = (k >= 1) ? a[k][o - 4] : (T)0;
+                a[k + 1][o - 3] = ((f + (T)k) * prev_k + ((T)o - f - (T)k) * prev_km1) * inv;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        w[k] = a[k + 1][3];
+        if (NP > 1) w[6 + k] = a[k + 1][2] - a[k][2];
+        if (NP > 2) w[12 + k] = a[k + 1][1] - 2 * a[k][1] + (k >= 1 ? a[k - 1][1] : (T)0);
+        if (NP > 3) w[18 + k] = a[k + 1][0] - 3 * a[k][0] + 3 * (k >= 1 ? a[k - 1][0] : (T)0) - (k >= 2 ? a[k - 2][0] : (T)0);
+    }
+}
+
+// per-atom mesh anchor: fractional coordinate x_d = Nstar[d].r (double: keeps the f32 build from
+// losing the sub-cell offset), m0 = ceil(x), f = m0 - x, first stencil index (m0 - 3) mod K
+__device__ __forceinline__ void mesh_anchor(const BoxInfo& B, double rx, double ry, double rz, int d, double& f, int& i0) {
+    const double x = B.nstar[3 * d] * rx + B.nstar[3 * d + 1] * ry + B.nstar[3 * d + 2] * rz;
+    const double m0 = ceil(x);
+    f = m0 - x;
+    const int K = B.K[d];
+    long long i = (long long)m0 - 3;
+    i %= K;
+    if (i < 0) i += K;
+    i0 = (int)i;
+}
+
+constexpr int SPREAD_WARPS = 4;
+
+// One warp per atom; lanes stride the 216 stencil points (z fastest => 6 contiguous reals).
+template <typename T, bool MULTIPOLE>
+__global__ void __launch_bounds__(SPREAD_WARPS * 32)
+spread_kernel(int n, const BoxInfo* __restrict__ Bp, const T* __restrict__ pos, const T* __restrict__ M, int m_stride,
+              const T* __restrict__ U, T* __restrict__ mesh) {
+    __shared__ T sw[SPREAD_WARPS][3][18];
+    __shared__ int si[SPREAD_WARPS][3];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int a = blockIdx.x * SPREAD_WARPS + warp;
+    if (a >= n) return;
+    const BoxInfo& B = *Bp;
+    if (lane < 3) {
+        double f; int i0;
+        mesh_anchor(B, (double)pos[3 * a], (double)pos[3 * a + 1], (double)pos[3 * a + 2], lane, f, i0);
+        bspline6<T, MULTIPOLE ? 3 : 1>((T)f, sw[warp][lane]);
+        si[warp][lane] = i0;
+    }
+    // fractional multipole coefficients (all lanes, redundantly: ~60 flop)
+    const T* m = M + (size_t)a * m_stride;
+    const T q = m[0];
+    T muf[3] = {0, 0, 0}, Tf[6] = {0, 0, 0, 0, 0, 0};
+    if (MULTIPOLE) {
+        T mu[3] = {m[1], m[2], m[3]};
+        if (U != nullptr) { mu[0] += U[3 * a]; mu[1] += U[3 * a + 1]; mu[2] += U[3 * a + 2]; }
+        const T Tm[9] = {m[4], m[5], m[6], m[5], m[7], m[8], m[6], m[8], m[9]};
+        T N[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) N[k] = (T)B.nstar[k];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) muf[d] = -(N[3 * d] * mu[0] + N[3 * d + 1] * mu[1] + N[3 * d + 2] * mu[2]);
+        T NT[9];   // NT[d][b] = sum_a N[d][a] T[a][b]
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) NT[3 * d + b] = N[3 * d] * Tm[b] + N[3 * d + 1] * Tm[3 + b] + N[3 * d + 2] * Tm[6 + b];
+        auto tf = [&](int d, int e) { return (NT[3 * d] * N[3 * e] + NT[3 * d + 1] * N[3 * e + 1] + NT[3 * d + 2] * N[3 * e + 2]) * (T)(1.0 / 3); };
+        Tf[0] = tf(0, 0); Tf[1] = 2 * tf(0, 1); Tf[2] = 2 * tf(0, 2); Tf[3] = tf(1, 1); Tf[4] = 2 * tf(1, 2); Tf[5] = tf(2, 2);
+    }
+    __syncwarp();
+    const T* w0 = sw[warp][0];
+    const T* w1 = sw[warp][1];
+    const T* w2 = sw[warp][2];
+    const int K1 = B.K[0], K2 = B.K[1], K3 = B.K[2];
+    const int i0 = si[warp][0], j0 = si[warp][1], k0 = si[warp][2];
+    for (int pt = lane; pt < 216; pt += 32) {
+        const int ia = pt / 36, ib = (pt / 6) % 6, ic = pt % 6;
+        T val;
+        if (MULTIPOLE) {
+            const T a0 = w0[ia], a1 = w0[6 + ia], a2 = w0[12 + ia];
+            const T b0 = w1[ib], b1 = w1[6 + ib], b2 = w1[12 + ib];
+            const T c0 = w2[ic], c1 = w2[6 + ic], c2 = w2[12 + ic];
+            const T t0 = q * a0 * b0 + muf[0] * a1 * b0 + muf[1] * a0 * b1 + Tf[0] * a2 * b0 + Tf[1] * a1 * b1 + Tf[3] * a0 * b2;
+            const T t1 = muf[2] * a0 * b0 + Tf[2] * a1 * b0 + Tf[4] * a0 * b1;
+            const T t2 = Tf[5] * a0 * b0;
+            val = t0 * c0 + t1 * c1 + t2 * c2;
+        } else {
+            val = q * w0[ia] * w1[ib] * w2[ic];
+        }
+        int gi = i0 + ia; if (gi >= K1) gi -= K1;
+        int gj = j0 + ib; if (gj >= K2) gj -= K2;
+        int gk = k0 + ic; if (gk >= K3) gk -= K3;
+        atomicAdd(mesh + ((size_t)gi * K2 + gj) * K3 + gk, val);
+    }
+}
+
+// ---------------------------------------------------------------------------- convolution
+__device__ __forceinline__ int kint(int i, int K) {      // recip.py:339: [0,1,...,-2,-1], even-K Nyquist negative
+    return (2 * i < K) ? i : i - K;
+}
+
+template <typename T> struct cplx { T x, y; };
+
+// In place on the half spectrum S (K1 x K2 x (K3/2+1)):  S <- 2*scale*C_k/theta_k^2 * S and
+// E += scale * sum_full C_k |S_k|^2 / theta_k^2   (recip.py:400-426, A16; R2C weights per plane).
+template <typename T>
+__global__ void __launch_bounds__(256)
+convolve_kernel(const BoxInfo* __restrict__ Bp, T kappa, int kind, const double* __restrict__ bt1,
+                const double* __restrict__ bt2, const double* __restrict__ bt3, cplx<T>* __restrict__ S,
+                double* __restrict__ scalars, int want_vir) {
+    __shared__ double red[7 * 8];
+    const BoxInfo& B = *Bp;
+    const int K1 = B.K[0], K2 = B.K[1], K3 = B.K[2], K3h = K3 / 2 + 1;
+    const size_t total = (size_t)K1 * K2 * K3h;
+    const double scale = (kind == ADMP_CK_COULOMB) ? ADMP_DIEL : 1.0;
+    const double twopi = 6.283185307179586;
+    const double kap = (double)kappa, V = B.vol;
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int i3 = (int)(idx % K3h);
+        const size_t rest = idx / K3h;
+        const int i2 = (int)(rest % K2), i1 = (int)(rest / K2);
+        const double m1 = kint(i1, K1), m2 = kint(i2, K2), m3 = i3;
+        double kv[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) kv[c] = twopi * (m1 * B.inv[c] + m2 * B.inv[3 + c] + m3 * B.inv[6 + c]);   // recip.py:360
+        const double ksq = kv[0] * kv[0] + kv[1] * kv[1] + kv[2] * kv[2];
+        double C, dC;
+        if (kind == ADMP_CK_COULOMB) {                                  // Ck_1, recip.py:434
+            if (idx == 0) { C = 0.0; dC = 0.0; }                        // gamma point dropped
+            else {
+                C = twopi / (V * ksq) * exp(-ksq / (4 * kap * kap));
+                dC = -C * (1.0 / ksq + 1.0 / (4 * kap * kap));
+            }
+        } else {                                                        // Ck_6/8/10, recip.py:437-462
+            const double x2 = ksq / (4 * kap * kap), x = sqrt(x2), e = exp(-x2), ec = ADMP_SQRT_PI * erfc(x);
+            double f, df, pref;
+            const double base = ADMP_SQRT_PI * 3.141592653589793 / 2 / V;
+            if (kind == ADMP_CK_DISP6) {
+                f = (1 - 2 * x2) * e + 2 * x2 * x * ec; df = -6 * e + 6 * x * ec; pref = base * kap * kap * kap / 3;
+            } else if (kind == ADMP_CK_DISP8) {
+                f = (3 - 2 * x2 + 4 * x2 * x2) * e - 4 * x2 * x2 * x * ec; df = e * (-10 + 20 * x2) - 20 * x2 * x * ec;
+                pref = base * kap * kap * kap * kap * kap / 45;
+            } else {
+                f = (15 - 6 * x2 + 4 * x2 * x2 - 8 * x2 * x2 * x2) * e + 8 * x2 * x2 * x2 * x * ec;
+                df = e * (-42 + 28 * x2 - 56 * x2 * x2) + 56 * x2 * x2 * x * ec;
+                pref = base * kap * kap * kap * kap * kap * kap * kap / 1260;
+            }
+            C = pref * f; dC = pref * df / (8 * kap * kap);
+        }
+        const double th = bt1[i1] * bt2[i2] * bt3[i3];                  // 1/theta_k^2
+        cplx<T> s = S[idx];
+        const double s2 = ((double)s.x * s.x + (double)s.y * s.y) * th;
+        const bool single = (i3 == 0) || (2 * i3 == K3);
+        const double wgt = single ? 1.0 : 2.0;
+        acc[0] += wgt * C * s2;
+        if (want_vir) {
+            const double b = dC * s2;
+            // Hermitian partner of a weight-2 point: k -> -k except on an even-K Nyquist index
+            const double s1 = (2 * i1 == K1) ? 1.0 : -1.0, s2n = (2 * i2 == K2) ? 1.0 : -1.0;
+            const double p0 = s1, p1 = s2n, p2 = -1.0;
+            // partner k' = sum_d p_d m_d inv[d][:]
+            double kq[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) kq[c] = twopi * (p0 * m1 * B.inv[c] + p1 * m2 * B.inv[3 + c] + p2 * m3 * B.inv[6 + c]);
+            const double pw = single ? 0.0 : 1.0;
+            acc[1] += b * (kv[0] * kv[0] + pw * kq[0] * kq[0]);
+            acc[2] += b * (kv[0] * kv[1] + pw * kq[0] * kq[1]);
+            acc[3] += b * (kv[0] * kv[2] + pw * kq[0] * kq[2]);
+            acc[4] += b * (kv[1] * kv[1] + pw * kq[1] * kq[1]);
+            acc[5] += b * (kv[1] * kv[2] + pw * kq[1] * kq[2]);
+            acc[6] += b * (kv[2] * kv[2] + pw * kq[2] * kq[2]);
+        }
+        const T g = (T)(2.0 * scale * C * th);
+        s.x *= g; s.y *= g;
+        S[idx] = s;
+    }
+    acc[0] *= scale;
+    if (want_vir) {
+#pragma unroll
+        for (int k = 1; k < 7; ++k) acc[k] *= scale;
+        // slots: E_RECIP then TK are not contiguous -> two accumulations
+        double e1[1] = {acc[0]};
+        block_accumulate<1>(e1, red, scalars + ADMP_S_E_RECIP);
+        double t6[6] = {acc[1], acc[2], acc[3], acc[4], acc[5], acc[6]};
+        block_accumulate<6>(t6, red, scalars + ADMP_S_TK);
+    } else {
+        double e1[1] = {acc[0]};
+        block_accumulate<1>(e1, red, scalars + ADMP_S_E_RECIP);
+    }
+}
+
+// ---------------------------------------------------------------------------- gather
+constexpr int GATHER_WARPS = 4;
+
+// MODE 0: everything (dE/dM, dE/dr, dE/dNstar).  MODE 1: field only (dE/dmu -> F).
+// One warp per atom; each lane owns a strided subset of the 216 points, partial sums of
+// phi * W[p1,p2,p3] are warp-reduced.
+template <typename T, bool MULTIPOLE, int MODE>
+__global__ void __launch_bounds__(GATHER_WARPS * 32)
+gather_kernel(int n, const BoxInfo* __restrict__ Bp, const T* __restrict__ pos, const T* __restrict__ M, int m_stride,
+              const T* __restrict__ U, const T* __restrict__ phi, uint32_t flags, T* __restrict__ dpos, T* __restrict__ G,
+              int g_stride, T* __restrict__ F, double* __restrict__ scalars) {
+    constexpr int NP = (MODE == 1) ? 2 : (MULTIPOLE ? 4 : 2);
+    __shared__ T sw[GATHER_WARPS][3][6 * NP];
+    __shared__ int si[GATHER_WARPS][3];
+    __shared__ double red[9 * GATHER_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int a = blockIdx.x * GATHER_WARPS + warp;
+    const BoxInfo& B = *Bp;
+    const bool want_vir = (flags & ADMP_WANT_VIRIAL) != 0 && MODE == 0;
+    double wacc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (a < n) {
+        if (lane < 3) {
+            double f; int i0;
+            mesh_anchor(B, (double)pos[3 * a], (double)pos[3 * a + 1], (double)pos[3 * a + 2], lane, f, i0);
+            bspline6<T, NP>((T)f, sw[warp][lane]);
+            si[warp][lane] = i0;
+        }
+        __syncwarp();
+        const T* w0 = sw[warp][0];
+        const T* w1 = sw[warp][1];
+        const T* w2 = sw[warp][2];
+        const int K1 = B.K[0], K2 = B.K[1], K3 = B.K[2];
+        const int i0 = si[warp][0], j0 = si[warp][1], k0 = si[warp][2];
+        // P index = p1*16 + p2*4 + p3 compressed to the combos with p1+p2+p3 <= NP-1
+        constexpr int NC = (NP == 4) ? 20 : 4;
+        T P[NC];
+#pragma unroll
+        for (int k = 0; k < NC; ++k) P[k] = (T)0;
+        for (int pt = lane; pt < 216; pt += 32) {
+            const int ia = pt / 36, ib = (pt / 6) % 6, ic = pt % 6;
+            int gi = i0 + ia; if (gi >= K1) gi -= K1;
+            int gj = j0 + ib; if (gj >= K2) gj -= K2;
+            int gk = k0 + ic; if (gk >= K3) gk -= K3;
+            const T ph = phi[((size_t)gi * K2 + gj) * K3 + gk];
+            if (NP == 4) {
+                const T a0 = w0[ia], a1 = w0[6 + ia], a2 = w0[12 + ia], a3 = w0[18 + ia];
+                const T b0 = w1[ib], b1 = w1[6 + ib], b2 = w1[12 + ib], b3 = w1[18 + ib];
+                const T c0 = ph * w2[ic], c1 = ph * w2[6 + ic], c2 = ph * w2[12 + ic], c3 = ph * w2[18 + ic];
+                const T ab00 = a0 * b0, ab10 = a1 * b0, ab01 = a0 * b1, ab20 = a2 * b0, ab11 = a1 * b1, ab02 = a0 * b2;
+                P[0] += ab00 * c0;                       // 000
+                P[1] += ab10 * c0; P[2] += ab01 * c0; P[3] += ab00 * c1;                   // 100 010 001
+                P[4] += ab20 * c0; P[5] += ab11 * c0; P[6] += ab10 * c1;                   // 200 110 101
+                P[7] += ab02 * c0; P[8] += ab01 * c1; P[9] += ab00 * c2;                   // 020 011 002
+                P[10] += a3 * b0 * c0; P[11] += a2 * b1 * c0; P[12] += ab20 * c1;           // 300 210 201
+                P[13] += a1 * b2 * c0; P[14] += ab11 * c1; P[15] += ab10 * c2;             // 120 111 102
+                P[16] += a0 * b3 * c0; P[17] += ab02 * c1; P[18] += ab01 * c2; P[19] += ab00 * c3;   // 030 021 012 003
+            } else {
+                const T a0 = w0[ia], a1 = w0[6 + ia], b0 = w1[ib], b1 = w1[6 + ib];
+                const T c0 = ph * w2[ic], c1 = ph * w2[6 + ic];
+                P[0] += a0 * b0 * c0; P[1] += a1 * b0 * c0; P[2] += a0 * b1 * c0; P[3] += a0 * b0 * c1;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NC; ++k) P[k] = warp_sum(P[k]);
+        if (lane == 0) {
+            T N[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) N[k] = (T)B.nstar[k];
+            const T ph1[3] = {P[1], P[2], P[3]};
+            if (MODE == 1) {
+                // dE/dmu_c = -sum_d N[d][c] ph1[d]
+#pragma unroll
+                for (int c = 0; c < 3; ++c) F[(size_t)a * 3 + c] = -(N[c] * ph1[0] + N[3 + c] * ph1[1] + N[6 + c] * ph1[2]);
+            } else if (!MULTIPOLE) {
+                const T q = M[(size_t)a * m_stride];
+                if (G != nullptr) atomicAdd(G + (size_t)a * g_stride, P[0]);
+                T dEdu[3] = {q * ph1[0], q * ph1[1], q * ph1[2]};
+                if (dpos != nullptr) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) atomicAdd(dpos + (size_t)a * 3 + c, -(N[c] * dEdu[0] + N[3 + c] * dEdu[1] + N[6 + c] * dEdu[2]));
+                }
+                if (want_vir) {
+#pragma unroll
+                    for (int d = 0; d < 3; ++d)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) wacc[3 * d + c] = -(double)(dEdu[d] * pos[3 * a + c]);
+                }
+            } else {
+                const T* m = M + (size_t)a * m_stride;
+                const T q = m[0];
+                T mu[3] = {m[1], m[2], m[3]};
+                if (U != nullptr) { mu[0] += U[3 * a]; mu[1] += U[3 * a + 1]; mu[2] += U[3 * a + 2]; }
+                const T Tm[9] = {m[4], m[5], m[6], m[5], m[7], m[8], m[6], m[8], m[9]};
+                // symmetric second / third derivative tables
+                const T ph2[9] = {P[4], P[5], P[6], P[5], P[7], P[8], P[6], P[8], P[9]};
+                // ph3[d][e][f]: index by sorted multiset
+                auto p3 = [&](int d, int e, int f) -> T {
+                    const int c0 = (d == 0) + (e == 0) + (f == 0), c1 = (d == 1) + (e == 1) + (f == 1);
+                    // (c0,c1,c2) -> slot
+                    if (c0 == 3) return P[10]; if (c0 == 2 && c1 == 1) return P[11]; if (c0 == 2) return P[12];
+                    if (c0 == 1 && c1 == 2) return P[13]; if (c0 == 1 && c1 == 1) return P[14]; if (c0 == 1) return P[15];
+                    if (c1 == 3) return P[16]; if (c1 == 2) return P[17]; if (c1 == 1) return P[18]; return P[19];
+                };
+                T muf[3], NT[9], Tf[9];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) muf[d] = -(N[3 * d] * mu[0] + N[3 * d + 1] * mu[1] + N[3 * d + 2] * mu[2]);
+#pragma unroll
+                for (int d = 0; d < 3; ++d)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) NT[3 * d + b] = N[3 * d] * Tm[b] + N[3 * d + 1] * Tm[3 + b] + N[3 * d + 2] * Tm[6 + b];
+#pragma unroll
+                for (int d = 0; d < 3; ++d)
+#pragma unroll
+                    for (int e = 0; e < 3; ++e)
+                        Tf[3 * d + e] = (NT[3 * d] * N[3 * e] + NT[3 * d + 1] * N[3 * e + 1] + NT[3 * d + 2] * N[3 * e + 2]) * (T)(1.0 / 3);
+                if (G != nullptr) {
+                    T* g = G + (size_t)a * g_stride;
+                    atomicAdd(g, P[0]);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) atomicAdd(g + 1 + c, -(N[c] * ph1[0] + N[3 + c] * ph1[1] + N[6 + c] * ph1[2]));
+                    // Gm = N^T ph2 N / 3
+                    T PN[9];
+#pragma unroll
+                    for (int d = 0; d < 3; ++d)
+#pragma unroll
+                        for (int b = 0; b < 3; ++b) PN[3 * d + b] = ph2[3 * d] * N[b] + ph2[3 * d + 1] * N[3 + b] + ph2[3 * d + 2] * N[6 + b];
+                    auto gm = [&](int p, int b) { return (N[p] * PN[b] + N[3 + p] * PN[3 + b] + N[6 + p] * PN[6 + b]) * (T)(1.0 / 3); };
+                    atomicAdd(g + 4, gm(0, 0)); atomicAdd(g + 5, 2 * gm(0, 1)); atomicAdd(g + 6, 2 * gm(0, 2));
+                    atomicAdd(g + 7, gm(1, 1)); atomicAdd(g + 8, 2 * gm(1, 2)); atomicAdd(g + 9, gm(2, 2));
+                }
+                if (F != nullptr) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) atomicAdd(F + (size_t)a * 3 + c, -(N[c] * ph1[0] + N[3 + c] * ph1[1] + N[6 + c] * ph1[2]));
+                }
+                T dEdu[3];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    T s = q * ph1[d];
+#pragma unroll
+                    for (int e = 0; e < 3; ++e) {
+                        s += ph2[3 * d + e] * muf[e];
+#pragma unroll
+                        for (int f = 0; f < 3; ++f) s += p3(d, e, f) * Tf[3 * e + f];
+                    }
+                    dEdu[d] = s;
+                }
+                if (dpos != nullptr) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) atomicAdd(dpos + (size_t)a * 3 + c, -(N[c] * dEdu[0] + N[3 + c] * dEdu[1] + N[6 + c] * dEdu[2]));
+                }
+                if (want_vir) {
+                    // W[d][c] = dEdu[d] (-r_c) + ph1[d] (-mu_c) + 2/3 sum_e ph2[d][e] (N T)[e][c]
+#pragma unroll
+                    for (int d = 0; d < 3; ++d)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            wacc[3 * d + c] = (double)(-dEdu[d] * pos[3 * a + c] - ph1[d] * mu[c]
+                                + (T)(2.0 / 3) * (ph2[3 * d] * NT[c] + ph2[3 * d + 1] * NT[3 + c] + ph2[3 * d + 2] * NT[6 + c]));
+                }
+            }
+        }
+    }
+    if (want_vir) block_accumulate<9>(wacc, red, scalars + ADMP_S_DNSTAR);
+}
+
+// ---------------------------------------------------------------------------- launchers
+template <typename T>
+void launch_spread(cudaStream_t st, int n, const BoxInfo* B, const void* pos, const void* M, int m_cols, int m_stride,
+                   const void* U, void* mesh) {
+    if (n <= 0) return;
+    const unsigned grid = (n + SPREAD_WARPS - 1) / SPREAD_WARPS;
+    if (m_cols >= 10) spread_kernel<T, true><<<grid, SPREAD_WARPS * 32, 0, st>>>(n, B, (const T*)pos, (const T*)M, m_stride, (const T*)U, (T*)mesh);
+    else spread_kernel<T, false><<<grid, SPREAD_WARPS * 32, 0, st>>>(n, B, (const T*)pos, (const T*)M, m_stride, nullptr, (T*)mesh);
+}
+template <typename T>
+void launch_convolve(cudaStream_t st, const BoxInfo* B, size_t n_half, int n_sm, double kappa, int kind, const double* bt1,
+                     const double* bt2, const double* bt3, void* S, double* scalars, int want_vir) {
+    size_t blocks = (n_half + 255) / 256;
+    const size_t cap = (size_t)n_sm * 8;            // grid sized in multiples of the SM count (grid-stride loop)
+    if (blocks > cap) blocks = cap;
+    convolve_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(B, (T)kappa, kind, bt1, bt2, bt3, (cplx<T>*)S, scalars, want_vir);
+}
+template <typename T>
+void launch_gather(cudaStream_t st, int n, const BoxInfo* B, const void* pos, const void* M, int m_cols, int m_stride, const void* U,
+                   const void* phi, int mode, uint32_t flags, void* dpos, void* G, int g_stride, void* F, double* scalars) {
+    if (n <= 0) return;
+    const unsigned grid = (n + GATHER_WARPS - 1) / GATHER_WARPS;
+#define ADMP_G_ARGS n, B, (const T*)pos, (const T*)M, m_stride, (const T*)U, (const T*)phi, flags, (T*)dpos, (T*)G, g_stride, (T*)F, scalars
+    if (mode == 1) gather_kernel<T, true, 1><<<grid, GATHER_WARPS * 32, 0, st>>>(ADMP_G_ARGS);
+    else if (m_cols >= 10) gather_kernel<T, true, 0><<<grid, GATHER_WARPS * 32, 0, st>>>(ADMP_G_ARGS);
+    else gather_kernel<T, false, 0><<<grid, GATHER_WARPS * 32, 0, st>>>(ADMP_G_ARGS);
+#undef ADMP_G_ARGS
+}
+#define ADMP_INST(T)                                                                                                              \
+    template void launch_spread<T>(cudaStream_t, int, const BoxInfo*, const void*, const void*, int, int, const void*, void*);    \
+    template void launch_convolve<T>(cudaStream_t, const BoxInfo*, size_t, int, double, int, const double*, const double*,        \
+                                     const double*, void*, double*, int);                                                         \
+    template void launch_gather<T>(cudaStream_t, int, const BoxInfo*, const void*, const void*, int, int, const void*, const void*, \
+                                   int, uint32_t, void*, void*, int, void*, double*);
+ADMP_INST(double)
+ADMP_INST(float)
+#undef ADMP_INST
+
+}  // namespace admp

@@ -1,0 +1,224 @@
+// Per-site terms and the device-side control of the induced-dipole loop.
+//   * box_setup_kernel   : BoxInfo (inverse, Nstar, volume) from the caller's box
+//   * self_kernel        : pme_self + pol_penalty (admp/pme.py:738-774) with adjoints
+//   * scf_* kernels      : optimize_Uind's convergence test / Jacobi update
+//                          (admp/pme.py:126-143) without a host round trip
+#include "kernels.h"
+
+namespace admp {
+
+template <typename T>
+__global__ void box_setup_kernel(const T* __restrict__ box, BoxInfo* __restrict__ B, int K1, int K2, int K3) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double b[9];
+    for (int k = 0; k < 9; ++k) { b[k] = (double)box[k]; B->box[k] = b[k]; }
+    const double det = b[0] * (b[4] * b[8] - b[5] * b[7]) - b[1] * (b[3] * b[8] - b[5] * b[6]) + b[2] * (b[3] * b[7] - b[4] * b[6]);
+    const double id = 1.0 / det;
+    double inv[9];
+    inv[0] = (b[4] * b[8] - b[5] * b[7]) * id; inv[1] = (b[2] * b[7] - b[1] * b[8]) * id; inv[2] = (b[1] * b[5] - b[2] * b[4]) * id;
+    inv[3] = (b[5] * b[6] - b[3] * b[8]) * id; inv[4] = (b[0] * b[8] - b[2] * b[6]) * id; inv[5] = (b[2] * b[3] - b[0] * b[5]) * id;
+    inv[6] = (b[3] * b[7] - b[4] * b[6]) * id; inv[7] = (b[1] * b[6] - b[0] * b[7]) * id; inv[8] = (b[0] * b[4] - b[1] * b[3]) * id;
+    const int K[3] = {K1, K2, K3};
+    for (int k = 0; k < 9; ++k) B->inv[k] = inv[k];
+    for (int d = 0; d < 3; ++d) {
+        B->K[d] = K[d];
+        for (int c = 0; c < 3; ++c) B->nstar[3 * d + c] = (double)K[d] * inv[3 * c + d];      // recip.py:55
+    }
+    B->vol = det;
+}
+
+// E_self = -DIEL sum_l kappa/sqrt(pi) (2 kappa^2)^l/(2l+1)!! |Q_l|^2 with |Q_2|^2 = (2/3) T:T,
+// E_pen = DIEL sum U^2 / (2 max(pol,1e-8)). mu_tot = mu + U enters the dipole term (pme.py:233-252).
+template <typename T>
+__global__ void __launch_bounds__(128)
+self_kernel(int n, T kappa, const T* __restrict__ M, const T* __restrict__ U, const T* __restrict__ pol, uint32_t flags,
+            T* __restrict__ G, T* __restrict__ F, T* __restrict__ dpol, double* __restrict__ scalars) {
+    __shared__ double red[2 * 4];
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    double acc[2] = {0.0, 0.0};
+    if (a < n) {
+        const double k = (double)kappa, D = ADMP_DIEL;
+        const double f0 = k / ADMP_SQRT_PI, f1 = f0 * (2 * k * k) / 3, f2 = f0 * (2 * k * k) * (2 * k * k) / 15;
+        const T* m = M + (size_t)a * 10;
+        double mu[3] = {(double)m[1], (double)m[2], (double)m[3]};
+        double u[3] = {0, 0, 0};
+        if (U != nullptr) { for (int c = 0; c < 3; ++c) { u[c] = (double)U[3 * a + c]; mu[c] += u[c]; } }
+        const double q = (double)m[0];
+        const double tt = (double)m[4] * m[4] + (double)m[7] * m[7] + (double)m[9] * m[9]
+                        + 2 * ((double)m[5] * m[5] + (double)m[6] * m[6] + (double)m[8] * m[8]);
+        acc[0] = -D * (f0 * q * q + f1 * (mu[0] * mu[0] + mu[1] * mu[1] + mu[2] * mu[2]) + f2 * (2.0 / 3) * tt);
+        double pt = 1.0, pen_g[3] = {0, 0, 0};
+        if (U != nullptr) {
+            const double p = (double)pol[a];
+            pt = p < 1e-8 ? 1e-8 : p;                                   // trim_val_0, pme.py:771
+            const double uu = u[0] * u[0] + u[1] * u[1] + u[2] * u[2];
+            acc[1] = D * 0.5 / pt * uu;
+            for (int c = 0; c < 3; ++c) pen_g[c] = D * u[c] / pt;
+            if ((flags & ADMP_WANT_PGRAD) && dpol != nullptr && p >= 1e-8) atomicAdd(dpol + a, (T)(-D * 0.5 * uu / (pt * pt)));
+        }
+        if (flags & ADMP_WANT_GRAD) {
+            if (G != nullptr) {
+                T* g = G + (size_t)a * 10;
+                atomicAdd(g, (T)(-2 * D * f0 * q));
+                for (int c = 0; c < 3; ++c) atomicAdd(g + 1 + c, (T)(-2 * D * f1 * mu[c]));
+                const double c1 = -D * f2 * (4.0 / 3), c2 = -D * f2 * (8.0 / 3);
+                atomicAdd(g + 4, (T)(c1 * m[4])); atomicAdd(g + 5, (T)(c2 * m[5])); atomicAdd(g + 6, (T)(c2 * m[6]));
+                atomicAdd(g + 7, (T)(c1 * m[7])); atomicAdd(g + 8, (T)(c2 * m[8])); atomicAdd(g + 9, (T)(c1 * m[9]));
+            }
+            if (F != nullptr && U != nullptr)
+                for (int c = 0; c < 3; ++c) atomicAdd(F + 3 * a + c, (T)(-2 * D * f1 * mu[c] + pen_g[c]));
+        }
+    }
+    block_accumulate<2>(acc, red, scalars + ADMP_S_E_SELF);     // E_SELF, E_PEN are adjacent slots
+}
+
+// dispersion self term, admp/disp_pme.py:254-279
+template <typename T>
+__global__ void __launch_bounds__(128)
+disp_self_kernel(int n, T kappa, int pmax, const T* __restrict__ c_list, uint32_t flags, T* __restrict__ dc,
+                 double* __restrict__ scalars) {
+    __shared__ double red[4];
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    double acc[1] = {0.0};
+    if (a < n) {
+        const double k2 = (double)kappa * kappa, k6 = k2 * k2 * k2;
+        const double f[3] = {-k6 / 12, -k6 * k2 / 48, -k6 * k2 * k2 / 240};
+        const int np = (pmax - 4) / 2;
+        for (int p = 0; p < 3 && p < np; ++p) {
+            const double c = (double)c_list[(size_t)a * 3 + p];
+            acc[0] += f[p] * c * c;
+            if ((flags & ADMP_WANT_PGRAD) && dc != nullptr) atomicAdd(dc + (size_t)a * 3 + p, (T)(2 * f[p] * c));
+        }
+    }
+    block_accumulate<1>(acc, red, scalars + ADMP_S_E_SELF);
+}
+
+// SCF: F += self/penalty part of dE/dU; reduce max |F| over sites with pol > 0.001 (pme.py:125,136)
+template <typename T>
+__global__ void __launch_bounds__(128)
+scf_field_kernel(int n, T kappa, const T* __restrict__ M, const T* __restrict__ U, const T* __restrict__ pol,
+                 T* __restrict__ F, double* __restrict__ scalars) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    double mx = 0.0;
+    if (a < n) {
+        const double k = (double)kappa, D = ADMP_DIEL;
+        const double f1 = k / ADMP_SQRT_PI * (2 * k * k) / 3;
+        const double p = (double)pol[a], pt = p < 1e-8 ? 1e-8 : p;
+        for (int c = 0; c < 3; ++c) {
+            const double u = (double)U[3 * a + c];
+            const double f = (double)F[3 * a + c] - 2 * D * f1 * ((double)M[(size_t)a * 10 + 1 + c] + u) + D * u / pt;
+            F[3 * a + c] = (T)f;
+            if (p > 0.001) mx = fmax(mx, fabs(f));
+        }
+    }
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0 && mx > 0.0) atomic_max_nonneg(scalars + ADMP_S_MAXFIELD, mx);
+}
+
+// Decision step of optimize_Uind (pme.py:133-143): test BEFORE the update; converging exactly on
+// the last iteration reports flag False. state: [0]=iter, [1]=do_update, [2]=final_pass,
+// [3]=n_cycle, [4]=converged, [5]=loop condition (mirrors the graph conditional handle).
+__global__ void scf_decide_kernel(int32_t* __restrict__ state, double* __restrict__ scalars, int maxiter, double thresh,
+                                  cudaGraphConditionalHandle handle, int use_handle) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int cond = 0;
+    if (state[2]) {                       // this pass only refreshed the field/mesh after the last update
+        state[1] = 0;
+    } else {
+        const int it = state[0];
+        const double mx = __longlong_as_double((long long)reinterpret_cast<unsigned long long*>(scalars)[ADMP_S_MAXFIELD]);
+        if (mx < thresh) {
+            state[1] = 0; state[3] = it; state[4] = (it == maxiter - 1) ? 0 : 1;
+        } else {
+            state[1] = 1;
+            if (it == maxiter - 1) { state[3] = it; state[4] = 0; state[2] = 1; }
+            else state[0] = it + 1;
+            cond = 1;
+        }
+    }
+    state[5] = cond;
+    if (use_handle) cudaGraphSetConditional(handle, cond);
+}
+
+// Jacobi update U <- U - F pol / DIEL (pme.py:138) when the decision says so; re-arms the
+// per-iteration accumulators either way.
+template <typename T>
+__global__ void __launch_bounds__(128)
+scf_update_kernel(int n, const int32_t* __restrict__ state, const T* __restrict__ F, const T* __restrict__ pol,
+                  T* __restrict__ U, double* __restrict__ scalars) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (state[1] && a < n) {
+        const T s = pol[a] * (T)(1.0 / ADMP_DIEL);
+        for (int c = 0; c < 3; ++c) U[3 * a + c] -= F[3 * a + c] * s;
+    }
+}
+
+__global__ void scf_rearm_kernel(double* __restrict__ scalars) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        scalars[ADMP_S_MAXFIELD] = 0.0; scalars[ADMP_S_E_RECIP] = 0.0;
+        for (int k = 0; k < 6; ++k) scalars[ADMP_S_TK + k] = 0.0;
+    }
+}
+
+// dE/dbox (3x3, row-major) += reciprocal-space part assembled from the accumulators:
+//   -inv^T (W^T Nstar)  [spread/gather, W = dE/dNstar]  - 2 T inv^T - E_recip inv^T  [k^2 and V in C_k]
+__global__ void virial_finalize_kernel(const BoxInfo* __restrict__ B, double* __restrict__ s) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double* W = s + ADMP_S_DNSTAR;
+    const double* tk = s + ADMP_S_TK;
+    const double T[9] = {tk[0], tk[1], tk[2], tk[1], tk[3], tk[4], tk[2], tk[4], tk[5]};
+    const double E = s[ADMP_S_E_RECIP];
+    double Mm[9];
+    for (int c = 0; c < 3; ++c)
+        for (int b = 0; b < 3; ++b) Mm[3 * c + b] = W[c] * B->nstar[b] + W[3 + c] * B->nstar[3 + b] + W[6 + c] * B->nstar[6 + b];
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+            double v = 0.0;
+            for (int c = 0; c < 3; ++c) v += -B->inv[3 * c + a] * Mm[3 * c + b] - 2.0 * T[3 * a + c] * B->inv[3 * b + c];
+            v -= E * B->inv[3 * b + a];
+            s[ADMP_S_DBOX + 3 * a + b] += v;
+        }
+}
+void launch_virial_finalize(cudaStream_t st, const BoxInfo* B, double* scalars) { virial_finalize_kernel<<<1, 32, 0, st>>>(B, scalars); }
+
+template <typename T>
+void launch_box_setup(cudaStream_t st, const void* box, BoxInfo* B, int K1, int K2, int K3) {
+    box_setup_kernel<T><<<1, 32, 0, st>>>((const T*)box, B, K1, K2, K3);
+}
+template <typename T>
+void launch_self(cudaStream_t st, int n, double kappa, const void* M, const void* U, const void* pol, uint32_t flags, void* G,
+                 void* F, void* dpol, double* scalars) {
+    if (n <= 0) return;
+    self_kernel<T><<<(n + 127) / 128, 128, 0, st>>>(n, (T)kappa, (const T*)M, (const T*)U, (const T*)pol, flags, (T*)G, (T*)F, (T*)dpol, scalars);
+}
+template <typename T>
+void launch_disp_self(cudaStream_t st, int n, double kappa, int pmax, const void* c_list, uint32_t flags, void* dc, double* scalars) {
+    if (n <= 0) return;
+    disp_self_kernel<T><<<(n + 127) / 128, 128, 0, st>>>(n, (T)kappa, pmax, (const T*)c_list, flags, (T*)dc, scalars);
+}
+template <typename T>
+void launch_scf_field(cudaStream_t st, int n, double kappa, const void* M, const void* U, const void* pol, void* F, double* scalars) {
+    scf_field_kernel<T><<<(n + 127) / 128, 128, 0, st>>>(n, (T)kappa, (const T*)M, (const T*)U, (const T*)pol, (T*)F, scalars);
+}
+void launch_scf_decide(cudaStream_t st, int32_t* state, double* scalars, int maxiter, double thresh,
+                       cudaGraphConditionalHandle handle, int use_handle) {
+    scf_decide_kernel<<<1, 32, 0, st>>>(state, scalars, maxiter, thresh, handle, use_handle);
+}
+template <typename T>
+void launch_scf_update(cudaStream_t st, int n, const int32_t* state, const void* F, const void* pol, void* U, double* scalars) {
+    scf_update_kernel<T><<<(n + 127) / 128, 128, 0, st>>>(n, state, (const T*)F, (const T*)pol, (T*)U, scalars);
+}
+void launch_scf_rearm(cudaStream_t st, double* scalars) { scf_rearm_kernel<<<1, 32, 0, st>>>(scalars); }
+
+#define ADMP_INST(T)                                                                                                         \
+    template void launch_box_setup<T>(cudaStream_t, const void*, BoxInfo*, int, int, int);                                   \
+    template void launch_self<T>(cudaStream_t, int, double, const void*, const void*, const void*, uint32_t, void*, void*,   \
+                                 void*, double*);                                                                            \
+    template void launch_disp_self<T>(cudaStream_t, int, double, int, const void*, uint32_t, void*, double*);                \
+    template void launch_scf_field<T>(cudaStream_t, int, double, const void*, const void*, const void*, void*, double*);     \
+    template void launch_scf_update<T>(cudaStream_t, int, const int32_t*, const void*, const void*, void*, double*);
+ADMP_INST(double)
+ADMP_INST(float)
+#undef ADMP_INST
+
+}  // namespace admp

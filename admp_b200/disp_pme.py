@@ -1,0 +1,106 @@
+"""Dispersion PME calculator - drop-in surface of admp/disp_pme.py:20-77.
+
+E = sum_pairs sum_{p=6,8,10} (m + g_p(kappa^2 r^2) - 1) c_i^p c_j^p / r^p
+    + three lmax=0 reciprocal passes (Ck_6/8/10, gamma point kept) + self term.
+The physical dispersion energy is -E (admp/api.py:199).  Differentiable inputs:
+positions, box, c_list, mScales.
+"""
+import torch
+
+from . import _lib
+from ._ctx import Context, to_dev, pairs_to_dev
+from .pme import setup_ewald_parameters
+
+
+class _DispFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, calc, pairs, positions, box, c_list, mScales):
+        n = ctx.needs_input_grad
+        flags = 0
+        if n[2] or n[3] or n[4] or n[5]:
+            flags |= _lib.WANT_GRAD
+        if n[3]:
+            flags |= _lib.WANT_VIRIAL
+        if n[4] or n[5]:
+            flags |= _lib.WANT_PGRAD
+        scal, dpos, dc = calc._eval(positions, box, pairs, c_list, mScales, flags)
+        ctx.saved = (scal, dpos, dc)
+        ctx.dtype = positions.dtype
+        return (scal[_lib.S_E_REAL] + scal[_lib.S_E_RECIP] + scal[_lib.S_E_SELF]).to(positions.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        scal, dpos, dc = ctx.saved
+        n, dt = ctx.needs_input_grad, ctx.dtype
+        return (None, None,
+                g * dpos if n[2] else None,
+                (g * scal[_lib.S_DBOX:_lib.S_DBOX + 9].reshape(3, 3)).to(dt) if n[3] else None,
+                g * dc if n[4] else None,
+                (g * scal[_lib.S_DMSCALE:_lib.S_DMSCALE + 5]).to(dt) if n[5] else None)
+
+
+class ADMPDispPmeForce:
+    '''
+    This is a convenient wrapper for dispersion PME calculations
+    (same constructor and attributes as admp/disp_pme.py:27-41)
+    '''
+
+    def __init__(self, box, covalent_map, rc, ethresh, pmax):
+        self.covalent_map = covalent_map
+        self.rc = rc
+        self.ethresh = ethresh
+        self.pmax = pmax
+        kappa, K1, K2, K3 = setup_ewald_parameters(rc, ethresh, box)
+        self.kappa = kappa
+        self.K1 = K1
+        self.K2 = K2
+        self.K3 = K3
+        self.pme_order = 6
+        self.n_atoms = int(covalent_map.shape[0])
+        self._ctx = Context()
+        self._dtype = self._ctx.dtype
+        self._topology_set = False
+        self.refresh_calculators()
+
+    def update_env(self, attr, val):
+        '''admp/disp_pme.py:53-58'''
+        setattr(self, attr, val)
+        if attr == 'covalent_map':
+            self._topology_set = False
+        self.refresh_calculators()
+
+    def refresh_calculators(self):
+        '''admp/disp_pme.py:61-77'''
+        if self.pmax not in (6, 8, 10):
+            raise ValueError('pmax must be 6, 8 or 10')
+        self._ctx.set_pme(self.kappa, self.K1, self.K2, self.K3, 0)
+        if not self._topology_set:
+            self._ctx.set_topology(self.n_atoms, None, None, self.covalent_map)
+            self._topology_set = True
+
+    def _eval(self, positions, box, pairs, c_list, mScales, flags):
+        c = self._ctx
+        n, dt, dev = self.n_atoms, self._dtype, c.device
+        if positions.shape != (n, 3) or c_list.shape != (n, 3):
+            raise ValueError('positions and c_list must be (%d, 3); c_list columns are C6, C8, C10' % n)
+        scal = torch.empty(_lib.S_COUNT, dtype=torch.float64, device=dev)
+        dpos = torch.empty((n, 3), dtype=dt, device=dev) if flags & _lib.WANT_GRAD else None
+        dc = torch.empty((n, 3), dtype=dt, device=dev) if flags & _lib.WANT_PGRAD else None
+        p = _lib.ptr
+        _lib.check(c.lib.admp_disp_eval(c.handle, _lib.stream_ptr(), p(positions), p(box), p(pairs), int(pairs.shape[0]),
+                                        p(c_list), p(mScales), int(self.pmax), flags, p(scal), p(dpos), p(dc)))
+        return scal, dpos, dc
+
+    def _prep(self, x):
+        return to_dev(x, self._dtype, self._ctx.device)
+
+    def get_energy(self, positions, box, pairs, c_list, mScales):
+        """admp/disp_pme.py:44-50"""
+        positions, box, c_list, mScales = map(self._prep, (positions, box, c_list, mScales))
+        return _DispFunction.apply(self, pairs_to_dev(pairs, self._ctx.device), positions, box, c_list, mScales)
+
+    def get_forces(self, positions, box, pairs, c_list, mScales):
+        """value_and_grad(get_energy): (E, +dE/dpositions)  (admp/disp_pme.py:76)"""
+        positions, box, c_list, mScales = (self._prep(x).detach() for x in (positions, box, c_list, mScales))
+        scal, dpos, _ = self._eval(positions, box, pairs_to_dev(pairs, self._ctx.device), c_list, mScales, _lib.WANT_GRAD)
+        return (scal[_lib.S_E_REAL] + scal[_lib.S_E_RECIP] + scal[_lib.S_E_SELF]).to(self._dtype), dpos

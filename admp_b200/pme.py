@@ -1,0 +1,296 @@
+"""Multipolar (polarizable) PME calculator - drop-in surface of admp/pme.py.
+
+``ADMPPmeForce`` keeps the reference's constructor, attributes and closures
+(``get_energy``, ``get_forces``, ``energy_fn``, ``grad_U_fn``, ``grad_pos_fn``,
+``optimize_Uind``, ``update_env``, ``refresh_calculators``; admp/pme.py:30-143) but every
+number comes from the sm_100a kernels behind libadmp_b200.so.  Derivatives are analytic
+adjoint kernels exposed through ``torch.autograd.Function`` (the analogue of the
+``jax.custom_vjp`` the north star asks for; JAX is not installable in this image):
+positions, box (virial), Q_local, Uind_global, pol, tholes, mScales and pScales are
+differentiable; dScales has zero gradient (it is unused upstream, admp/pme.py:470).
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import settings
+from ._ctx import Context, to_dev, pairs_to_dev
+
+DIELECTRIC = 1389.35455846       # admp/pme.py:16
+DEFAULT_THOLE_WIDTH = 0.3        # admp/pme.py:17
+
+
+def setup_ewald_parameters(rc, ethresh, box):
+    """admp/pme.py:146-172 (same algorithm as OpenMM): kappa, K1, K2, K3."""
+    if isinstance(box, torch.Tensor):
+        box = box.detach().cpu().numpy()
+    box = np.asarray(box, dtype=np.float64)
+    kappa = math.sqrt(-math.log(2 * ethresh)) / rc
+    K = [int(math.ceil(2 * kappa * box[d, d] / 3 / ethresh**0.2)) for d in range(3)]
+    return kappa, K[0], K[1], K[2]
+
+
+def _flags(need_grad, need_box, need_pgrad):
+    f = 0
+    if need_grad or need_box or need_pgrad:
+        f |= _lib.WANT_GRAD
+    if need_box:
+        f |= _lib.WANT_VIRIAL
+    if need_pgrad:
+        f |= _lib.WANT_PGRAD
+    return f
+
+
+class EvalResult:
+    """Raw outputs of one admp_pme_eval call (device tensors)."""
+    __slots__ = ('scalars', 'dpos', 'dQ', 'F', 'dpol', 'dtholes', 'scf', 'U')
+
+    @property
+    def energy(self):
+        return self.scalars[_lib.S_E_REAL] + self.scalars[_lib.S_E_RECIP] + self.scalars[_lib.S_E_SELF] + self.scalars[_lib.S_E_PEN]
+
+    @property
+    def dbox(self):
+        return self.scalars[_lib.S_DBOX:_lib.S_DBOX + 9].reshape(3, 3)
+
+
+class _PmeFunction(torch.autograd.Function):
+    """E(positions, box, Q_local, U, pol, tholes, mScales, pScales) with analytic backward."""
+
+    @staticmethod
+    def forward(ctx, calc, pairs, do_scf, U_init, positions, box, Q_local, U, pol, tholes, mScales, pScales):
+        needs = ctx.needs_input_grad[4:]
+        polz = pol is not None
+        need_box = needs[1]
+        need_pg = any(needs[k] for k in (4, 5, 6, 7) if k < len(needs))
+        need_grad = needs[0] or needs[2] or (polz and needs[3])
+        flags = _flags(need_grad, need_box, need_pg)
+        res = calc._eval(positions, box, pairs, Q_local, U if not do_scf else U_init, pol, tholes, mScales, pScales,
+                         flags, do_scf)
+        ctx.res = res
+        ctx.polz = polz
+        ctx.dtype = positions.dtype
+        return res.energy.to(positions.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        r = ctx.res
+        n = ctx.needs_input_grad
+        dt = ctx.dtype
+        out = [None, None, None, None]
+        out.append(g * r.dpos if n[4] else None)
+        out.append((g * r.dbox).to(dt) if n[5] else None)
+        out.append(g * r.dQ if n[6] else None)
+        out.append(g * r.F if (ctx.polz and n[7]) else None)
+        out.append(g * r.dpol if (ctx.polz and n[8]) else None)
+        out.append(g * r.dtholes if (ctx.polz and n[9]) else None)
+        out.append((g * r.scalars[_lib.S_DMSCALE:_lib.S_DMSCALE + 5]).to(dt) if n[10] else None)
+        out.append((g * r.scalars[_lib.S_DPSCALE:_lib.S_DPSCALE + 5]).to(dt) if (ctx.polz and n[11]) else None)
+        return tuple(out)
+
+
+class ADMPPmeForce:
+    '''
+    This is a convenient wrapper for multipolar PME calculations
+    It wraps all the environment parameters of multipolar PME calculation
+    (same constructor and attributes as admp/pme.py:30-55)
+    '''
+
+    def __init__(self, box, axis_type, axis_indices, covalent_map, rc, ethresh, lmax, lpol=False):
+        self.axis_type = axis_type
+        self.axis_indices = axis_indices
+        self.rc = rc
+        self.ethresh = ethresh
+        self.lmax = int(lmax)
+        if self.lmax > 2:
+            raise NotImplementedError('l > 2 (beyond quadrupole) not supported')   # admp/multipole.py:111
+        kappa, K1, K2, K3 = setup_ewald_parameters(rc, ethresh, box)
+        self.kappa = kappa
+        self.K1 = K1
+        self.K2 = K2
+        self.K3 = K3
+        self.pme_order = 6
+        self.covalent_map = covalent_map
+        self.lpol = lpol
+        self.n_atoms = int(covalent_map.shape[0])
+        self._ctx = Context()
+        self._dtype = self._ctx.dtype
+        self._topology_set = False
+        self.U_ind = None
+        self._scf = None
+        self.refresh_calculators()
+
+    # ------------------------------------------------------------------ environment
+    def update_env(self, attr, val):
+        '''Update the environment of the calculator (admp/pme.py:89-94; K* are NOT recomputed
+        when kappa changes).'''
+        setattr(self, attr, val)
+        if attr in ('axis_type', 'axis_indices', 'covalent_map'):
+            self._topology_set = False
+        self.refresh_calculators()
+
+    def refresh_calculators(self):
+        '''admp/pme.py:97-109: (re)builds plans/workspaces for the current environment.'''
+        if self.pme_order != 6:
+            raise NotImplementedError('only pme_order = 6 is implemented (as in admp/recip.py:25)')
+        self._ctx.set_pme(self.kappa, self.K1, self.K2, self.K3, self.lmax)
+        if not self._topology_set:
+            at, ai = (self.axis_type, self.axis_indices) if self.lmax > 0 else (None, None)
+            self._ctx.set_topology(self.n_atoms, at, ai, self.covalent_map)
+            self._topology_set = True
+        if self.lpol:
+            if self.U_ind is None:
+                self.U_ind = torch.zeros((self.n_atoms, 3), dtype=self._dtype, device=self._ctx.device)
+            self.get_energy = self._get_energy_pol
+            self.get_forces = self._get_forces_pol
+        else:
+            self.get_energy = self._get_energy_nonpol
+            self.get_forces = self._get_forces_nonpol
+        self.construct_local_frames = self._construct_local_frames
+
+    # ------------------------------------------------------------------ SCF status (lazy host sync)
+    @property
+    def lconverg(self):
+        return None if self._scf is None else bool(self._scf[1].item())
+
+    @property
+    def n_cycle(self):
+        return None if self._scf is None else int(self._scf[0].item())
+
+    # ------------------------------------------------------------------ core call
+    def _prep(self, x):
+        return None if x is None else to_dev(x, self._dtype, self._ctx.device)
+
+    def _eval(self, positions, box, pairs, Q_local, U, pol, tholes, mScales, pScales, flags, do_scf,
+              maxiter=None, thresh=None, hostsync=False, cache_scf=True):
+        """One admp_pme_eval launch on the current stream. All tensors already on device.
+        Paths that run the SCF cache U_ind / status on self, as the reference's get_energy does
+        (admp/pme.py:82)."""
+        c = self._ctx
+        n, dt, dev = self.n_atoms, self._dtype, c.device
+        nh = (self.lmax + 1) ** 2
+        if positions.shape != (n, 3):
+            raise ValueError('positions must be (%d, 3)' % n)
+        if Q_local.shape != (n, nh):
+            raise ValueError('Q_local must be (%d, %d) for lmax = %d' % (n, nh, self.lmax))
+        polz = pol is not None
+        r = EvalResult()
+        r.scalars = torch.empty(_lib.S_COUNT, dtype=torch.float64, device=dev)
+        want_grad = bool(flags & _lib.WANT_GRAD)
+        r.dpos = torch.empty((n, 3), dtype=dt, device=dev) if want_grad else None
+        r.dQ = torch.empty((n, nh), dtype=dt, device=dev) if want_grad else None
+        r.F = torch.empty((n, 3), dtype=dt, device=dev) if (polz and want_grad) else None
+        pg = bool(flags & _lib.WANT_PGRAD) and polz
+        r.dpol = torch.empty(n, dtype=dt, device=dev) if pg else None
+        r.dtholes = torch.empty(n, dtype=dt, device=dev) if pg else None
+        r.scf = torch.zeros(2, dtype=torch.int32, device=dev) if (polz and do_scf) else None
+        r.U = None
+        if polz:
+            r.U = U.detach().clone().contiguous() if U is not None else torch.zeros((n, 3), dtype=dt, device=dev)
+        f = flags | (_lib.SCF if (polz and do_scf) else 0) | (_lib.SCF_HOSTSYNC if hostsync else 0)
+        p = _lib.ptr
+        _lib.check(c.lib.admp_pme_eval(
+            c.handle, _lib.stream_ptr(), p(positions), p(box), p(pairs), int(pairs.shape[0]), p(Q_local), p(r.U),
+            p(pol), p(tholes), p(mScales), p(pScales), f,
+            int(settings.MAX_N_POL if maxiter is None else maxiter), float(settings.POL_CONV if thresh is None else thresh),
+            p(r.scalars), p(r.dpos), p(r.dQ), p(r.F), p(r.dpol), p(r.dtholes), p(r.scf)))
+        if polz and do_scf and cache_scf:
+            self.U_ind = r.U
+            self._scf = r.scf
+        return r
+
+    # ------------------------------------------------------------------ non-polarizable closures
+    def _get_energy_nonpol(self, positions, box, pairs, Q_local, mScales):
+        """get_energy(positions, box, pairs, Q_local, mScales)  (admp/pme.py:61-67)"""
+        positions, box, Q_local, mScales = map(self._prep, (positions, box, Q_local, mScales))
+        pairs = pairs_to_dev(pairs, self._ctx.device)
+        return _PmeFunction.apply(self, pairs, False, None, positions, box, Q_local, None, None, None, mScales, None)
+
+    def _get_forces_nonpol(self, positions, box, pairs, Q_local, mScales):
+        """value_and_grad(get_energy): returns (E, +dE/dpositions) - the gradient, not the force (A1)."""
+        positions, box, Q_local, mScales = (self._prep(x).detach() for x in (positions, box, Q_local, mScales))
+        pairs = pairs_to_dev(pairs, self._ctx.device)
+        r = self._eval(positions, box, pairs, Q_local, None, None, None, mScales, None, _lib.WANT_GRAD, False)
+        return r.energy.to(self._dtype), r.dpos
+
+    # ------------------------------------------------------------------ polarizable closures
+    def energy_fn(self, positions, box, pairs, Q_local, Uind_global, pol, tholes, mScales, pScales, dScales):
+        """The bare energy with Uind as explicit input (admp/pme.py:70-75)."""
+        positions, box, Q_local, U, pol, tholes, mScales, pScales = map(
+            self._prep, (positions, box, Q_local, Uind_global, pol, tholes, mScales, pScales))
+        pairs = pairs_to_dev(pairs, self._ctx.device)
+        return _PmeFunction.apply(self, pairs, False, None, positions, box, Q_local, U, pol, tholes, mScales, pScales)
+
+    def grad_U_fn(self, positions, box, pairs, Q_local, Uind_global, pol, tholes, mScales, pScales, dScales):
+        """grad(energy_fn, argnums=4): dE/dUind_global (admp/pme.py:77)."""
+        args = [self._prep(x).detach() for x in (positions, box, Q_local, Uind_global, pol, tholes, mScales, pScales)]
+        pairs = pairs_to_dev(pairs, self._ctx.device)
+        r = self._eval(args[0], args[1], pairs, args[2], args[3], args[4], args[5], args[6], args[7], _lib.WANT_GRAD, False)
+        return r.F
+
+    def grad_pos_fn(self, positions, box, pairs, Q_local, Uind_global, pol, tholes, mScales, pScales, dScales):
+        """grad(energy_fn, argnums=0) (admp/pme.py:78)."""
+        args = [self._prep(x).detach() for x in (positions, box, Q_local, Uind_global, pol, tholes, mScales, pScales)]
+        pairs = pairs_to_dev(pairs, self._ctx.device)
+        r = self._eval(args[0], args[1], pairs, args[2], args[3], args[4], args[5], args[6], args[7], _lib.WANT_GRAD, False)
+        return r.dpos
+
+    def optimize_Uind(self, positions, box, pairs, Q_local, pol, tholes, mScales, pScales, dScales,
+                      U_init=None, maxiter=None, thresh=None):
+        '''Converges the induced dipoles with the reference's Jacobi iteration and stopping rule
+        (admp/pme.py:111-143), as device-resident iterations (CUDA-graph WHILE loop).
+        Returns (U, flag, i) like the reference; reading flag / i synchronises the host.'''
+        args = [self._prep(x).detach() for x in (positions, box, Q_local, pol, tholes, mScales, pScales)]
+        pairs = pairs_to_dev(pairs, self._ctx.device)
+        U0 = None if U_init is None else self._prep(U_init).detach()
+        r = self._eval(args[0], args[1], pairs, args[2], U0, args[3], args[4], args[5], args[6], 0, True,
+                       maxiter=maxiter, thresh=thresh, cache_scf=False)
+        scf = r.scf.cpu()
+        return r.U, bool(scf[1].item()), int(scf[0].item())
+
+    def _get_energy_pol(self, positions, box, pairs, Q_local, pol, tholes, mScales, pScales, dScales, U_init=None):
+        """get_energy(..., U_init=self.U_ind)  (admp/pme.py:81-85): SCF, then the energy at fixed U
+        (Hellmann-Feynman: gradients do not flow through the SCF)."""
+        positions, box, Q_local, pol, tholes, mScales, pScales = map(
+            self._prep, (positions, box, Q_local, pol, tholes, mScales, pScales))
+        pairs = pairs_to_dev(pairs, self._ctx.device)
+        U0 = self.U_ind if U_init is None else self._prep(U_init).detach()
+        E = _PmeFunction.apply(self, pairs, True, U0, positions, box, Q_local, None, pol, tholes, mScales, pScales)
+        return E
+
+    def _get_forces_pol(self, positions, box, pairs, Q_local, pol, tholes, mScales, pScales, dScales, U_init=None):
+        positions, box, Q_local, pol, tholes, mScales, pScales = (
+            self._prep(x).detach() for x in (positions, box, Q_local, pol, tholes, mScales, pScales))
+        pairs = pairs_to_dev(pairs, self._ctx.device)
+        U0 = self.U_ind if U_init is None else self._prep(U_init).detach()
+        r = self._eval(positions, box, pairs, Q_local, U0, pol, tholes, mScales, pScales, _lib.WANT_GRAD, True)
+        return r.energy.to(self._dtype), r.dpos
+
+    # ------------------------------------------------------------------ extras
+    def get_forces_and_virial(self, positions, box, pairs, Q_local, *rest, U_init=None):
+        """(E, dE/dpositions, dE/dbox) in one evaluation (the reference reaches dE/dbox through
+        jax.grad(..., argnums=1); README.md:7)."""
+        positions, box, Q_local = (self._prep(x).detach() for x in (positions, box, Q_local))
+        pairs = pairs_to_dev(pairs, self._ctx.device)
+        fl = _lib.WANT_GRAD | _lib.WANT_VIRIAL
+        if self.lpol:
+            pol, tholes, mScales, pScales = (self._prep(x).detach() for x in rest[:4])
+            U0 = self.U_ind if U_init is None else self._prep(U_init).detach()
+            r = self._eval(positions, box, pairs, Q_local, U0, pol, tholes, mScales, pScales, fl, True)
+        else:
+            mScales = self._prep(rest[0]).detach()
+            r = self._eval(positions, box, pairs, Q_local, None, None, None, mScales, None, fl, False)
+        return r.energy.to(self._dtype), r.dpos, r.dbox.to(self._dtype)
+
+    def _construct_local_frames(self, positions, box):
+        """generate_construct_local_frames(axis_type, axis_indices)(positions, box) -> (Na,3,3)."""
+        c = self._ctx
+        positions, box = self._prep(positions).detach(), self._prep(box).detach()
+        nh = (self.lmax + 1) ** 2
+        fr = torch.empty((self.n_atoms, 3, 3), dtype=self._dtype, device=c.device)
+        dummy = torch.zeros((self.n_atoms, nh), dtype=self._dtype, device=c.device)
+        _lib.check(c.lib.admp_frames_fwd(c.handle, _lib.stream_ptr(), _lib.ptr(positions), _lib.ptr(box), _lib.ptr(dummy),
+                                         None, None, _lib.ptr(fr)))
+        return fr

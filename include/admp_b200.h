@@ -1,0 +1,155 @@
+/*
+ * admp_b200.h - C ABI of libadmp_b200.so: B200 (sm_100a) kernels for ADMP's multipolar
+ * PME hot path.  Plain pointers and sizes only; no torch / jax types.
+ *
+ * The reference (Roy-Kid/ADMP) is pure Python on JAX and has no FFI of its own; the
+ * entry points below are what a jax.ffi / ctypes binding for this path binds to, one
+ * per reference function (cited as admp/<file>:<line>).  INTEGRATION.md shows the
+ * reference-side stubs.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; admp_last_error() gives
+ *     the message of the last failure on the calling thread;
+ *   - `stream` is a cudaStream_t passed as void*; compute calls never synchronise the
+ *     host, never allocate, and are CUDA-graph capturable (workspaces live in the ctx
+ *     and are sized by admp_ctx_set_* calls);
+ *   - all array arguments of compute calls are DEVICE pointers; `real` means double
+ *     when the ctx dtype is ADMP_F64 and float when ADMP_F32 (settings.PRECISION,
+ *     admp/settings.py:5); scalar accumulators (energies, virial, scale gradients) are
+ *     always double;
+ *   - units: Angstrom, e, kJ/mol (DIELECTRIC = 1389.35455846, admp/pme.py:16);
+ *   - box is 3x3 row-major, rows = lattice vectors (admp/spatial.py:13-32);
+ *   - harmonic multipole order 00,10,11c,11s,20,21c,21s,22c,22s (admp/multipole.py);
+ *   - internal Cartesian site layout ("M", 10 reals per site):
+ *         q, mu_x, mu_y, mu_z, T_xx, T_xy, T_xz, T_yy, T_yz, T_zz
+ *     with T the traceless Cartesian quadrupole of Stone's convention; gradients w.r.t.
+ *     M ("G") use the same layout, one variable per off-diagonal element.
+ */
+#ifndef ADMP_B200_H
+#define ADMP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADMP_F64 0
+#define ADMP_F32 1
+
+/* reciprocal-space influence functions, admp/recip.py:434-462 */
+#define ADMP_CK_COULOMB 1
+#define ADMP_CK_DISP6 6
+#define ADMP_CK_DISP8 8
+#define ADMP_CK_DISP10 10
+
+/* slots of the double-precision scalar block ("scalars") every compute call accumulates into */
+#define ADMP_S_E_REAL 0    /* pme_real / disp_pme_real / pair_int energy */
+#define ADMP_S_E_RECIP 1   /* pme_recip energy (last convolution) */
+#define ADMP_S_E_SELF 2    /* pme_self / disp_pme_self */
+#define ADMP_S_E_PEN 3     /* pol_penalty */
+#define ADMP_S_DBOX 4      /* 9 slots: dE/dbox[a][b] from real space + frames (image shifts) */
+#define ADMP_S_DNSTAR 13   /* 9 slots: dE/dNstar[d][c] from spread/gather */
+#define ADMP_S_TK 22       /* 6 slots: sum_k dC/dk2 |S|^2/theta^2 k_a k_c (xx,xy,xz,yy,yz,zz) */
+#define ADMP_S_DMSCALE 28  /* 5 slots: dE/dmScales */
+#define ADMP_S_DPSCALE 33  /* 5 slots: dE/dpScales */
+#define ADMP_S_MAXFIELD 38 /* max |dE/dU| over polarizable sites (bit pattern of a double) */
+#define ADMP_S_COUNT 48
+
+/* flags for admp_pme_eval */
+#define ADMP_WANT_GRAD 1u     /* dE/dpositions, dE/dQ_local, dE/dU */
+#define ADMP_WANT_VIRIAL 2u   /* dE/dbox */
+#define ADMP_WANT_PGRAD 4u    /* dE/dmScales, dE/dpScales, dE/dtholes, dE/dpol */
+#define ADMP_SCF 8u           /* run optimize_Uind before the final evaluation */
+#define ADMP_SCF_HOSTSYNC 16u /* debug: host-synchronised SCF loop instead of the device-resident graph */
+
+typedef struct admp_ctx admp_ctx;
+
+const char* admp_last_error(void);
+int admp_version(void);
+
+/* ---- context / environment: ADMPPmeForce.__init__, update_env (admp/pme.py:37-55, :89-94) */
+int admp_ctx_create(admp_ctx** out, int device, int dtype);
+int admp_ctx_destroy(admp_ctx* ctx);
+/* kappa, K1..K3 are independent env values. lmax in {0,1,2}. Re-plans cuFFT. */
+int admp_ctx_set_pme(admp_ctx* ctx, double kappa, int K1, int K2, int K3, int lmax);
+/* HOST pointers, copied: axis types / anchor indices (admp/spatial.py:44-74) and the sparse
+ * covalent map (CSR over atoms; replaces the dense Na x Na matrix of admp/pme.py:681). Either
+ * group may be NULL (no multipole frames / no bonded pairs). */
+int admp_ctx_set_topology(admp_ctx* ctx, int n_atoms, const int32_t* axis_type,
+                          const int32_t* axis_indices, const int32_t* cov_offsets,
+                          const int32_t* cov_index, const int8_t* cov_nbonds);
+int64_t admp_ctx_workspace_bytes(const admp_ctx* ctx);
+/* 1 when optimize_Uind runs as the device-resident CUDA-graph WHILE loop, 0 when the
+ * host-synchronised loop is in use (ADMP_SCF_HOSTSYNC or graph construction failed). */
+int admp_ctx_scf_graph_active(const admp_ctx* ctx);
+
+/* ---- stage entry points (each mirrors one reference function) ------------------------- */
+
+/* generate_construct_local_frames + rot_local2global (admp/spatial.py:76-142,
+ * admp/multipole.py:183-201). Outputs (any may be NULL): M (n,10), Qg (n,9) harmonic,
+ * frames (n,9). */
+int admp_frames_fwd(admp_ctx* ctx, void* stream, const void* pos, const void* box,
+                    const void* Q_local, void* M, void* Qg, void* frames);
+/* adjoint of the above: G (n,10) -> dQ_local (n,9) written, dpos (n,3) and
+ * scalars[ADMP_S_DBOX..] accumulated. */
+int admp_frames_bwd(admp_ctx* ctx, void* stream, const void* pos, const void* box,
+                    const void* Q_local, const void* G, void* dQ_local, void* dpos,
+                    double* scalars);
+
+/* rot_global2local (to_local = 1) / rot_local2global (to_local = 0) with explicit frames
+ * (admp/multipole.py:92-201): Q, out (n,(lmax+1)^2) harmonic; frames (n,9) rows = axes. */
+int admp_rotate(admp_ctx* ctx, void* stream, int64_t n, int lmax, int to_local, const void* Q,
+                const void* frames, void* out);
+
+/* pme_real + pme_real_kernel + calc_e_perm + calc_e_ind (admp/pme.py:258-729), fused with
+ * every adjoint. pairs: (n_rows,2) int32, rows with p0<p1 are evaluated (pme.py:671).
+ * U/pol/tholes/pScales NULL => non-polarizable. mode 0: energy + adjoints, 1: dE/dU only. */
+int admp_pme_real(admp_ctx* ctx, void* stream, const void* pos, const void* box,
+                  const int32_t* pairs, int64_t n_rows, const void* M, const void* U,
+                  const void* pol, const void* tholes, const void* mScales, const void* pScales,
+                  int mode, uint32_t flags, void* dpos, void* G, void* F, void* dpol,
+                  void* dtholes, double* scalars);
+
+/* generate_pme_recip / pme_recip (admp/recip.py:21-431): spread -> cuFFT -> influence
+ * function (kind = ADMP_CK_*) + energy -> cuFFT -> gather. M_cols = 10 (multipoles) or 1
+ * (lmax = 0: charges / dispersion coefficients, stride `M_stride` reals). U may be NULL. */
+int admp_pme_recip(admp_ctx* ctx, void* stream, const void* pos, const void* box,
+                   const void* M, int M_cols, int M_stride, const void* U, int kind, int mode,
+                   uint32_t flags, void* dpos, void* G, int G_stride, void* F, double* scalars);
+
+/* pme_self + pol_penalty (admp/pme.py:738-774). */
+int admp_pme_self(admp_ctx* ctx, void* stream, const void* M, const void* U, const void* pol,
+                  uint32_t flags, void* G, void* F, void* dpol, double* scalars);
+
+/* energy_pme / get_energy / get_forces incl. optimize_Uind (admp/pme.py:58-143, :176-254).
+ * U_io (n,3): in = U_init, out = converged U (ignored when non-polarizable: pass NULL with
+ * pol/tholes/pScales NULL). scf_out[0]=n_cycle, [1]=converged flag (device int32[2]). */
+int admp_pme_eval(admp_ctx* ctx, void* stream, const void* pos, const void* box,
+                  const int32_t* pairs, int64_t n_rows, const void* Q_local, void* U_io,
+                  const void* pol, const void* tholes, const void* mScales, const void* pScales,
+                  uint32_t flags, int maxiter, double thresh, double* scalars, void* dpos,
+                  void* dQ_local, void* F, void* dpol, void* dtholes, int32_t* scf_out);
+
+/* energy_disp_pme (admp/disp_pme.py:80-279): c_list (n,3) reals. dc (n,3) may be NULL. */
+int admp_disp_eval(admp_ctx* ctx, void* stream, const void* pos, const void* box,
+                   const int32_t* pairs, int64_t n_rows, const void* c_list, const void* mScales,
+                   int pmax, uint32_t flags, double* scalars, void* dpos, void* dc);
+
+/* generate_pairwise_interaction(TT_damping_qq_c6_kernel) (admp/pairwise.py:45-113).
+ * params: a, b, q, c (n each). dparams (4 pointers worth, (4,n) reals) may be NULL. */
+int admp_tt_pair(admp_ctx* ctx, void* stream, const void* pos, const void* box,
+                 const int32_t* pairs, int64_t n_rows, const void* mScales, const void* a,
+                 const void* b, const void* q, const void* c, uint32_t flags, double* scalars,
+                 void* dpos, void* dparams);
+
+/* jax_md.partition.neighbor_list(..., format=OrderedSparse) replacement (call sites:
+ * examples/water_1024/run_admp.py:109-112). pairs (capacity,2) int32 padded with (N,N);
+ * info[0] = number of pairs found, info[1] = overflow flag (device int32[2]). */
+int admp_nblist_build(admp_ctx* ctx, void* stream, const void* pos, const void* box, int n_atoms,
+                      double rc, int32_t* pairs, int64_t capacity, int32_t* info);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADMP_B200_H */

@@ -161,3 +161,48 @@ def water1024():
 def water2():
     """examples/water_pol_1024/water2.pdb (2 waters, 31.289 A cubic)."""
     return _load('water2.npz')
+
+
+# rigid TIP3P-like geometry used for synthetic lattices (SURVEY 8(d) "dense" workload)
+_R_OH = 0.9572
+_ANGLE = 104.52 * np.pi / 180.0
+
+
+def _random_rotations(rng, n):
+    q = rng.normal(size=(n, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    a, b, c, d = q.T
+    return np.stack([np.stack([a*a+b*b-c*c-d*d, 2*(b*c-a*d), 2*(b*d+a*c)], 1),
+                     np.stack([2*(b*c+a*d), a*a-b*b+c*c-d*d, 2*(c*d-a*b)], 1),
+                     np.stack([2*(b*d-a*c), 2*(c*d+a*b), a*a-b*b-c*c+d*d], 1)], 1)
+
+
+def lattice_water(n_side, spacing=3.104, seed=7, jitter=0.1):
+    """n_side^3 water molecules on a simple-cubic lattice (spacing in A), random orientation from
+    default_rng(seed), centre jitter N(0, jitter); MPID water parameters of mpidwater.xml. A
+    liquid-like system on which the reference's Jacobi SCF converges (the shipped 50 A box has
+    O-O contacts of 1.14 A on which it diverges)."""
+    base = water1024()
+    rng = np.random.default_rng(seed)
+    nmol = n_side ** 3
+    g = np.stack(np.meshgrid(*[np.arange(n_side)] * 3, indexing='ij'), -1).reshape(-1, 3).astype(np.float64)
+    centres = (g + 0.5) * spacing + rng.normal(0.0, jitter, size=(nmol, 3))
+    h = _ANGLE / 2
+    local = np.array([[0.0, 0.0, 0.0],
+                      [_R_OH * np.sin(h), 0.0, _R_OH * np.cos(h)],
+                      [-_R_OH * np.sin(h), 0.0, _R_OH * np.cos(h)]])
+    R = _random_rotations(rng, nmol)
+    pos = (centres[:, None, :] + np.einsum('mab,kb->mka', R, local)).reshape(-1, 3)
+    n = 3 * nmol
+    mol = np.arange(nmol) * 3
+    ai = np.empty((n, 3), dtype=np.int64)
+    ai[0::3] = np.stack([mol + 1, mol + 2, -np.ones(nmol, dtype=np.int64)], 1)
+    ai[1::3] = np.stack([mol, mol + 2, -np.ones(nmol, dtype=np.int64)], 1)
+    ai[2::3] = np.stack([mol, mol + 1, -np.ones(nmol, dtype=np.int64)], 1)
+    ci = np.concatenate([mol, mol, mol + 1, mol + 2, mol + 1, mol + 2])
+    cj = np.concatenate([mol + 1, mol + 2, mol, mol, mol + 2, mol + 1])
+    cn = np.concatenate([np.ones(4 * nmol), 2 * np.ones(2 * nmol)]).astype(np.int8)
+    cov = MoleculeCovalentMap(n, ci, cj, cn)
+    return WaterSystem(pos, np.full(3, n_side * spacing), np.tile(base.Q_cart[:3], (nmol, 1)),
+                       np.tile(base.axis_type[:3], nmol), ai, np.tile(base.pol.numpy()[:3], nmol),
+                       np.tile(base.tholes.numpy()[:3], nmol), cov)
