@@ -357,6 +357,49 @@ extern "C" int admp_pme_recip(admp_ctx* c, void* stream, const void* pos, const 
     return 0;
 }
 
+// ---- individual reciprocal stages on the context's mesh (used by stage-level tests and by the
+// per-kernel roofline timing of bench.py; admp_pme_recip chains them)
+extern "C" int admp_pme_spread(admp_ctx* c, void* stream, const void* pos, const void* box, const void* M, int M_cols, int M_stride,
+                               const void* U) {
+    if (need(c, true, true)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(c->device));
+    DISPATCH(c, launch_box_setup, st, box, c->box, c->K[0], c->K[1], c->K[2]);
+    CK(cudaMemsetAsync(c->mesh, 0, c->mesh_bytes, st));
+    DISPATCH(c, launch_spread, st, c->n_atoms, c->box, pos, M, M_cols, M_stride, U, c->mesh);
+    CKLAUNCH();
+    return 0;
+}
+extern "C" int admp_pme_spread_only(admp_ctx* c, void* stream, const void* pos, const void* M, int M_cols, int M_stride, const void* U) {
+    if (need(c, true, true)) return 1;     // no zero-fill, no box set-up: the bare scatter kernel
+    DISPATCH(c, launch_spread, (cudaStream_t)stream, c->n_atoms, c->box, pos, M, M_cols, M_stride, U, c->mesh);
+    CKLAUNCH();
+    return 0;
+}
+extern "C" int admp_pme_fft(admp_ctx* c, void* stream, int inverse) {
+    if (need(c, true, false)) return 1;
+    CK(cudaSetDevice(c->device));
+    return inverse ? fft_inv(c, (cudaStream_t)stream) : fft_fwd(c, (cudaStream_t)stream);
+}
+extern "C" int admp_pme_convolve(admp_ctx* c, void* stream, int kind, uint32_t flags, double* scalars) {
+    if (need(c, true, false)) return 1;
+    const size_t nh = (size_t)c->K[0] * c->K[1] * (c->K[2] / 2 + 1);
+    DISPATCH(c, launch_convolve, (cudaStream_t)stream, c->box, nh, c->n_sm, c->kappa, kind, c->bt[0], c->bt[1], c->bt[2], c->spec, scalars,
+             (flags & ADMP_WANT_VIRIAL) ? 1 : 0);
+    CKLAUNCH();
+    return 0;
+}
+extern "C" int admp_pme_gather(admp_ctx* c, void* stream, const void* pos, const void* M, int M_cols, int M_stride, const void* U,
+                               int mode, uint32_t flags, void* dpos, void* G, int G_stride, void* F, double* scalars) {
+    if (need(c, true, true)) return 1;
+    DISPATCH(c, launch_gather, (cudaStream_t)stream, c->n_atoms, c->box, pos, M, M_cols, M_stride, U, c->mesh, mode, flags, dpos, G,
+             G_stride, F, scalars);
+    CKLAUNCH();
+    return 0;
+}
+/* which: 0 = real mesh (K1*K2*K3 reals), 1 = half spectrum (K1*K2*(K3/2+1) complex) */
+extern "C" void* admp_ctx_buffer(admp_ctx* c, int which) { return !c ? nullptr : (which == 0 ? c->mesh : c->spec); }
+
 extern "C" int admp_pme_self(admp_ctx* c, void* stream, const void* M, const void* U, const void* pol, uint32_t flags, void* G,
                              void* F, void* dpol, double* scalars) {
     if (need(c, false, true)) return 1;

@@ -118,6 +118,21 @@ int admp_pme_recip(admp_ctx* ctx, void* stream, const void* pos, const void* box
                    const void* M, int M_cols, int M_stride, const void* U, int kind, int mode,
                    uint32_t flags, void* dpos, void* G, int G_stride, void* F, double* scalars);
 
+/* the individual stages admp_pme_recip chains, operating on the context's mesh / spectrum
+ * (recip.py:368-392 spread_Q; :410 fftn; :400-426 influence function + energy; gather = adjoint of
+ * spread). admp_pme_spread zero-fills then scatters; _spread_only is the bare scatter kernel. */
+int admp_pme_spread(admp_ctx* ctx, void* stream, const void* pos, const void* box, const void* M,
+                    int M_cols, int M_stride, const void* U);
+int admp_pme_spread_only(admp_ctx* ctx, void* stream, const void* pos, const void* M, int M_cols,
+                         int M_stride, const void* U);
+int admp_pme_fft(admp_ctx* ctx, void* stream, int inverse);
+int admp_pme_convolve(admp_ctx* ctx, void* stream, int kind, uint32_t flags, double* scalars);
+int admp_pme_gather(admp_ctx* ctx, void* stream, const void* pos, const void* M, int M_cols,
+                    int M_stride, const void* U, int mode, uint32_t flags, void* dpos, void* G,
+                    int G_stride, void* F, double* scalars);
+/* which: 0 = real mesh (K1*K2*K3 reals), 1 = half spectrum (K1*K2*(K3/2+1) complex) */
+void* admp_ctx_buffer(admp_ctx* ctx, int which);
+
 /* pme_self + pol_penalty (admp/pme.py:738-774). */
 int admp_pme_self(admp_ctx* ctx, void* stream, const void* M, const void* U, const void* pol,
                   uint32_t flags, void* G, void* F, void* dpol, double* scalars);
