@@ -10,6 +10,7 @@ positions, box (virial), Q_local, Uind_global, pol, tholes, mScales and pScales 
 differentiable; dScales has zero gradient (it is unused upstream, admp/pme.py:470).
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -189,6 +190,8 @@ class ADMPPmeForce:
         r.U = None
         if polz:
             r.U = U.detach().clone().contiguous() if U is not None else torch.zeros((n, 3), dtype=dt, device=dev)
+        # ADMP_SCF_HOSTSYNC=1 selects the host-synchronised loop (same kernels; used under profilers)
+        hostsync = hostsync or os.environ.get('ADMP_SCF_HOSTSYNC', '0') == '1'
         f = flags | (_lib.SCF if (polz and do_scf) else 0) | (_lib.SCF_HOSTSYNC if hostsync else 0)
         p = _lib.ptr
         _lib.check(c.lib.admp_pme_eval(

@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""Benchmark of the multipolar-PME hot path (BASELINE.json metric: force+energy evals/s).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One step = one get_forces-equivalent evaluation (E, dE/dpositions, dE/dbox; polarizable: the full
+induced-dipole SCF from U = 0) of config C2 = examples/water_pol_1024 (1024 waters, 3072 atoms,
+rc 4 A, kappa 0.657065221219616, 154^3 mesh).  N > 1: independent frames (config C4 sharding: rank r
+evaluates frames r, r+N, ...; no data-path collective), weak scaling.
+
+Printed line (rank 0): value = device-timed throughput with inputs resident in HBM; e2e = the same
+metric through the public API with host (pinned) inputs and host outputs; roofline = the dominant
+hand-written kernel, timed alone with CUDA events on its launch stream, L2 flushed before each
+launch; cpu_baseline = the CPU oracle (PyTorch float64 restatement of the reference) on the box's
+host cores for a bounded sample of the same workload.  --impl reference times that CPU port as the
+reference arm (the reference's own JAX code cannot be installed here: no jax / jax_md wheels).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'force+energy evals/s (water_pol_1024, polarizable PME: SCF + E + dE/dr + dE/dbox)'
+UNIT = 'evals/s'
+WORKLOAD = 'C2 examples/water_pol_1024: 1024 waters (3072 atoms), 50 A box, rc 4 A, K 154^3, lmax 2, SCF from U=0 (POL_CONV 10, MAX_N_POL 30)'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-large', action='store_true', help='skip the C3-size kernel rooflines')
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# ----------------------------------------------------------------------------------- CPU oracle timing
+def cpu_oracle_sample(n_iter=3):
+    """Times the CPU port on C2: n_iter SCF iterations (each one dE/dU evaluation = forward+backward,
+    exactly what optimize_Uind does per cycle) plus the final energy + dE/dr + dE/dbox, and
+    extrapolates to the reference's 30 cycles on this input.  Only place bench.py touches oracle/."""
+    import torch
+    from oracle import fixtures, pairlist
+    from oracle.realspace import OraclePmeForce
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    s = fixtures.water1024()
+    pairs, _ = pairlist.build_pairs(s.positions.numpy(), s.box.numpy(), 4.0)
+    f = OraclePmeForce(s.box, s.axis_type, s.axis_indices, s.covalent_map, 4.0, 1e-4, 2, lpol=True)
+    f.update_env('kappa', fixtures.KAPPA_EXAMPLE)
+    args = (s.positions, s.box, pairs, s.Q_local)
+    rest = (s.pol, s.tholes, s.mScales, s.pScales, s.dScales)
+    U = torch.zeros(s.n_atoms, 3, dtype=torch.float64)
+    f.grad_U_fn(*args, U, *rest)                      # warm-up (allocator, FFT plans)
+    t0 = time.perf_counter()
+    for _ in range(n_iter):
+        fld = f.grad_U_fn(*args, U, *rest)
+        U = U - fld * s.pol[:, None] / 1389.35455846
+    t_iter = (time.perf_counter() - t0) / n_iter
+    pos = s.positions.clone().requires_grad_(True)
+    box = s.box.clone().requires_grad_(True)
+    t0 = time.perf_counter()
+    E = f.energy_fn(pos, box, pairs, s.Q_local, U, *rest)
+    torch.autograd.grad(E, [pos, box])
+    t_final = time.perf_counter() - t0
+    n_cycles = 30                                     # the reference's Jacobi loop does not converge on this box
+    t_eval = n_cycles * t_iter + t_final
+    return dict(value=1.0 / t_eval, unit=UNIT, cores=cores, kind='port',
+                sample='%d of 30 SCF cycles (%.2f s each) + final E/dE/dr/dE/dbox (%.2f s), PyTorch f64 oracle, %d threads; '
+                       'extrapolated to 30 cycles + final = %.1f s per eval' % (n_iter, t_iter, t_final, cores, t_eval)), t_eval
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    vals = []
+    base = None
+    for _ in range(max(1, min(args.steps, 2))):
+        base, t_eval = cpu_oracle_sample(n_iter=2)
+        vals.append(t_eval)
+    t = statistics.mean(vals)
+    out = dict(metric=METRIC, value=1.0 / t, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+               ms_per_step=1e3 * t, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64', data='synthetic',
+               impl='reference', config=dict(workload=WORKLOAD, note='CPU restatement of the reference (PyTorch f64), NOT the '
+                                             "reference's JAX: jax/jax_md/openmm are not installable in this image"),
+               cpu_baseline=dict(base, value=1.0 / t),
+               e2e=dict(value=1.0 / t, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(out))
+
+
+# ----------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                       '-lms', '100'], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(',')]
+            if len(c) < 6:
+                continue
+            try:
+                sm.append(float(c[0])); mx.append(float(c[1]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if c[2 + k].lower().startswith('active'):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ----------------------------------------------------------------------------------- GPU arm
+def kernel_rooflines(torch, _lib, reps, peak, flush, n_launch=10):
+    """Times spread / convolve / gather alone (CUDA events on the launch stream, L2 flushed before each
+    launch) on the mesh of water_box(reps); returns {name: roofline dict}.  Algorithmic bytes are the
+    SURVEY 8(d) figures: spread w*G (zero-fill, separate memset) + 216*2*w*Na scatter RMW;
+    convolve 2*(2w)*(G/2); gather 216*w*Na + Na*13*w."""
+    from admp_b200 import workloads
+    from admp_b200._ctx import Context, to_dev
+    w = workloads.water_box(reps, polarizable=True)
+    cx = Context()
+    cx.set_topology(w.n_atoms, w.axis_type, w.axis_indices, w.covalent_map)
+    cx.set_pme(w.kappa, w.K[0], w.K[1], w.K[2], 2)
+    dt, dev = cx.dtype, cx.device
+    pos, box, Ql = (to_dev(x, dt, dev) for x in (w.positions, w.box, w.Q_local))
+    n = w.n_atoms
+    M = torch.empty((n, 10), dtype=dt, device=dev)
+    p, sp = _lib.ptr, _lib.stream_ptr
+    _lib.check(cx.lib.admp_frames_fwd(cx.handle, sp(), p(pos), p(box), p(Ql), p(M), None, None))
+    scal = torch.zeros(_lib.S_COUNT, dtype=torch.float64, device=dev)
+    dpos = torch.zeros((n, 3), dtype=dt, device=dev)
+    G = torch.zeros((n, 10), dtype=dt, device=dev)
+    Gpts = w.K[0] * w.K[1] * w.K[2]
+    wb = 8
+    stages = {
+        'spread_kernel': (lambda: cx.lib.admp_pme_spread_only(cx.handle, sp(), p(pos), p(M), 10, 10, None),
+                          216 * 2 * wb * n + n * 13 * wb),
+        'convolve_kernel': (lambda: cx.lib.admp_pme_convolve(cx.handle, sp(), _lib.CK_COULOMB, 0, p(scal)),
+                            2 * 2 * wb * (w.K[0] * w.K[1] * (w.K[2] // 2 + 1))),
+        'gather_kernel': (lambda: cx.lib.admp_pme_gather(cx.handle, sp(), p(pos), p(M), 10, 10, None, 0, _lib.WANT_GRAD, p(dpos), p(G), 10,
+                                                         None, p(scal)), 216 * wb * n + n * 23 * wb),
+    }
+    _lib.check(cx.lib.admp_pme_spread(cx.handle, sp(), p(pos), p(box), p(M), 10, 10, None))
+    _lib.check(cx.lib.admp_pme_fft(cx.handle, sp(), 0))
+    out = {}
+    for name, (fn, nbytes) in stages.items():
+        ts = []
+        for it in range(n_launch + 2):
+            flush()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            _lib.check(fn())
+            b.record()
+            b.synchronize()
+            if it >= 2:
+                ts.append(a.elapsed_time(b))
+        ms = statistics.mean(ts)
+        ach = nbytes / (ms * 1e-3) / 1e9
+        out[name] = dict(bound='hbm', achieved=round(ach, 1), peak=peak, unit='GB/s', frac=round(ach / peak, 4),
+                         traffic=None, ms=round(ms, 4), algorithmic_bytes=nbytes, mesh='%dx%dx%d' % w.K, n_atoms=n)
+    # cuFFT (library) round trip, for the share table only
+    ts = []
+    for it in range(n_launch + 2):
+        flush()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _lib.check(cx.lib.admp_pme_fft(cx.handle, sp(), 0))
+        _lib.check(cx.lib.admp_pme_fft(cx.handle, sp(), 1))
+        b.record()
+        b.synchronize()
+        if it >= 2:
+            ts.append(a.elapsed_time(b))
+    ms = statistics.mean(ts)
+    nbytes = 12 * wb * Gpts
+    out['cufft_r2c_c2r'] = dict(bound='hbm', achieved=round(nbytes / (ms * 1e-3) / 1e9, 1), peak=peak, unit='GB/s',
+                                frac=round(nbytes / (ms * 1e-3) / 1e9 / peak, 4), traffic=None, ms=round(ms, 4),
+                                algorithmic_bytes=nbytes, mesh='%dx%dx%d' % w.K, note='library (cuFFT), not a hand-written kernel')
+    cx.close()
+    return out
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    from admp_b200 import _lib, workloads
+    from admp_b200.pme import ADMPPmeForce
+    from admp_b200.neighbor import neighbor_list
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    _lib.require_cuda()
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    dev = torch.device('cuda', local)
+
+    w = workloads.water_box((1, 1, 1), polarizable=True)
+    calc = ADMPPmeForce(w.box, w.axis_type, w.axis_indices, w.covalent_map, w.rc, w.ethresh, 2, lpol=True)
+    calc.update_env('kappa', w.kappa)
+    assert (calc.K1, calc.K2, calc.K3) == w.K
+    dt = calc._dtype
+    pairs = neighbor_list(w.box, w.rc).allocate(w.positions).pairs
+    box, Ql, pol, th, mS, pS = (calc._prep(x) for x in (w.box, w.Q_local, w.pol, w.tholes, w.mScales, w.pScales))
+    flags = _lib.WANT_GRAD | _lib.WANT_VIRIAL
+    n_frames = args.warmup + args.steps
+    frames = [calc._prep(workloads.jitter_frame(w, rank + world * f) if world > 1 else w.positions) for f in range(n_frames)]
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def flush():
+        flush_buf.zero_()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(pos):
+        return calc._eval(pos, box, pairs, Ql, None, pol, th, mS, pS, flags, True)
+
+    for f in range(args.warmup):
+        r = step(frames[f])
+    barrier()
+    n_cycle, conv = [int(x) for x in r.scf.cpu()]
+    bodies = n_cycle + 1 + (0 if conv or n_cycle < 29 else 1)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for k in range(args.steps):
+        flush()
+        ev[k][0].record()
+        r = step(frames[args.warmup + k])
+        ev[k][1].record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    t_ms = sum(a.elapsed_time(b) for a, b in ev)
+    tt = torch.tensor([t_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_ms = tt.item()
+    value = world * args.steps / (t_ms * 1e-3)
+    E_last = r.energy.item()
+
+    # ---- end to end through the public API: pinned host inputs, host outputs, wall clock
+    n = w.n_atoms
+    host_pos = [torch.as_tensor(np.ascontiguousarray(f.cpu().numpy())).pin_memory() for f in frames]
+    host_box = torch.as_tensor(w.box).pin_memory()
+    out_E = torch.empty((), dtype=dt).pin_memory()
+    out_F = torch.empty((n, 3), dtype=dt).pin_memory()
+    out_V = torch.empty((3, 3), dtype=dt).pin_memory()
+    rest = (pol, th, mS, pS, mS)
+    zero_U = torch.zeros((n, 3), dtype=dt, device=dev)
+
+    def e2e_step(k):
+        E, F, V = calc.get_forces_and_virial(host_pos[k].to(dev, non_blocking=True), host_box.to(dev, non_blocking=True), pairs, Ql,
+                                             *rest[:4], U_init=zero_U)
+        out_E.copy_(E, non_blocking=True)
+        out_F.copy_(F, non_blocking=True)
+        out_V.copy_(V, non_blocking=True)
+
+    for k in range(args.warmup):
+        e2e_step(k)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        e2e_step(args.warmup + k)
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.steps / te.item()
+    esz = 8 if dt == torch.float64 else 4
+    h2d = (n * 3 + 9) * esz
+    d2h = (1 + n * 3 + 9) * esz
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    peak, peak_src = measured_peaks()
+    roof_small = kernel_rooflines(torch, _lib, (1, 1, 1), peak, flush)
+    roof_large = None if args.no_large else kernel_rooflines(torch, _lib, (2, 4, 4), peak, flush, n_launch=5)
+    dominant = 'convolve_kernel'
+    roofline = dict(roof_small[dominant])
+    roofline['kernel'] = dominant
+    roofline['peak_source'] = peak_src
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu, _ = cpu_oracle_sample(n_iter=3)
+    out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+               ms_per_step=t_ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64' if esz == 8 else 'f32',
+               data='synthetic',
+               config=dict(workload=WORKLOAD, parallelism='frames' if world > 1 else 'single', timing='CUDA events per step, summed; '
+                           'L2 flushed (256 MiB write) between timed steps', scf_cycles=n_cycle + 1, scf_converged=bool(conv),
+                           scf_note='the reference Jacobi loop does not converge on the shipped gas-like box: 30 cycles, flag False '
+                                    '(reproduced iteration for iteration)', scf_graph=calc._ctx.scf_graph_active, energy=E_last),
+               e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
+               gpu_launches=args.steps * (2 + 8 * bodies + 5), clocks=clocks, roofline=roofline,
+               kernels=dict(C2=roof_small, C3=roof_large), cpu_baseline=cpu)
+    print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()
