@@ -2,7 +2,9 @@
 // evaluation (energy_pme + optimize_Uind + all adjoints) - see include/admp_b200.h.
 #include <cufft.h>
 
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -55,6 +57,12 @@ struct admp_ctx {
     cufftHandle plan_fwd = 0, plan_inv = 0;
     bool plans = false;
     double* bt[3] = {nullptr, nullptr, nullptr};
+    double *ek = nullptr, *k2 = nullptr;     // separable influence-function tables (per evaluation)
+    int* ortho = nullptr;
+    ConvTables tb = {};
+    Fft3d* fft = nullptr;                    // hand-written FFT (nullptr: sizes unsupported -> cuFFT)
+    bool use_custom_fft = false;
+    std::string fft_note;
     // per-atom workspaces and staged inputs of admp_pme_eval
     void *M = nullptr, *G = nullptr, *Fscf = nullptr;
     void *s_pos = nullptr, *s_U = nullptr, *s_pol = nullptr, *s_th = nullptr, *s_mS = nullptr, *s_pS = nullptr, *s_box = nullptr;
@@ -124,6 +132,9 @@ static void free_recip(admp_ctx* c) {
     dfree(c->mesh); dfree(c->spec); dfree(c->fftwork);
     c->mesh_bytes = c->spec_bytes = c->fftwork_bytes = 0;
     for (int d = 0; d < 3; ++d) dfree(c->bt[d]);
+    dfree(c->ek); dfree(c->k2); dfree(c->ortho);
+    if (c->fft) { fft3d_destroy(c->fft); c->fft = nullptr; }
+    c->use_custom_fft = false;
 }
 
 static void free_atoms(admp_ctx* c) {
@@ -197,7 +208,34 @@ extern "C" int admp_ctx_set_pme(admp_ctx* c, double kappa, int K1, int K2, int K
         CK(cudaMalloc(&c->bt[d], sizeof(double) * cnt[d]));
         CK(cudaMemcpy(c->bt[d], t.data(), sizeof(double) * cnt[d], cudaMemcpyHostToDevice));
     }
+    const int ntab = cnt[0] + cnt[1] + cnt[2];
+    CK(cudaMalloc(&c->ek, sizeof(double) * ntab));
+    CK(cudaMalloc(&c->k2, sizeof(double) * ntab));
+    CK(cudaMalloc(&c->ortho, sizeof(int)));
+    int off = 0;
+    for (int d = 0; d < 3; ++d) {
+        c->tb.ek[d] = c->ek + off; c->tb.k2[d] = c->k2 + off; c->tb.bt[d] = c->bt[d];
+        off += cnt[d];
+    }
+    c->tb.ortho = c->ortho;
+    // hand-written FFT fused with the convolution whenever the mesh sizes allow it
+    const char* why = "";
+    const char* env = getenv("ADMP_FFT");
+    c->fft = fft3d_create(K1, K2, K3, c->dtype, &why);
+    c->use_custom_fft = (c->fft != nullptr) && !(env && strcmp(env, "cufft") == 0);
+    c->fft_note = c->fft ? "" : why;
+    cudaGetLastError();
     c->ws_bytes += c->mesh_bytes + c->spec_bytes + c->fftwork_bytes;
+    return 0;
+}
+
+/* 1: hand-written fused FFT, 0: cuFFT + separate convolution kernel */
+extern "C" int admp_ctx_fft_backend(const admp_ctx* c) { return (c && c->use_custom_fft) ? 1 : 0; }
+extern "C" int admp_ctx_set_fft_backend(admp_ctx* c, int custom) {
+    if (!c) return fail("null ctx");
+    if (custom && !c->fft) return fail("hand-written FFT unavailable for this mesh: %s", c->fft_note.c_str());
+    c->use_custom_fft = custom != 0;
+    drop_graph(c);
     return 0;
 }
 
@@ -279,12 +317,19 @@ static int fft_inv(admp_ctx* c, cudaStream_t st) {
 // spread -> FFT -> influence function (+energy) -> inverse FFT; leaves phi = dE/dmesh in c->mesh
 static int recip_field(admp_ctx* c, cudaStream_t st, const void* pos, const void* M, int cols, int stride, const void* U,
                        int kind, double* scalars, int want_vir) {
+    const int maxK = std::max(c->K[0], std::max(c->K[1], c->K[2]));
+    launch_conv_tables(st, c->box, c->kappa, c->bt[0], c->bt[1], c->bt[2], c->ek, c->k2, c->ortho, maxK);
     CK(cudaMemsetAsync(c->mesh, 0, c->mesh_bytes, st));
     DISPATCH(c, launch_spread, st, c->n_atoms, c->box, pos, M, cols, stride, U, c->mesh);
     CKLAUNCH();
+    if (c->use_custom_fft) {
+        fft3d_convolve_roundtrip(c->fft, st, c->mesh, c->spec, c->box, c->kappa, kind, c->tb, scalars, want_vir);
+        CKLAUNCH();
+        return 0;
+    }
     if (fft_fwd(c, st)) return 1;
     const size_t nh = (size_t)c->K[0] * c->K[1] * (c->K[2] / 2 + 1);
-    DISPATCH(c, launch_convolve, st, c->box, nh, c->n_sm, c->kappa, kind, c->bt[0], c->bt[1], c->bt[2], c->spec, scalars, want_vir);
+    DISPATCH(c, launch_convolve, st, c->box, nh, c->n_sm, c->kappa, kind, c->tb, c->spec, scalars, want_vir);
     CKLAUNCH();
     if (fft_inv(c, st)) return 1;
     return 0;
@@ -379,12 +424,31 @@ extern "C" int admp_pme_spread_only(admp_ctx* c, void* stream, const void* pos, 
 extern "C" int admp_pme_fft(admp_ctx* c, void* stream, int inverse) {
     if (need(c, true, false)) return 1;
     CK(cudaSetDevice(c->device));
+    if (c->use_custom_fft) {
+        if (inverse) fft3d_inverse(c->fft, (cudaStream_t)stream, c->spec, c->mesh);
+        else fft3d_forward(c->fft, (cudaStream_t)stream, c->mesh, c->spec);
+        CKLAUNCH();
+        return 0;
+    }
     return inverse ? fft_inv(c, (cudaStream_t)stream) : fft_fwd(c, (cudaStream_t)stream);
+}
+/* the fused five-pass round trip on the context's mesh (mesh -> phi), hand-written FFT only */
+extern "C" int admp_pme_fft_convolve(admp_ctx* c, void* stream, int kind, uint32_t flags, double* scalars) {
+    if (need(c, true, false)) return 1;
+    if (!c->fft) return fail("hand-written FFT unavailable for this mesh: %s", c->fft_note.c_str());
+    cudaStream_t st = (cudaStream_t)stream;
+    const int maxK = std::max(c->K[0], std::max(c->K[1], c->K[2]));
+    launch_conv_tables(st, c->box, c->kappa, c->bt[0], c->bt[1], c->bt[2], c->ek, c->k2, c->ortho, maxK);
+    fft3d_convolve_roundtrip(c->fft, st, c->mesh, c->spec, c->box, c->kappa, kind, c->tb, scalars, (flags & ADMP_WANT_VIRIAL) ? 1 : 0);
+    CKLAUNCH();
+    return 0;
 }
 extern "C" int admp_pme_convolve(admp_ctx* c, void* stream, int kind, uint32_t flags, double* scalars) {
     if (need(c, true, false)) return 1;
     const size_t nh = (size_t)c->K[0] * c->K[1] * (c->K[2] / 2 + 1);
-    DISPATCH(c, launch_convolve, (cudaStream_t)stream, c->box, nh, c->n_sm, c->kappa, kind, c->bt[0], c->bt[1], c->bt[2], c->spec, scalars,
+    const int maxK = std::max(c->K[0], std::max(c->K[1], c->K[2]));
+    launch_conv_tables((cudaStream_t)stream, c->box, c->kappa, c->bt[0], c->bt[1], c->bt[2], c->ek, c->k2, c->ortho, maxK);
+    DISPATCH(c, launch_convolve, (cudaStream_t)stream, c->box, nh, c->n_sm, c->kappa, kind, c->tb, c->spec, scalars,
              (flags & ADMP_WANT_VIRIAL) ? 1 : 0);
     CKLAUNCH();
     return 0;
@@ -399,6 +463,15 @@ extern "C" int admp_pme_gather(admp_ctx* c, void* stream, const void* pos, const
 }
 /* which: 0 = real mesh (K1*K2*K3 reals), 1 = half spectrum (K1*K2*(K3/2+1) complex) */
 extern "C" void* admp_ctx_buffer(admp_ctx* c, int which) { return !c ? nullptr : (which == 0 ? c->mesh : c->spec); }
+/* copy between a caller device buffer and the context's mesh (which = 0) / spectrum (which = 1) */
+extern "C" int admp_ctx_buffer_io(admp_ctx* c, void* stream, int which, void* user, int64_t nbytes, int to_ctx) {
+    if (need(c, true, false)) return 1;
+    void* buf = which == 0 ? c->mesh : c->spec;
+    const size_t cap = which == 0 ? c->mesh_bytes : c->spec_bytes;
+    if (nbytes < 0 || (size_t)nbytes > cap) return fail("admp_ctx_buffer_io: %lld bytes exceed the buffer (%zu)", (long long)nbytes, cap);
+    CK(cudaMemcpyAsync(to_ctx ? buf : user, to_ctx ? user : buf, (size_t)nbytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
 
 extern "C" int admp_pme_self(admp_ctx* c, void* stream, const void* M, const void* U, const void* pol, uint32_t flags, void* G,
                              void* F, void* dpol, double* scalars) {

@@ -1,0 +1,452 @@
+// Hand-written 3-D real FFT for PME meshes whose sizes cuFFT handles badly, fused with the
+// influence-function convolution.
+//
+// Why: the reference's Ewald set-up gives K = 154 per 50 A (154 = 2*7*11); cuFFT splits each
+// transform into 6-7 generic kernels (regular_fft_factor<2|7|11>, pre/postprocess) and the
+// separate convolution pass re-reads and re-writes the spectrum. Here one reciprocal round trip is
+// five passes over the mesh instead of cuFFT's ~14 kernel launches + 1:
+//     Z-forward (R2C)  ->  Y-forward  ->  [X-forward * C_k/theta^2 (+energy, +virial) * X-inverse]
+//     ->  Y-inverse  ->  Z-inverse (C2R)
+// i.e. 10*w*G bytes of traffic instead of 14*w*G, and the spectrum never exists in its x-transformed
+// form outside shared memory.
+//
+// Each block transforms TL lines in shared memory with a Stockham autosort mixed-radix FFT
+// (radices 2,3,4,5,7,11,13; odd radices use the symmetric cos/sin formulation, tables folded to
+// immediates). Lines of the Y/X passes are strided in memory: a block takes TL neighbouring lines
+// so every global access is a TL*sizeof(complex) contiguous segment. Line stride in shared memory is
+// odd (in complex units) to keep the transposing loads bank-conflict free.
+// Index math validated by tools/fft_model.py (tests/test_fft_model.py).
+#include <cmath>
+#include <vector>
+
+#include "fft_trig.h"
+#include "influence.cuh"
+#include "kernels.h"
+
+namespace admp {
+
+template <typename T> struct cx { T x, y; };
+template <typename T> __device__ __forceinline__ cx<T> operator+(cx<T> a, cx<T> b) { return {a.x + b.x, a.y + b.y}; }
+template <typename T> __device__ __forceinline__ cx<T> operator-(cx<T> a, cx<T> b) { return {a.x - b.x, a.y - b.y}; }
+template <typename T> __device__ __forceinline__ cx<T> cmul(cx<T> a, cx<T> b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+
+// r-point DFT, SIGN = +1: e^{-i..} (forward), -1: e^{+i..} (inverse)
+template <typename T, int R, int SIGN> struct Dft;
+
+template <typename T, int SIGN> struct Dft<T, 2, SIGN> {
+    static __device__ __forceinline__ void run(cx<T> (&v)[2]) {
+        const cx<T> a = v[0], b = v[1];
+        v[0] = a + b; v[1] = a - b;
+    }
+};
+template <typename T, int SIGN> struct Dft<T, 4, SIGN> {
+    static __device__ __forceinline__ void run(cx<T> (&v)[4]) {
+        const cx<T> s02 = v[0] + v[2], d02 = v[0] - v[2], s13 = v[1] + v[3], d13 = v[1] - v[3];
+        // forward: X1 = d02 - i d13, X3 = d02 + i d13
+        const cx<T> id13 = {-(T)SIGN * -d13.y, (T)SIGN * -d13.x};   // (-i*SIGN) * d13
+        v[0] = s02 + s13; v[2] = s02 - s13;
+        v[1] = d02 + id13; v[3] = d02 - id13;
+    }
+};
+// odd radix: X_k, X_{R-k} from a_j = x_j + x_{R-j}, b_j = x_j - x_{R-j}
+template <typename T, int R, int SIGN> struct Dft {
+    static __device__ __forceinline__ void run(cx<T> (&v)[R]) {
+        constexpr int H = (R - 1) / 2;
+        cx<T> a[H], b[H];
+        cx<T> sum = v[0];
+#pragma unroll
+        for (int j = 1; j <= H; ++j) { a[j - 1] = v[j] + v[R - j]; b[j - 1] = v[j] - v[R - j]; sum = sum + a[j - 1]; }
+        const cx<T> x0 = v[0];
+        v[0] = sum;
+#pragma unroll
+        for (int k = 1; k <= H; ++k) {
+            T rc = x0.x, ic = x0.y, rs = 0, is = 0;
+#pragma unroll
+            for (int j = 1; j <= H; ++j) {
+                const T c = (T)trig_cos<R>((j * k) % R), s = (T)trig_sin<R>((j * k) % R);
+                rc += a[j - 1].x * c; ic += a[j - 1].y * c;
+                rs += b[j - 1].x * s; is += b[j - 1].y * s;
+            }
+            v[k] = {rc + (T)SIGN * is, ic - (T)SIGN * rs};
+            v[R - k] = {rc - (T)SIGN * is, ic + (T)SIGN * rs};
+        }
+    }
+};
+
+// one Stockham stage over TL lines: src -> dst (both [TL][LS] complex in shared memory)
+template <typename T, int R, int SIGN>
+__device__ __forceinline__ void stage(const cx<T>* __restrict__ src, cx<T>* __restrict__ dst, int N, int TL, int LS, int Ns,
+                                      const cx<T>* __restrict__ tw, int twmul) {
+    const int m = N / R;
+    const int total = TL * m;
+    const int step = (m / Ns) * twmul;            // W_N^{t*k*(N/(Ns*R))} = table[t*k*step]
+    for (int b = threadIdx.x; b < total; b += blockDim.x) {
+        const int l = b / m, j = b - l * m, k = j % Ns;
+        const cx<T>* s = src + l * LS + j;
+        cx<T> v[R];
+        v[0] = s[0];
+#pragma unroll
+        for (int t = 1; t < R; ++t) {
+            cx<T> w = tw[t * k * step];
+            if (SIGN < 0) w.y = -w.y;
+            v[t] = cmul(s[t * m], w);
+        }
+        Dft<T, R, SIGN>::run(v);
+        cx<T>* d = dst + l * LS + (j - k) * R + k;
+#pragma unroll
+        for (int t = 0; t < R; ++t) d[t * Ns] = v[t];
+    }
+}
+
+struct FftPlan {
+    int N;          // complex line length
+    int nst;
+    int radix[12];
+};
+
+// in-shared-memory FFT of TL lines; returns the buffer holding the result (A or B)
+template <typename T, int SIGN>
+__device__ __forceinline__ cx<T>* fft_lines(cx<T>* A, cx<T>* B, const FftPlan& P, int TL, int LS, const cx<T>* __restrict__ tw, int twmul) {
+    int Ns = 1;
+    for (int s = 0; s < P.nst; ++s) {
+        const int r = P.radix[s];
+        switch (r) {
+            case 2: stage<T, 2, SIGN>(A, B, P.N, TL, LS, Ns, tw, twmul); break;
+            case 3: stage<T, 3, SIGN>(A, B, P.N, TL, LS, Ns, tw, twmul); break;
+            case 4: stage<T, 4, SIGN>(A, B, P.N, TL, LS, Ns, tw, twmul); break;
+            case 5: stage<T, 5, SIGN>(A, B, P.N, TL, LS, Ns, tw, twmul); break;
+            case 7: stage<T, 7, SIGN>(A, B, P.N, TL, LS, Ns, tw, twmul); break;
+            case 11: stage<T, 11, SIGN>(A, B, P.N, TL, LS, Ns, tw, twmul); break;
+            default: stage<T, 13, SIGN>(A, B, P.N, TL, LS, Ns, tw, twmul); break;
+        }
+        __syncthreads();
+        cx<T>* t = A; A = B; B = t;
+        Ns *= r;
+    }
+    return A;
+}
+
+template <typename T>
+__device__ __forceinline__ void load_twiddles(cx<T>* stw, const cx<T>* __restrict__ gtw, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) stw[i] = gtw[i];
+}
+
+// ------------------------------------------------------------------------------------------ Z passes
+// forward: K3 reals per line -> K3/2+1 complex (packed real FFT, tools/fft_model.py r2c)
+template <typename T>
+__global__ void __launch_bounds__(256)
+fft_z_fwd_kernel(FftPlan P, int TL, int LS, int nlines, int K3, const T* __restrict__ mesh, cx<T>* __restrict__ spec,
+                 const cx<T>* __restrict__ gtw) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cx<T>* A = reinterpret_cast<cx<T>*>(smem_raw);
+    cx<T>* Bf = A + TL * LS;
+    cx<T>* stw = Bf + TL * LS;
+    const int M = K3 / 2, K3h = M + 1;
+    const int L0 = blockIdx.x * TL;
+    const int nl = min(TL, nlines - L0);
+    load_twiddles(stw, gtw, K3);
+    T* Ar = reinterpret_cast<T*>(A);
+    for (int e = threadIdx.x; e < nl * K3; e += blockDim.x) {
+        const int l = e / K3, n = e - l * K3;
+        Ar[2 * l * LS + n] = mesh[(size_t)(L0 + l) * K3 + n];
+    }
+    __syncthreads();
+    cx<T>* Z = fft_lines<T, 1>(A, Bf, P, nl, LS, stw, 2);       // W_M = W_K3^2
+    for (int e = threadIdx.x; e < nl * K3h; e += blockDim.x) {
+        const int l = e / K3h, k = e - l * K3h;
+        const cx<T> zk = Z[l * LS + (k == M ? 0 : k)];
+        cx<T> zc = Z[l * LS + ((k == 0 || k == M) ? 0 : M - k)];
+        zc.y = -zc.y;
+        const cx<T> a = {(T)0.5 * (zk.x + zc.x), (T)0.5 * (zk.y + zc.y)}, b = {(T)0.5 * (zk.x - zc.x), (T)0.5 * (zk.y - zc.y)};
+        const cx<T> w = stw[k];                                   // (cos phi, -sin phi), phi = 2 pi k / K3
+        // X = a + (-sin phi - i cos phi) b = a + (w.y - i w.x) b
+        const cx<T> f = {w.y, -w.x};
+        spec[(size_t)(L0 + l) * K3h + k] = a + cmul(f, b);
+    }
+}
+
+// inverse: K3/2+1 complex -> K3 reals, unnormalised (tools/fft_model.py c2r)
+template <typename T>
+__global__ void __launch_bounds__(256)
+fft_z_inv_kernel(FftPlan P, int TL, int LS, int nlines, int K3, const cx<T>* __restrict__ spec, T* __restrict__ mesh,
+                 const cx<T>* __restrict__ gtw) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cx<T>* A = reinterpret_cast<cx<T>*>(smem_raw);
+    cx<T>* Bf = A + TL * LS;
+    cx<T>* stw = Bf + TL * LS;
+    const int M = K3 / 2, K3h = M + 1;
+    const int L0 = blockIdx.x * TL;
+    const int nl = min(TL, nlines - L0);
+    load_twiddles(stw, gtw, K3);
+    // stage the half spectrum in B (needs M+1 <= LS: LS = M|1 >= M+... ensured by the host: LS >= M+1)
+    for (int e = threadIdx.x; e < nl * K3h; e += blockDim.x) {
+        const int l = e / K3h, k = e - l * K3h;
+        Bf[l * LS + k] = spec[(size_t)(L0 + l) * K3h + k];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nl * M; e += blockDim.x) {
+        const int l = e / M, k = e - l * M;
+        const cx<T> xk = Bf[l * LS + k];
+        cx<T> xc = Bf[l * LS + M - k];
+        xc.y = -xc.y;
+        const cx<T> s = xk + xc, d = xk - xc;
+        const cx<T> w = stw[k];                                   // conj gives (cos phi, +sin phi)
+        // Z = s + i (cos phi + i sin phi) d = s + (-sin phi + i cos phi) d = s + (w.y + i w.x) d
+        const cx<T> f = {w.y, w.x};
+        A[l * LS + k] = s + cmul(f, d);
+    }
+    __syncthreads();
+    cx<T>* z = fft_lines<T, -1>(A, Bf, P, nl, LS, stw, 2);
+    const T* zr = reinterpret_cast<const T*>(z);
+    for (int e = threadIdx.x; e < nl * K3; e += blockDim.x) {
+        const int l = e / K3, n = e - l * K3;
+        mesh[(size_t)(L0 + l) * K3 + n] = zr[2 * l * LS + n];
+    }
+}
+
+// ------------------------------------------------------------------------------------------ strided passes (Y, X)
+struct StrideGeom {
+    int n_outer;          // Y: K1 ; X: 1
+    int n_inner;          // Y: K3h ; X: K2*K3h   (contiguous index the TL lines of a block walk)
+    size_t outer_stride;  // Y: K2*K3h ; X: 0
+    size_t line_stride;   // Y: K3h ; X: K2*K3h   (distance between consecutive points of one line)
+    int tiles;            // ceil(n_inner / TL)
+};
+
+template <typename T>
+__device__ __forceinline__ void load_tile(cx<T>* A, const cx<T>* __restrict__ g, int N, int nl, int TL, int LS, size_t stride) {
+    for (int e = threadIdx.x; e < N * TL; e += blockDim.x) {
+        const int pos = e / TL, l = e - pos * TL;
+        if (l < nl) A[l * LS + pos] = g[(size_t)pos * stride + l];
+    }
+}
+template <typename T>
+__device__ __forceinline__ void store_tile(const cx<T>* A, cx<T>* __restrict__ g, int N, int nl, int TL, int LS, size_t stride) {
+    for (int e = threadIdx.x; e < N * TL; e += blockDim.x) {
+        const int pos = e / TL, l = e - pos * TL;
+        if (l < nl) g[(size_t)pos * stride + l] = A[l * LS + pos];
+    }
+}
+
+template <typename T, int SIGN>
+__global__ void __launch_bounds__(256)
+fft_strided_kernel(FftPlan P, int TL, int LS, StrideGeom g, cx<T>* __restrict__ spec, const cx<T>* __restrict__ gtw) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cx<T>* A = reinterpret_cast<cx<T>*>(smem_raw);
+    cx<T>* Bf = A + TL * LS;
+    cx<T>* stw = Bf + TL * LS;
+    const int o = blockIdx.x / g.tiles, t = blockIdx.x - o * g.tiles;
+    const int c0 = t * TL;
+    const int nl = min(TL, g.n_inner - c0);
+    cx<T>* base = spec + (size_t)o * g.outer_stride + c0;
+    load_twiddles(stw, gtw, P.N);
+    load_tile(A, base, P.N, nl, TL, LS, g.line_stride);
+    __syncthreads();
+    cx<T>* R = fft_lines<T, SIGN>(A, Bf, P, nl, LS, stw, 1);
+    store_tile(R, base, P.N, nl, TL, LS, g.line_stride);
+}
+
+// X-forward, multiply by 2*scale*C_k/theta_k^2 with energy (+virial) accumulation, X-inverse: the
+// x-transformed spectrum only ever lives in shared memory (admp/recip.py:410-426 fused with its adjoint)
+template <typename T>
+__global__ void __launch_bounds__(256)
+fft_x_conv_kernel(FftPlan P, int TL, int LS, StrideGeom g, const BoxInfo* __restrict__ Bp, T kappa, int kind, ConvTables tb,
+                  cx<T>* __restrict__ spec, const cx<T>* __restrict__ gtw, double* __restrict__ scalars, int want_vir) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red[7 * 8];
+    cx<T>* A = reinterpret_cast<cx<T>*>(smem_raw);
+    cx<T>* Bf = A + TL * LS;
+    cx<T>* stw = Bf + TL * LS;
+    const BoxInfo& B = *Bp;
+    const int c0 = blockIdx.x * TL;
+    const int nl = min(TL, g.n_inner - c0);
+    cx<T>* base = spec + c0;
+    load_twiddles(stw, gtw, P.N);
+    load_tile(A, base, P.N, nl, TL, LS, g.line_stride);
+    __syncthreads();
+    cx<T>* R = fft_lines<T, 1>(A, Bf, P, nl, LS, stw, 1);
+    cx<T>* O = (R == A) ? Bf : A;
+    // influence function on the tile: element (pos = i1, line l -> flattened (i2, i3))
+    const int K3 = B.K[2], K3h = K3 / 2 + 1;
+    const double scale = (kind == ADMP_CK_COULOMB) ? ADMP_DIEL : 1.0;
+    const bool ortho = *tb.ortho != 0;
+    const double kap = (double)kappa;
+    double acc_e = 0.0, acc_t[6] = {0, 0, 0, 0, 0, 0};
+    for (int e = threadIdx.x; e < P.N * nl; e += blockDim.x) {
+        const int l = e / P.N, i1 = e - l * P.N;
+        const int c = c0 + l;
+        const int i2 = c / K3h, i3 = c - i2 * K3h;
+        cx<T> s = R[l * LS + i1];
+        const double s2 = (double)s.x * s.x + (double)s.y * s.y;
+        const bool single = (i3 == 0) || (2 * i3 == K3);
+        double gk;
+        if (want_vir) {
+            const Influence f = influence<true>(B, tb, ortho, kap, kind, i1, i2, i3);
+            virial_terms(B, f.kv, i1, i2, i3, single, f.dg * s2, acc_t);
+            gk = f.g;
+        } else {
+            gk = influence<false>(B, tb, ortho, kap, kind, i1, i2, i3).g;
+        }
+        acc_e += (single ? 1.0 : 2.0) * gk * s2;
+        const T gg = (T)(2.0 * scale * gk);
+        s.x *= gg; s.y *= gg;
+        R[l * LS + i1] = s;
+    }
+    __syncthreads();
+    cx<T>* R2 = fft_lines<T, -1>(R, O, P, nl, LS, stw, 1);
+    store_tile(R2, base, P.N, nl, TL, LS, g.line_stride);
+    double e1[1] = {acc_e * scale};
+    block_accumulate<1>(e1, red, scalars + ADMP_S_E_RECIP);
+    if (want_vir) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) acc_t[k] *= scale;
+        block_accumulate<6>(acc_t, red, scalars + ADMP_S_TK);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+bool fft_factorize(int n, FftPlan& P) {
+    P.N = n;
+    P.nst = 0;
+    const int odd[5] = {13, 11, 7, 5, 3};
+    for (int r : odd)
+        while (n % r == 0) { if (P.nst >= 12) return false; P.radix[P.nst++] = r; n /= r; }
+    while (n % 4 == 0) { if (P.nst >= 12) return false; P.radix[P.nst++] = 4; n /= 4; }
+    while (n % 2 == 0) { if (P.nst >= 12) return false; P.radix[P.nst++] = 2; n /= 2; }
+    return n == 1 && P.nst > 0;
+}
+
+struct FftDimCfg { FftPlan P; int TL, LS; size_t smem; };
+
+static bool dim_cfg(int N, int tw_len, size_t esz, size_t smem_cap, int min_ls, FftDimCfg& c) {
+    if (!fft_factorize(N, c.P)) return false;
+    c.LS = N | 1;
+    if (c.LS < min_ls) c.LS = min_ls | 1;
+    for (int TL = 8; TL >= 1; TL >>= 1) {
+        const size_t need = (size_t)2 * TL * c.LS * 2 * esz + (size_t)tw_len * 2 * esz;
+        if (need <= smem_cap) { c.TL = TL; c.smem = need; return true; }
+    }
+    return false;
+}
+
+struct Fft3dImpl {
+    int K[3];
+    size_t esz;
+    FftDimCfg z, y, x;
+    void* tw[3];     // device twiddle tables: exp(-2 pi i m / K_d), m < K_d
+};
+
+template <typename T>
+static cudaError_t set_smem_attr(size_t zs, size_t ys, size_t xs) {
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(fft_z_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zs)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(fft_z_inv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zs)) != cudaSuccess) return e;
+    const size_t m = ys > xs ? ys : xs;
+    if ((e = cudaFuncSetAttribute(fft_strided_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(fft_strided_kernel<T, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(fft_x_conv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xs);
+}
+
+Fft3d* fft3d_create(int K1, int K2, int K3, int dtype, const char** why) {
+    static const char* msg_odd = "K3 is odd";
+    static const char* msg_fac = "a mesh dimension has a prime factor outside {2,3,5,7,11,13} or does not fit in shared memory";
+    static const char* msg_cuda = "CUDA error while preparing the FFT";
+    if (K3 % 2) { *why = msg_odd; return nullptr; }
+    Fft3dImpl* f = new Fft3dImpl();
+    f->K[0] = K1; f->K[1] = K2; f->K[2] = K3;
+    f->esz = dtype == ADMP_F64 ? 8 : 4;
+    const size_t cap = 200 * 1024;
+    const int M = K3 / 2;
+    if (!dim_cfg(M, K3, f->esz, cap, M + 1, f->z) || !dim_cfg(K2, K2, f->esz, cap, 0, f->y) || !dim_cfg(K1, K1, f->esz, cap, 0, f->x)) {
+        *why = msg_fac;
+        delete f;
+        return nullptr;
+    }
+    cudaError_t e = dtype == ADMP_F64 ? set_smem_attr<double>(f->z.smem, f->y.smem, f->x.smem)
+                                      : set_smem_attr<float>(f->z.smem, f->y.smem, f->x.smem);
+    if (e != cudaSuccess) { *why = msg_cuda; delete f; return nullptr; }
+    for (int d = 0; d < 3; ++d) {
+        const int n = f->K[d];
+        std::vector<double> h(2 * (size_t)n);
+        for (int m = 0; m < n; ++m) {
+            const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)m / (long double)n;
+            h[2 * m] = (double)cosl(a);
+            h[2 * m + 1] = (double)sinl(a);
+        }
+        if (cudaMalloc(&f->tw[d], 2 * (size_t)n * f->esz) != cudaSuccess) { *why = msg_cuda; delete f; return nullptr; }
+        if (dtype == ADMP_F64) cudaMemcpy(f->tw[d], h.data(), 2 * (size_t)n * 8, cudaMemcpyHostToDevice);
+        else {
+            std::vector<float> hf(h.begin(), h.end());
+            cudaMemcpy(f->tw[d], hf.data(), 2 * (size_t)n * 4, cudaMemcpyHostToDevice);
+        }
+    }
+    return reinterpret_cast<Fft3d*>(f);
+}
+
+void fft3d_destroy(Fft3d* p) {
+    Fft3dImpl* f = reinterpret_cast<Fft3dImpl*>(p);
+    if (!f) return;
+    for (int d = 0; d < 3; ++d) if (f->tw[d]) cudaFree(f->tw[d]);
+    delete f;
+}
+
+template <typename T>
+static void run_fwd_zy(Fft3dImpl* f, cudaStream_t st, const void* mesh, void* spec) {
+    const int K1 = f->K[0], K2 = f->K[1], K3 = f->K[2], K3h = K3 / 2 + 1;
+    const int nlines = K1 * K2;
+    fft_z_fwd_kernel<T><<<(nlines + f->z.TL - 1) / f->z.TL, 256, f->z.smem, st>>>(f->z.P, f->z.TL, f->z.LS, nlines, K3, (const T*)mesh,
+                                                                               (cx<T>*)spec, (const cx<T>*)f->tw[2]);
+    StrideGeom g = {K1, K3h, (size_t)K2 * K3h, (size_t)K3h, (K3h + f->y.TL - 1) / f->y.TL};
+    fft_strided_kernel<T, 1><<<g.n_outer * g.tiles, 256, f->y.smem, st>>>(f->y.P, f->y.TL, f->y.LS, g, (cx<T>*)spec, (const cx<T>*)f->tw[1]);
+}
+template <typename T>
+static void run_inv_yz(Fft3dImpl* f, cudaStream_t st, void* spec, void* mesh) {
+    const int K1 = f->K[0], K2 = f->K[1], K3 = f->K[2], K3h = K3 / 2 + 1;
+    StrideGeom g = {K1, K3h, (size_t)K2 * K3h, (size_t)K3h, (K3h + f->y.TL - 1) / f->y.TL};
+    fft_strided_kernel<T, -1><<<g.n_outer * g.tiles, 256, f->y.smem, st>>>(f->y.P, f->y.TL, f->y.LS, g, (cx<T>*)spec, (const cx<T>*)f->tw[1]);
+    const int nlines = K1 * K2;
+    fft_z_inv_kernel<T><<<(nlines + f->z.TL - 1) / f->z.TL, 256, f->z.smem, st>>>(f->z.P, f->z.TL, f->z.LS, nlines, K3, (const cx<T>*)spec,
+                                                                               (T*)mesh, (const cx<T>*)f->tw[2]);
+}
+template <typename T>
+static void run_x(Fft3dImpl* f, cudaStream_t st, void* spec, int sign) {
+    const int K2 = f->K[1], K3h = f->K[2] / 2 + 1;
+    const int inner = K2 * K3h;
+    StrideGeom g = {1, inner, 0, (size_t)inner, (inner + f->x.TL - 1) / f->x.TL};
+    if (sign > 0) fft_strided_kernel<T, 1><<<g.tiles, 256, f->x.smem, st>>>(f->x.P, f->x.TL, f->x.LS, g, (cx<T>*)spec, (const cx<T>*)f->tw[0]);
+    else fft_strided_kernel<T, -1><<<g.tiles, 256, f->x.smem, st>>>(f->x.P, f->x.TL, f->x.LS, g, (cx<T>*)spec, (const cx<T>*)f->tw[0]);
+}
+
+// plain transforms (same conventions as cuFFT D2Z / Z2D: unnormalised)
+void fft3d_forward(Fft3d* p, cudaStream_t st, const void* mesh, void* spec) {
+    Fft3dImpl* f = reinterpret_cast<Fft3dImpl*>(p);
+    if (f->esz == 8) { run_fwd_zy<double>(f, st, mesh, spec); run_x<double>(f, st, spec, 1); }
+    else { run_fwd_zy<float>(f, st, mesh, spec); run_x<float>(f, st, spec, 1); }
+}
+void fft3d_inverse(Fft3d* p, cudaStream_t st, void* spec, void* mesh) {
+    Fft3dImpl* f = reinterpret_cast<Fft3dImpl*>(p);
+    if (f->esz == 8) { run_x<double>(f, st, spec, -1); run_inv_yz<double>(f, st, spec, mesh); }
+    else { run_x<float>(f, st, spec, -1); run_inv_yz<float>(f, st, spec, mesh); }
+}
+
+// mesh -> phi = dE/dmesh in place of the mesh, energy (+virial sums) accumulated: 5 passes
+void fft3d_convolve_roundtrip(Fft3d* p, cudaStream_t st, void* mesh, void* spec, const BoxInfo* B, double kappa, int kind,
+                              const ConvTables& tb, double* scalars, int want_vir) {
+    Fft3dImpl* f = reinterpret_cast<Fft3dImpl*>(p);
+    const int K2 = f->K[1], K3h = f->K[2] / 2 + 1;
+    const int inner = K2 * K3h;
+    StrideGeom g = {1, inner, 0, (size_t)inner, (inner + f->x.TL - 1) / f->x.TL};
+    if (f->esz == 8) {
+        run_fwd_zy<double>(f, st, mesh, spec);
+        fft_x_conv_kernel<double><<<g.tiles, 256, f->x.smem, st>>>(f->x.P, f->x.TL, f->x.LS, g, B, kappa, kind, tb, (cx<double>*)spec,
+                                                                  (const cx<double>*)f->tw[0], scalars, want_vir);
+        run_inv_yz<double>(f, st, spec, mesh);
+    } else {
+        run_fwd_zy<float>(f, st, mesh, spec);
+        fft_x_conv_kernel<float><<<g.tiles, 256, f->x.smem, st>>>(f->x.P, f->x.TL, f->x.LS, g, B, (float)kappa, kind, tb, (cx<float>*)spec,
+                                                                 (const cx<float>*)f->tw[0], scalars, want_vir);
+        run_inv_yz<float>(f, st, spec, mesh);
+    }
+}
+
+}  // namespace admp

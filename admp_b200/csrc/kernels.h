@@ -1,6 +1,7 @@
 // Internal launcher declarations shared by the translation units of libadmp_b200.
 #pragma once
 #include "common.cuh"
+#include "influence.cuh"
 
 namespace admp {
 
@@ -34,11 +35,22 @@ template <typename T>
 void launch_spread(cudaStream_t st, int n, const BoxInfo* B, const void* pos, const void* M, int m_cols, int m_stride,
                    const void* U, void* mesh);
 template <typename T>
-void launch_convolve(cudaStream_t st, const BoxInfo* B, size_t n_half, int n_sm, double kappa, int kind, const double* bt1,
-                     const double* bt2, const double* bt3, void* S, double* scalars, int want_vir);
+void launch_convolve(cudaStream_t st, const BoxInfo* B, size_t n_half, int n_sm, double kappa, int kind, const ConvTables& tb,
+                     void* S, double* scalars, int want_vir);
+void launch_conv_tables(cudaStream_t st, const BoxInfo* B, double kappa, const double* bt1, const double* bt2, const double* bt3,
+                        double* ek, double* k2, int* ortho, int maxK);
 template <typename T>
 void launch_gather(cudaStream_t st, int n, const BoxInfo* B, const void* pos, const void* M, int m_cols, int m_stride, const void* U,
                    const void* phi, int mode, uint32_t flags, void* dpos, void* G, int g_stride, void* F, double* scalars);
+
+// fft.cu - hand-written 3-D real FFT fused with the influence-function convolution
+struct Fft3d;
+Fft3d* fft3d_create(int K1, int K2, int K3, int dtype, const char** why);     // nullptr when the sizes are unsupported
+void fft3d_destroy(Fft3d* f);
+void fft3d_forward(Fft3d* f, cudaStream_t st, const void* mesh, void* spec);
+void fft3d_inverse(Fft3d* f, cudaStream_t st, void* spec, void* mesh);
+void fft3d_convolve_roundtrip(Fft3d* f, cudaStream_t st, void* mesh, void* spec, const BoxInfo* B, double kappa, int kind,
+                              const ConvTables& tb, double* scalars, int want_vir);
 
 // site.cu
 template <typename T> void launch_box_setup(cudaStream_t st, const void* box, BoxInfo* B, int K1, int K2, int K3);

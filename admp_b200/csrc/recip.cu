@@ -13,6 +13,7 @@
 //   mesh(g) += q W000 + sum_d muf_d W[e_d] + sum_de Tf_de W[e_d+e_e]
 //   muf_d = -sum_c Nstar[d][c] mu_c ; Tf_de = sum_ab Nstar[d][a] Nstar[e][b] T_ab / 3
 #include "kernels.h"
+#include "influence.cuh"
 
 namespace admp {
 
@@ -132,98 +133,77 @@ spread_kernel(int n, const BoxInfo* __restrict__ Bp, const T* __restrict__ pos, 
 }
 
 // ---------------------------------------------------------------------------- convolution
-__device__ __forceinline__ int kint(int i, int K) {      // recip.py:339: [0,1,...,-2,-1], even-K Nyquist negative
-    return (2 * i < K) ? i : i - K;
-}
-
 template <typename T> struct cplx { T x, y; };
+
+// per-evaluation separable tables for the Coulomb / orthorhombic fast path (see influence.cuh)
+__global__ void conv_tables_kernel(const BoxInfo* __restrict__ Bp, double kappa, const double* __restrict__ bt1,
+                                   const double* __restrict__ bt2, const double* __restrict__ bt3, double* __restrict__ ek,
+                                   double* __restrict__ k2, int* __restrict__ ortho) {
+    const BoxInfo& B = *Bp;
+    const int K[3] = {B.K[0], B.K[1], B.K[2]};
+    const int cnt[3] = {K[0], K[1], K[2] / 2 + 1};
+    const double* bt[3] = {bt1, bt2, bt3};
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int off = 0;
+    for (int d = 0; d < 3; ++d) {
+        if (i < cnt[d]) {
+            const double m = (d == 2) ? (double)i : (double)kint(i, K[d]);
+            const double k = 6.283185307179586 * m * B.inv[4 * d];
+            k2[off + i] = k * k;
+            ek[off + i] = exp(-k * k / (4 * kappa * kappa)) * bt[d][i];
+        }
+        off += cnt[d];
+    }
+    if (i == 0) {
+        bool o = true;
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b)
+                if (a != b && B.box[3 * a + b] != 0.0) o = false;
+        *ortho = o ? 1 : 0;
+    }
+}
 
 // In place on the half spectrum S (K1 x K2 x (K3/2+1)):  S <- 2*scale*C_k/theta_k^2 * S and
 // E += scale * sum_full C_k |S_k|^2 / theta_k^2   (recip.py:400-426, A16; R2C weights per plane).
 template <typename T>
 __global__ void __launch_bounds__(256)
-convolve_kernel(const BoxInfo* __restrict__ Bp, T kappa, int kind, const double* __restrict__ bt1,
-                const double* __restrict__ bt2, const double* __restrict__ bt3, cplx<T>* __restrict__ S,
+convolve_kernel(const BoxInfo* __restrict__ Bp, T kappa, int kind, ConvTables tb, cplx<T>* __restrict__ S,
                 double* __restrict__ scalars, int want_vir) {
     __shared__ double red[7 * 8];
     const BoxInfo& B = *Bp;
-    const int K1 = B.K[0], K2 = B.K[1], K3 = B.K[2], K3h = K3 / 2 + 1;
-    const size_t total = (size_t)K1 * K2 * K3h;
+    const unsigned K2 = B.K[1], K3 = B.K[2], K3h = K3 / 2 + 1;
+    const size_t total = (size_t)B.K[0] * K2 * K3h;
     const double scale = (kind == ADMP_CK_COULOMB) ? ADMP_DIEL : 1.0;
-    const double twopi = 6.283185307179586;
-    const double kap = (double)kappa, V = B.vol;
-    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    const bool ortho = *tb.ortho != 0;
+    const double kap = (double)kappa;
+    double acc_e = 0.0, acc_t[6] = {0, 0, 0, 0, 0, 0};
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const int i3 = (int)(idx % K3h);
         const size_t rest = idx / K3h;
-        const int i2 = (int)(rest % K2), i1 = (int)(rest / K2);
-        const double m1 = kint(i1, K1), m2 = kint(i2, K2), m3 = i3;
-        double kv[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) kv[c] = twopi * (m1 * B.inv[c] + m2 * B.inv[3 + c] + m3 * B.inv[6 + c]);   // recip.py:360
-        const double ksq = kv[0] * kv[0] + kv[1] * kv[1] + kv[2] * kv[2];
-        double C, dC;
-        if (kind == ADMP_CK_COULOMB) {                                  // Ck_1, recip.py:434
-            if (idx == 0) { C = 0.0; dC = 0.0; }                        // gamma point dropped
-            else {
-                C = twopi / (V * ksq) * exp(-ksq / (4 * kap * kap));
-                dC = -C * (1.0 / ksq + 1.0 / (4 * kap * kap));
-            }
-        } else {                                                        // Ck_6/8/10, recip.py:437-462
-            const double x2 = ksq / (4 * kap * kap), x = sqrt(x2), e = exp(-x2), ec = ADMP_SQRT_PI * erfc(x);
-            double f, df, pref;
-            const double base = ADMP_SQRT_PI * 3.141592653589793 / 2 / V;
-            if (kind == ADMP_CK_DISP6) {
-                f = (1 - 2 * x2) * e + 2 * x2 * x * ec; df = -6 * e + 6 * x * ec; pref = base * kap * kap * kap / 3;
-            } else if (kind == ADMP_CK_DISP8) {
-                f = (3 - 2 * x2 + 4 * x2 * x2) * e - 4 * x2 * x2 * x * ec; df = e * (-10 + 20 * x2) - 20 * x2 * x * ec;
-                pref = base * kap * kap * kap * kap * kap / 45;
-            } else {
-                f = (15 - 6 * x2 + 4 * x2 * x2 - 8 * x2 * x2 * x2) * e + 8 * x2 * x2 * x2 * x * ec;
-                df = e * (-42 + 28 * x2 - 56 * x2 * x2) + 56 * x2 * x2 * x * ec;
-                pref = base * kap * kap * kap * kap * kap * kap * kap / 1260;
-            }
-            C = pref * f; dC = pref * df / (8 * kap * kap);
-        }
-        const double th = bt1[i1] * bt2[i2] * bt3[i3];                  // 1/theta_k^2
+        const int i3 = (int)(idx - rest * K3h);
+        const int i1 = (int)(rest / K2), i2 = (int)(rest - (size_t)i1 * K2);
         cplx<T> s = S[idx];
-        const double s2 = ((double)s.x * s.x + (double)s.y * s.y) * th;
-        const bool single = (i3 == 0) || (2 * i3 == K3);
-        const double wgt = single ? 1.0 : 2.0;
-        acc[0] += wgt * C * s2;
+        const double s2 = (double)s.x * s.x + (double)s.y * s.y;
+        const bool single = (i3 == 0) || (2 * i3 == (int)K3);
         if (want_vir) {
-            const double b = dC * s2;
-            // Hermitian partner of a weight-2 point: k -> -k except on an even-K Nyquist index
-            const double s1 = (2 * i1 == K1) ? 1.0 : -1.0, s2n = (2 * i2 == K2) ? 1.0 : -1.0;
-            const double p0 = s1, p1 = s2n, p2 = -1.0;
-            // partner k' = sum_d p_d m_d inv[d][:]
-            double kq[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) kq[c] = twopi * (p0 * m1 * B.inv[c] + p1 * m2 * B.inv[3 + c] + p2 * m3 * B.inv[6 + c]);
-            const double pw = single ? 0.0 : 1.0;
-            acc[1] += b * (kv[0] * kv[0] + pw * kq[0] * kq[0]);
-            acc[2] += b * (kv[0] * kv[1] + pw * kq[0] * kq[1]);
-            acc[3] += b * (kv[0] * kv[2] + pw * kq[0] * kq[2]);
-            acc[4] += b * (kv[1] * kv[1] + pw * kq[1] * kq[1]);
-            acc[5] += b * (kv[1] * kv[2] + pw * kq[1] * kq[2]);
-            acc[6] += b * (kv[2] * kv[2] + pw * kq[2] * kq[2]);
+            const Influence f = influence<true>(B, tb, ortho, kap, kind, i1, i2, i3);
+            acc_e += (single ? 1.0 : 2.0) * f.g * s2;
+            virial_terms(B, f.kv, i1, i2, i3, single, f.dg * s2, acc_t);
+            const T g = (T)(2.0 * scale * f.g);
+            s.x *= g; s.y *= g;
+        } else {
+            const Influence f = influence<false>(B, tb, ortho, kap, kind, i1, i2, i3);
+            acc_e += (single ? 1.0 : 2.0) * f.g * s2;
+            const T g = (T)(2.0 * scale * f.g);
+            s.x *= g; s.y *= g;
         }
-        const T g = (T)(2.0 * scale * C * th);
-        s.x *= g; s.y *= g;
         S[idx] = s;
     }
-    acc[0] *= scale;
+    double e1[1] = {acc_e * scale};
+    block_accumulate<1>(e1, red, scalars + ADMP_S_E_RECIP);
     if (want_vir) {
 #pragma unroll
-        for (int k = 1; k < 7; ++k) acc[k] *= scale;
-        // slots: E_RECIP then TK are not contiguous -> two accumulations
-        double e1[1] = {acc[0]};
-        block_accumulate<1>(e1, red, scalars + ADMP_S_E_RECIP);
-        double t6[6] = {acc[1], acc[2], acc[3], acc[4], acc[5], acc[6]};
-        block_accumulate<6>(t6, red, scalars + ADMP_S_TK);
-    } else {
-        double e1[1] = {acc[0]};
-        block_accumulate<1>(e1, red, scalars + ADMP_S_E_RECIP);
+        for (int k = 0; k < 6; ++k) acc_t[k] *= scale;
+        block_accumulate<6>(acc_t, red, scalars + ADMP_S_TK);
     }
 }
 
@@ -402,12 +382,16 @@ void launch_spread(cudaStream_t st, int n, const BoxInfo* B, const void* pos, co
     else spread_kernel<T, false><<<grid, SPREAD_WARPS * 32, 0, st>>>(n, B, (const T*)pos, (const T*)M, m_stride, nullptr, (T*)mesh);
 }
 template <typename T>
-void launch_convolve(cudaStream_t st, const BoxInfo* B, size_t n_half, int n_sm, double kappa, int kind, const double* bt1,
-                     const double* bt2, const double* bt3, void* S, double* scalars, int want_vir) {
+void launch_convolve(cudaStream_t st, const BoxInfo* B, size_t n_half, int n_sm, double kappa, int kind, const ConvTables& tb,
+                     void* S, double* scalars, int want_vir) {
     size_t blocks = (n_half + 255) / 256;
     const size_t cap = (size_t)n_sm * 8;            // grid sized in multiples of the SM count (grid-stride loop)
     if (blocks > cap) blocks = cap;
-    convolve_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(B, (T)kappa, kind, bt1, bt2, bt3, (cplx<T>*)S, scalars, want_vir);
+    convolve_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(B, (T)kappa, kind, tb, (cplx<T>*)S, scalars, want_vir);
+}
+void launch_conv_tables(cudaStream_t st, const BoxInfo* B, double kappa, const double* bt1, const double* bt2, const double* bt3,
+                        double* ek, double* k2, int* ortho, int maxK) {
+    conv_tables_kernel<<<(maxK + 127) / 128, 128, 0, st>>>(B, kappa, bt1, bt2, bt3, ek, k2, ortho);
 }
 template <typename T>
 void launch_gather(cudaStream_t st, int n, const BoxInfo* B, const void* pos, const void* M, int m_cols, int m_stride, const void* U,
@@ -422,8 +406,8 @@ void launch_gather(cudaStream_t st, int n, const BoxInfo* B, const void* pos, co
 }
 #define ADMP_INST(T)                                                                                                              \
     template void launch_spread<T>(cudaStream_t, int, const BoxInfo*, const void*, const void*, int, int, const void*, void*);    \
-    template void launch_convolve<T>(cudaStream_t, const BoxInfo*, size_t, int, double, int, const double*, const double*,        \
-                                     const double*, void*, double*, int);                                                         \
+    template void launch_convolve<T>(cudaStream_t, const BoxInfo*, size_t, int, double, int, const ConvTables&, void*, double*,   \
+                                     int);                                                                                        \
     template void launch_gather<T>(cudaStream_t, int, const BoxInfo*, const void*, const void*, int, int, const void*, const void*, \
                                    int, uint32_t, void*, void*, int, void*, double*);
 ADMP_INST(double)

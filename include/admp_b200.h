@@ -83,6 +83,11 @@ int64_t admp_ctx_workspace_bytes(const admp_ctx* ctx);
 /* 1 when optimize_Uind runs as the device-resident CUDA-graph WHILE loop, 0 when the
  * host-synchronised loop is in use (ADMP_SCF_HOSTSYNC or graph construction failed). */
 int admp_ctx_scf_graph_active(const admp_ctx* ctx);
+/* FFT backend: 1 = hand-written mixed-radix FFT fused with the convolution (mesh sizes with prime
+ * factors in {2,3,5,7,11,13}, K3 even), 0 = cuFFT + separate convolution kernel. ADMP_FFT=cufft in
+ * the environment selects cuFFT at set_pme time. */
+int admp_ctx_fft_backend(const admp_ctx* ctx);
+int admp_ctx_set_fft_backend(admp_ctx* ctx, int custom);
 
 /* ---- stage entry points (each mirrors one reference function) ------------------------- */
 
@@ -127,11 +132,16 @@ int admp_pme_spread_only(admp_ctx* ctx, void* stream, const void* pos, const voi
                          int M_stride, const void* U);
 int admp_pme_fft(admp_ctx* ctx, void* stream, int inverse);
 int admp_pme_convolve(admp_ctx* ctx, void* stream, int kind, uint32_t flags, double* scalars);
+/* fused five-pass round trip mesh -> phi (Z-fwd, Y-fwd, [X-fwd * C_k/theta^2 * X-inv], Y-inv, Z-inv)
+ * of the hand-written FFT; admp_pme_recip / admp_pme_eval use it whenever the mesh sizes allow. */
+int admp_pme_fft_convolve(admp_ctx* ctx, void* stream, int kind, uint32_t flags, double* scalars);
 int admp_pme_gather(admp_ctx* ctx, void* stream, const void* pos, const void* M, int M_cols,
                     int M_stride, const void* U, int mode, uint32_t flags, void* dpos, void* G,
                     int G_stride, void* F, double* scalars);
 /* which: 0 = real mesh (K1*K2*K3 reals), 1 = half spectrum (K1*K2*(K3/2+1) complex) */
 void* admp_ctx_buffer(admp_ctx* ctx, int which);
+/* device-to-device copy between a caller buffer and the context's mesh / spectrum (tests, tools) */
+int admp_ctx_buffer_io(admp_ctx* ctx, void* stream, int which, void* user, int64_t nbytes, int to_ctx);
 
 /* pme_self + pol_penalty (admp/pme.py:738-774). */
 int admp_pme_self(admp_ctx* ctx, void* stream, const void* M, const void* U, const void* pol,

@@ -1,0 +1,104 @@
+"""Hand-written mixed-radix FFT (admp_b200/csrc/fft.cu) against torch.fft and against the cuFFT
+backend of the same library; fused convolution round trip against the unfused path."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from admp_b200 import _lib                       # noqa: E402
+from admp_b200._ctx import Context               # noqa: E402
+
+SIZES = [(154, 154, 154), (44, 42, 60), (22, 26, 30), (6, 10, 14), (308, 154, 22), (96, 100, 98)]
+
+
+def _ctx(K, precision='double'):
+    cx = Context(precision)
+    cx.set_pme(0.45, K[0], K[1], K[2], 2)
+    return cx
+
+
+@pytest.mark.parametrize('K', SIZES)
+@pytest.mark.parametrize('precision', ['double', 'single'])
+def test_forward_and_inverse_match_torch_fft(K, precision):
+    cx = _ctx(K, precision)
+    assert cx.lib.admp_ctx_fft_backend(cx.handle) == 1
+    dt = cx.dtype
+    cdt = torch.complex128 if dt == torch.float64 else torch.complex64
+    g = torch.Generator(device='cuda').manual_seed(K[0] * 7 + K[2])
+    mesh = torch.randn(K, dtype=dt, device='cuda', generator=g)
+    sp, p = _lib.stream_ptr, _lib.ptr
+    _lib.check(cx.lib.admp_ctx_buffer_io(cx.handle, sp(), 0, p(mesh), mesh.numel() * mesh.element_size(), 1))
+    _lib.check(cx.lib.admp_pme_fft(cx.handle, sp(), 0))
+    spec = torch.empty((K[0], K[1], K[2] // 2 + 1), dtype=cdt, device='cuda')
+    _lib.check(cx.lib.admp_ctx_buffer_io(cx.handle, sp(), 1, p(spec), spec.numel() * spec.element_size(), 0))
+    ref = torch.fft.rfftn(mesh.double())
+    tol = 1e-12 if dt == torch.float64 else 2e-5
+    assert (spec.to(torch.complex128) - ref).abs().max().item() < tol * ref.abs().max().item()
+    _lib.check(cx.lib.admp_pme_fft(cx.handle, sp(), 1))
+    back = torch.empty_like(mesh)
+    _lib.check(cx.lib.admp_ctx_buffer_io(cx.handle, sp(), 0, p(back), back.numel() * back.element_size(), 0))
+    n = K[0] * K[1] * K[2]
+    assert (back.double() / n - mesh.double()).abs().max().item() < tol * 10
+
+
+@pytest.mark.parametrize('K', [(154, 154, 154), (44, 42, 60)])
+@pytest.mark.parametrize('kind', [_lib.CK_COULOMB, _lib.CK_DISP6, _lib.CK_DISP10])
+def test_fused_roundtrip_equals_cufft_plus_convolve(K, kind):
+    cx = _ctx(K)
+    cx.set_topology(4, None, None, None)
+    sp, p = _lib.stream_ptr, _lib.ptr
+    box = torch.diag(torch.tensor([31.0, 29.0, 37.0], dtype=torch.float64, device='cuda'))
+    pos = torch.rand((4, 3), dtype=torch.float64, device='cuda') * 20
+    Q = torch.rand((4, 1), dtype=torch.float64, device='cuda')
+    g = torch.Generator(device='cuda').manual_seed(3)
+    mesh = torch.randn(K, dtype=torch.float64, device='cuda', generator=g)
+    out = {}
+    for backend in (1, 0):
+        _lib.check(cx.lib.admp_ctx_set_fft_backend(cx.handle, backend))
+        # admp_pme_spread sets up the box on the context; its mesh is then overwritten
+        _lib.check(cx.lib.admp_pme_spread(cx.handle, sp(), p(pos), p(box), p(Q), 1, 1, None))
+        _lib.check(cx.lib.admp_ctx_buffer_io(cx.handle, sp(), 0, p(mesh), mesh.numel() * 8, 1))
+        scal = torch.zeros(_lib.S_COUNT, dtype=torch.float64, device='cuda')
+        if backend == 1:
+            _lib.check(cx.lib.admp_pme_fft_convolve(cx.handle, sp(), kind, _lib.WANT_VIRIAL, p(scal)))
+        else:
+            _lib.check(cx.lib.admp_pme_fft(cx.handle, sp(), 0))
+            _lib.check(cx.lib.admp_pme_convolve(cx.handle, sp(), kind, _lib.WANT_VIRIAL, p(scal)))
+            _lib.check(cx.lib.admp_pme_fft(cx.handle, sp(), 1))
+        phi = torch.empty_like(mesh)
+        _lib.check(cx.lib.admp_ctx_buffer_io(cx.handle, sp(), 0, p(phi), phi.numel() * 8, 0))
+        out[backend] = (phi, scal.clone())
+    a, b = out[1], out[0]
+    assert (a[0] - b[0]).abs().max().item() < 1e-11 * b[0].abs().max().item()
+    assert abs(a[1][_lib.S_E_RECIP].item() - b[1][_lib.S_E_RECIP].item()) < 1e-11 * abs(b[1][_lib.S_E_RECIP].item())
+    tk_a, tk_b = a[1][_lib.S_TK:_lib.S_TK + 6], b[1][_lib.S_TK:_lib.S_TK + 6]
+    assert (tk_a - tk_b).abs().max().item() < 1e-10 * tk_b.abs().max().item()
+
+
+def test_unsupported_sizes_fall_back_to_cufft():
+    cx = _ctx((31, 62, 34))          # 31 and 17 are outside the radix set
+    assert cx.lib.admp_ctx_fft_backend(cx.handle) == 0
+    assert cx.lib.admp_ctx_set_fft_backend(cx.handle, 1) != 0
+    cx2 = _ctx((22, 22, 21))         # odd K3
+    assert cx2.lib.admp_ctx_fft_backend(cx2.handle) == 0
+
+
+def test_full_evaluation_identical_on_both_backends():
+    """Config C1 (154^3): energy, forces and virial with the fused hand-written FFT vs cuFFT."""
+    from admp_b200 import workloads
+    from admp_b200.pme import ADMPPmeForce
+    from admp_b200.neighbor import neighbor_list
+    w = workloads.water_box((1, 1, 1), polarizable=True)
+    pairs = neighbor_list(w.box, w.rc).allocate(w.positions).pairs
+    res = {}
+    for backend in (1, 0):
+        calc = ADMPPmeForce(w.box, w.axis_type, w.axis_indices, w.covalent_map, w.rc, w.ethresh, 2, lpol=True)
+        calc.update_env('kappa', w.kappa)
+        _lib.check(calc._ctx.lib.admp_ctx_set_fft_backend(calc._ctx.handle, backend))
+        E, F, V = calc.get_forces_and_virial(w.positions, w.box, pairs, w.Q_local, w.pol, w.tholes, w.mScales, w.pScales)
+        res[backend] = (E.item(), F.clone(), V.clone(), calc.n_cycle)
+    assert res[0][3] == res[1][3]
+    assert abs(res[0][0] - res[1][0]) < 1e-9 * abs(res[0][0])
+    assert (res[0][1] - res[1][1]).abs().max().item() < 1e-9 * res[0][1].abs().max().item()
+    assert (res[0][2] - res[1][2]).abs().max().item() < 1e-8 * res[0][2].abs().max().item()
