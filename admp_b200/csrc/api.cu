@@ -315,10 +315,15 @@ static int fft_inv(admp_ctx* c, cudaStream_t st) {
 }
 
 // spread -> FFT -> influence function (+energy) -> inverse FFT; leaves phi = dE/dmesh in c->mesh
-static int recip_field(admp_ctx* c, cudaStream_t st, const void* pos, const void* M, int cols, int stride, const void* U,
-                       int kind, double* scalars, int want_vir) {
+static void conv_tables(admp_ctx* c, cudaStream_t st) {
     const int maxK = std::max(c->K[0], std::max(c->K[1], c->K[2]));
     launch_conv_tables(st, c->box, c->kappa, c->bt[0], c->bt[1], c->bt[2], c->ek, c->k2, c->ortho, maxK);
+}
+
+// `tables`: rebuild the separable influence tables first (needed once per box, i.e. per evaluation)
+static int recip_field(admp_ctx* c, cudaStream_t st, const void* pos, const void* M, int cols, int stride, const void* U,
+                       int kind, double* scalars, int want_vir, bool tables = true) {
+    if (tables) conv_tables(c, st);
     CK(cudaMemsetAsync(c->mesh, 0, c->mesh_bytes, st));
     DISPATCH(c, launch_spread, st, c->n_atoms, c->box, pos, M, cols, stride, U, c->mesh);
     CKLAUNCH();
@@ -443,6 +448,15 @@ extern "C" int admp_pme_fft_convolve(admp_ctx* c, void* stream, int kind, uint32
     CKLAUNCH();
     return 0;
 }
+/* one of the five passes of the fused round trip (0 Z-fwd, 1 Y-fwd, 2 X-fwd*conv*X-inv, 3 Y-inv, 4 Z-inv) */
+extern "C" int admp_pme_fft_pass(admp_ctx* c, void* stream, int which, int kind, double* scalars) {
+    if (need(c, true, false)) return 1;
+    if (!c->fft) return fail("hand-written FFT unavailable for this mesh: %s", c->fft_note.c_str());
+    if (which < 0 || which > 4) return fail("admp_pme_fft_pass: pass index %d", which);
+    fft3d_single_pass(c->fft, (cudaStream_t)stream, which, c->mesh, c->spec, c->box, c->kappa, kind, c->tb, scalars);
+    CKLAUNCH();
+    return 0;
+}
 extern "C" int admp_pme_convolve(admp_ctx* c, void* stream, int kind, uint32_t flags, double* scalars) {
     if (need(c, true, false)) return 1;
     const size_t nh = (size_t)c->K[0] * c->K[1] * (c->K[2] / 2 + 1);
@@ -487,7 +501,7 @@ extern "C" int admp_pme_self(admp_ctx* c, void* stream, const void* M, const voi
 // one pass of optimize_Uind's loop body on staged inputs (admp/pme.py:132-138)
 static int scf_body(admp_ctx* c, cudaStream_t st, int maxiter, double thresh, uint32_t flags, cudaGraphConditionalHandle h, int use_h) {
     launch_scf_rearm(st, c->scal);
-    if (recip_field(c, st, c->s_pos, c->M, 10, 10, c->s_U, ADMP_CK_COULOMB, c->scal, (flags & ADMP_WANT_VIRIAL) ? 1 : 0)) return 1;
+    if (recip_field(c, st, c->s_pos, c->M, 10, 10, c->s_U, ADMP_CK_COULOMB, c->scal, (flags & ADMP_WANT_VIRIAL) ? 1 : 0, false)) return 1;
     DISPATCH(c, launch_gather, st, c->n_atoms, c->box, c->s_pos, c->M, 10, 10, c->s_U, c->mesh, 1, 0u, nullptr, nullptr, 10, c->Fscf, c->scal);
     DISPATCH(c, launch_pme_pair, st, c->pairs_cap, c->n_atoms, c->box, c->kappa, c->s_pos, c->s_pairs, c->cov_off, c->cov_idx, c->cov_nb,
              c->M, c->s_U, c->s_pol, c->s_th, c->s_mS, c->s_pS, 1, 0u, nullptr, nullptr, c->Fscf, nullptr, nullptr, c->scal);
@@ -599,6 +613,7 @@ extern "C" int admp_pme_eval(admp_ctx* c, void* stream, const void* pos, const v
     if (dtholes) CK(cudaMemsetAsync(dtholes, 0, (size_t)n * w, st));
     DISPATCH(c, launch_box_setup, st, c->s_box, c->box, c->K[0], c->K[1], c->K[2]);
     DISPATCH(c, launch_frames_fwd, st, n, c->lmax, c->box, c->s_pos, c->axis_type, c->axis_idx, Ql, c->M, nullptr, nullptr);
+    conv_tables(c, st);
     CKLAUNCH();
     const int want_vir = (flags & ADMP_WANT_VIRIAL) ? 1 : 0;
     if (polz && (flags & ADMP_SCF)) {

@@ -17,6 +17,8 @@
 // odd (in complex units) to keep the transposing loads bank-conflict free.
 // Index math validated by tools/fft_model.py (tests/test_fft_model.py).
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "fft_trig.h"
@@ -69,6 +71,40 @@ template <typename T, int R, int SIGN> struct Dft {
             }
             v[k] = {rc + (T)SIGN * is, ic - (T)SIGN * rs};
             v[R - k] = {rc - (T)SIGN * is, ic + (T)SIGN * rs};
+        }
+    }
+};
+
+template <typename T, int SIGN> struct Dft<T, 8, SIGN> {
+    static __device__ __forceinline__ void run(cx<T> (&v)[8]) {
+        // two radix-4 on even/odd inputs, then twiddles W8^k and a radix-2 combine
+        cx<T> e[4] = {v[0], v[2], v[4], v[6]}, o[4] = {v[1], v[3], v[5], v[7]};
+        Dft<T, 4, SIGN>::run(e);
+        Dft<T, 4, SIGN>::run(o);
+        const T h = (T)0.70710678118654752440;
+        // W8^1 = (1 - i s)/sqrt2, W8^2 = -i s, W8^3 = (-1 - i s)/sqrt2   with s = SIGN
+        const cx<T> o1 = {h * (o[1].x + (T)SIGN * o[1].y), h * (o[1].y - (T)SIGN * o[1].x)};
+        const cx<T> o2 = {(T)SIGN * o[2].y, -(T)SIGN * o[2].x};
+        const cx<T> o3 = {h * (-o[3].x + (T)SIGN * o[3].y), h * (-o[3].y - (T)SIGN * o[3].x)};
+        v[0] = e[0] + o[0]; v[4] = e[0] - o[0];
+        v[1] = e[1] + o1;   v[5] = e[1] - o1;
+        v[2] = e[2] + o2;   v[6] = e[2] - o2;
+        v[3] = e[3] + o3;   v[7] = e[3] - o3;
+    }
+};
+// 14 = 2 x 7 by the prime-factor (Good-Thomas) map: no internal twiddles.
+//   input  n = (7 n1 + 2 n2) mod 14 ; output k = (7 k1 + 8 k2) mod 14
+template <typename T, int SIGN> struct Dft<T, 14, SIGN> {
+    static __device__ __forceinline__ void run(cx<T> (&v)[14]) {
+        cx<T> a[7], b[7];
+#pragma unroll
+        for (int n2 = 0; n2 < 7; ++n2) { a[n2] = v[(2 * n2) % 14]; b[n2] = v[(7 + 2 * n2) % 14]; }
+        Dft<T, 7, SIGN>::run(a);
+        Dft<T, 7, SIGN>::run(b);
+#pragma unroll
+        for (int k2 = 0; k2 < 7; ++k2) {
+            v[(8 * k2) % 14] = a[k2] + b[k2];
+            v[(7 + 8 * k2) % 14] = a[k2] - b[k2];
         }
     }
 };
@@ -304,6 +340,243 @@ fft_x_conv_kernel(FftPlan P, int TL, int LS, StrideGeom g, const BoxInfo* __rest
     }
 }
 
+// ------------------------------------------------------------------------------------------ register-blocked fast path
+// N = R1*R2*R3 (R3 = 1: two stages). One butterfly per thread per stage; stage 1 reads its inputs
+// through `in(pos)` (global memory -> registers), the last stage hands its outputs to `out(pos, v)`
+// (registers -> global memory); the exchange between stages goes through shared memory
+// (one __syncthreads per boundary). Thread (j, l): butterfly j of line l.
+template <typename T, int R1, int R2, int R3, int SIGN, typename In, typename Out>
+__device__ __forceinline__ void fft_block(int j, int l, bool live, cx<T>* __restrict__ sA, cx<T>* __restrict__ sB, int LS,
+                                          const cx<T>* __restrict__ tw, int twmul, In in, Out out) {
+    constexpr int N = R1 * R2 * R3, m1 = N / R1, m2 = N / R2, m3 = N / R3;
+    if (live && j < m1) {
+        cx<T> v[R1];
+#pragma unroll
+        for (int t = 0; t < R1; ++t) v[t] = in(j + t * m1);
+        Dft<T, R1, SIGN>::run(v);
+        cx<T>* d = sA + l * LS + j * R1;
+#pragma unroll
+        for (int t = 0; t < R1; ++t) d[t] = v[t];
+    }
+    __syncthreads();
+    if (R3 == 1) {
+        if (live && j < m2) {              // m2 == R1, so k = j
+            cx<T> v[R2];
+            const cx<T>* s = sA + l * LS + j;
+            v[0] = s[0];
+#pragma unroll
+            for (int t = 1; t < R2; ++t) {
+                cx<T> w = tw[t * j * twmul];
+                if (SIGN < 0) w.y = -w.y;
+                v[t] = cmul(s[t * m2], w);
+            }
+            Dft<T, R2, SIGN>::run(v);
+#pragma unroll
+            for (int t = 0; t < R2; ++t) out(j + t * R1, v[t]);
+        }
+    } else {
+        if (live && j < m2) {
+            const int k = j % R1;
+            cx<T> v[R2];
+            const cx<T>* s = sA + l * LS + j;
+            v[0] = s[0];
+#pragma unroll
+            for (int t = 1; t < R2; ++t) {
+                cx<T> w = tw[t * k * (m2 / R1) * twmul];
+                if (SIGN < 0) w.y = -w.y;
+                v[t] = cmul(s[t * m2], w);
+            }
+            Dft<T, R2, SIGN>::run(v);
+            cx<T>* d = sB + l * LS + (j - k) * R2 + k;
+#pragma unroll
+            for (int t = 0; t < R2; ++t) d[t * R1] = v[t];
+        }
+        __syncthreads();
+        if (live && j < m3) {              // m3 == R1*R2, so k = j
+            constexpr int R3e = R3 > 1 ? R3 : 2;
+            cx<T> v[R3e];
+            const cx<T>* s = sB + l * LS + j;
+            v[0] = s[0];
+#pragma unroll
+            for (int t = 1; t < R3e; ++t) {
+                cx<T> w = tw[t * j * twmul];
+                if (SIGN < 0) w.y = -w.y;
+                v[t] = cmul(s[t * m3], w);
+            }
+            Dft<T, R3e, SIGN>::run(v);
+#pragma unroll
+            for (int t = 0; t < R3e; ++t) out(j + t * (R1 * R2), v[t]);
+        }
+    }
+}
+
+template <int R1, int R2, int R3> struct FastGeom {
+    static constexpr int N = R1 * R2 * R3;
+    static constexpr int mn = R1 < R2 ? (R3 > 1 && R3 < R1 ? R3 : R1) : (R3 > 1 && R3 < R2 ? R3 : R2);
+    static constexpr int BPL = N / mn;             // threads per line = most butterflies in any stage
+};
+
+// strided pass (Y or X), in place on the spectrum: thread -> (l fastest, j)
+template <typename T, int R1, int R2, int R3, int SIGN>
+__global__ void __launch_bounds__(384)
+fast_strided_kernel(int TL, int LS, StrideGeom g, cx<T>* __restrict__ spec, const cx<T>* __restrict__ gtw) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cx<T>* sA = reinterpret_cast<cx<T>*>(smem_raw);
+    cx<T>* sB = sA + TL * LS;
+    const int o = blockIdx.x / g.tiles, t = blockIdx.x - o * g.tiles;
+    const int c0 = t * TL;
+    const int nl = min(TL, g.n_inner - c0);
+    cx<T>* base = spec + (size_t)o * g.outer_stride + c0;
+    const int l = threadIdx.x % TL, j = threadIdx.x / TL;
+    const size_t ls = g.line_stride;
+    fft_block<T, R1, R2, R3, SIGN>(j, l, l < nl, sA, sB, LS, gtw, 1,
+                                   [&](int pos) { return base[(size_t)pos * ls + l]; },
+                                   [&](int pos, cx<T> v) { base[(size_t)pos * ls + l] = v; });
+}
+
+// fused X pass: forward, influence function (+energy, +virial), inverse
+template <typename T, int R1, int R2, int R3, int MAXT>
+__global__ void __launch_bounds__(MAXT, MAXT <= 128 ? 4 : 1)
+fast_x_conv_kernel(int TL, int LS, StrideGeom g, const BoxInfo* __restrict__ Bp, T kappa, int kind, ConvTables tb,
+                                   cx<T>* __restrict__ spec, const cx<T>* __restrict__ gtw, double* __restrict__ scalars, int want_vir) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red[7 * 32];
+    cx<T>* sA = reinterpret_cast<cx<T>*>(smem_raw);
+    cx<T>* sB = sA + TL * LS;
+    const BoxInfo& B = *Bp;
+    const int c0 = blockIdx.x * TL;
+    const int nl = min(TL, g.n_inner - c0);
+    cx<T>* base = spec + c0;
+    const int l = threadIdx.x % TL, j = threadIdx.x / TL;
+    const size_t ls = g.line_stride;
+    const int K3 = B.K[2], K3h = K3 / 2 + 1;
+    const int c = c0 + l;
+    const int i2 = c / K3h, i3 = c - i2 * K3h;
+    const bool single = (i3 == 0) || (2 * i3 == K3);
+    const double scale = (kind == ADMP_CK_COULOMB) ? ADMP_DIEL : 1.0;
+    const bool ortho = *tb.ortho != 0;
+    const double kap = (double)kappa;
+    double acc_e = 0.0, acc_t[6] = {0, 0, 0, 0, 0, 0};
+    // forward output lands in sX (the buffer the last forward stage is not reading)
+    cx<T>* sX = (R3 == 1) ? sB : sA;
+    cx<T>* sY = (R3 == 1) ? sA : sB;
+    // a thread owns one line (fixed i2, i3): hoist the separable Coulomb factors of that line
+    const bool quick = ortho && kind == ADMP_CK_COULOMB && !want_vir && l < nl;
+    const double e23 = quick ? 6.283185307179586 / B.vol * tb.ek[1][i2] * tb.ek[2][i3] : 0.0;
+    const double k23 = quick ? tb.k2[1][i2] + tb.k2[2][i3] : 1.0;
+    const bool origin_line = (i2 == 0 && i3 == 0);
+    const double wgt = single ? 1.0 : 2.0;
+    fft_block<T, R1, R2, R3, 1>(j, l, l < nl, sA, sB, LS, gtw, 1,
+                                [&](int pos) { return base[(size_t)pos * ls + l]; },
+                                [&](int i1, cx<T> s) {
+                                    const double s2 = (double)s.x * s.x + (double)s.y * s.y;
+                                    double gk;
+                                    if (quick) {
+                                        gk = (origin_line && i1 == 0) ? 0.0 : e23 * tb.ek[0][i1] / (tb.k2[0][i1] + k23);
+                                    } else if (want_vir) {
+                                        const Influence f = influence<true>(B, tb, ortho, kap, kind, i1, i2, i3);
+                                        virial_terms(B, f.kv, i1, i2, i3, single, f.dg * s2, acc_t);
+                                        gk = f.g;
+                                    } else {
+                                        gk = influence<false>(B, tb, ortho, kap, kind, i1, i2, i3).g;
+                                    }
+                                    acc_e += wgt * gk * s2;
+                                    const T gg = (T)(2.0 * scale * gk);
+                                    sX[l * LS + i1] = {s.x * gg, s.y * gg};
+                                });
+    __syncthreads();
+    fft_block<T, R1, R2, R3, -1>(j, l, l < nl, sY, sX, LS, gtw, 1,
+                                 [&](int pos) { return sX[l * LS + pos]; },
+                                 [&](int pos, cx<T> v) { base[(size_t)pos * ls + l] = v; });
+    double e1[1] = {acc_e * scale};
+    block_accumulate<1>(e1, red, scalars + ADMP_S_E_RECIP);
+    if (want_vir) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) acc_t[k] *= scale;
+        block_accumulate<6>(acc_t, red, scalars + ADMP_S_TK);
+    }
+}
+
+// Z passes (contiguous lines): thread -> (j fastest, l); M = R1*R2*R3 = K3/2
+template <typename T, int R1, int R2, int R3>
+__global__ void __launch_bounds__(384)
+fast_z_fwd_kernel(int TL, int LS, int nlines, const T* __restrict__ mesh, cx<T>* __restrict__ spec,
+                                  const cx<T>* __restrict__ gtw) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cx<T>* sA = reinterpret_cast<cx<T>*>(smem_raw);
+    cx<T>* sB = sA + TL * LS;
+    constexpr int M = R1 * R2 * R3, K3 = 2 * M, K3h = M + 1, BPL = FastGeom<R1, R2, R3>::BPL;
+    const int L0 = blockIdx.x * TL;
+    const int nl = min(TL, nlines - L0);
+    const int j = threadIdx.x % BPL, l = threadIdx.x / BPL;
+    const cx<T>* line = reinterpret_cast<const cx<T>*>(mesh + (size_t)(L0 + l) * K3);
+    cx<T>* sZ = (R3 == 1) ? sB : sA;
+    fft_block<T, R1, R2, R3, 1>(j, l, l < nl, sA, sB, LS, gtw, 2,
+                                [&](int pos) { return line[pos]; },
+                                [&](int pos, cx<T> v) { sZ[l * LS + pos] = v; });
+    __syncthreads();
+    for (int e = threadIdx.x; e < nl * K3h; e += blockDim.x) {
+        const int ll = e / K3h, k = e - ll * K3h;
+        const cx<T> zk = sZ[ll * LS + (k == M ? 0 : k)];
+        cx<T> zc = sZ[ll * LS + ((k == 0 || k == M) ? 0 : M - k)];
+        zc.y = -zc.y;
+        const cx<T> a = {(T)0.5 * (zk.x + zc.x), (T)0.5 * (zk.y + zc.y)}, b = {(T)0.5 * (zk.x - zc.x), (T)0.5 * (zk.y - zc.y)};
+        const cx<T> w = gtw[k];
+        const cx<T> f = {w.y, -w.x};
+        spec[(size_t)(L0 + ll) * K3h + k] = a + cmul(f, b);
+    }
+}
+
+template <typename T, int R1, int R2, int R3>
+__global__ void __launch_bounds__(384)
+fast_z_inv_kernel(int TL, int LS, int nlines, const cx<T>* __restrict__ spec, T* __restrict__ mesh,
+                                  const cx<T>* __restrict__ gtw) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cx<T>* sA = reinterpret_cast<cx<T>*>(smem_raw);
+    cx<T>* sB = sA + TL * LS;
+    cx<T>* sX = sB + TL * LS;                 // staged half spectrum (LS >= M+1)
+    constexpr int M = R1 * R2 * R3, K3 = 2 * M, K3h = M + 1, BPL = FastGeom<R1, R2, R3>::BPL;
+    const int L0 = blockIdx.x * TL;
+    const int nl = min(TL, nlines - L0);
+    for (int e = threadIdx.x; e < nl * K3h; e += blockDim.x) {
+        const int ll = e / K3h, k = e - ll * K3h;
+        sX[ll * LS + k] = spec[(size_t)(L0 + ll) * K3h + k];
+    }
+    __syncthreads();
+    const int j = threadIdx.x % BPL, l = threadIdx.x / BPL;
+    cx<T>* line = reinterpret_cast<cx<T>*>(mesh + (size_t)(L0 + l) * K3);
+    const cx<T>* X = sX + l * LS;
+    fft_block<T, R1, R2, R3, -1>(j, l, l < nl, sA, sB, LS, gtw, 2,
+                                 [&](int k) {
+                                     const cx<T> xk = X[k];
+                                     cx<T> xc = X[M - k];
+                                     xc.y = -xc.y;
+                                     const cx<T> s = xk + xc, d = xk - xc;
+                                     const cx<T> w = gtw[k];
+                                     const cx<T> f = {w.y, w.x};
+                                     return s + cmul(f, d);
+                                 },
+                                 [&](int pos, cx<T> v) { line[pos] = v; });
+}
+
+// the (R1,R2,R3) decompositions with a fast kernel: the reference's mesh family 154*2^n (and halves)
+#define ADMP_FAST_LIST(X) X(11, 7, 1) X(11, 14, 1) X(11, 7, 4) X(11, 7, 8) X(11, 14, 8)
+
+static int fast_index(int N) {
+    int idx = 0;
+#define X(a, b, c) if (N == (a) * (b) * (c)) return idx; ++idx;
+    ADMP_FAST_LIST(X)
+#undef X
+    return -1;
+}
+static int fast_bpl(int idx) {
+    int i = 0;
+#define X(a, b, c) if (i++ == idx) return FastGeom<a, b, c>::BPL;
+    ADMP_FAST_LIST(X)
+#undef X
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------ host side
 bool fft_factorize(int n, FftPlan& P) {
     P.N = n;
@@ -316,17 +589,40 @@ bool fft_factorize(int n, FftPlan& P) {
     return n == 1 && P.nst > 0;
 }
 
-struct FftDimCfg { FftPlan P; int TL, LS; size_t smem; };
+struct FftDimCfg {
+    FftPlan P; int TL, LS; size_t smem;          // generic Stockham kernels
+    int fast, fTL, fLS, fthreads; size_t fsmem;  // register-blocked kernels (fast < 0: unavailable)
+};
 
-static bool dim_cfg(int N, int tw_len, size_t esz, size_t smem_cap, int min_ls, FftDimCfg& c) {
+static bool dim_cfg(int N, int tw_len, size_t esz, size_t smem_cap, int min_ls, bool zpass, FftDimCfg& c) {
     if (!fft_factorize(N, c.P)) return false;
     c.LS = N | 1;
     if (c.LS < min_ls) c.LS = min_ls | 1;
+    bool ok = false;
     for (int TL = 8; TL >= 1; TL >>= 1) {
         const size_t need = (size_t)2 * TL * c.LS * 2 * esz + (size_t)tw_len * 2 * esz;
-        if (need <= smem_cap) { c.TL = TL; c.smem = need; return true; }
+        if (need <= smem_cap) { c.TL = TL; c.smem = need; ok = true; break; }
     }
-    return false;
+    if (!ok) return false;
+    c.fast = fast_index(N);
+    if (c.fast >= 0) {
+        const int bpl = fast_bpl(c.fast);
+        const int nbuf = zpass ? 3 : 2;
+        c.fLS = c.LS;
+        c.fTL = 0;
+        // lines per block: as many as fit in 384 threads / 96 KB, at most 8 (128-byte segments in f64)
+        int tl_max = 8, thr_max = 384;                 // 384 threads x <= 168 registers
+        if (const char* e = getenv("ADMP_FFT_TL")) tl_max = atoi(e) > 0 ? atoi(e) : tl_max;       // tuning knobs
+        if (const char* e = getenv("ADMP_FFT_THREADS")) thr_max = atoi(e) > 0 ? atoi(e) : thr_max;
+        if (thr_max > 384) thr_max = 384;
+        for (int TL = tl_max; TL >= 1; TL >>= 1) {
+            const size_t need = (size_t)nbuf * TL * c.fLS * 2 * esz;
+            if (TL * bpl <= thr_max && need <= 96 * 1024) { c.fTL = TL; c.fsmem = need; break; }
+        }
+        if (c.fTL == 0) c.fast = -1;
+        else c.fthreads = c.fTL * bpl;
+    }
+    return true;
 }
 
 struct Fft3dImpl {
@@ -337,14 +633,26 @@ struct Fft3dImpl {
 };
 
 template <typename T>
-static cudaError_t set_smem_attr(size_t zs, size_t ys, size_t xs) {
+static cudaError_t set_smem_attr(const Fft3dImpl* f) {
     cudaError_t e;
+    const size_t zs = f->z.smem, ys = f->y.smem, xs = f->x.smem;
     if ((e = cudaFuncSetAttribute(fft_z_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zs)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(fft_z_inv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zs)) != cudaSuccess) return e;
     const size_t m = ys > xs ? ys : xs;
     if ((e = cudaFuncSetAttribute(fft_strided_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(fft_strided_kernel<T, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m)) != cudaSuccess) return e;
-    return cudaFuncSetAttribute(fft_x_conv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xs);
+    if ((e = cudaFuncSetAttribute(fft_x_conv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xs)) != cudaSuccess) return e;
+    const int cap = 96 * 1024;
+#define X(a, b, c)                                                                                                            \
+    if ((e = cudaFuncSetAttribute(fast_strided_kernel<T, a, b, c, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap)) != cudaSuccess) return e;  \
+    if ((e = cudaFuncSetAttribute(fast_strided_kernel<T, a, b, c, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap)) != cudaSuccess) return e; \
+    if ((e = cudaFuncSetAttribute(fast_x_conv_kernel<T, a, b, c, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap)) != cudaSuccess) return e; \
+    if ((e = cudaFuncSetAttribute(fast_x_conv_kernel<T, a, b, c, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap)) != cudaSuccess) return e; \
+    if ((e = cudaFuncSetAttribute(fast_z_fwd_kernel<T, a, b, c>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap)) != cudaSuccess) return e;       \
+    if ((e = cudaFuncSetAttribute(fast_z_inv_kernel<T, a, b, c>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap)) != cudaSuccess) return e;
+    ADMP_FAST_LIST(X)
+#undef X
+    return cudaSuccess;
 }
 
 Fft3d* fft3d_create(int K1, int K2, int K3, int dtype, const char** why) {
@@ -357,13 +665,15 @@ Fft3d* fft3d_create(int K1, int K2, int K3, int dtype, const char** why) {
     f->esz = dtype == ADMP_F64 ? 8 : 4;
     const size_t cap = 200 * 1024;
     const int M = K3 / 2;
-    if (!dim_cfg(M, K3, f->esz, cap, M + 1, f->z) || !dim_cfg(K2, K2, f->esz, cap, 0, f->y) || !dim_cfg(K1, K1, f->esz, cap, 0, f->x)) {
+    if (!dim_cfg(M, K3, f->esz, cap, M + 1, true, f->z) || !dim_cfg(K2, K2, f->esz, cap, 0, false, f->y) ||
+        !dim_cfg(K1, K1, f->esz, cap, 0, false, f->x)) {
         *why = msg_fac;
         delete f;
         return nullptr;
     }
-    cudaError_t e = dtype == ADMP_F64 ? set_smem_attr<double>(f->z.smem, f->y.smem, f->x.smem)
-                                      : set_smem_attr<float>(f->z.smem, f->y.smem, f->x.smem);
+    const char* env = getenv("ADMP_FFT");
+    if (env && strcmp(env, "generic") == 0) f->z.fast = f->y.fast = f->x.fast = -1;
+    cudaError_t e = dtype == ADMP_F64 ? set_smem_attr<double>(f) : set_smem_attr<float>(f);
     if (e != cudaSuccess) { *why = msg_cuda; delete f; return nullptr; }
     for (int d = 0; d < 3; ++d) {
         const int n = f->K[d];
@@ -390,62 +700,128 @@ void fft3d_destroy(Fft3d* p) {
     delete f;
 }
 
-template <typename T>
-static void run_fwd_zy(Fft3dImpl* f, cudaStream_t st, const void* mesh, void* spec) {
-    const int K1 = f->K[0], K2 = f->K[1], K3 = f->K[2], K3h = K3 / 2 + 1;
-    const int nlines = K1 * K2;
-    fft_z_fwd_kernel<T><<<(nlines + f->z.TL - 1) / f->z.TL, 256, f->z.smem, st>>>(f->z.P, f->z.TL, f->z.LS, nlines, K3, (const T*)mesh,
-                                                                               (cx<T>*)spec, (const cx<T>*)f->tw[2]);
-    StrideGeom g = {K1, K3h, (size_t)K2 * K3h, (size_t)K3h, (K3h + f->y.TL - 1) / f->y.TL};
-    fft_strided_kernel<T, 1><<<g.n_outer * g.tiles, 256, f->y.smem, st>>>(f->y.P, f->y.TL, f->y.LS, g, (cx<T>*)spec, (const cx<T>*)f->tw[1]);
+static StrideGeom geom_y(const Fft3dImpl* f, int TL) {
+    const int K1 = f->K[0], K2 = f->K[1], K3h = f->K[2] / 2 + 1;
+    return {K1, K3h, (size_t)K2 * K3h, (size_t)K3h, (K3h + TL - 1) / TL};
 }
-template <typename T>
-static void run_inv_yz(Fft3dImpl* f, cudaStream_t st, void* spec, void* mesh) {
-    const int K1 = f->K[0], K2 = f->K[1], K3 = f->K[2], K3h = K3 / 2 + 1;
-    StrideGeom g = {K1, K3h, (size_t)K2 * K3h, (size_t)K3h, (K3h + f->y.TL - 1) / f->y.TL};
-    fft_strided_kernel<T, -1><<<g.n_outer * g.tiles, 256, f->y.smem, st>>>(f->y.P, f->y.TL, f->y.LS, g, (cx<T>*)spec, (const cx<T>*)f->tw[1]);
-    const int nlines = K1 * K2;
-    fft_z_inv_kernel<T><<<(nlines + f->z.TL - 1) / f->z.TL, 256, f->z.smem, st>>>(f->z.P, f->z.TL, f->z.LS, nlines, K3, (const cx<T>*)spec,
-                                                                               (T*)mesh, (const cx<T>*)f->tw[2]);
+static StrideGeom geom_x(const Fft3dImpl* f, int TL) {
+    const int inner = f->K[1] * (f->K[2] / 2 + 1);
+    return {1, inner, 0, (size_t)inner, (inner + TL - 1) / TL};
 }
+
 template <typename T>
-static void run_x(Fft3dImpl* f, cudaStream_t st, void* spec, int sign) {
-    const int K2 = f->K[1], K3h = f->K[2] / 2 + 1;
-    const int inner = K2 * K3h;
-    StrideGeom g = {1, inner, 0, (size_t)inner, (inner + f->x.TL - 1) / f->x.TL};
-    if (sign > 0) fft_strided_kernel<T, 1><<<g.tiles, 256, f->x.smem, st>>>(f->x.P, f->x.TL, f->x.LS, g, (cx<T>*)spec, (const cx<T>*)f->tw[0]);
-    else fft_strided_kernel<T, -1><<<g.tiles, 256, f->x.smem, st>>>(f->x.P, f->x.TL, f->x.LS, g, (cx<T>*)spec, (const cx<T>*)f->tw[0]);
+static void run_z(Fft3dImpl* f, cudaStream_t st, void* mesh, void* spec, int sign) {
+    const int K3 = f->K[2];
+    const int nlines = f->K[0] * f->K[1];
+    const FftDimCfg& c = f->z;
+    const cx<T>* tw = (const cx<T>*)f->tw[2];
+    if (c.fast >= 0) {
+        const int grid = (nlines + c.fTL - 1) / c.fTL;
+        int i = 0;
+#define X(a, b, cc)                                                                                                              \
+        if (i++ == c.fast) {                                                                                                     \
+            if (sign > 0) fast_z_fwd_kernel<T, a, b, cc><<<grid, c.fthreads, c.fsmem, st>>>(c.fTL, c.fLS, nlines, (const T*)mesh, (cx<T>*)spec, tw); \
+            else fast_z_inv_kernel<T, a, b, cc><<<grid, c.fthreads, c.fsmem, st>>>(c.fTL, c.fLS, nlines, (const cx<T>*)spec, (T*)mesh, tw);          \
+        }
+        ADMP_FAST_LIST(X)
+#undef X
+        return;
+    }
+    const int grid = (nlines + c.TL - 1) / c.TL;
+    if (sign > 0) fft_z_fwd_kernel<T><<<grid, 256, c.smem, st>>>(c.P, c.TL, c.LS, nlines, K3, (const T*)mesh, (cx<T>*)spec, tw);
+    else fft_z_inv_kernel<T><<<grid, 256, c.smem, st>>>(c.P, c.TL, c.LS, nlines, K3, (const cx<T>*)spec, (T*)mesh, tw);
+}
+
+template <typename T>
+static void run_strided(Fft3dImpl* f, cudaStream_t st, void* spec, int dim, int sign) {
+    const FftDimCfg& c = dim == 1 ? f->y : f->x;
+    const cx<T>* tw = (const cx<T>*)f->tw[dim == 1 ? 1 : 0];
+    if (c.fast >= 0) {
+        const StrideGeom g = dim == 1 ? geom_y(f, c.fTL) : geom_x(f, c.fTL);
+        const int grid = g.n_outer * g.tiles;
+        int i = 0;
+#define X(a, b, cc)                                                                                                              \
+        if (i++ == c.fast) {                                                                                                     \
+            if (sign > 0) fast_strided_kernel<T, a, b, cc, 1><<<grid, c.fthreads, c.fsmem, st>>>(c.fTL, c.fLS, g, (cx<T>*)spec, tw); \
+            else fast_strided_kernel<T, a, b, cc, -1><<<grid, c.fthreads, c.fsmem, st>>>(c.fTL, c.fLS, g, (cx<T>*)spec, tw);         \
+        }
+        ADMP_FAST_LIST(X)
+#undef X
+        return;
+    }
+    const StrideGeom g = dim == 1 ? geom_y(f, c.TL) : geom_x(f, c.TL);
+    const int grid = g.n_outer * g.tiles;
+    if (sign > 0) fft_strided_kernel<T, 1><<<grid, 256, c.smem, st>>>(c.P, c.TL, c.LS, g, (cx<T>*)spec, tw);
+    else fft_strided_kernel<T, -1><<<grid, 256, c.smem, st>>>(c.P, c.TL, c.LS, g, (cx<T>*)spec, tw);
+}
+
+template <typename T>
+static void run_x_conv(Fft3dImpl* f, cudaStream_t st, void* spec, const BoxInfo* B, double kappa, int kind, const ConvTables& tb,
+                       double* scalars, int want_vir) {
+    const FftDimCfg& c = f->x;
+    const cx<T>* tw = (const cx<T>*)f->tw[0];
+    if (c.fast >= 0) {
+        const StrideGeom g = geom_x(f, c.fTL);
+        int i = 0;
+#define X(a, b, cc)                                                                                                              \
+        if (i++ == c.fast) {                                                                                                     \
+            if (c.fthreads <= 128)                                                                                               \
+                fast_x_conv_kernel<T, a, b, cc, 128><<<g.tiles, c.fthreads, c.fsmem, st>>>(c.fTL, c.fLS, g, B, (T)kappa, kind, tb,          \
+                                                                                         (cx<T>*)spec, tw, scalars, want_vir);   \
+            else                                                                                                                 \
+                fast_x_conv_kernel<T, a, b, cc, 384><<<g.tiles, c.fthreads, c.fsmem, st>>>(c.fTL, c.fLS, g, B, (T)kappa, kind, tb,          \
+                                                                                         (cx<T>*)spec, tw, scalars, want_vir);   \
+        }
+        ADMP_FAST_LIST(X)
+#undef X
+        return;
+    }
+    const StrideGeom g = geom_x(f, c.TL);
+    fft_x_conv_kernel<T><<<g.tiles, 256, c.smem, st>>>(c.P, c.TL, c.LS, g, B, (T)kappa, kind, tb, (cx<T>*)spec, tw, scalars, want_vir);
 }
 
 // plain transforms (same conventions as cuFFT D2Z / Z2D: unnormalised)
 void fft3d_forward(Fft3d* p, cudaStream_t st, const void* mesh, void* spec) {
     Fft3dImpl* f = reinterpret_cast<Fft3dImpl*>(p);
-    if (f->esz == 8) { run_fwd_zy<double>(f, st, mesh, spec); run_x<double>(f, st, spec, 1); }
-    else { run_fwd_zy<float>(f, st, mesh, spec); run_x<float>(f, st, spec, 1); }
+    if (f->esz == 8) { run_z<double>(f, st, const_cast<void*>(mesh), spec, 1); run_strided<double>(f, st, spec, 1, 1); run_strided<double>(f, st, spec, 0, 1); }
+    else { run_z<float>(f, st, const_cast<void*>(mesh), spec, 1); run_strided<float>(f, st, spec, 1, 1); run_strided<float>(f, st, spec, 0, 1); }
 }
 void fft3d_inverse(Fft3d* p, cudaStream_t st, void* spec, void* mesh) {
     Fft3dImpl* f = reinterpret_cast<Fft3dImpl*>(p);
-    if (f->esz == 8) { run_x<double>(f, st, spec, -1); run_inv_yz<double>(f, st, spec, mesh); }
-    else { run_x<float>(f, st, spec, -1); run_inv_yz<float>(f, st, spec, mesh); }
+    if (f->esz == 8) { run_strided<double>(f, st, spec, 0, -1); run_strided<double>(f, st, spec, 1, -1); run_z<double>(f, st, mesh, spec, -1); }
+    else { run_strided<float>(f, st, spec, 0, -1); run_strided<float>(f, st, spec, 1, -1); run_z<float>(f, st, mesh, spec, -1); }
+}
+
+// a single pass of the five (0: Z-forward, 1: Y-forward, 2: fused X, 3: Y-inverse, 4: Z-inverse): profiling / roofline timing
+void fft3d_single_pass(Fft3d* p, cudaStream_t st, int which, void* mesh, void* spec, const BoxInfo* B, double kappa, int kind,
+                       const ConvTables& tb, double* scalars) {
+    Fft3dImpl* f = reinterpret_cast<Fft3dImpl*>(p);
+    const bool d = f->esz == 8;
+    switch (which) {
+        case 0: d ? run_z<double>(f, st, mesh, spec, 1) : run_z<float>(f, st, mesh, spec, 1); break;
+        case 1: d ? run_strided<double>(f, st, spec, 1, 1) : run_strided<float>(f, st, spec, 1, 1); break;
+        case 2: d ? run_x_conv<double>(f, st, spec, B, kappa, kind, tb, scalars, 0) : run_x_conv<float>(f, st, spec, B, kappa, kind, tb, scalars, 0); break;
+        case 3: d ? run_strided<double>(f, st, spec, 1, -1) : run_strided<float>(f, st, spec, 1, -1); break;
+        default: d ? run_z<double>(f, st, mesh, spec, -1) : run_z<float>(f, st, mesh, spec, -1); break;
+    }
 }
 
 // mesh -> phi = dE/dmesh in place of the mesh, energy (+virial sums) accumulated: 5 passes
 void fft3d_convolve_roundtrip(Fft3d* p, cudaStream_t st, void* mesh, void* spec, const BoxInfo* B, double kappa, int kind,
                               const ConvTables& tb, double* scalars, int want_vir) {
     Fft3dImpl* f = reinterpret_cast<Fft3dImpl*>(p);
-    const int K2 = f->K[1], K3h = f->K[2] / 2 + 1;
-    const int inner = K2 * K3h;
-    StrideGeom g = {1, inner, 0, (size_t)inner, (inner + f->x.TL - 1) / f->x.TL};
     if (f->esz == 8) {
-        run_fwd_zy<double>(f, st, mesh, spec);
-        fft_x_conv_kernel<double><<<g.tiles, 256, f->x.smem, st>>>(f->x.P, f->x.TL, f->x.LS, g, B, kappa, kind, tb, (cx<double>*)spec,
-                                                                  (const cx<double>*)f->tw[0], scalars, want_vir);
-        run_inv_yz<double>(f, st, spec, mesh);
+        run_z<double>(f, st, mesh, spec, 1);
+        run_strided<double>(f, st, spec, 1, 1);
+        run_x_conv<double>(f, st, spec, B, kappa, kind, tb, scalars, want_vir);
+        run_strided<double>(f, st, spec, 1, -1);
+        run_z<double>(f, st, mesh, spec, -1);
     } else {
-        run_fwd_zy<float>(f, st, mesh, spec);
-        fft_x_conv_kernel<float><<<g.tiles, 256, f->x.smem, st>>>(f->x.P, f->x.TL, f->x.LS, g, B, (float)kappa, kind, tb, (cx<float>*)spec,
-                                                                 (const cx<float>*)f->tw[0], scalars, want_vir);
-        run_inv_yz<float>(f, st, spec, mesh);
+        run_z<float>(f, st, mesh, spec, 1);
+        run_strided<float>(f, st, spec, 1, 1);
+        run_x_conv<float>(f, st, spec, B, kappa, kind, tb, scalars, want_vir);
+        run_strided<float>(f, st, spec, 1, -1);
+        run_z<float>(f, st, mesh, spec, -1);
     }
 }
 

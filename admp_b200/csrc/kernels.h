@@ -49,6 +49,8 @@ Fft3d* fft3d_create(int K1, int K2, int K3, int dtype, const char** why);     //
 void fft3d_destroy(Fft3d* f);
 void fft3d_forward(Fft3d* f, cudaStream_t st, const void* mesh, void* spec);
 void fft3d_inverse(Fft3d* f, cudaStream_t st, void* spec, void* mesh);
+void fft3d_single_pass(Fft3d* f, cudaStream_t st, int which, void* mesh, void* spec, const BoxInfo* B, double kappa, int kind,
+                       const ConvTables& tb, double* scalars);
 void fft3d_convolve_roundtrip(Fft3d* f, cudaStream_t st, void* mesh, void* spec, const BoxInfo* B, double kappa, int kind,
                               const ConvTables& tb, double* scalars, int want_vir);
 

@@ -171,18 +171,28 @@ def kernel_rooflines(torch, _lib, reps, peak, flush, n_launch=10):
     G = torch.zeros((n, 10), dtype=dt, device=dev)
     Gpts = w.K[0] * w.K[1] * w.K[2]
     wb = 8
+    K3h = w.K[2] // 2 + 1
+    spec_bytes = 2 * wb * w.K[0] * w.K[1] * K3h
+    mesh_bytes = wb * Gpts
+    custom = bool(cx.lib.admp_ctx_fft_backend(cx.handle))
     stages = {
         'spread_kernel': (lambda: cx.lib.admp_pme_spread_only(cx.handle, sp(), p(pos), p(M), 10, 10, None),
                           216 * 2 * wb * n + n * 13 * wb),
-        'convolve_kernel': (lambda: cx.lib.admp_pme_convolve(cx.handle, sp(), _lib.CK_COULOMB, 0, p(scal)),
-                            2 * 2 * wb * (w.K[0] * w.K[1] * (w.K[2] // 2 + 1))),
         'gather_kernel': (lambda: cx.lib.admp_pme_gather(cx.handle, sp(), p(pos), p(M), 10, 10, None, 0, _lib.WANT_GRAD, p(dpos), p(G), 10,
                                                          None, p(scal)), 216 * wb * n + n * 23 * wb),
     }
+    if custom:
+        names = ['fft_z_fwd', 'fft_y_fwd', 'fft_x_conv (X-fwd * C_k/theta^2 + energy * X-inv)', 'fft_y_inv', 'fft_z_inv']
+        nbytes = [mesh_bytes + spec_bytes, 2 * spec_bytes, 2 * spec_bytes, 2 * spec_bytes, spec_bytes + mesh_bytes]
+        for k in range(5):
+            stages[names[k]] = ((lambda k=k: cx.lib.admp_pme_fft_pass(cx.handle, sp(), k, _lib.CK_COULOMB, p(scal))), nbytes[k])
+    else:
+        stages['convolve_kernel'] = (lambda: cx.lib.admp_pme_convolve(cx.handle, sp(), _lib.CK_COULOMB, 0, p(scal)), 2 * spec_bytes)
     _lib.check(cx.lib.admp_pme_spread(cx.handle, sp(), p(pos), p(box), p(M), 10, 10, None))
     _lib.check(cx.lib.admp_pme_fft(cx.handle, sp(), 0))
     out = {}
-    for name, (fn, nbytes) in stages.items():
+
+    def time_stage(fn):
         ts = []
         for it in range(n_launch + 2):
             flush()
@@ -193,27 +203,25 @@ def kernel_rooflines(torch, _lib, reps, peak, flush, n_launch=10):
             b.synchronize()
             if it >= 2:
                 ts.append(a.elapsed_time(b))
-        ms = statistics.mean(ts)
-        ach = nbytes / (ms * 1e-3) / 1e9
+        return statistics.mean(ts)
+
+    for name, (fn, nb) in stages.items():
+        ms = time_stage(fn)
+        ach = nb / (ms * 1e-3) / 1e9
         out[name] = dict(bound='hbm', achieved=round(ach, 1), peak=peak, unit='GB/s', frac=round(ach / peak, 4),
-                         traffic=None, ms=round(ms, 4), algorithmic_bytes=nbytes, mesh='%dx%dx%d' % w.K, n_atoms=n)
-    # cuFFT (library) round trip, for the share table only
-    ts = []
-    for it in range(n_launch + 2):
-        flush()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        _lib.check(cx.lib.admp_pme_fft(cx.handle, sp(), 0))
-        _lib.check(cx.lib.admp_pme_fft(cx.handle, sp(), 1))
-        b.record()
-        b.synchronize()
-        if it >= 2:
-            ts.append(a.elapsed_time(b))
-    ms = statistics.mean(ts)
-    nbytes = 12 * wb * Gpts
-    out['cufft_r2c_c2r'] = dict(bound='hbm', achieved=round(nbytes / (ms * 1e-3) / 1e9, 1), peak=peak, unit='GB/s',
-                                frac=round(nbytes / (ms * 1e-3) / 1e9 / peak, 4), traffic=None, ms=round(ms, 4),
-                                algorithmic_bytes=nbytes, mesh='%dx%dx%d' % w.K, note='library (cuFFT), not a hand-written kernel')
+                         traffic=None, ms=round(ms, 4), algorithmic_bytes=nb, mesh='%dx%dx%d' % w.K, n_atoms=n)
+    if custom:
+        ms = time_stage(lambda: cx.lib.admp_pme_fft_convolve(cx.handle, sp(), _lib.CK_COULOMB, 0, p(scal)))
+        nb = 2 * (mesh_bytes + spec_bytes) + 6 * spec_bytes
+        out['fused_roundtrip_5_passes'] = dict(bound='hbm', achieved=round(nb / (ms * 1e-3) / 1e9, 1), peak=peak, unit='GB/s',
+                                               frac=round(nb / (ms * 1e-3) / 1e9 / peak, 4), traffic=None, ms=round(ms, 4),
+                                               algorithmic_bytes=nb, mesh='%dx%dx%d' % w.K)
+        # the library alternative on the same mesh, for the share table only
+        _lib.check(cx.lib.admp_ctx_set_fft_backend(cx.handle, 0))
+        ms = time_stage(lambda: cx.lib.admp_pme_fft(cx.handle, sp(), 0)) + time_stage(lambda: cx.lib.admp_pme_fft(cx.handle, sp(), 1)) \
+            + time_stage(lambda: cx.lib.admp_pme_convolve(cx.handle, sp(), _lib.CK_COULOMB, 0, p(scal)))
+        out['cufft_d2z_z2d_plus_convolve'] = dict(ms=round(ms, 4), mesh='%dx%dx%d' % w.K,
+                                                 note='library (cuFFT) + separate convolution kernel, NOT the path in use')
     cx.close()
     return out
 
@@ -323,7 +331,7 @@ def run_ours(args):
     peak, peak_src = measured_peaks()
     roof_small = kernel_rooflines(torch, _lib, (1, 1, 1), peak, flush)
     roof_large = None if args.no_large else kernel_rooflines(torch, _lib, (2, 4, 4), peak, flush, n_launch=5)
-    dominant = 'convolve_kernel'
+    dominant = next((k for k in roof_small if k.startswith('fft_x_conv')), 'convolve_kernel')
     roofline = dict(roof_small[dominant])
     roofline['kernel'] = dominant
     roofline['peak_source'] = peak_src

@@ -135,6 +135,8 @@ int admp_pme_convolve(admp_ctx* ctx, void* stream, int kind, uint32_t flags, dou
 /* fused five-pass round trip mesh -> phi (Z-fwd, Y-fwd, [X-fwd * C_k/theta^2 * X-inv], Y-inv, Z-inv)
  * of the hand-written FFT; admp_pme_recip / admp_pme_eval use it whenever the mesh sizes allow. */
 int admp_pme_fft_convolve(admp_ctx* ctx, void* stream, int kind, uint32_t flags, double* scalars);
+/* one pass of that round trip: 0 Z-fwd, 1 Y-fwd, 2 fused X, 3 Y-inv, 4 Z-inv (profiling / roofline timing) */
+int admp_pme_fft_pass(admp_ctx* ctx, void* stream, int which, int kind, double* scalars);
 int admp_pme_gather(admp_ctx* ctx, void* stream, const void* pos, const void* M, int M_cols,
                     int M_stride, const void* U, int mode, uint32_t flags, void* dpos, void* G,
                     int G_stride, void* F, double* scalars);

@@ -9,7 +9,8 @@ pytestmark = pytest.mark.gpu
 from admp_b200 import _lib                       # noqa: E402
 from admp_b200._ctx import Context               # noqa: E402
 
-SIZES = [(154, 154, 154), (44, 42, 60), (22, 26, 30), (6, 10, 14), (308, 154, 22), (96, 100, 98)]
+SIZES = [(154, 154, 154), (44, 42, 60), (22, 26, 30), (6, 10, 14), (308, 154, 22), (96, 100, 98),
+         (616, 22, 308), (22, 1232, 616), (26, 308, 1232)]
 
 
 def _ctx(K, precision='double'):
