@@ -22,7 +22,8 @@ EXPORTS = [
     'admp_last_error', 'admp_version', 'admp_ctx_create', 'admp_ctx_destroy', 'admp_ctx_set_pme',
     'admp_ctx_set_topology', 'admp_ctx_workspace_bytes', 'admp_ctx_scf_graph_active',
     'admp_frames_fwd', 'admp_frames_bwd', 'admp_rotate', 'admp_pme_real', 'admp_pme_recip', 'admp_pme_self',
-    'admp_pme_spread', 'admp_pme_spread_only', 'admp_pme_fft', 'admp_pme_convolve', 'admp_pme_gather', 'admp_ctx_buffer', 'admp_ctx_buffer_io', 'admp_pme_fft_convolve', 'admp_pme_fft_pass', 'admp_ctx_fft_backend', 'admp_ctx_set_fft_backend',
+    'admp_pme_spread', 'admp_pme_spread_only', 'admp_pme_fft', 'admp_pme_convolve', 'admp_pme_gather', 'admp_ctx_buffer', 'admp_ctx_buffer_io', 'admp_pme_fft_convolve', 'admp_pme_fft_pass', 'admp_set_box', 'admp_mesh_zero', 'admp_pme_spread_range',
+    'admp_pme_gather_range', 'admp_pme_self_range', 'admp_frames_bwd_range', 'admp_scf_step', 'admp_virial_finalize', 'admp_ctx_fft_backend', 'admp_ctx_set_fft_backend',
     'admp_pme_eval', 'admp_disp_eval', 'admp_tt_pair', 'admp_nblist_build',
 ]
 
@@ -69,6 +70,14 @@ def load():
     lib.admp_ctx_buffer_io.argtypes = [vp, vp, i32, vp, i64, i32]
     lib.admp_pme_fft_convolve.argtypes = [vp, vp, i32, u32, vp]
     lib.admp_pme_fft_pass.argtypes = [vp, vp, i32, i32, vp]
+    lib.admp_set_box.argtypes = [vp, vp, vp]
+    lib.admp_mesh_zero.argtypes = [vp, vp]
+    lib.admp_pme_spread_range.argtypes = [vp, vp, vp, vp, i32, i32, vp, i32, i32]
+    lib.admp_pme_gather_range.argtypes = [vp, vp, vp, vp, i32, i32, vp, i32, u32, vp, vp, i32, vp, vp, i32, i32]
+    lib.admp_pme_self_range.argtypes = [vp, vp, vp, vp, vp, u32, vp, vp, vp, vp, i32, i32]
+    lib.admp_frames_bwd_range.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32]
+    lib.admp_scf_step.argtypes = [vp, vp, vp, vp, vp, vp, i32, dbl, vp, vp]
+    lib.admp_virial_finalize.argtypes = [vp, vp, vp]
     lib.admp_ctx_fft_backend.argtypes = [vp]
     lib.admp_ctx_set_fft_backend.argtypes = [vp, i32]
     lib.admp_ctx_buffer.restype = vp

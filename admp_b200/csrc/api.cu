@@ -497,6 +497,92 @@ extern "C" int admp_pme_self(admp_ctx* c, void* stream, const void* M, const voi
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------ atom-range stages
+// Building blocks of the multi-GPU atom-block decomposition (admp_b200/parallel.py): every rank holds
+// replicated positions / multipoles, works on atoms [first, first+count) and on its slice of the pair
+// rows, and the caller reduces mesh / field / gradient arrays across ranks between the stages.
+template <typename P> static P* shift(P* p, size_t elems, size_t w) {
+    return p ? (P*)((char*)p + elems * w) : nullptr;
+}
+extern "C" int admp_set_box(admp_ctx* c, void* stream, const void* box) {
+    if (need(c, true, false)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(c->device));
+    DISPATCH(c, launch_box_setup, st, box, c->box, c->K[0], c->K[1], c->K[2]);
+    conv_tables(c, st);
+    CKLAUNCH();
+    return 0;
+}
+extern "C" int admp_mesh_zero(admp_ctx* c, void* stream) {
+    if (need(c, true, false)) return 1;
+    CK(cudaMemsetAsync(c->mesh, 0, c->mesh_bytes, (cudaStream_t)stream));
+    return 0;
+}
+extern "C" int admp_pme_spread_range(admp_ctx* c, void* stream, const void* pos, const void* M, int M_cols, int M_stride,
+                                     const void* U, int first, int count) {
+    if (need(c, true, true)) return 1;
+    if (first < 0 || count < 0 || first + count > c->n_atoms) return fail("atom range [%d,%d) outside [0,%d)", first, first + count, c->n_atoms);
+    const size_t w = c->w;
+    DISPATCH(c, launch_spread, (cudaStream_t)stream, count, c->box, shift(pos, (size_t)first * 3, w), shift(M, (size_t)first * M_stride, w),
+             M_cols, M_stride, shift(U, (size_t)first * 3, w), c->mesh);
+    CKLAUNCH();
+    return 0;
+}
+extern "C" int admp_pme_gather_range(admp_ctx* c, void* stream, const void* pos, const void* M, int M_cols, int M_stride, const void* U,
+                                     int mode, uint32_t flags, void* dpos, void* G, int G_stride, void* F, double* scalars, int first,
+                                     int count) {
+    if (need(c, true, true)) return 1;
+    if (first < 0 || count < 0 || first + count > c->n_atoms) return fail("atom range [%d,%d) outside [0,%d)", first, first + count, c->n_atoms);
+    const size_t w = c->w;
+    DISPATCH(c, launch_gather, (cudaStream_t)stream, count, c->box, shift(pos, (size_t)first * 3, w), shift(M, (size_t)first * M_stride, w),
+             M_cols, M_stride, shift(U, (size_t)first * 3, w), c->mesh, mode, flags, shift(dpos, (size_t)first * 3, w),
+             shift(G, (size_t)first * G_stride, w), G_stride, shift(F, (size_t)first * 3, w), scalars);
+    CKLAUNCH();
+    return 0;
+}
+extern "C" int admp_pme_self_range(admp_ctx* c, void* stream, const void* M, const void* U, const void* pol, uint32_t flags, void* G,
+                                   void* F, void* dpol, double* scalars, int first, int count) {
+    if (need(c, false, true)) return 1;
+    if (first < 0 || count < 0 || first + count > c->n_atoms) return fail("atom range [%d,%d) outside [0,%d)", first, first + count, c->n_atoms);
+    const size_t w = c->w;
+    DISPATCH(c, launch_self, (cudaStream_t)stream, count, c->kappa, shift(M, (size_t)first * 10, w), shift(U, (size_t)first * 3, w),
+             shift(pol, (size_t)first, w), flags, shift(G, (size_t)first * 10, w), shift(F, (size_t)first * 3, w), shift(dpol, (size_t)first, w),
+             scalars);
+    CKLAUNCH();
+    return 0;
+}
+extern "C" int admp_frames_bwd_range(admp_ctx* c, void* stream, const void* pos, const void* Ql, const void* G, void* dQl, void* dpos,
+                                     double* scalars, int first, int count) {
+    if (need(c, false, true)) return 1;
+    if (first < 0 || count < 0 || first + count > c->n_atoms) return fail("atom range [%d,%d) outside [0,%d)", first, first + count, c->n_atoms);
+    DISPATCH(c, launch_frames_bwd, (cudaStream_t)stream, first + count, c->lmax, c->box, pos, c->axis_type, c->axis_idx, Ql, G, dQl, dpos,
+             scalars, 1, first);
+    CKLAUNCH();
+    return 0;
+}
+/* one Jacobi decision on an already-assembled field F (pair + reciprocal parts, all atoms): adds the
+ * self/penalty part, reduces max|F|, tests, updates U (admp/pme.py:133-138). state: int32[8] device,
+ * zeroed by the caller before the first cycle; state[5] = continue flag. */
+extern "C" int admp_scf_step(admp_ctx* c, void* stream, const void* M, void* U, const void* pol, void* F, int maxiter, double thresh,
+                             int32_t* state, double* scalars) {
+    if (need(c, false, true)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaGraphConditionalHandle none;
+    memset(&none, 0, sizeof(none));
+    CK(cudaMemsetAsync(scalars + ADMP_S_MAXFIELD, 0, sizeof(double), st));
+    DISPATCH(c, launch_scf_field, st, c->n_atoms, c->kappa, M, U, pol, F, scalars);
+    launch_scf_decide(st, state, scalars, maxiter, thresh, none, 0);
+    DISPATCH(c, launch_scf_update, st, c->n_atoms, state, F, pol, U, scalars);
+    CKLAUNCH();
+    return 0;
+}
+extern "C" int admp_virial_finalize(admp_ctx* c, void* stream, double* scalars) {
+    if (need(c, true, false)) return 1;
+    launch_virial_finalize((cudaStream_t)stream, c->box, scalars);
+    CKLAUNCH();
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------ fused evaluation
 // one pass of optimize_Uind's loop body on staged inputs (admp/pme.py:132-138)
 static int scf_body(admp_ctx* c, cudaStream_t st, int maxiter, double thresh, uint32_t flags, cudaGraphConditionalHandle h, int use_h) {

@@ -145,12 +145,12 @@ frames_fwd_kernel(int n, int lmax, const BoxInfo* __restrict__ Bp, const T* __re
 
 template <typename T>
 __global__ void __launch_bounds__(128)
-frames_bwd_kernel(int n, int lmax, const BoxInfo* __restrict__ Bp, const T* __restrict__ pos,
+frames_bwd_kernel(int first, int n, int lmax, const BoxInfo* __restrict__ Bp, const T* __restrict__ pos,
                   const int32_t* __restrict__ atype, const int32_t* __restrict__ ai,
                   const T* __restrict__ Ql, const T* __restrict__ G, T* __restrict__ dQl,
                   T* __restrict__ dpos, double* __restrict__ scalars, int want_box) {
     __shared__ double red[9 * 4];
-    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const int a = first + blockIdx.x * blockDim.x + threadIdx.x;     // atoms [first, n)
     double dbox[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (a < n) {
         const int nh = (lmax + 1) * (lmax + 1);
@@ -270,14 +270,15 @@ void launch_frames_fwd(cudaStream_t st, int n, int lmax, const BoxInfo* B, const
 }
 template <typename T>
 void launch_frames_bwd(cudaStream_t st, int n, int lmax, const BoxInfo* B, const void* pos, const int32_t* atype,
-                       const int32_t* ai, const void* Ql, const void* G, void* dQl, void* dpos, double* scalars, int want_box) {
-    if (n <= 0) return;
-    frames_bwd_kernel<T><<<(n + 127) / 128, 128, 0, st>>>(n, lmax, B, (const T*)pos, atype, ai, (const T*)Ql, (const T*)G,
-                                                          (T*)dQl, (T*)dpos, scalars, want_box);
+                       const int32_t* ai, const void* Ql, const void* G, void* dQl, void* dpos, double* scalars, int want_box,
+                       int first) {
+    if (n - first <= 0) return;
+    frames_bwd_kernel<T><<<(n - first + 127) / 128, 128, 0, st>>>(first, n, lmax, B, (const T*)pos, atype, ai, (const T*)Ql, (const T*)G,
+                                                                  (T*)dQl, (T*)dpos, scalars, want_box);
 }
 template void launch_frames_fwd<double>(cudaStream_t, int, int, const BoxInfo*, const void*, const int32_t*, const int32_t*, const void*, void*, void*, void*);
 template void launch_frames_fwd<float>(cudaStream_t, int, int, const BoxInfo*, const void*, const int32_t*, const int32_t*, const void*, void*, void*, void*);
-template void launch_frames_bwd<double>(cudaStream_t, int, int, const BoxInfo*, const void*, const int32_t*, const int32_t*, const void*, const void*, void*, void*, double*, int);
-template void launch_frames_bwd<float>(cudaStream_t, int, int, const BoxInfo*, const void*, const int32_t*, const int32_t*, const void*, const void*, void*, void*, double*, int);
+template void launch_frames_bwd<double>(cudaStream_t, int, int, const BoxInfo*, const void*, const int32_t*, const int32_t*, const void*, const void*, void*, void*, double*, int, int);
+template void launch_frames_bwd<float>(cudaStream_t, int, int, const BoxInfo*, const void*, const int32_t*, const int32_t*, const void*, const void*, void*, void*, double*, int, int);
 
 }  // namespace admp

@@ -11,7 +11,8 @@ void launch_frames_fwd(cudaStream_t st, int n, int lmax, const BoxInfo* B, const
                        const int32_t* ai, const void* Ql, void* M, void* Qg, void* Fr);
 template <typename T>
 void launch_frames_bwd(cudaStream_t st, int n, int lmax, const BoxInfo* B, const void* pos, const int32_t* atype,
-                       const int32_t* ai, const void* Ql, const void* G, void* dQl, void* dpos, double* scalars, int want_box);
+                       const int32_t* ai, const void* Ql, const void* G, void* dQl, void* dpos, double* scalars, int want_box,
+                       int first = 0);
 
 template <typename T> void launch_rotate(cudaStream_t st, int64_t n, int lmax, int to_local, const void* Q, const void* Fr, void* out);
 

@@ -149,6 +149,30 @@ int admp_ctx_buffer_io(admp_ctx* ctx, void* stream, int which, void* user, int64
 int admp_pme_self(admp_ctx* ctx, void* stream, const void* M, const void* U, const void* pol,
                   uint32_t flags, void* G, void* F, void* dpol, double* scalars);
 
+/* ---- atom-range stages: building blocks of the multi-GPU atom-block decomposition -------------
+ * (admp_b200/parallel.py). Array arguments are the FULL (Na, ...) arrays; the call works
+ * on atoms [first, first+count). The caller reduces mesh / field / gradient arrays across ranks. */
+int admp_set_box(admp_ctx* ctx, void* stream, const void* box);          /* cell + influence tables */
+int admp_mesh_zero(admp_ctx* ctx, void* stream);
+int admp_pme_spread_range(admp_ctx* ctx, void* stream, const void* pos, const void* M, int M_cols,
+                          int M_stride, const void* U, int first, int count);
+int admp_pme_gather_range(admp_ctx* ctx, void* stream, const void* pos, const void* M, int M_cols,
+                          int M_stride, const void* U, int mode, uint32_t flags, void* dpos, void* G,
+                          int G_stride, void* F, double* scalars, int first, int count);
+int admp_pme_self_range(admp_ctx* ctx, void* stream, const void* M, const void* U, const void* pol,
+                        uint32_t flags, void* G, void* F, void* dpol, double* scalars, int first,
+                        int count);
+int admp_frames_bwd_range(admp_ctx* ctx, void* stream, const void* pos, const void* Q_local,
+                          const void* G, void* dQ_local, void* dpos, double* scalars, int first,
+                          int count);
+/* one optimize_Uind cycle on an assembled field (admp/pme.py:133-138): adds the self/penalty part to F,
+ * tests max|F| < thresh over pol > 0.001 sites BEFORE updating U. state: device int32[8], zero before the
+ * first cycle; state[0]=cycle, [3]=n_cycle, [4]=converged, [5]=continue. */
+int admp_scf_step(admp_ctx* ctx, void* stream, const void* M, void* U, const void* pol, void* F,
+                  int maxiter, double thresh, int32_t* state, double* scalars);
+/* folds the reciprocal-space accumulators of `scalars` into dE/dbox (ADMP_S_DBOX) */
+int admp_virial_finalize(admp_ctx* ctx, void* stream, double* scalars);
+
 /* energy_pme / get_energy / get_forces incl. optimize_Uind (admp/pme.py:58-143, :176-254).
  * U_io (n,3): in = U_init, out = converged U (ignored when non-polarizable: pass NULL with
  * pol/tholes/pScales NULL). scf_out[0]=n_cycle, [1]=converged flag (device int32[2]). */

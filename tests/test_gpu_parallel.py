@@ -1,0 +1,73 @@
+"""Multi-GPU decomposition on the device: the atom-block algebra walked in one process
+(emulate_blocks) must reproduce the fused single-context evaluation; frame sharding at world 1; and,
+when >= 2 GPUs are visible, a real 2-rank NCCL run (tools/run_multigpu.py)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from admp_b200 import _lib, workloads                      # noqa: E402
+from admp_b200.parallel import AtomBlockPme, evaluate_frames   # noqa: E402
+from admp_b200.pme import ADMPPmeForce                     # noqa: E402
+from admp_b200.neighbor import neighbor_list               # noqa: E402
+from oracle import fixtures                                # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def rel(a, b):
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-300)
+
+
+@pytest.mark.parametrize('polz', [False, True])
+@pytest.mark.parametrize('nblocks', [2, 5])
+def test_atom_block_algebra_matches_fused_evaluation(polz, nblocks):
+    s = fixtures.lattice_water(4, 3.15, seed=5)
+    calc = ADMPPmeForce(s.box, s.axis_type, s.axis_indices, s.covalent_map, 5.0, 1e-4, 2, lpol=polz)
+    pairs = neighbor_list(s.box, 5.0).allocate(s.positions).pairs
+    ab = AtomBlockPme(calc, emulate_blocks=nblocks)
+    if polz:
+        out = ab.evaluate(s.positions, s.box, pairs, s.Q_local, s.pol, s.tholes, s.mScales, s.pScales, thresh=1e-3)
+        args = [calc._prep(x) for x in (s.positions, s.box, s.Q_local, s.pol, s.tholes, s.mScales, s.pScales)]
+        ref = calc._eval(args[0], args[1], pairs, args[2], None, args[3], args[4], args[5], args[6],
+                         _lib.WANT_GRAD | _lib.WANT_VIRIAL, True, thresh=1e-3, cache_scf=False)
+        assert [out['n_cycle'], int(out['converged'])] == ref.scf.cpu().tolist()
+        assert rel(out['U'], ref.U) < 1e-12 and rel(out['F'], ref.F) < 1e-9
+    else:
+        out = ab.evaluate(s.positions, s.box, pairs, s.Q_local, mScales=s.mScales)
+        args = [calc._prep(x) for x in (s.positions, s.box, s.Q_local, s.mScales)]
+        ref = calc._eval(args[0], args[1], pairs, args[2], None, None, None, args[3], None, _lib.WANT_GRAD | _lib.WANT_VIRIAL, False)
+    assert abs(out['E'].item() - ref.energy.item()) < 1e-11 * abs(ref.energy.item())
+    assert rel(out['dpos'], ref.dpos) < 1e-10 and rel(out['dQ_local'], ref.dQ) < 1e-10
+    assert rel(out['dbox'], ref.dbox) < 1e-9
+
+
+def test_frame_sharding_world_1():
+    w = workloads.water_box((1, 1, 1), polarizable=False)
+    calc = ADMPPmeForce(w.box, w.axis_type, w.axis_indices, w.covalent_map, w.rc, w.ethresh, 2)
+    calc.update_env('kappa', w.kappa)
+    frames = [workloads.jitter_frame(w, f) for f in range(3)]
+    nl = neighbor_list(w.box, w.rc)
+    res = evaluate_frames(calc, frames, w.box, lambda f: nl.allocate(frames[f]).pairs, w.Q_local, mScales=w.mScales)
+    assert res['frames'] == [0, 1, 2] and res['energies'].shape == (3,)
+    m = torch.tensor(w.mScales, device='cuda', requires_grad=True)
+    tot = torch.zeros(5, dtype=torch.float64, device='cuda')
+    for f in range(3):
+        E = calc.get_energy(frames[f], w.box, nl.allocate(frames[f]).pairs, w.Q_local, m)
+        tot += torch.autograd.grad(E, m)[0]
+        assert abs(E.item() - res['energies'][f].item()) < 1e-12 * abs(E.item())
+    assert rel(res['param_grads']['dmScales'], tot) < 1e-12
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+def test_two_rank_nccl_run():
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2', '--master-addr', '127.0.0.1',
+           '--master-port', '29541', os.path.join(ROOT, 'tools', 'run_multigpu.py'), '--check']
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert 'MULTIGPU CHECK OK' in out.stdout

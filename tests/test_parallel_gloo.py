@@ -1,0 +1,109 @@
+"""World-size-2 gloo tests (CPU) of the multi-GPU host logic in admp_b200/parallel.py: partitioning,
+the packed all-reduce, and the decomposition algebra (frame sharding; atom-block real space +
+linear mesh) evaluated with the CPU oracle under a real process group."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from admp_b200 import parallel
+
+
+def test_partitions_cover_everything():
+    for n, w in [(3072, 2), (3072, 8), (99, 4), (786432, 8)]:
+        blocks = parallel.partition_atoms(n, w, 3)
+        assert blocks[0][0] == 0 and sum(c for _, c in blocks) == n
+        assert all(f % 3 == 0 and c % 3 == 0 for f, c in blocks)
+        assert all(blocks[k][0] + blocks[k][1] == blocks[k + 1][0] for k in range(w - 1))
+        assert max(c for _, c in blocks) - min(c for _, c in blocks) <= 3
+    rows = parallel.partition_rows(12272, 8)
+    assert sum(c for _, c in rows) == 12272 and rows[-1][0] + rows[-1][1] == 12272
+    assert sorted(sum((parallel.shard_frames(10, r, 4) for r in range(4)), [])) == list(range(10))
+    with pytest.raises(ValueError):
+        parallel.partition_atoms(10, 2, 3)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.set_num_threads(2)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from oracle import fixtures, pairlist
+        from oracle import realspace as orc
+        from oracle import reciprocal as orecip
+        from oracle.frames import construct_local_frames
+        from oracle.harmonics import rot_local2global
+        # 1. packed all-reduce: several tensors, one collective
+        a = torch.full((3, 2), float(rank + 1), dtype=torch.float64)
+        b = torch.arange(5, dtype=torch.float32) * (rank + 1)
+        parallel.allreduce_sum_([a, None, b])
+        assert torch.all(a == 3.0) and torch.allclose(b, torch.arange(5, dtype=torch.float32) * 3)
+
+        s = fixtures.lattice_water(3, 3.3, seed=4)
+        pairs, npairs = pairlist.build_pairs(s.positions.numpy(), s.box.numpy(), 4.9)
+        pairs = pairs[:npairs]
+        kappa, K = 0.55, (24, 24, 24)
+        # 2. frame sharding: every frame evaluated exactly once, parameter gradients summed
+        frames = [s.jitter(1000 + f) for f in range(5)]
+        mine = parallel.shard_frames(len(frames), rank, world)
+        mS = s.mScales.clone().requires_grad_(True)
+        g_local = torch.zeros(5, dtype=torch.float64)
+        e_local = torch.zeros(len(frames), dtype=torch.float64)
+        for f in mine:
+            E = orc.energy_pme(frames[f], s.box, pairs, s.Q_local, None, None, None, mS, None, None, s.covalent_map, s.axis_type,
+                               s.axis_indices, kappa, *K, 2, False)
+            g_local += torch.autograd.grad(E, mS)[0]
+            e_local[f] = E.detach()
+        parallel.allreduce_sum_([g_local, e_local])
+        # 3. atom-block algebra: pair energy over row slices + mesh linear in atoms
+        fr = construct_local_frames(s.positions, s.box, s.axis_type, s.axis_indices)
+        Qg = rot_local2global(s.Q_local, fr, 2)
+        r0, rc = parallel.partition_rows(npairs, world)[rank]
+        e_real = orc.pme_real(s.positions, s.box, pairs[r0:r0 + rc], Qg, None, None, None, s.mScales, None, None, s.covalent_map,
+                              kappa, 2, False).reshape(1)
+        a0, ac = parallel.partition_atoms(s.n_atoms, world, 3)[rank]
+        mesh = orecip.spread(s.positions[a0:a0 + ac], s.box, Qg[a0:a0 + ac], K, 2)
+        parallel.allreduce_sum_([e_real, mesh])
+        if rank == 0:
+            ref_g = torch.zeros(5, dtype=torch.float64)
+            ref_e = []
+            for f in range(len(frames)):
+                E = orc.energy_pme(frames[f], s.box, pairs, s.Q_local, None, None, None, mS, None, None, s.covalent_map, s.axis_type,
+                                   s.axis_indices, kappa, *K, 2, False)
+                ref_g += torch.autograd.grad(E, mS)[0]
+                ref_e.append(E.item())
+            full_real = orc.pme_real(s.positions, s.box, pairs, Qg, None, None, None, s.mScales, None, None, s.covalent_map, kappa, 2, False)
+            full_mesh = orecip.spread(s.positions, s.box, Qg, K, 2)
+            out.put(dict(g=(g_local - ref_g).abs().max().item() / ref_g.abs().max().item(),
+                         e=float(np.abs(e_local.numpy() - np.array(ref_e)).max()),
+                         real=abs(e_real.item() - full_real.item()) / abs(full_real.item()),
+                         mesh=(mesh - full_mesh).abs().max().item()))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo():
+    ctx = mp.get_context('spawn')
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = out.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert res['g'] < 1e-12 and res['e'] < 1e-9 and res['real'] < 1e-12 and res['mesh'] < 1e-12

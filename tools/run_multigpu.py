@@ -1,0 +1,94 @@
+#!/usr/bin/env python
+"""Multi-rank driver (launch with torchrun, one rank per GPU):
+    torchrun --nproc-per-node N tools/run_multigpu.py --check          # parity of both shardings vs 1 rank
+    torchrun --nproc-per-node N tools/run_multigpu.py --config C5      # atom-block timing on a big box
+"""
+import argparse
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np                                  # noqa: E402
+import torch                                        # noqa: E402
+import torch.distributed as dist                    # noqa: E402
+from admp_b200 import _lib, workloads               # noqa: E402
+from admp_b200.parallel import AtomBlockPme, evaluate_frames   # noqa: E402
+from admp_b200.pme import ADMPPmeForce              # noqa: E402
+from admp_b200.neighbor import neighbor_list        # noqa: E402
+
+REPS = {'C2': (1, 1, 1), 'C3': (2, 4, 4), 'C5': (4, 8, 8), 'C2x4': (1, 2, 2)}
+
+
+def rel(a, b):
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-300)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--check', action='store_true')
+    ap.add_argument('--config', default='C3')
+    ap.add_argument('--steps', type=int, default=2)
+    a = ap.parse_args()
+    rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+    torch.cuda.set_device(local)
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    if a.check:
+        from oracle import fixtures
+        s = fixtures.lattice_water(4, 3.15, seed=5)
+        calc = ADMPPmeForce(s.box, s.axis_type, s.axis_indices, s.covalent_map, 5.0, 1e-4, 2, lpol=True)
+        pairs = neighbor_list(s.box, 5.0).allocate(s.positions).pairs
+        out = AtomBlockPme(calc, rank, world).evaluate(s.positions, s.box, pairs, s.Q_local, s.pol, s.tholes, s.mScales, s.pScales,
+                                                       thresh=1e-3)
+        args = [calc._prep(x) for x in (s.positions, s.box, s.Q_local, s.pol, s.tholes, s.mScales, s.pScales)]
+        ref = calc._eval(args[0], args[1], pairs, args[2], None, args[3], args[4], args[5], args[6],
+                         _lib.WANT_GRAD | _lib.WANT_VIRIAL, True, thresh=1e-3, cache_scf=False)
+        ok = [out['n_cycle'], int(out['converged'])] == ref.scf.cpu().tolist()
+        errs = dict(E=abs(out['E'].item() - ref.energy.item()) / abs(ref.energy.item()), dpos=rel(out['dpos'], ref.dpos),
+                    U=rel(out['U'], ref.U), dbox=rel(out['dbox'], ref.dbox), dQ=rel(out['dQ_local'], ref.dQ))
+        ok = ok and all(v < 1e-9 for v in errs.values())
+        # frames: 6 jittered frames, parameter gradients all-reduced
+        frames = [s.jitter(1000 + f).numpy() for f in range(6)]
+        res = evaluate_frames(calc, frames, s.box, pairs, s.Q_local, s.pol, s.tholes, s.mScales, s.pScales, rank=rank, world=world)
+        one = evaluate_frames(calc, frames, s.box, pairs, s.Q_local, s.pol, s.tholes, s.mScales, s.pScales, rank=0, world=1)
+        for k in res['param_grads']:
+            ok = ok and rel(res['param_grads'][k], one['param_grads'][k]) < 1e-10
+        for j, f in enumerate(res['frames']):
+            ok = ok and abs(res['energies'][j].item() - one['energies'][f].item()) < 1e-10 * abs(one['energies'][f].item())
+        flag = torch.tensor([1.0 if ok else 0.0], device='cuda')
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print('atom-block errors', errs)
+            print('MULTIGPU CHECK OK' if flag.item() > 0 else 'MULTIGPU CHECK FAILED')
+        dist.barrier()
+        dist.destroy_process_group()
+        sys.exit(0 if flag.item() > 0 else 1)
+    reps = REPS[a.config]
+    w = workloads.water_box(reps, polarizable=True)
+    calc = ADMPPmeForce(workloads.water_box((1, 1, 1)).box, w.axis_type, w.axis_indices, w.covalent_map, w.rc, w.ethresh, 2, lpol=True)
+    calc.update_env('kappa', w.kappa)
+    for d in range(3):
+        calc.update_env('K%d' % (d + 1), w.K[d])
+    pairs = neighbor_list(w.box, w.rc).allocate(w.positions).pairs
+    ab = AtomBlockPme(calc, rank, world)
+    ts = []
+    for k in range(a.steps + 1):
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = ab.evaluate(w.positions, w.box, pairs, w.Q_local, w.pol, w.tholes, w.mScales, w.pScales)
+        torch.cuda.synchronize()
+        dist.barrier()
+        if k:
+            ts.append(time.perf_counter() - t0)
+    t = torch.tensor([np.mean(ts)], device='cuda')
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print('%s atom-block on %d GPU(s): %.1f ms/eval (%.3f evals/s), E = %.6f, scf [%d, %s]' % (
+            a.config, world, 1e3 * t.item(), 1.0 / t.item(), out['E'].item(), out['n_cycle'], out['converged']))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
