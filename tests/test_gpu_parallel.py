@@ -60,8 +60,8 @@ def test_frame_sharding_world_1():
     for f in range(3):
         E = calc.get_energy(frames[f], w.box, nl.allocate(frames[f]).pairs, w.Q_local, m)
         tot += torch.autograd.grad(E, m)[0]
-        assert abs(E.item() - res['energies'][f].item()) < 1e-12 * abs(E.item())
-    assert rel(res['param_grads']['dmScales'], tot) < 1e-12
+        assert abs(E.item() - res['energies'][f].item()) < 1e-10 * abs(E.item())   # atomic summation order differs run to run
+    assert rel(res['param_grads']['dmScales'], tot) < 1e-10
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
