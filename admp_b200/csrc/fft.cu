@@ -27,7 +27,7 @@
 
 namespace admp {
 
-template <typename T> struct cx { T x, y; };
+template <typename T> struct alignas(2 * sizeof(T)) cx { T x, y; };   // 16-byte (8-byte for float) vector loads / stores
 template <typename T> __device__ __forceinline__ cx<T> operator+(cx<T> a, cx<T> b) { return {a.x + b.x, a.y + b.y}; }
 template <typename T> __device__ __forceinline__ cx<T> operator-(cx<T> a, cx<T> b) { return {a.x - b.x, a.y - b.y}; }
 template <typename T> __device__ __forceinline__ cx<T> cmul(cx<T> a, cx<T> b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
@@ -340,242 +340,7 @@ fft_x_conv_kernel(FftPlan P, int TL, int LS, StrideGeom g, const BoxInfo* __rest
     }
 }
 
-// ------------------------------------------------------------------------------------------ register-blocked fast path
-// N = R1*R2*R3 (R3 = 1: two stages). One butterfly per thread per stage; stage 1 reads its inputs
-// through `in(pos)` (global memory -> registers), the last stage hands its outputs to `out(pos, v)`
-// (registers -> global memory); the exchange between stages goes through shared memory
-// (one __syncthreads per boundary). Thread (j, l): butterfly j of line l.
-template <typename T, int R1, int R2, int R3, int SIGN, typename In, typename Out>
-__device__ __forceinline__ void fft_block(int j, int l, bool live, cx<T>* __restrict__ sA, cx<T>* __restrict__ sB, int LS,
-                                          const cx<T>* __restrict__ tw, int twmul, In in, Out out) {
-    constexpr int N = R1 * R2 * R3, m1 = N / R1, m2 = N / R2, m3 = N / R3;
-    if (live && j < m1) {
-        cx<T> v[R1];
-#pragma unroll
-        for (int t = 0; t < R1; ++t) v[t] = in(j + t * m1);
-        Dft<T, R1, SIGN>::run(v);
-        cx<T>* d = sA + l * LS + j * R1;
-#pragma unroll
-        for (int t = 0; t < R1; ++t) d[t] = v[t];
-    }
-    __syncthreads();
-    if (R3 == 1) {
-        if (live && j < m2) {              // m2 == R1, so k = j
-            cx<T> v[R2];
-            const cx<T>* s = sA + l * LS + j;
-            v[0] = s[0];
-#pragma unroll
-            for (int t = 1; t < R2; ++t) {
-                cx<T> w = tw[t * j * twmul];
-                if (SIGN < 0) w.y = -w.y;
-                v[t] = cmul(s[t * m2], w);
-            }
-            Dft<T, R2, SIGN>::run(v);
-#pragma unroll
-            for (int t = 0; t < R2; ++t) out(j + t * R1, v[t]);
-        }
-    } else {
-        if (live && j < m2) {
-            const int k = j % R1;
-            cx<T> v[R2];
-            const cx<T>* s = sA + l * LS + j;
-            v[0] = s[0];
-#pragma unroll
-            for (int t = 1; t < R2; ++t) {
-                cx<T> w = tw[t * k * (m2 / R1) * twmul];
-                if (SIGN < 0) w.y = -w.y;
-                v[t] = cmul(s[t * m2], w);
-            }
-            Dft<T, R2, SIGN>::run(v);
-            cx<T>* d = sB + l * LS + (j - k) * R2 + k;
-#pragma unroll
-            for (int t = 0; t < R2; ++t) d[t * R1] = v[t];
-        }
-        __syncthreads();
-        if (live && j < m3) {              // m3 == R1*R2, so k = j
-            constexpr int R3e = R3 > 1 ? R3 : 2;
-            cx<T> v[R3e];
-            const cx<T>* s = sB + l * LS + j;
-            v[0] = s[0];
-#pragma unroll
-            for (int t = 1; t < R3e; ++t) {
-                cx<T> w = tw[t * j * twmul];
-                if (SIGN < 0) w.y = -w.y;
-                v[t] = cmul(s[t * m3], w);
-            }
-            Dft<T, R3e, SIGN>::run(v);
-#pragma unroll
-            for (int t = 0; t < R3e; ++t) out(j + t * (R1 * R2), v[t]);
-        }
-    }
-}
-
-template <int R1, int R2, int R3> struct FastGeom {
-    static constexpr int N = R1 * R2 * R3;
-    static constexpr int mn = R1 < R2 ? (R3 > 1 && R3 < R1 ? R3 : R1) : (R3 > 1 && R3 < R2 ? R3 : R2);
-    static constexpr int BPL = N / mn;             // threads per line = most butterflies in any stage
-};
-
-// strided pass (Y or X), in place on the spectrum: thread -> (l fastest, j)
-template <typename T, int R1, int R2, int R3, int SIGN>
-__global__ void __launch_bounds__(384)
-fast_strided_kernel(int TL, int LS, StrideGeom g, cx<T>* __restrict__ spec, const cx<T>* __restrict__ gtw) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    cx<T>* sA = reinterpret_cast<cx<T>*>(smem_raw);
-    cx<T>* sB = sA + TL * LS;
-    const int o = blockIdx.x / g.tiles, t = blockIdx.x - o * g.tiles;
-    const int c0 = t * TL;
-    const int nl = min(TL, g.n_inner - c0);
-    cx<T>* base = spec + (size_t)o * g.outer_stride + c0;
-    const int l = threadIdx.x % TL, j = threadIdx.x / TL;
-    const size_t ls = g.line_stride;
-    fft_block<T, R1, R2, R3, SIGN>(j, l, l < nl, sA, sB, LS, gtw, 1,
-                                   [&](int pos) { return base[(size_t)pos * ls + l]; },
-                                   [&](int pos, cx<T> v) { base[(size_t)pos * ls + l] = v; });
-}
-
-// fused X pass: forward, influence function (+energy, +virial), inverse
-template <typename T, int R1, int R2, int R3, int MAXT>
-__global__ void __launch_bounds__(MAXT, MAXT <= 128 ? 4 : 1)
-fast_x_conv_kernel(int TL, int LS, StrideGeom g, const BoxInfo* __restrict__ Bp, T kappa, int kind, ConvTables tb,
-                                   cx<T>* __restrict__ spec, const cx<T>* __restrict__ gtw, double* __restrict__ scalars, int want_vir) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ double red[7 * 32];
-    cx<T>* sA = reinterpret_cast<cx<T>*>(smem_raw);
-    cx<T>* sB = sA + TL * LS;
-    const BoxInfo& B = *Bp;
-    const int c0 = blockIdx.x * TL;
-    const int nl = min(TL, g.n_inner - c0);
-    cx<T>* base = spec + c0;
-    const int l = threadIdx.x % TL, j = threadIdx.x / TL;
-    const size_t ls = g.line_stride;
-    const int K3 = B.K[2], K3h = K3 / 2 + 1;
-    const int c = c0 + l;
-    const int i2 = c / K3h, i3 = c - i2 * K3h;
-    const bool single = (i3 == 0) || (2 * i3 == K3);
-    const double scale = (kind == ADMP_CK_COULOMB) ? ADMP_DIEL : 1.0;
-    const bool ortho = *tb.ortho != 0;
-    const double kap = (double)kappa;
-    double acc_e = 0.0, acc_t[6] = {0, 0, 0, 0, 0, 0};
-    // forward output lands in sX (the buffer the last forward stage is not reading)
-    cx<T>* sX = (R3 == 1) ? sB : sA;
-    cx<T>* sY = (R3 == 1) ? sA : sB;
-    // a thread owns one line (fixed i2, i3): hoist the separable Coulomb factors of that line
-    const bool quick = ortho && kind == ADMP_CK_COULOMB && !want_vir && l < nl;
-    const double e23 = quick ? 6.283185307179586 / B.vol * tb.ek[1][i2] * tb.ek[2][i3] : 0.0;
-    const double k23 = quick ? tb.k2[1][i2] + tb.k2[2][i3] : 1.0;
-    const bool origin_line = (i2 == 0 && i3 == 0);
-    const double wgt = single ? 1.0 : 2.0;
-    fft_block<T, R1, R2, R3, 1>(j, l, l < nl, sA, sB, LS, gtw, 1,
-                                [&](int pos) { return base[(size_t)pos * ls + l]; },
-                                [&](int i1, cx<T> s) {
-                                    const double s2 = (double)s.x * s.x + (double)s.y * s.y;
-                                    double gk;
-                                    if (quick) {
-                                        gk = (origin_line && i1 == 0) ? 0.0 : e23 * tb.ek[0][i1] / (tb.k2[0][i1] + k23);
-                                    } else if (want_vir) {
-                                        const Influence f = influence<true>(B, tb, ortho, kap, kind, i1, i2, i3);
-                                        virial_terms(B, f.kv, i1, i2, i3, single, f.dg * s2, acc_t);
-                                        gk = f.g;
-                                    } else {
-                                        gk = influence<false>(B, tb, ortho, kap, kind, i1, i2, i3).g;
-                                    }
-                                    acc_e += wgt * gk * s2;
-                                    const T gg = (T)(2.0 * scale * gk);
-                                    sX[l * LS + i1] = {s.x * gg, s.y * gg};
-                                });
-    __syncthreads();
-    fft_block<T, R1, R2, R3, -1>(j, l, l < nl, sY, sX, LS, gtw, 1,
-                                 [&](int pos) { return sX[l * LS + pos]; },
-                                 [&](int pos, cx<T> v) { base[(size_t)pos * ls + l] = v; });
-    double e1[1] = {acc_e * scale};
-    block_accumulate<1>(e1, red, scalars + ADMP_S_E_RECIP);
-    if (want_vir) {
-#pragma unroll
-        for (int k = 0; k < 6; ++k) acc_t[k] *= scale;
-        block_accumulate<6>(acc_t, red, scalars + ADMP_S_TK);
-    }
-}
-
-// Z passes (contiguous lines): thread -> (j fastest, l); M = R1*R2*R3 = K3/2
-template <typename T, int R1, int R2, int R3>
-__global__ void __launch_bounds__(384)
-fast_z_fwd_kernel(int TL, int LS, int nlines, const T* __restrict__ mesh, cx<T>* __restrict__ spec,
-                                  const cx<T>* __restrict__ gtw) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    cx<T>* sA = reinterpret_cast<cx<T>*>(smem_raw);
-    cx<T>* sB = sA + TL * LS;
-    constexpr int M = R1 * R2 * R3, K3 = 2 * M, K3h = M + 1, BPL = FastGeom<R1, R2, R3>::BPL;
-    const int L0 = blockIdx.x * TL;
-    const int nl = min(TL, nlines - L0);
-    const int j = threadIdx.x % BPL, l = threadIdx.x / BPL;
-    const cx<T>* line = reinterpret_cast<const cx<T>*>(mesh + (size_t)(L0 + l) * K3);
-    cx<T>* sZ = (R3 == 1) ? sB : sA;
-    fft_block<T, R1, R2, R3, 1>(j, l, l < nl, sA, sB, LS, gtw, 2,
-                                [&](int pos) { return line[pos]; },
-                                [&](int pos, cx<T> v) { sZ[l * LS + pos] = v; });
-    __syncthreads();
-    for (int e = threadIdx.x; e < nl * K3h; e += blockDim.x) {
-        const int ll = e / K3h, k = e - ll * K3h;
-        const cx<T> zk = sZ[ll * LS + (k == M ? 0 : k)];
-        cx<T> zc = sZ[ll * LS + ((k == 0 || k == M) ? 0 : M - k)];
-        zc.y = -zc.y;
-        const cx<T> a = {(T)0.5 * (zk.x + zc.x), (T)0.5 * (zk.y + zc.y)}, b = {(T)0.5 * (zk.x - zc.x), (T)0.5 * (zk.y - zc.y)};
-        const cx<T> w = gtw[k];
-        const cx<T> f = {w.y, -w.x};
-        spec[(size_t)(L0 + ll) * K3h + k] = a + cmul(f, b);
-    }
-}
-
-template <typename T, int R1, int R2, int R3>
-__global__ void __launch_bounds__(384)
-fast_z_inv_kernel(int TL, int LS, int nlines, const cx<T>* __restrict__ spec, T* __restrict__ mesh,
-                                  const cx<T>* __restrict__ gtw) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    cx<T>* sA = reinterpret_cast<cx<T>*>(smem_raw);
-    cx<T>* sB = sA + TL * LS;
-    cx<T>* sX = sB + TL * LS;                 // staged half spectrum (LS >= M+1)
-    constexpr int M = R1 * R2 * R3, K3 = 2 * M, K3h = M + 1, BPL = FastGeom<R1, R2, R3>::BPL;
-    const int L0 = blockIdx.x * TL;
-    const int nl = min(TL, nlines - L0);
-    for (int e = threadIdx.x; e < nl * K3h; e += blockDim.x) {
-        const int ll = e / K3h, k = e - ll * K3h;
-        sX[ll * LS + k] = spec[(size_t)(L0 + ll) * K3h + k];
-    }
-    __syncthreads();
-    const int j = threadIdx.x % BPL, l = threadIdx.x / BPL;
-    cx<T>* line = reinterpret_cast<cx<T>*>(mesh + (size_t)(L0 + l) * K3);
-    const cx<T>* X = sX + l * LS;
-    fft_block<T, R1, R2, R3, -1>(j, l, l < nl, sA, sB, LS, gtw, 2,
-                                 [&](int k) {
-                                     const cx<T> xk = X[k];
-                                     cx<T> xc = X[M - k];
-                                     xc.y = -xc.y;
-                                     const cx<T> s = xk + xc, d = xk - xc;
-                                     const cx<T> w = gtw[k];
-                                     const cx<T> f = {w.y, w.x};
-                                     return s + cmul(f, d);
-                                 },
-                                 [&](int pos, cx<T> v) { line[pos] = v; });
-}
-
-// the (R1,R2,R3) decompositions with a fast kernel: the reference's mesh family 154*2^n (and halves)
-#define ADMP_FAST_LIST(X) X(11, 7, 1) X(11, 14, 1) X(11, 7, 4) X(11, 7, 8) X(11, 14, 8)
-
-static int fast_index(int N) {
-    int idx = 0;
-#define X(a, b, c) if (N == (a) * (b) * (c)) return idx; ++idx;
-    ADMP_FAST_LIST(X)
-#undef X
-    return -1;
-}
-static int fast_bpl(int idx) {
-    int i = 0;
-#define X(a, b, c) if (i++ == idx) return FastGeom<a, b, c>::BPL;
-    ADMP_FAST_LIST(X)
-#undef X
-    return 0;
-}
+#include "fft_fast.cuh"
 
 // ------------------------------------------------------------------------------------------ host side
 bool fft_factorize(int n, FftPlan& P) {
@@ -591,10 +356,11 @@ bool fft_factorize(int n, FftPlan& P) {
 
 struct FftDimCfg {
     FftPlan P; int TL, LS; size_t smem;          // generic Stockham kernels
-    int fast, fTL, fLS, fthreads; size_t fsmem;  // register-blocked kernels (fast < 0: unavailable)
+    bool fast;                                   // pipelined register-blocked kernels (fft_fast.cuh)
+    FastOps ops;
 };
 
-static bool dim_cfg(int N, int tw_len, size_t esz, size_t smem_cap, int min_ls, bool zpass, FftDimCfg& c) {
+static bool dim_cfg(int N, int tw_len, size_t esz, size_t smem_cap, int min_ls, bool zpass, bool allow_fast, FftDimCfg& c) {
     if (!fft_factorize(N, c.P)) return false;
     c.LS = N | 1;
     if (c.LS < min_ls) c.LS = min_ls | 1;
@@ -604,23 +370,16 @@ static bool dim_cfg(int N, int tw_len, size_t esz, size_t smem_cap, int min_ls, 
         if (need <= smem_cap) { c.TL = TL; c.smem = need; ok = true; break; }
     }
     if (!ok) return false;
-    c.fast = fast_index(N);
-    if (c.fast >= 0) {
-        const int bpl = fast_bpl(c.fast);
-        const int nbuf = zpass ? 3 : 2;
-        c.fLS = c.LS;
-        c.fTL = 0;
-        // lines per block: as many as fit in 384 threads / 96 KB, at most 8 (128-byte segments in f64)
-        int tl_max = 8, thr_max = 384;                 // 384 threads x <= 168 registers
-        if (const char* e = getenv("ADMP_FFT_TL")) tl_max = atoi(e) > 0 ? atoi(e) : tl_max;       // tuning knobs
-        if (const char* e = getenv("ADMP_FFT_THREADS")) thr_max = atoi(e) > 0 ? atoi(e) : thr_max;
-        if (thr_max > 384) thr_max = 384;
-        for (int TL = tl_max; TL >= 1; TL >>= 1) {
-            const size_t need = (size_t)nbuf * TL * c.fLS * 2 * esz;
-            if (TL * bpl <= thr_max && need <= 96 * 1024) { c.fTL = TL; c.fsmem = need; break; }
+    c.fast = false;
+    if (allow_fast) {
+        const char* e = getenv("ADMP_FFT_WIDE");
+        const bool wide = e && atoi(e) > 0;
+        c.fast = esz == 8 ? fast_lookup<double>(N, wide, c.ops) : fast_lookup<float>(N, wide, c.ops);
+        if (c.fast) {
+            c.ops.prepare(c.ops);
+            const bool usable = zpass ? (c.ops.occ[3] > 0 && c.ops.occ[4] > 0) : (c.ops.occ[0] > 0 && c.ops.occ[1] > 0 && c.ops.occ[2] > 0 && c.ops.occ[5] > 0);
+            if (!usable) c.fast = false;
         }
-        if (c.fTL == 0) c.fast = -1;
-        else c.fthreads = c.fTL * bpl;
     }
     return true;
 }
@@ -628,6 +387,7 @@ static bool dim_cfg(int N, int tw_len, size_t esz, size_t smem_cap, int min_ls, 
 struct Fft3dImpl {
     int K[3];
     size_t esz;
+    int n_sm;
     FftDimCfg z, y, x;
     void* tw[3];     // device twiddle tables: exp(-2 pi i m / K_d), m < K_d
 };
@@ -642,16 +402,6 @@ static cudaError_t set_smem_attr(const Fft3dImpl* f) {
     if ((e = cudaFuncSetAttribute(fft_strided_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(fft_strided_kernel<T, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(fft_x_conv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xs)) != cudaSuccess) return e;
-    const int cap = 96 * 1024;
-#define X(a, b, c)                                                                                                            \
-    if ((e = cudaFuncSetAttribute(fast_strided_kernel<T, a, b, c, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap)) != cudaSuccess) return e;  \
-    if ((e = cudaFuncSetAttribute(fast_strided_kernel<T, a, b, c, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap)) != cudaSuccess) return e; \
-    if ((e = cudaFuncSetAttribute(fast_x_conv_kernel<T, a, b, c, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap)) != cudaSuccess) return e; \
-    if ((e = cudaFuncSetAttribute(fast_x_conv_kernel<T, a, b, c, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap)) != cudaSuccess) return e; \
-    if ((e = cudaFuncSetAttribute(fast_z_fwd_kernel<T, a, b, c>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap)) != cudaSuccess) return e;       \
-    if ((e = cudaFuncSetAttribute(fast_z_inv_kernel<T, a, b, c>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap)) != cudaSuccess) return e;
-    ADMP_FAST_LIST(X)
-#undef X
     return cudaSuccess;
 }
 
@@ -663,16 +413,20 @@ Fft3d* fft3d_create(int K1, int K2, int K3, int dtype, const char** why) {
     Fft3dImpl* f = new Fft3dImpl();
     f->K[0] = K1; f->K[1] = K2; f->K[2] = K3;
     f->esz = dtype == ADMP_F64 ? 8 : 4;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    f->n_sm = 148;
+    cudaDeviceGetAttribute(&f->n_sm, cudaDevAttrMultiProcessorCount, dev);
     const size_t cap = 200 * 1024;
     const int M = K3 / 2;
-    if (!dim_cfg(M, K3, f->esz, cap, M + 1, true, f->z) || !dim_cfg(K2, K2, f->esz, cap, 0, false, f->y) ||
-        !dim_cfg(K1, K1, f->esz, cap, 0, false, f->x)) {
+    const char* env = getenv("ADMP_FFT");
+    const bool allow_fast = !(env && strcmp(env, "generic") == 0);
+    if (!dim_cfg(M, K3, f->esz, cap, M + 1, true, allow_fast, f->z) || !dim_cfg(K2, K2, f->esz, cap, 0, false, allow_fast, f->y) ||
+        !dim_cfg(K1, K1, f->esz, cap, 0, false, allow_fast, f->x)) {
         *why = msg_fac;
         delete f;
         return nullptr;
     }
-    const char* env = getenv("ADMP_FFT");
-    if (env && strcmp(env, "generic") == 0) f->z.fast = f->y.fast = f->x.fast = -1;
     cudaError_t e = dtype == ADMP_F64 ? set_smem_attr<double>(f) : set_smem_attr<float>(f);
     if (e != cudaSuccess) { *why = msg_cuda; delete f; return nullptr; }
     for (int d = 0; d < 3; ++d) {
@@ -708,6 +462,11 @@ static StrideGeom geom_x(const Fft3dImpl* f, int TL) {
     const int inner = f->K[1] * (f->K[2] / 2 + 1);
     return {1, inner, 0, (size_t)inner, (inner + TL - 1) / TL};
 }
+// persistent grid: every SM gets `occ` resident blocks, tiles are dealt round-robin
+static int persistent_grid(const Fft3dImpl* f, int occ, int ntiles) {
+    const long long g = (long long)f->n_sm * (occ > 0 ? occ : 1);
+    return (int)(g < ntiles ? g : ntiles);
+}
 
 template <typename T>
 static void run_z(Fft3dImpl* f, cudaStream_t st, void* mesh, void* spec, int sign) {
@@ -715,16 +474,10 @@ static void run_z(Fft3dImpl* f, cudaStream_t st, void* mesh, void* spec, int sig
     const int nlines = f->K[0] * f->K[1];
     const FftDimCfg& c = f->z;
     const cx<T>* tw = (const cx<T>*)f->tw[2];
-    if (c.fast >= 0) {
-        const int grid = (nlines + c.fTL - 1) / c.fTL;
-        int i = 0;
-#define X(a, b, cc)                                                                                                              \
-        if (i++ == c.fast) {                                                                                                     \
-            if (sign > 0) fast_z_fwd_kernel<T, a, b, cc><<<grid, c.fthreads, c.fsmem, st>>>(c.fTL, c.fLS, nlines, (const T*)mesh, (cx<T>*)spec, tw); \
-            else fast_z_inv_kernel<T, a, b, cc><<<grid, c.fthreads, c.fsmem, st>>>(c.fTL, c.fLS, nlines, (const cx<T>*)spec, (T*)mesh, tw);          \
-        }
-        ADMP_FAST_LIST(X)
-#undef X
+    if (c.fast) {
+        const int ntiles = (nlines + c.ops.zTL - 1) / c.ops.zTL;
+        if (sign > 0) c.ops.zfwd(st, nlines, ntiles, persistent_grid(f, c.ops.occ[3], ntiles), mesh, spec, tw);
+        else c.ops.zinv(st, nlines, ntiles, persistent_grid(f, c.ops.occ[4], ntiles), spec, mesh, tw);
         return;
     }
     const int grid = (nlines + c.TL - 1) / c.TL;
@@ -736,17 +489,10 @@ template <typename T>
 static void run_strided(Fft3dImpl* f, cudaStream_t st, void* spec, int dim, int sign) {
     const FftDimCfg& c = dim == 1 ? f->y : f->x;
     const cx<T>* tw = (const cx<T>*)f->tw[dim == 1 ? 1 : 0];
-    if (c.fast >= 0) {
-        const StrideGeom g = dim == 1 ? geom_y(f, c.fTL) : geom_x(f, c.fTL);
-        const int grid = g.n_outer * g.tiles;
-        int i = 0;
-#define X(a, b, cc)                                                                                                              \
-        if (i++ == c.fast) {                                                                                                     \
-            if (sign > 0) fast_strided_kernel<T, a, b, cc, 1><<<grid, c.fthreads, c.fsmem, st>>>(c.fTL, c.fLS, g, (cx<T>*)spec, tw); \
-            else fast_strided_kernel<T, a, b, cc, -1><<<grid, c.fthreads, c.fsmem, st>>>(c.fTL, c.fLS, g, (cx<T>*)spec, tw);         \
-        }
-        ADMP_FAST_LIST(X)
-#undef X
+    if (c.fast) {
+        const StrideGeom g = dim == 1 ? geom_y(f, c.ops.TL) : geom_x(f, c.ops.TL);
+        const int ntiles = g.n_outer * g.tiles;
+        c.ops.strided(st, sign, g, ntiles, persistent_grid(f, c.ops.occ[sign > 0 ? 0 : 1], ntiles), spec, tw);
         return;
     }
     const StrideGeom g = dim == 1 ? geom_y(f, c.TL) : geom_x(f, c.TL);
@@ -760,20 +506,9 @@ static void run_x_conv(Fft3dImpl* f, cudaStream_t st, void* spec, const BoxInfo*
                        double* scalars, int want_vir) {
     const FftDimCfg& c = f->x;
     const cx<T>* tw = (const cx<T>*)f->tw[0];
-    if (c.fast >= 0) {
-        const StrideGeom g = geom_x(f, c.fTL);
-        int i = 0;
-#define X(a, b, cc)                                                                                                              \
-        if (i++ == c.fast) {                                                                                                     \
-            if (c.fthreads <= 128)                                                                                               \
-                fast_x_conv_kernel<T, a, b, cc, 128><<<g.tiles, c.fthreads, c.fsmem, st>>>(c.fTL, c.fLS, g, B, (T)kappa, kind, tb,          \
-                                                                                         (cx<T>*)spec, tw, scalars, want_vir);   \
-            else                                                                                                                 \
-                fast_x_conv_kernel<T, a, b, cc, 384><<<g.tiles, c.fthreads, c.fsmem, st>>>(c.fTL, c.fLS, g, B, (T)kappa, kind, tb,          \
-                                                                                         (cx<T>*)spec, tw, scalars, want_vir);   \
-        }
-        ADMP_FAST_LIST(X)
-#undef X
+    if (c.fast) {
+        const StrideGeom g = geom_x(f, c.ops.TL);
+        c.ops.xconv(st, g, g.tiles, persistent_grid(f, c.ops.occ[(kind == ADMP_CK_COULOMB && !want_vir) ? 2 : 5], g.tiles), B, kappa, kind, tb, spec, tw, scalars, want_vir);
         return;
     }
     const StrideGeom g = geom_x(f, c.TL);

@@ -1,0 +1,538 @@
+// Fragment of fft.cu (included inside namespace admp, after Dft<> / cx<> / StrideGeom):
+// the pipelined line-FFT kernels for the reference's mesh family K = 154 * 2^n (and the halves the
+// packed real transform needs): N = R1*R2*R3 in {77, 154, 308, 616, 1232}.
+//
+// Design (B200, FP64: the passes need ~30-70 FP64 instructions per 16-byte point, so both the
+// HBM stream and the FP64 pipe have to stay busy at the same time):
+//   * persistent blocks, one tile (TL lines) per loop iteration, tiles round-robin over the grid;
+//   * the next tile is fetched with cp.async (LDGSTS) into the second input buffer while the
+//     current one is transformed: three tile buffers I0 / I1 / A rotate through the stages
+//     (stage 1: I -> A, stage 2: A -> I, stage 3: I -> global), so no thread ever waits on
+//     a global load inside the butterfly code (an in-place two-buffer variant was measured slower:
+//     the values held across the extra barriers push the kernels into register spills);
+//   * strided passes (Y, X) keep the tile position-major in shared memory ([pos][TL], TL
+//     consecutive lines = one contiguous global segment), thread = (line fastest, butterfly):
+//     every shared-memory access of a quarter warp is one contiguous 128-byte row - no bank
+//     conflicts, no padding, and the cp.async chunks map 1:1 onto global segments;
+//   * butterflies are register blocked (one radix-R DFT per thread per step, JT threads per
+//     line looping over the N/R butterflies of a stage), twiddles come from compact per-stage
+//     shared-memory tables laid out [t][k] (conflict-free), all offsets are compile-time constants;
+//   * the X pass is fused with the influence function: X-forward, C_k/theta_k^2 scaling with the
+//     energy (+ virial) sums, X-inverse - the x-transformed spectrum never leaves the SM.
+
+// ------------------------------------------------------------------------------------------ cp.async
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// 1/x to ~1 ulp from the SFU approximation and two Newton steps (x normal, positive; x = 0 gives NaN:
+// callers select around it). Replaces the ~20-instruction IEEE division in the per-point influence function.
+__device__ __forceinline__ double fast_rcp(double x) {
+    float rf;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"((float)x));
+    double r = (double)rf;
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return r;
+}
+
+// resident blocks per SM the kernels are compiled for: caps the register count at 128 per thread
+template <int NT> struct MinBlocks { static constexpr int value = (512 / ((NT + 31) / 32 * 32)) > 0 ? (512 / ((NT + 31) / 32 * 32)) : 1; };
+
+// ------------------------------------------------------------------------------------------ one Stockham stage
+// Butterflies jj = j, j + JT, ... < N/R of the stage with stride NS (= product of the earlier radices):
+//   v[t] = in(jj + t*N/R) * W_N^(t * k * N/(NS*R)),  k = jj mod NS ;  DFT_R ;  out((jj-k)*R + k + t*NS)
+// run() leaves the results in registers, put() hands them to `out`: the caller places a barrier in between
+// when `out` overwrites the buffer `in` reads (in-place exchange).
+// `tws`: compact twiddle table of the stage, entry (t-1)*NS + k = W_N^(t*k*N/(NS*R)) (unused when NS == 1).
+template <typename T, int R, int SIGN, int N, int NS, int JT>
+struct FStage {
+    static constexpr int m = N / R, iters = (m + JT - 1) / JT;
+    cx<T> v[iters][R];
+    template <typename In>
+    __device__ __forceinline__ void run(int j, const cx<T>* __restrict__ tws, In in) {
+#pragma unroll
+        for (int it = 0; it < iters; ++it) {
+            const int jj = j + it * JT;
+            if ((it + 1) * JT <= m || jj < m) {
+                const int k = (NS == 1) ? 0 : (jj % NS);
+                v[it][0] = in(jj);
+#pragma unroll
+                for (int t = 1; t < R; ++t) {
+                    cx<T> x = in(jj + t * m);
+                    if (NS > 1) {
+                        cx<T> w = tws[(t - 1) * NS + k];
+                        if (SIGN < 0) w.y = -w.y;
+                        x = cmul(x, w);
+                    }
+                    v[it][t] = x;
+                }
+                Dft<T, R, SIGN>::run(v[it]);
+            }
+            if (it + 1 < iters) asm volatile("" ::: "memory");       // keep the next butterfly's loads behind this one (registers)
+        }
+    }
+    template <typename Out>
+    __device__ __forceinline__ void put(int j, Out out) const {
+#pragma unroll
+        for (int it = 0; it < iters; ++it) {
+            const int jj = j + it * JT;
+            if ((it + 1) * JT <= m || jj < m) {
+                const int k = (NS == 1) ? 0 : (jj % NS);
+                const int base = (jj - k) * R + k;
+#pragma unroll
+                for (int t = 0; t < R; ++t) out(base + t * NS, v[it][t]);
+            }
+        }
+    }
+};
+
+// number of entries of the per-stage twiddle tables
+template <int R1, int R2, int R3> struct TwGeom {
+    static constexpr int N2 = (R2 - 1) * R1;                          // stage 2: NS = R1
+    static constexpr int N3 = R3 > 1 ? (R3 - 1) * R1 * R2 : 0;        // stage 3: NS = R1*R2
+    static constexpr int TOTAL = N2 + N3;
+};
+// fills tw2 / tw3 from the global table gtw[i] = exp(-2 pi i / (N*TWMUL))
+template <typename T, int R1, int R2, int R3, int TWMUL>
+__device__ __forceinline__ void build_twiddles(cx<T>* tw2, cx<T>* tw3, const cx<T>* __restrict__ gtw, int nthreads) {
+    constexpr int N = R1 * R2 * R3;
+    for (int i = threadIdx.x; i < TwGeom<R1, R2, R3>::N2; i += nthreads) {
+        const int t = i / R1 + 1, k = i - (t - 1) * R1;
+        tw2[i] = gtw[t * k * (N / (R1 * R2)) * TWMUL];
+    }
+    if (R3 > 1) {
+        for (int i = threadIdx.x; i < TwGeom<R1, R2, R3>::N3; i += nthreads) {
+            const int t = i / (R1 * R2) + 1, k = i - (t - 1) * (R1 * R2);
+            tw3[i] = gtw[t * k * TWMUL];
+        }
+    }
+}
+
+// full line FFT through the rotating buffers: ld0 (tile, possibly pre-processed) -> a -> c -> last(pos, v),
+// two stages when R3 == 1 (ld0 -> a -> last). `c` may alias the buffer ld0 reads: stage 1 is complete at
+// the first barrier. All threads of the block must call (barriers inside); `live` masks the tile's tail lines.
+template <typename T, int R1, int R2, int R3, int SIGN, int JT, typename Ld0, typename StA, typename LdA, typename StC, typename LdC,
+          typename Last>
+__device__ __forceinline__ void fft_rotate(int j, bool live, const cx<T>* __restrict__ tw2, const cx<T>* __restrict__ tw3, Ld0 ld0, StA stA,
+                                           LdA ldA, StC stC, LdC ldC, Last last) {
+    constexpr int N = R1 * R2 * R3;
+    if (live) {
+        FStage<T, R1, SIGN, N, 1, JT> s;
+        s.run(j, nullptr, ld0);
+        s.put(j, stA);
+    }
+    __syncthreads();
+    if (R3 == 1) {
+        if (live) {
+            FStage<T, R2, SIGN, N, R1, JT> s;
+            s.run(j, tw2, ldA);
+            s.put(j, last);
+        }
+    } else {
+        if (live) {
+            FStage<T, R2, SIGN, N, R1, JT> s;
+            s.run(j, tw2, ldA);
+            s.put(j, stC);
+        }
+        __syncthreads();
+        if (live) {
+            constexpr int R3e = R3 > 1 ? R3 : 2;
+            FStage<T, R3e, SIGN, N, R1 * R2, JT> s;
+            s.run(j, tw3, ldC);
+            s.put(j, last);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ strided passes (Y, X)
+template <typename T, int N, int TL, int JT>
+__device__ __forceinline__ void issue_tile(const StrideGeom& g, int tile, const cx<T>* __restrict__ spec, cx<T>* dst, int l, int j) {
+    const int o = tile / g.tiles, t = tile - o * g.tiles;
+    const int c0 = t * TL;
+    const int nl = min(TL, g.n_inner - c0);
+    const cx<T>* base = spec + (size_t)o * g.outer_stride + c0 + l;
+    if (l < nl) {
+#pragma unroll 4
+        for (int pos = j; pos < N; pos += JT) cp_async<sizeof(cx<T>)>(dst + pos * TL + l, base + (size_t)pos * g.line_stride);
+    }
+    cp_async_commit();
+}
+
+template <typename T, int R1, int R2, int R3, int SIGN, int TL, int JT>
+__global__ void __launch_bounds__(TL* JT)
+fast_strided_kernel(StrideGeom g, int ntiles, cx<T>* __restrict__ spec, const cx<T>* __restrict__ gtw) {
+    constexpr int N = R1 * R2 * R3, TILE = N * TL, NT = TL * JT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cx<T>* I0 = reinterpret_cast<cx<T>*>(smem_raw);
+    cx<T>* I1 = I0 + TILE;
+    cx<T>* A = I1 + TILE;
+    cx<T>* tw2 = A + TILE;
+    cx<T>* tw3 = tw2 + TwGeom<R1, R2, R3>::N2;
+    const int l = threadIdx.x % TL, j = threadIdx.x / TL;
+    int tile = blockIdx.x;
+    if (tile < ntiles) issue_tile<T, N, TL, JT>(g, tile, spec, I0, l, j);
+    build_twiddles<T, R1, R2, R3, 1>(tw2, tw3, gtw, NT);
+    for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+        cx<T>* cur = (it & 1) ? I1 : I0;
+        cx<T>* nxt = (it & 1) ? I0 : I1;
+        cp_async_wait_all();
+        __syncthreads();
+        if (tile + (int)gridDim.x < ntiles) issue_tile<T, N, TL, JT>(g, tile + gridDim.x, spec, nxt, l, j);
+        const int o = tile / g.tiles, t = tile - o * g.tiles;
+        const int c0 = t * TL;
+        const bool live = l < g.n_inner - c0;
+        cx<T>* out = spec + (size_t)o * g.outer_stride + c0 + l;
+        const size_t ls = g.line_stride;
+        cx<T>* a = A + l;
+        cx<T>* c = cur + l;
+        fft_rotate<T, R1, R2, R3, SIGN, JT>(
+            j, live, tw2, tw3,
+            [&](int pos) { return c[pos * TL]; }, [&](int pos, cx<T> v) { a[pos * TL] = v; },
+            [&](int pos) { return a[pos * TL]; }, [&](int pos, cx<T> v) { c[pos * TL] = v; },
+            [&](int pos) { return c[pos * TL]; }, [&](int pos, cx<T> v) { out[(size_t)pos * ls] = v; });
+    }
+}
+
+// general influence function (any kind, any cell, optional virial sums): cold path of the fused X pass
+__device__ __noinline__ double influence_general(const BoxInfo* Bp, const ConvTables* tbp, int kind, double kap, int i1, int i2, int i3,
+                                                 double s2, int want_vir, double* acc_t) {
+    const BoxInfo& B = *Bp;
+    const ConvTables& tb = *tbp;
+    const bool ortho = *tb.ortho != 0;
+    const bool single = (i3 == 0) || (2 * i3 == B.K[2]);
+    if (want_vir) {
+        const Influence f = influence<true>(B, tb, ortho, kap, kind, i1, i2, i3);
+        double a[6] = {0, 0, 0, 0, 0, 0};
+        virial_terms(B, f.kv, i1, i2, i3, single, f.dg * s2, a);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) acc_t[k] += a[k];
+        return f.g;
+    }
+    return influence<false>(B, tb, ortho, kap, kind, i1, i2, i3).g;
+}
+
+// X-forward, multiply by 2*scale*C_k/theta_k^2 with energy (+ virial) accumulation, X-inverse
+// (admp/recip.py:410-426 fused with its adjoint). QUICK = Coulomb energy only (every SCF cycle): separable
+// tables of conv_tables_kernel + one reciprocal per point when the cell is orthorhombic (device flag),
+// inline exp otherwise; !QUICK = any kind / virial sums through influence_general.
+template <typename T, int R1, int R2, int R3, int TL, int JT, bool QUICK>
+__global__ void __launch_bounds__(TL* JT)
+fast_x_conv_kernel(StrideGeom g, int ntiles, const BoxInfo* __restrict__ Bp, T kappa, int kind, ConvTables tb, cx<T>* __restrict__ spec,
+                   const cx<T>* __restrict__ gtw, double* __restrict__ scalars, int want_vir) {
+    constexpr int N = R1 * R2 * R3, TILE = N * TL, NT = TL * JT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red[7 * ((NT + 31) / 32)];
+    cx<T>* I0 = reinterpret_cast<cx<T>*>(smem_raw);
+    cx<T>* I1 = I0 + TILE;
+    cx<T>* A = I1 + TILE;
+    cx<T>* tw2 = A + TILE;
+    cx<T>* tw3 = tw2 + TwGeom<R1, R2, R3>::N2;
+    double* sek = reinterpret_cast<double*>(tw3 + TwGeom<R1, R2, R3>::N3);     // exp(-k1^2/4kappa^2)/theta_1^2  (ortho) | 1/theta_1^2
+    double* sk2 = sek + N;                                                    // k1^2 (ortho) | signed index m1
+    const BoxInfo& B = *Bp;
+    const int l = threadIdx.x % TL, j = threadIdx.x / TL;
+    int tile = blockIdx.x;
+    if (tile < ntiles) issue_tile<T, N, TL, JT>(g, tile, spec, I0, l, j);
+    const bool ortho = (*tb.ortho != 0);
+    build_twiddles<T, R1, R2, R3, 1>(tw2, tw3, gtw, NT);
+    if (QUICK) {
+        for (int i = threadIdx.x; i < N; i += NT) {
+            sek[i] = ortho ? tb.ek[0][i] : tb.bt[0][i];
+            sk2[i] = ortho ? tb.k2[0][i] : (double)kint(i, N);
+        }
+    }
+    const int K2 = B.K[1], K3 = B.K[2], K3h = K3 / 2 + 1;
+    const double scale = (kind == ADMP_CK_COULOMB) ? ADMP_DIEL : 1.0;
+    const double kap = (double)kappa;
+    const double pref = 2.0 * scale * 6.283185307179586 / B.vol;
+    const double q4k = -1.0 / (4.0 * kap * kap);
+    double acc_e = 0.0, acc_t[6] = {0, 0, 0, 0, 0, 0};
+    for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+        cx<T>* cur = (it & 1) ? I1 : I0;
+        cx<T>* nxt = (it & 1) ? I0 : I1;
+        cp_async_wait_all();
+        __syncthreads();
+        if (tile + (int)gridDim.x < ntiles) issue_tile<T, N, TL, JT>(g, tile + gridDim.x, spec, nxt, l, j);
+        const int c0 = tile * TL;
+        const bool live = l < g.n_inner - c0;
+        const int cl = live ? c0 + l : 0;
+        const int i2 = cl / K3h, i3 = cl - i2 * K3h;
+        const double wgt = ((i3 == 0) || (2 * i3 == K3)) ? 1.0 : 2.0;
+        const bool origin_line = (i2 == 0 && i3 == 0);
+        // per-line constants of the Coulomb influence function
+        double e23 = 0.0, k23 = 1.0, kb[3] = {0, 0, 0};
+        if (QUICK) {
+            if (ortho) {
+                e23 = pref * tb.ek[1][i2] * tb.ek[2][i3];         // 2*scale*(2 pi/V) * the y, z factors
+                k23 = tb.k2[1][i2] + tb.k2[2][i3];
+            } else {
+                e23 = pref * tb.bt[1][i2] * tb.bt[2][i3];
+                const double m2 = kint(i2, K2), m3 = i3;
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) kb[cc] = 6.283185307179586 * (m2 * B.inv[3 + cc] + m3 * B.inv[6 + cc]);
+            }
+        }
+        double acc_line = 0.0;
+        cx<T>* out = spec + c0 + l;
+        const size_t ls = g.line_stride;
+        cx<T>* a = A + l;
+        cx<T>* c = cur + l;
+        // the scaled spectrum goes to the buffer the forward transform's last stage is not reading
+        cx<T>* sx = (R3 == 1) ? c : a;
+        cx<T>* sy = (R3 == 1) ? a : c;
+        auto scale_point = [&](int i1, cx<T> s) {
+            const double s2 = (double)s.x * s.x + (double)s.y * s.y;
+            double gg;                                        // 2*scale*C_k/theta_k^2
+            if (QUICK) {
+                if (ortho) {
+                    gg = e23 * sek[i1] * fast_rcp(sk2[i1] + k23);
+                } else {
+                    const double m1 = sk2[i1];
+                    const double kx = kb[0] + 6.283185307179586 * m1 * B.inv[0], ky = kb[1] + 6.283185307179586 * m1 * B.inv[1],
+                                 kz = kb[2] + 6.283185307179586 * m1 * B.inv[2];
+                    const double ksq = kx * kx + ky * ky + kz * kz;
+                    gg = e23 * sek[i1] * exp(ksq * q4k) * fast_rcp(ksq);
+                }
+                if (origin_line && i1 == 0) gg = 0.0;         // gamma point dropped (recip.py:416)
+            } else {
+                gg = 2.0 * scale * influence_general(Bp, &tb, kind, kap, i1, i2, i3, s2 * scale, want_vir, acc_t);
+            }
+            acc_line = fma(gg, s2, acc_line);
+            const T gt = (T)gg;
+            sx[i1 * TL] = {s.x * gt, s.y * gt};
+        };
+        fft_rotate<T, R1, R2, R3, 1, JT>(
+            j, live, tw2, tw3,
+            [&](int pos) { return c[pos * TL]; }, [&](int pos, cx<T> v) { a[pos * TL] = v; },
+            [&](int pos) { return a[pos * TL]; }, [&](int pos, cx<T> v) { c[pos * TL] = v; },
+            [&](int pos) { return c[pos * TL]; }, scale_point);
+        acc_e = fma(0.5 * wgt, acc_line, acc_e);              // E = scale * sum wgt g |S|^2 = sum wgt/2 * gg |S|^2
+        __syncthreads();
+        fft_rotate<T, R1, R2, R3, -1, JT>(
+            j, live, tw2, tw3,
+            [&](int pos) { return sx[pos * TL]; }, [&](int pos, cx<T> v) { sy[pos * TL] = v; },
+            [&](int pos) { return sy[pos * TL]; }, [&](int pos, cx<T> v) { sx[pos * TL] = v; },
+            [&](int pos) { return sx[pos * TL]; }, [&](int pos, cx<T> v) { out[(size_t)pos * ls] = v; });
+    }
+    double e1[1] = {acc_e};
+    block_accumulate<1>(e1, red, scalars + ADMP_S_E_RECIP);
+    if (!QUICK && want_vir) block_accumulate<6>(acc_t, red, scalars + ADMP_S_TK);
+}
+
+// ------------------------------------------------------------------------------------------ Z passes (contiguous lines)
+// thread = (butterfly fastest, line); line-major tile [TL][LS] in shared memory, M = R1*R2*R3 = K3/2.
+template <int M> struct ZGeom {
+    static constexpr int LS = (M + 1) | 1;        // holds the M+1 half-spectrum points of a line; odd stride
+};
+
+// forward: K3 reals per line -> K3/2+1 complex (packed real FFT, tools/fft_model.py r2c)
+template <typename T, int R1, int R2, int R3, int TL, int JT>
+__global__ void __launch_bounds__(TL* JT)
+fast_z_fwd_kernel(int nlines, int ntiles, const T* __restrict__ mesh, cx<T>* __restrict__ spec, const cx<T>* __restrict__ gtw) {
+    constexpr int M = R1 * R2 * R3, K3 = 2 * M, K3h = M + 1, LS = ZGeom<M>::LS, TILE = TL * LS, NT = TL * JT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cx<T>* I0 = reinterpret_cast<cx<T>*>(smem_raw);
+    cx<T>* I1 = I0 + TILE;
+    cx<T>* A = I1 + TILE;
+    cx<T>* tw2 = A + TILE;
+    cx<T>* tw3 = tw2 + TwGeom<R1, R2, R3>::N2;
+    cx<T>* zt = tw3 + TwGeom<R1, R2, R3>::N3;       // M+1 entries: exp(-2 pi i k / K3)
+    const int j = threadIdx.x % JT, l = threadIdx.x / JT;
+    auto issue = [&](int tile, cx<T>* dst) {
+        const int L0 = tile * TL;
+        const int nl = min(TL, nlines - L0);
+        const cx<T>* src = reinterpret_cast<const cx<T>*>(mesh + (size_t)L0 * K3);
+        for (int e = threadIdx.x; e < nl * M; e += NT) {
+            const int ll = e / M, pos = e - ll * M;
+            cp_async<sizeof(cx<T>)>(dst + ll * LS + pos, src + e);
+        }
+        cp_async_commit();
+    };
+    int tile = blockIdx.x;
+    if (tile < ntiles) issue(tile, I0);
+    build_twiddles<T, R1, R2, R3, 2>(tw2, tw3, gtw, NT);
+    for (int i = threadIdx.x; i < K3h; i += NT) zt[i] = gtw[i];
+    for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+        cx<T>* cur = (it & 1) ? I1 : I0;
+        cx<T>* nxt = (it & 1) ? I0 : I1;
+        cp_async_wait_all();
+        __syncthreads();
+        if (tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x, nxt);
+        const int L0 = tile * TL;
+        const int nl = min(TL, nlines - L0);
+        const bool live = l < nl;
+        cx<T>* a = A + l * LS;
+        cx<T>* c = cur + l * LS;
+        // the transformed line Z ends in A for three stages, in cur for two
+        cx<T>* z = (R3 == 1) ? c : a;
+        fft_rotate<T, R1, R2, R3, 1, JT>(
+            j, live, tw2, tw3,
+            [&](int pos) { return c[pos]; }, [&](int pos, cx<T> v) { a[pos] = v; },
+            [&](int pos) { return a[pos]; }, [&](int pos, cx<T> v) { c[pos] = v; },
+            [&](int pos) { return c[pos]; }, [&](int pos, cx<T> v) { z[pos] = v; });
+        __syncthreads();
+        const cx<T>* Z = (R3 == 1) ? cur : A;
+        cx<T>* dst = spec + (size_t)L0 * K3h;
+        for (int e = threadIdx.x; e < nl * K3h; e += NT) {
+            const int ll = e / K3h, k = e - ll * K3h;
+            const cx<T> zk = Z[ll * LS + (k == M ? 0 : k)];
+            cx<T> zc = Z[ll * LS + ((k == 0 || k == M) ? 0 : M - k)];
+            zc.y = -zc.y;
+            const cx<T> s = {(T)0.5 * (zk.x + zc.x), (T)0.5 * (zk.y + zc.y)}, d = {(T)0.5 * (zk.x - zc.x), (T)0.5 * (zk.y - zc.y)};
+            const cx<T> tw = zt[k];                                   // (cos phi, -sin phi), phi = 2 pi k / K3
+            const cx<T> f = {tw.y, -tw.x};                            // X = s + (-sin phi - i cos phi) d
+            dst[e] = s + cmul(f, d);
+        }
+    }
+}
+
+// inverse: K3/2+1 complex -> K3 reals, unnormalised (tools/fft_model.py c2r)
+template <typename T, int R1, int R2, int R3, int TL, int JT>
+__global__ void __launch_bounds__(TL* JT)
+fast_z_inv_kernel(int nlines, int ntiles, const cx<T>* __restrict__ spec, T* __restrict__ mesh, const cx<T>* __restrict__ gtw) {
+    constexpr int M = R1 * R2 * R3, K3 = 2 * M, K3h = M + 1, LS = ZGeom<M>::LS, TILE = TL * LS, NT = TL * JT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cx<T>* I0 = reinterpret_cast<cx<T>*>(smem_raw);
+    cx<T>* I1 = I0 + TILE;
+    cx<T>* A = I1 + TILE;
+    cx<T>* tw2 = A + TILE;
+    cx<T>* tw3 = tw2 + TwGeom<R1, R2, R3>::N2;
+    cx<T>* zt = tw3 + TwGeom<R1, R2, R3>::N3;
+    const int j = threadIdx.x % JT, l = threadIdx.x / JT;
+    auto issue = [&](int tile, cx<T>* dst) {
+        const int L0 = tile * TL;
+        const int nl = min(TL, nlines - L0);
+        const cx<T>* src = spec + (size_t)L0 * K3h;
+        for (int e = threadIdx.x; e < nl * K3h; e += NT) {
+            const int ll = e / K3h, k = e - ll * K3h;
+            cp_async<sizeof(cx<T>)>(dst + ll * LS + k, src + e);
+        }
+        cp_async_commit();
+    };
+    int tile = blockIdx.x;
+    if (tile < ntiles) issue(tile, I0);
+    build_twiddles<T, R1, R2, R3, 2>(tw2, tw3, gtw, NT);
+    for (int i = threadIdx.x; i < K3h; i += NT) zt[i] = gtw[i];
+    for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+        cx<T>* cur = (it & 1) ? I1 : I0;
+        cx<T>* nxt = (it & 1) ? I0 : I1;
+        cp_async_wait_all();
+        __syncthreads();
+        if (tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x, nxt);
+        const int L0 = tile * TL;
+        const bool live = l < nlines - L0;
+        cx<T>* a = A + l * LS;
+        cx<T>* c = cur + l * LS;
+        cx<T>* line = reinterpret_cast<cx<T>*>(mesh + (size_t)(L0 + l) * K3);
+        fft_rotate<T, R1, R2, R3, -1, JT>(
+            j, live, tw2, tw3,
+            [&](int k) {
+                const cx<T> xk = c[k];
+                cx<T> xc = c[M - k];
+                xc.y = -xc.y;
+                const cx<T> s = xk + xc, d = xk - xc;
+                const cx<T> tw = zt[k];                               // conj gives (cos phi, +sin phi)
+                const cx<T> f = {tw.y, tw.x};                         // Z = s + (-sin phi + i cos phi) d
+                return s + cmul(f, d);
+            },
+            [&](int pos, cx<T> v) { a[pos] = v; },
+            [&](int pos) { return a[pos]; }, [&](int pos, cx<T> v) { c[pos] = v; },
+            [&](int pos) { return c[pos]; }, [&](int pos, cx<T> v) { line[pos] = v; });
+    }
+}
+
+// ------------------------------------------------------------------------------------------ configuration table
+// (R1, R2, R3 | strided: TL, JT | z (when the size is K3/2): TL, JT); line counts are for double, float doubles TL.
+// Two tile widths for the large sizes: the wide one keeps 128-byte global segments, the narrow one lets
+// more blocks share an SM (shared memory: 3 * N * TL * 16 B). `pick` selects (ADMP_FFT_WIDE=1 -> wide).
+#define ADMP_FAST_LIST(X)            \
+    X(0, 11, 7, 1, 8, 7, 16, 7)      \
+    X(1, 11, 14, 1, 8, 14, 8, 14)    \
+    X(2, 11, 7, 4, 4, 28, 4, 28)     \
+    X(3, 11, 7, 4, 8, 28, 8, 28)     \
+    X(4, 11, 7, 8, 2, 56, 2, 56)     \
+    X(5, 11, 7, 8, 4, 56, 4, 56)     \
+    X(6, 11, 14, 8, 2, 56, 2, 56)
+
+struct FastOps {
+    int N, TL, threads, zTL, zthreads;
+    size_t smem, smem_x, zsmem;
+    int occ[6];      // strided fwd, strided inv, x conv (quick), z fwd, z inv, x conv (general)
+    void (*prepare)(FastOps&);
+    void (*strided)(cudaStream_t, int sign, const StrideGeom&, int ntiles, int grid, void* spec, const void* tw);
+    void (*xconv)(cudaStream_t, const StrideGeom&, int ntiles, int grid, const BoxInfo*, double kappa, int kind, const ConvTables&,
+                  void* spec, const void* tw, double* scalars, int want_vir);
+    void (*zfwd)(cudaStream_t, int nlines, int ntiles, int grid, const void* mesh, void* spec, const void* tw);
+    void (*zinv)(cudaStream_t, int nlines, int ntiles, int grid, const void* spec, void* mesh, const void* tw);
+};
+
+template <typename K>
+static int prep_kernel(K kern, int threads, size_t smem) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return occ;
+}
+
+template <typename T, int R1, int R2, int R3, int TLd, int JT, int ZTLd, int ZJT>
+struct FastImpl {
+    static constexpr int N = R1 * R2 * R3;
+    static constexpr int TL = TLd * (sizeof(T) == 4 ? 2 : 1), ZTL = ZTLd * (sizeof(T) == 4 ? 2 : 1);
+    static void prepare(FastOps& o) {
+        o.occ[0] = prep_kernel(fast_strided_kernel<T, R1, R2, R3, 1, TL, JT>, o.threads, o.smem);
+        o.occ[1] = prep_kernel(fast_strided_kernel<T, R1, R2, R3, -1, TL, JT>, o.threads, o.smem);
+        o.occ[2] = prep_kernel(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, true>, o.threads, o.smem_x);
+        o.occ[5] = prep_kernel(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, false>, o.threads, o.smem_x);
+        o.occ[3] = prep_kernel(fast_z_fwd_kernel<T, R1, R2, R3, ZTL, ZJT>, o.zthreads, o.zsmem);
+        o.occ[4] = prep_kernel(fast_z_inv_kernel<T, R1, R2, R3, ZTL, ZJT>, o.zthreads, o.zsmem);
+    }
+    static void strided(cudaStream_t st, int sign, const StrideGeom& g, int ntiles, int grid, void* spec, const void* tw) {
+        const size_t smem = (size_t)(3 * N * TL + TwGeom<R1, R2, R3>::TOTAL) * sizeof(cx<T>);
+        if (sign > 0) fast_strided_kernel<T, R1, R2, R3, 1, TL, JT><<<grid, TL * JT, smem, st>>>(g, ntiles, (cx<T>*)spec, (const cx<T>*)tw);
+        else fast_strided_kernel<T, R1, R2, R3, -1, TL, JT><<<grid, TL * JT, smem, st>>>(g, ntiles, (cx<T>*)spec, (const cx<T>*)tw);
+    }
+    static void xconv(cudaStream_t st, const StrideGeom& g, int ntiles, int grid, const BoxInfo* B, double kappa, int kind,
+                      const ConvTables& tb, void* spec, const void* tw, double* scalars, int want_vir) {
+        const size_t smem = (size_t)(3 * N * TL + TwGeom<R1, R2, R3>::TOTAL) * sizeof(cx<T>) + 2 * N * sizeof(double);
+        if (kind == ADMP_CK_COULOMB && !want_vir)
+            fast_x_conv_kernel<T, R1, R2, R3, TL, JT, true><<<grid, TL * JT, smem, st>>>(g, ntiles, B, (T)kappa, kind, tb, (cx<T>*)spec,
+                                                                                        (const cx<T>*)tw, scalars, want_vir);
+        else
+            fast_x_conv_kernel<T, R1, R2, R3, TL, JT, false><<<grid, TL * JT, smem, st>>>(g, ntiles, B, (T)kappa, kind, tb, (cx<T>*)spec,
+                                                                                         (const cx<T>*)tw, scalars, want_vir);
+    }
+    static void zfwd(cudaStream_t st, int nlines, int ntiles, int grid, const void* mesh, void* spec, const void* tw) {
+        const size_t smem = (size_t)(3 * ZTL * ZGeom<N>::LS + TwGeom<R1, R2, R3>::TOTAL + N + 1) * sizeof(cx<T>);
+        fast_z_fwd_kernel<T, R1, R2, R3, ZTL, ZJT><<<grid, ZTL * ZJT, smem, st>>>(nlines, ntiles, (const T*)mesh, (cx<T>*)spec, (const cx<T>*)tw);
+    }
+    static void zinv(cudaStream_t st, int nlines, int ntiles, int grid, const void* spec, void* mesh, const void* tw) {
+        const size_t smem = (size_t)(3 * ZTL * ZGeom<N>::LS + TwGeom<R1, R2, R3>::TOTAL + N + 1) * sizeof(cx<T>);
+        fast_z_inv_kernel<T, R1, R2, R3, ZTL, ZJT><<<grid, ZTL * ZJT, smem, st>>>(nlines, ntiles, (const cx<T>*)spec, (T*)mesh, (const cx<T>*)tw);
+    }
+    static FastOps ops() {
+        FastOps o = {};
+        o.N = N; o.TL = TL; o.threads = TL * JT; o.zTL = ZTL; o.zthreads = ZTL * ZJT;
+        o.smem = (size_t)(3 * N * TL + TwGeom<R1, R2, R3>::TOTAL) * sizeof(cx<T>);
+        o.smem_x = o.smem + 2 * N * sizeof(double);
+        o.zsmem = (size_t)(3 * ZTL * ZGeom<N>::LS + TwGeom<R1, R2, R3>::TOTAL + N + 1) * sizeof(cx<T>);
+        o.prepare = &prepare; o.strided = &strided; o.xconv = &xconv; o.zfwd = &zfwd; o.zinv = &zinv;
+        return o;
+    }
+};
+
+// the table entries for (size N, element size); wide = prefer the wider tile when two are listed
+template <typename T>
+static bool fast_lookup(int N, bool wide, FastOps& out) {
+    bool found = false;
+#define X(id, a, b, c, tl, jt, ztl, zjt)                                                   \
+    if (N == (a) * (b) * (c) && (!found || wide)) { out = FastImpl<T, a, b, c, tl, jt, ztl, zjt>::ops(); found = true; }
+    ADMP_FAST_LIST(X)
+#undef X
+    return found;
+}

@@ -47,6 +47,9 @@ def timed(name, fn):
 timed('spread (zero + scatter)', lambda: cx.lib.admp_pme_spread(cx.handle, sp(), p(pos), p(box), p(M), 10, 10, None))
 if cx.lib.admp_ctx_fft_backend(cx.handle):
     timed('fused fft+convolve roundtrip', lambda: cx.lib.admp_pme_fft_convolve(cx.handle, sp(), _lib.CK_COULOMB, 0, p(scal)))
+if cx.lib.admp_ctx_fft_backend(cx.handle):
+    for k, nm in enumerate(['pass z_fwd', 'pass y_fwd', 'pass x_conv', 'pass y_inv', 'pass z_inv']):
+        timed(nm, lambda k=k: cx.lib.admp_pme_fft_pass(cx.handle, sp(), k, _lib.CK_COULOMB, p(scal)))
 timed('fft forward', lambda: cx.lib.admp_pme_fft(cx.handle, sp(), 0))
 timed('fft inverse', lambda: cx.lib.admp_pme_fft(cx.handle, sp(), 1))
 timed('gather (full)', lambda: cx.lib.admp_pme_gather(cx.handle, sp(), p(pos), p(M), 10, 10, None, 0, _lib.WANT_GRAD, p(dpos), p(G), 10,
