@@ -74,7 +74,8 @@ struct admp_ctx {
     // SCF graph cache
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;
-    cudaStream_t cap_stream = nullptr;
+    cudaStream_t cap_stream = nullptr, side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int g_maxiter = -1;
     double g_thresh = -1.0;
     uint32_t g_flags = 0;
@@ -121,6 +122,9 @@ extern "C" int admp_ctx_create(admp_ctx** out, int device, int dtype) {
     CK(cudaMalloc(&c->s_box, 9 * 8));
     CK(cudaMallocHost(&c->h_state, sizeof(int32_t) * 8));
     CK(cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     c->ws_bytes = sizeof(BoxInfo) + sizeof(double) * ADMP_S_COUNT + 256;
     *out = c;
     return 0;
@@ -152,6 +156,9 @@ extern "C" int admp_ctx_destroy(admp_ctx* c) {
     dfree(c->nb.cell_of); dfree(c->nb.cell_count); dfree(c->nb.cell_start); dfree(c->nb.sorted); dfree(c->nb.nbr_count); dfree(c->nb.nbr_start);
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
+    if (c->side_stream) cudaStreamDestroy(c->side_stream);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     delete c;
     return 0;
 }
@@ -571,8 +578,8 @@ extern "C" int admp_scf_step(admp_ctx* c, void* stream, const void* M, void* U, 
     memset(&none, 0, sizeof(none));
     CK(cudaMemsetAsync(scalars + ADMP_S_MAXFIELD, 0, sizeof(double), st));
     DISPATCH(c, launch_scf_field, st, c->n_atoms, c->kappa, M, U, pol, F, scalars);
-    launch_scf_decide(st, state, scalars, maxiter, thresh, none, 0);
-    DISPATCH(c, launch_scf_update, st, c->n_atoms, state, F, pol, U, scalars);
+    launch_scf_decide(st, state, scalars, maxiter, thresh, 1, none, 0);
+    DISPATCH(c, launch_scf_update, st, c->n_atoms, state, F, pol, U, 0);
     CKLAUNCH();
     return 0;
 }
@@ -584,16 +591,26 @@ extern "C" int admp_virial_finalize(admp_ctx* c, void* stream, double* scalars) 
 }
 
 // ------------------------------------------------------------------------------------------ fused evaluation
-// one pass of optimize_Uind's loop body on staged inputs (admp/pme.py:132-138)
+// one pass of optimize_Uind's loop body on staged inputs (admp/pme.py:132-138). The reciprocal chain
+// (zero-fill, spread, five FFT passes, field gather) and the real-space pair field are independent: the
+// pair kernel runs on a forked stream (a parallel branch of the captured graph) and both accumulate dE/dU
+// into Fscf with atomics (Fscf is zero on entry: initial memset, then scf_update_kernel re-zeroes it).
+// SCF cycles never accumulate the k-space virial sums (Coulomb QUICK path of the fused X pass); when the
+// caller wants the virial, admp_pme_eval runs one more reciprocal pass after the loop, which also serves
+// as the refresh pass after the last update (refresh_in_loop = 0).
 static int scf_body(admp_ctx* c, cudaStream_t st, int maxiter, double thresh, uint32_t flags, cudaGraphConditionalHandle h, int use_h) {
-    launch_scf_rearm(st, c->scal);
-    if (recip_field(c, st, c->s_pos, c->M, 10, 10, c->s_U, ADMP_CK_COULOMB, c->scal, (flags & ADMP_WANT_VIRIAL) ? 1 : 0, false)) return 1;
+    const int refresh_in_loop = (flags & ADMP_WANT_VIRIAL) ? 0 : 1;
+    CK(cudaEventRecord(c->ev_fork, st));
+    CK(cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
+    DISPATCH(c, launch_pme_pair, c->side_stream, c->pairs_cap, c->n_atoms, c->box, c->kappa, c->s_pos, c->s_pairs, c->cov_off, c->cov_idx,
+             c->cov_nb, c->M, c->s_U, c->s_pol, c->s_th, c->s_mS, c->s_pS, 1, 0u, nullptr, nullptr, c->Fscf, nullptr, nullptr, c->scal);
+    CK(cudaEventRecord(c->ev_join, c->side_stream));
+    if (recip_field(c, st, c->s_pos, c->M, 10, 10, c->s_U, ADMP_CK_COULOMB, c->scal, 0, false)) return 1;
     DISPATCH(c, launch_gather, st, c->n_atoms, c->box, c->s_pos, c->M, 10, 10, c->s_U, c->mesh, 1, 0u, nullptr, nullptr, 10, c->Fscf, c->scal);
-    DISPATCH(c, launch_pme_pair, st, c->pairs_cap, c->n_atoms, c->box, c->kappa, c->s_pos, c->s_pairs, c->cov_off, c->cov_idx, c->cov_nb,
-             c->M, c->s_U, c->s_pol, c->s_th, c->s_mS, c->s_pS, 1, 0u, nullptr, nullptr, c->Fscf, nullptr, nullptr, c->scal);
+    CK(cudaStreamWaitEvent(st, c->ev_join, 0));
     DISPATCH(c, launch_scf_field, st, c->n_atoms, c->kappa, c->M, c->s_U, c->s_pol, c->Fscf, c->scal);
-    launch_scf_decide(st, c->state, c->scal, maxiter, thresh, h, use_h);
-    DISPATCH(c, launch_scf_update, st, c->n_atoms, c->state, c->Fscf, c->s_pol, c->s_U, c->scal);
+    launch_scf_decide(st, c->state, c->scal, maxiter, thresh, refresh_in_loop, h, use_h);
+    DISPATCH(c, launch_scf_update, st, c->n_atoms, c->state, c->Fscf, c->s_pol, c->s_U, 1);
     CKLAUNCH();
     return 0;
 }
@@ -703,7 +720,14 @@ extern "C" int admp_pme_eval(admp_ctx* c, void* stream, const void* pos, const v
     CKLAUNCH();
     const int want_vir = (flags & ADMP_WANT_VIRIAL) ? 1 : 0;
     if (polz && (flags & ADMP_SCF)) {
+        CK(cudaMemsetAsync(c->Fscf, 0, (size_t)n * 3 * w, st));
         if (run_scf(c, st, maxiter, thresh, flags)) return 1;
+        if (want_vir) {
+            // final reciprocal pass on the converged / last-updated U with the k-space virial sums
+            CK(cudaMemsetAsync(c->scal + ADMP_S_E_RECIP, 0, sizeof(double), st));
+            CK(cudaMemsetAsync(c->scal + ADMP_S_TK, 0, 6 * sizeof(double), st));
+            if (recip_field(c, st, c->s_pos, c->M, 10, 10, c->s_U, ADMP_CK_COULOMB, c->scal, 1, false)) return 1;
+        }
         if (scf_out) CK(cudaMemcpyAsync(scf_out, c->state + 3, sizeof(int32_t) * 2, cudaMemcpyDeviceToDevice, st));
         CK(cudaMemcpyAsync(U_io, c->s_U, (size_t)n * 3 * w, cudaMemcpyDeviceToDevice, st));
     } else {

@@ -64,11 +64,10 @@ template <typename T>
 void launch_disp_self(cudaStream_t st, int n, double kappa, int pmax, const void* c_list, uint32_t flags, void* dc, double* scalars);
 template <typename T>
 void launch_scf_field(cudaStream_t st, int n, double kappa, const void* M, const void* U, const void* pol, void* F, double* scalars);
-void launch_scf_decide(cudaStream_t st, int32_t* state, double* scalars, int maxiter, double thresh,
+void launch_scf_decide(cudaStream_t st, int32_t* state, double* scalars, int maxiter, double thresh, int refresh_in_loop,
                        cudaGraphConditionalHandle handle, int use_handle);
 template <typename T>
-void launch_scf_update(cudaStream_t st, int n, const int32_t* state, const void* F, const void* pol, void* U, double* scalars);
-void launch_scf_rearm(cudaStream_t st, double* scalars);
+void launch_scf_update(cudaStream_t st, int n, const int32_t* state, void* F, const void* pol, void* U, int zero_F);
 void launch_virial_finalize(cudaStream_t st, const BoxInfo* B, double* scalars);
 
 // nblist.cu

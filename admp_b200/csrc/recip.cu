@@ -208,164 +208,191 @@ convolve_kernel(const BoxInfo* __restrict__ Bp, T kappa, int kind, ConvTables tb
 }
 
 // ---------------------------------------------------------------------------- gather
-constexpr int GATHER_WARPS = 4;
+constexpr int GATHER_LPA = 4;                       // lanes per atom: 36 (x, y) stencil columns = 9 per lane
+constexpr int GATHER_APB = 128 / GATHER_LPA;        // atoms per 128-thread block
 
-// MODE 0: everything (dE/dM, dE/dr, dE/dNstar).  MODE 1: field only (dE/dmu -> F).
-// One warp per atom; each lane owns a strided subset of the 216 points, partial sums of
-// phi * W[p1,p2,p3] are warp-reduced.
+// MODE 0: everything (dE/dM, dE/dr, dE/dNstar).  MODE 1: field only (dE/dmu accumulated into F).
+// Four lanes per atom, each lane owns 9 of the 36 (ia, ib) stencil columns. A column is 6 consecutive mesh
+// points in z (one 48-byte segment); the stencil sum is evaluated separably:
+//   S_p3 = sum_ic phi[ia, ib, ic] * d^p3 M6(z)[ic] ;  P[p1 p2 p3] += d^p1 M6(x)[ia] * d^p2 M6(y)[ib] * S_p3
+// (54 FMA-class operations per column instead of ~50 per mesh point), then two shuffle steps reduce the
+// 20 (4 in field mode) partial sums over the four lanes and lane 0 of the group does the per-atom algebra.
 template <typename T, bool MULTIPOLE, int MODE>
-__global__ void __launch_bounds__(GATHER_WARPS * 32)
+__global__ void __launch_bounds__(128)
 gather_kernel(int n, const BoxInfo* __restrict__ Bp, const T* __restrict__ pos, const T* __restrict__ M, int m_stride,
               const T* __restrict__ U, const T* __restrict__ phi, uint32_t flags, T* __restrict__ dpos, T* __restrict__ G,
               int g_stride, T* __restrict__ F, double* __restrict__ scalars) {
     constexpr int NP = (MODE == 1) ? 2 : (MULTIPOLE ? 4 : 2);
-    __shared__ T sw[GATHER_WARPS][3][6 * NP];
-    __shared__ int si[GATHER_WARPS][3];
-    __shared__ double red[9 * GATHER_WARPS];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int a = blockIdx.x * GATHER_WARPS + warp;
+    __shared__ T sw[GATHER_APB][3][6 * NP];
+    __shared__ int si[GATHER_APB][3];
+    __shared__ double red[9 * 4];
+    const int lane = threadIdx.x & 31;
+    const int sub = lane & (GATHER_LPA - 1);
+    const int slot = threadIdx.x / GATHER_LPA;
+    const int a = blockIdx.x * GATHER_APB + slot;
     const BoxInfo& B = *Bp;
     const bool want_vir = (flags & ADMP_WANT_VIRIAL) != 0 && MODE == 0;
     double wacc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    if (a < n) {
-        if (lane < 3) {
-            double f; int i0;
-            mesh_anchor(B, (double)pos[3 * a], (double)pos[3 * a + 1], (double)pos[3 * a + 2], lane, f, i0);
-            bspline6<T, NP>((T)f, sw[warp][lane]);
-            si[warp][lane] = i0;
-        }
-        __syncwarp();
-        const T* w0 = sw[warp][0];
-        const T* w1 = sw[warp][1];
-        const T* w2 = sw[warp][2];
-        const int K1 = B.K[0], K2 = B.K[1], K3 = B.K[2];
-        const int i0 = si[warp][0], j0 = si[warp][1], k0 = si[warp][2];
-        // P index = p1*16 + p2*4 + p3 compressed to the combos with p1+p2+p3 <= NP-1
-        constexpr int NC = (NP == 4) ? 20 : 4;
-        T P[NC];
+    const bool valid = a < n;
+    if (valid && sub < 3) {
+        double f; int i0;
+        mesh_anchor(B, (double)pos[3 * a], (double)pos[3 * a + 1], (double)pos[3 * a + 2], sub, f, i0);
+        bspline6<T, NP>((T)f, sw[slot][sub]);
+        si[slot][sub] = i0;
+    }
+    __syncwarp();
+    // P index = derivative orders (p1 p2 p3) with p1+p2+p3 <= NP-1, in the order listed below
+    constexpr int NC = (NP == 4) ? 20 : 4;
+    T P[NC];
 #pragma unroll
-        for (int k = 0; k < NC; ++k) P[k] = (T)0;
-        for (int pt = lane; pt < 216; pt += 32) {
-            const int ia = pt / 36, ib = (pt / 6) % 6, ic = pt % 6;
+    for (int k = 0; k < NC; ++k) P[k] = (T)0;
+    if (valid) {
+        const T* w0 = sw[slot][0];
+        const T* w1 = sw[slot][1];
+        const T* w2 = sw[slot][2];
+        const int K1 = B.K[0], K2 = B.K[1], K3 = B.K[2];
+        const int i0 = si[slot][0], j0 = si[slot][1], k0 = si[slot][2];
+        const bool wrap = k0 + 5 >= K3;
+#pragma unroll
+        for (int c = 0; c < 36 / GATHER_LPA; ++c) {
+            const int col = sub + GATHER_LPA * c;
+            const int ia = col / 6, ib = col - 6 * ia;
             int gi = i0 + ia; if (gi >= K1) gi -= K1;
             int gj = j0 + ib; if (gj >= K2) gj -= K2;
-            int gk = k0 + ic; if (gk >= K3) gk -= K3;
-            const T ph = phi[((size_t)gi * K2 + gj) * K3 + gk];
+            const T* line = phi + ((size_t)gi * K2 + gj) * K3;
+            T ph[6];
+            if (!wrap) {
+#pragma unroll
+                for (int ic = 0; ic < 6; ++ic) ph[ic] = line[k0 + ic];
+            } else {
+#pragma unroll
+                for (int ic = 0; ic < 6; ++ic) { int gk = k0 + ic; if (gk >= K3) gk -= K3; ph[ic] = line[gk]; }
+            }
+            T S[NP];
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                T s = ph[0] * w2[6 * q];
+#pragma unroll
+                for (int ic = 1; ic < 6; ++ic) s += ph[ic] * w2[6 * q + ic];
+                S[q] = s;
+            }
             if (NP == 4) {
                 const T a0 = w0[ia], a1 = w0[6 + ia], a2 = w0[12 + ia], a3 = w0[18 + ia];
                 const T b0 = w1[ib], b1 = w1[6 + ib], b2 = w1[12 + ib], b3 = w1[18 + ib];
-                const T c0 = ph * w2[ic], c1 = ph * w2[6 + ic], c2 = ph * w2[12 + ic], c3 = ph * w2[18 + ic];
                 const T ab00 = a0 * b0, ab10 = a1 * b0, ab01 = a0 * b1, ab20 = a2 * b0, ab11 = a1 * b1, ab02 = a0 * b2;
-                P[0] += ab00 * c0;                       // 000
-                P[1] += ab10 * c0; P[2] += ab01 * c0; P[3] += ab00 * c1;                   // 100 010 001
-                P[4] += ab20 * c0; P[5] += ab11 * c0; P[6] += ab10 * c1;                   // 200 110 101
-                P[7] += ab02 * c0; P[8] += ab01 * c1; P[9] += ab00 * c2;                   // 020 011 002
-                P[10] += a3 * b0 * c0; P[11] += a2 * b1 * c0; P[12] += ab20 * c1;           // 300 210 201
-                P[13] += a1 * b2 * c0; P[14] += ab11 * c1; P[15] += ab10 * c2;             // 120 111 102
-                P[16] += a0 * b3 * c0; P[17] += ab02 * c1; P[18] += ab01 * c2; P[19] += ab00 * c3;   // 030 021 012 003
+                P[0] += ab00 * S[0];                                                              // 000
+                P[1] += ab10 * S[0]; P[2] += ab01 * S[0]; P[3] += ab00 * S[1];                     // 100 010 001
+                P[4] += ab20 * S[0]; P[5] += ab11 * S[0]; P[6] += ab10 * S[1];                     // 200 110 101
+                P[7] += ab02 * S[0]; P[8] += ab01 * S[1]; P[9] += ab00 * S[2];                     // 020 011 002
+                P[10] += a3 * b0 * S[0]; P[11] += a2 * b1 * S[0]; P[12] += ab20 * S[1];            // 300 210 201
+                P[13] += a1 * b2 * S[0]; P[14] += ab11 * S[1]; P[15] += ab10 * S[2];               // 120 111 102
+                P[16] += a0 * b3 * S[0]; P[17] += ab02 * S[1]; P[18] += ab01 * S[2]; P[19] += ab00 * S[3];   // 030 021 012 003
             } else {
                 const T a0 = w0[ia], a1 = w0[6 + ia], b0 = w1[ib], b1 = w1[6 + ib];
-                const T c0 = ph * w2[ic], c1 = ph * w2[6 + ic];
-                P[0] += a0 * b0 * c0; P[1] += a1 * b0 * c0; P[2] += a0 * b1 * c0; P[3] += a0 * b0 * c1;
+                const T ab00 = a0 * b0;
+                P[0] += ab00 * S[0]; P[1] += a1 * b0 * S[0]; P[2] += a0 * b1 * S[0]; P[3] += ab00 * S[1];
             }
         }
+    }
 #pragma unroll
-        for (int k = 0; k < NC; ++k) P[k] = warp_sum(P[k]);
-        if (lane == 0) {
-            T N[9];
+    for (int k = 0; k < NC; ++k) {
+        P[k] += __shfl_xor_sync(0xffffffffu, P[k], 1);
+        P[k] += __shfl_xor_sync(0xffffffffu, P[k], 2);
+    }
+    if (valid && sub == 0) {
+        T N[9];
 #pragma unroll
-            for (int k = 0; k < 9; ++k) N[k] = (T)B.nstar[k];
-            const T ph1[3] = {P[1], P[2], P[3]};
-            if (MODE == 1) {
-                // dE/dmu_c = -sum_d N[d][c] ph1[d]
+        for (int k = 0; k < 9; ++k) N[k] = (T)B.nstar[k];
+        const T ph1[3] = {P[1], P[2], P[3]};
+        if (MODE == 1) {
+            // dE/dmu_c = -sum_d N[d][c] ph1[d]
 #pragma unroll
-                for (int c = 0; c < 3; ++c) F[(size_t)a * 3 + c] = -(N[c] * ph1[0] + N[3 + c] * ph1[1] + N[6 + c] * ph1[2]);
-            } else if (!MULTIPOLE) {
-                const T q = M[(size_t)a * m_stride];
-                if (G != nullptr) atomicAdd(G + (size_t)a * g_stride, P[0]);
-                T dEdu[3] = {q * ph1[0], q * ph1[1], q * ph1[2]};
-                if (dpos != nullptr) {
+            for (int c = 0; c < 3; ++c) atomicAdd(F + (size_t)a * 3 + c, -(N[c] * ph1[0] + N[3 + c] * ph1[1] + N[6 + c] * ph1[2]));
+        } else if (!MULTIPOLE) {
+            const T q = M[(size_t)a * m_stride];
+            if (G != nullptr) atomicAdd(G + (size_t)a * g_stride, P[0]);
+            T dEdu[3] = {q * ph1[0], q * ph1[1], q * ph1[2]};
+            if (dpos != nullptr) {
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) atomicAdd(dpos + (size_t)a * 3 + c, -(N[c] * dEdu[0] + N[3 + c] * dEdu[1] + N[6 + c] * dEdu[2]));
-                }
-                if (want_vir) {
-#pragma unroll
-                    for (int d = 0; d < 3; ++d)
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) wacc[3 * d + c] = -(double)(dEdu[d] * pos[3 * a + c]);
-                }
-            } else {
-                const T* m = M + (size_t)a * m_stride;
-                const T q = m[0];
-                T mu[3] = {m[1], m[2], m[3]};
-                if (U != nullptr) { mu[0] += U[3 * a]; mu[1] += U[3 * a + 1]; mu[2] += U[3 * a + 2]; }
-                const T Tm[9] = {m[4], m[5], m[6], m[5], m[7], m[8], m[6], m[8], m[9]};
-                // symmetric second / third derivative tables
-                const T ph2[9] = {P[4], P[5], P[6], P[5], P[7], P[8], P[6], P[8], P[9]};
-                // ph3[d][e][f]: index by sorted multiset
-                auto p3 = [&](int d, int e, int f) -> T {
-                    const int c0 = (d == 0) + (e == 0) + (f == 0), c1 = (d == 1) + (e == 1) + (f == 1);
-                    // (c0,c1,c2) -> slot
-                    if (c0 == 3) return P[10]; if (c0 == 2 && c1 == 1) return P[11]; if (c0 == 2) return P[12];
-                    if (c0 == 1 && c1 == 2) return P[13]; if (c0 == 1 && c1 == 1) return P[14]; if (c0 == 1) return P[15];
-                    if (c1 == 3) return P[16]; if (c1 == 2) return P[17]; if (c1 == 1) return P[18]; return P[19];
-                };
-                T muf[3], NT[9], Tf[9];
-#pragma unroll
-                for (int d = 0; d < 3; ++d) muf[d] = -(N[3 * d] * mu[0] + N[3 * d + 1] * mu[1] + N[3 * d + 2] * mu[2]);
+                for (int c = 0; c < 3; ++c) atomicAdd(dpos + (size_t)a * 3 + c, -(N[c] * dEdu[0] + N[3 + c] * dEdu[1] + N[6 + c] * dEdu[2]));
+            }
+            if (want_vir) {
 #pragma unroll
                 for (int d = 0; d < 3; ++d)
 #pragma unroll
-                    for (int b = 0; b < 3; ++b) NT[3 * d + b] = N[3 * d] * Tm[b] + N[3 * d + 1] * Tm[3 + b] + N[3 * d + 2] * Tm[6 + b];
+                    for (int c = 0; c < 3; ++c) wacc[3 * d + c] = -(double)(dEdu[d] * pos[3 * a + c]);
+            }
+        } else {
+            const T* m = M + (size_t)a * m_stride;
+            const T q = m[0];
+            T mu[3] = {m[1], m[2], m[3]};
+            if (U != nullptr) { mu[0] += U[3 * a]; mu[1] += U[3 * a + 1]; mu[2] += U[3 * a + 2]; }
+            const T Tm[9] = {m[4], m[5], m[6], m[5], m[7], m[8], m[6], m[8], m[9]};
+            // symmetric second / third derivative tables
+            const T ph2[9] = {P[4], P[5], P[6], P[5], P[7], P[8], P[6], P[8], P[9]};
+            // ph3[d][e][f]: index by sorted multiset
+            auto p3 = [&](int d, int e, int f) -> T {
+                const int c0 = (d == 0) + (e == 0) + (f == 0), c1 = (d == 1) + (e == 1) + (f == 1);
+                // (c0,c1,c2) -> slot
+                if (c0 == 3) return P[10]; if (c0 == 2 && c1 == 1) return P[11]; if (c0 == 2) return P[12];
+                if (c0 == 1 && c1 == 2) return P[13]; if (c0 == 1 && c1 == 1) return P[14]; if (c0 == 1) return P[15];
+                if (c1 == 3) return P[16]; if (c1 == 2) return P[17]; if (c1 == 1) return P[18]; return P[19];
+            };
+            T muf[3], NT[9], Tf[9];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) muf[d] = -(N[3 * d] * mu[0] + N[3 * d + 1] * mu[1] + N[3 * d + 2] * mu[2]);
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) NT[3 * d + b] = N[3 * d] * Tm[b] + N[3 * d + 1] * Tm[3 + b] + N[3 * d + 2] * Tm[6 + b];
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+#pragma unroll
+                for (int e = 0; e < 3; ++e)
+                    Tf[3 * d + e] = (NT[3 * d] * N[3 * e] + NT[3 * d + 1] * N[3 * e + 1] + NT[3 * d + 2] * N[3 * e + 2]) * (T)(1.0 / 3);
+            if (G != nullptr) {
+                T* g = G + (size_t)a * g_stride;
+                atomicAdd(g, P[0]);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) atomicAdd(g + 1 + c, -(N[c] * ph1[0] + N[3 + c] * ph1[1] + N[6 + c] * ph1[2]));
+                // Gm = N^T ph2 N / 3
+                T PN[9];
 #pragma unroll
                 for (int d = 0; d < 3; ++d)
 #pragma unroll
-                    for (int e = 0; e < 3; ++e)
-                        Tf[3 * d + e] = (NT[3 * d] * N[3 * e] + NT[3 * d + 1] * N[3 * e + 1] + NT[3 * d + 2] * N[3 * e + 2]) * (T)(1.0 / 3);
-                if (G != nullptr) {
-                    T* g = G + (size_t)a * g_stride;
-                    atomicAdd(g, P[0]);
+                    for (int b = 0; b < 3; ++b) PN[3 * d + b] = ph2[3 * d] * N[b] + ph2[3 * d + 1] * N[3 + b] + ph2[3 * d + 2] * N[6 + b];
+                auto gm = [&](int p, int b) { return (N[p] * PN[b] + N[3 + p] * PN[3 + b] + N[6 + p] * PN[6 + b]) * (T)(1.0 / 3); };
+                atomicAdd(g + 4, gm(0, 0)); atomicAdd(g + 5, 2 * gm(0, 1)); atomicAdd(g + 6, 2 * gm(0, 2));
+                atomicAdd(g + 7, gm(1, 1)); atomicAdd(g + 8, 2 * gm(1, 2)); atomicAdd(g + 9, gm(2, 2));
+            }
+            if (F != nullptr) {
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) atomicAdd(g + 1 + c, -(N[c] * ph1[0] + N[3 + c] * ph1[1] + N[6 + c] * ph1[2]));
-                    // Gm = N^T ph2 N / 3
-                    T PN[9];
+                for (int c = 0; c < 3; ++c) atomicAdd(F + (size_t)a * 3 + c, -(N[c] * ph1[0] + N[3 + c] * ph1[1] + N[6 + c] * ph1[2]));
+            }
+            T dEdu[3];
 #pragma unroll
-                    for (int d = 0; d < 3; ++d)
+            for (int d = 0; d < 3; ++d) {
+                T s = q * ph1[d];
 #pragma unroll
-                        for (int b = 0; b < 3; ++b) PN[3 * d + b] = ph2[3 * d] * N[b] + ph2[3 * d + 1] * N[3 + b] + ph2[3 * d + 2] * N[6 + b];
-                    auto gm = [&](int p, int b) { return (N[p] * PN[b] + N[3 + p] * PN[3 + b] + N[6 + p] * PN[6 + b]) * (T)(1.0 / 3); };
-                    atomicAdd(g + 4, gm(0, 0)); atomicAdd(g + 5, 2 * gm(0, 1)); atomicAdd(g + 6, 2 * gm(0, 2));
-                    atomicAdd(g + 7, gm(1, 1)); atomicAdd(g + 8, 2 * gm(1, 2)); atomicAdd(g + 9, gm(2, 2));
+                for (int e = 0; e < 3; ++e) {
+                    s += ph2[3 * d + e] * muf[e];
+#pragma unroll
+                    for (int f = 0; f < 3; ++f) s += p3(d, e, f) * Tf[3 * e + f];
                 }
-                if (F != nullptr) {
+                dEdu[d] = s;
+            }
+            if (dpos != nullptr) {
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) atomicAdd(F + (size_t)a * 3 + c, -(N[c] * ph1[0] + N[3 + c] * ph1[1] + N[6 + c] * ph1[2]));
-                }
-                T dEdu[3];
+                for (int c = 0; c < 3; ++c) atomicAdd(dpos + (size_t)a * 3 + c, -(N[c] * dEdu[0] + N[3 + c] * dEdu[1] + N[6 + c] * dEdu[2]));
+            }
+            if (want_vir) {
+                // W[d][c] = dEdu[d] (-r_c) + ph1[d] (-mu_c) + 2/3 sum_e ph2[d][e] (N T)[e][c]
 #pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                    T s = q * ph1[d];
+                for (int d = 0; d < 3; ++d)
 #pragma unroll
-                    for (int e = 0; e < 3; ++e) {
-                        s += ph2[3 * d + e] * muf[e];
-#pragma unroll
-                        for (int f = 0; f < 3; ++f) s += p3(d, e, f) * Tf[3 * e + f];
-                    }
-                    dEdu[d] = s;
-                }
-                if (dpos != nullptr) {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) atomicAdd(dpos + (size_t)a * 3 + c, -(N[c] * dEdu[0] + N[3 + c] * dEdu[1] + N[6 + c] * dEdu[2]));
-                }
-                if (want_vir) {
-                    // W[d][c] = dEdu[d] (-r_c) + ph1[d] (-mu_c) + 2/3 sum_e ph2[d][e] (N T)[e][c]
-#pragma unroll
-                    for (int d = 0; d < 3; ++d)
-#pragma unroll
-                        for (int c = 0; c < 3; ++c)
-                            wacc[3 * d + c] = (double)(-dEdu[d] * pos[3 * a + c] - ph1[d] * mu[c]
-                                + (T)(2.0 / 3) * (ph2[3 * d] * NT[c] + ph2[3 * d + 1] * NT[3 + c] + ph2[3 * d + 2] * NT[6 + c]));
-                }
+                    for (int c = 0; c < 3; ++c)
+                        wacc[3 * d + c] = (double)(-dEdu[d] * pos[3 * a + c] - ph1[d] * mu[c]
+                            + (T)(2.0 / 3) * (ph2[3 * d] * NT[c] + ph2[3 * d + 1] * NT[3 + c] + ph2[3 * d + 2] * NT[6 + c]));
             }
         }
     }
@@ -397,11 +424,11 @@ template <typename T>
 void launch_gather(cudaStream_t st, int n, const BoxInfo* B, const void* pos, const void* M, int m_cols, int m_stride, const void* U,
                    const void* phi, int mode, uint32_t flags, void* dpos, void* G, int g_stride, void* F, double* scalars) {
     if (n <= 0) return;
-    const unsigned grid = (n + GATHER_WARPS - 1) / GATHER_WARPS;
+    const unsigned grid = (n + GATHER_APB - 1) / GATHER_APB;
 #define ADMP_G_ARGS n, B, (const T*)pos, (const T*)M, m_stride, (const T*)U, (const T*)phi, flags, (T*)dpos, (T*)G, g_stride, (T*)F, scalars
-    if (mode == 1) gather_kernel<T, true, 1><<<grid, GATHER_WARPS * 32, 0, st>>>(ADMP_G_ARGS);
-    else if (m_cols >= 10) gather_kernel<T, true, 0><<<grid, GATHER_WARPS * 32, 0, st>>>(ADMP_G_ARGS);
-    else gather_kernel<T, false, 0><<<grid, GATHER_WARPS * 32, 0, st>>>(ADMP_G_ARGS);
+    if (mode == 1) gather_kernel<T, true, 1><<<grid, 128, 0, st>>>(ADMP_G_ARGS);
+    else if (m_cols >= 10) gather_kernel<T, true, 0><<<grid, 128, 0, st>>>(ADMP_G_ARGS);
+    else gather_kernel<T, false, 0><<<grid, 128, 0, st>>>(ADMP_G_ARGS);
 #undef ADMP_G_ARGS
 }
 #define ADMP_INST(T)                                                                                                              \

@@ -119,7 +119,7 @@ scf_field_kernel(int n, T kappa, const T* __restrict__ M, const T* __restrict__ 
 // the last iteration reports flag False. state: [0]=iter, [1]=do_update, [2]=final_pass,
 // [3]=n_cycle, [4]=converged, [5]=loop condition (mirrors the graph conditional handle).
 __global__ void scf_decide_kernel(int32_t* __restrict__ state, double* __restrict__ scalars, int maxiter, double thresh,
-                                  cudaGraphConditionalHandle handle, int use_handle) {
+                                  cudaGraphConditionalHandle handle, int use_handle, int refresh_in_loop) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     int cond = 0;
     if (state[2]) {                       // this pass only refreshed the field/mesh after the last update
@@ -131,12 +131,22 @@ __global__ void scf_decide_kernel(int32_t* __restrict__ state, double* __restric
             state[1] = 0; state[3] = it; state[4] = (it == maxiter - 1) ? 0 : 1;
         } else {
             state[1] = 1;
-            if (it == maxiter - 1) { state[3] = it; state[4] = 0; state[2] = 1; }
-            else state[0] = it + 1;
-            cond = 1;
+            if (it == maxiter - 1) {
+                // last allowed cycle: U is still updated (pme.py:138), flag False. The mesh of the updated U is
+                // rebuilt by one more pass of the loop body, or by the caller's final (virial) pass.
+                state[3] = it; state[4] = 0;
+                if (refresh_in_loop) { state[2] = 1; cond = 1; }
+            } else {
+                state[0] = it + 1;
+                cond = 1;
+            }
         }
     }
     state[5] = cond;
+    if (cond) {                           // re-arm the per-cycle accumulators for the next pass
+        scalars[ADMP_S_MAXFIELD] = 0.0;
+        scalars[ADMP_S_E_RECIP] = 0.0;
+    }
     if (use_handle) cudaGraphSetConditional(handle, cond);
 }
 
@@ -144,19 +154,16 @@ __global__ void scf_decide_kernel(int32_t* __restrict__ state, double* __restric
 // per-iteration accumulators either way.
 template <typename T>
 __global__ void __launch_bounds__(128)
-scf_update_kernel(int n, const int32_t* __restrict__ state, const T* __restrict__ F, const T* __restrict__ pol,
-                  T* __restrict__ U, double* __restrict__ scalars) {
+scf_update_kernel(int n, const int32_t* __restrict__ state, T* __restrict__ F, const T* __restrict__ pol,
+                  T* __restrict__ U, int zero_F) {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (state[1] && a < n) {
+    if (a >= n) return;
+    if (state[1]) {
         const T s = pol[a] * (T)(1.0 / ADMP_DIEL);
         for (int c = 0; c < 3; ++c) U[3 * a + c] -= F[3 * a + c] * s;
     }
-}
-
-__global__ void scf_rearm_kernel(double* __restrict__ scalars) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        scalars[ADMP_S_MAXFIELD] = 0.0; scalars[ADMP_S_E_RECIP] = 0.0;
-        for (int k = 0; k < 6; ++k) scalars[ADMP_S_TK + k] = 0.0;
+    if (zero_F) {                         // the next cycle accumulates its field with atomics
+        for (int c = 0; c < 3; ++c) F[3 * a + c] = (T)0;
     }
 }
 
@@ -200,15 +207,14 @@ template <typename T>
 void launch_scf_field(cudaStream_t st, int n, double kappa, const void* M, const void* U, const void* pol, void* F, double* scalars) {
     scf_field_kernel<T><<<(n + 127) / 128, 128, 0, st>>>(n, (T)kappa, (const T*)M, (const T*)U, (const T*)pol, (T*)F, scalars);
 }
-void launch_scf_decide(cudaStream_t st, int32_t* state, double* scalars, int maxiter, double thresh,
+void launch_scf_decide(cudaStream_t st, int32_t* state, double* scalars, int maxiter, double thresh, int refresh_in_loop,
                        cudaGraphConditionalHandle handle, int use_handle) {
-    scf_decide_kernel<<<1, 32, 0, st>>>(state, scalars, maxiter, thresh, handle, use_handle);
+    scf_decide_kernel<<<1, 32, 0, st>>>(state, scalars, maxiter, thresh, handle, use_handle, refresh_in_loop);
 }
 template <typename T>
-void launch_scf_update(cudaStream_t st, int n, const int32_t* state, const void* F, const void* pol, void* U, double* scalars) {
-    scf_update_kernel<T><<<(n + 127) / 128, 128, 0, st>>>(n, state, (const T*)F, (const T*)pol, (T*)U, scalars);
+void launch_scf_update(cudaStream_t st, int n, const int32_t* state, void* F, const void* pol, void* U, int zero_F) {
+    scf_update_kernel<T><<<(n + 127) / 128, 128, 0, st>>>(n, state, (T*)F, (const T*)pol, (T*)U, zero_F);
 }
-void launch_scf_rearm(cudaStream_t st, double* scalars) { scf_rearm_kernel<<<1, 32, 0, st>>>(scalars); }
 
 #define ADMP_INST(T)                                                                                                         \
     template void launch_box_setup<T>(cudaStream_t, const void*, BoxInfo*, int, int, int);                                   \
@@ -216,7 +222,7 @@ void launch_scf_rearm(cudaStream_t st, double* scalars) { scf_rearm_kernel<<<1, 
                                  void*, double*);                                                                            \
     template void launch_disp_self<T>(cudaStream_t, int, double, int, const void*, uint32_t, void*, double*);                \
     template void launch_scf_field<T>(cudaStream_t, int, double, const void*, const void*, const void*, void*, double*);     \
-    template void launch_scf_update<T>(cudaStream_t, int, const int32_t*, const void*, const void*, void*, double*);
+    template void launch_scf_update<T>(cudaStream_t, int, const int32_t*, void*, const void*, void*, int);
 ADMP_INST(double)
 ADMP_INST(float)
 #undef ADMP_INST

@@ -125,7 +125,8 @@ int admp_pme_recip(admp_ctx* ctx, void* stream, const void* pos, const void* box
 
 /* the individual stages admp_pme_recip chains, operating on the context's mesh / spectrum
  * (recip.py:368-392 spread_Q; :410 fftn; :400-426 influence function + energy; gather = adjoint of
- * spread). admp_pme_spread zero-fills then scatters; _spread_only is the bare scatter kernel. */
+ * spread; mode 1 = field only, ACCUMULATED into F with atomics). admp_pme_spread zero-fills then scatters;
+ * _spread_only is the bare scatter kernel. */
 int admp_pme_spread(admp_ctx* ctx, void* stream, const void* pos, const void* box, const void* M,
                     int M_cols, int M_stride, const void* U);
 int admp_pme_spread_only(admp_ctx* ctx, void* stream, const void* pos, const void* M, int M_cols,
