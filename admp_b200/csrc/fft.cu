@@ -372,8 +372,10 @@ static bool dim_cfg(int N, int tw_len, size_t esz, size_t smem_cap, int min_ls, 
     if (!ok) return false;
     c.fast = false;
     if (allow_fast) {
+        // two tile widths exist for the larger sizes: strided passes default to the wide tile (longer contiguous
+        // global segments), the contiguous Z passes to the narrow one (more resident blocks); measured on B200
         const char* e = getenv("ADMP_FFT_WIDE");
-        const bool wide = e && atoi(e) > 0;
+        const bool wide = e ? atoi(e) > 0 : !zpass;
         c.fast = esz == 8 ? fast_lookup<double>(N, wide, c.ops) : fast_lookup<float>(N, wide, c.ops);
         if (c.fast) {
             c.ops.prepare(c.ops);

@@ -5,11 +5,11 @@
 // Design (B200, FP64: the passes need ~30-70 FP64 instructions per 16-byte point, so both the
 // HBM stream and the FP64 pipe have to stay busy at the same time):
 //   * persistent blocks, one tile (TL lines) per loop iteration, tiles round-robin over the grid;
-//   * the next tile is fetched with cp.async (LDGSTS) into the second input buffer while the
-//     current one is transformed: three tile buffers I0 / I1 / A rotate through the stages
-//     (stage 1: I -> A, stage 2: A -> I, stage 3: I -> global), so no thread ever waits on
-//     a global load inside the butterfly code (an in-place two-buffer variant was measured slower:
-//     the values held across the extra barriers push the kernels into register spills);
+//   * two tile buffers per block: I (cp.async / LDGSTS target) and A (work). Stage 1 moves the tile
+//     I -> A; as soon as it is complete the NEXT tile is fetched into I with cp.async while the
+//     remaining stages run (a middle stage of a three-stage transform exchanges in place in A:
+//     shared -> registers, DFT, barrier, registers -> shared), so no thread waits on a global
+//     load inside the butterfly code and five 112-thread blocks fit on an SM;
 //   * strided passes (Y, X) keep the tile position-major in shared memory ([pos][TL], TL
 //     consecutive lines = one contiguous global segment), thread = (line fastest, butterfly):
 //     every shared-memory access of a quarter warp is one contiguous 128-byte row - no bank
@@ -41,8 +41,13 @@ __device__ __forceinline__ double fast_rcp(double x) {
     return r;
 }
 
-// resident blocks per SM the kernels are compiled for: caps the register count at 128 per thread
-template <int NT> struct MinBlocks { static constexpr int value = (512 / ((NT + 31) / 32 * 32)) > 0 ? (512 / ((NT + 31) / 32 * 32)) : 1; };
+// resident blocks per SM the kernels are compiled for: caps the register count at 128 per thread for the
+// two-stage transforms and 168 for the three-stage ones (their in-place middle stage keeps a butterfly's
+// outputs in registers across a barrier)
+template <int NT, int R3 = 1> struct MinBlocks {
+    static constexpr int budget = R3 == 1 ? 512 : 384;      // threads per SM at 128 / 168 registers per thread
+    static constexpr int value = (budget / ((NT + 31) / 32 * 32)) > 0 ? (budget / ((NT + 31) / 32 * 32)) : 1;
+};
 
 // ------------------------------------------------------------------------------------------ one Stockham stage
 // Butterflies jj = j, j + JT, ... < N/R of the stage with stride NS (= product of the earlier radices):
@@ -75,6 +80,33 @@ struct FStage {
                 Dft<T, R, SIGN>::run(v[it]);
             }
             if (it + 1 < iters) asm volatile("" ::: "memory");       // keep the next butterfly's loads behind this one (registers)
+        }
+    }
+    // last forward stage only (NS == N/R, so butterfly jj holds the points jj + t*m): scale them and run the
+    // first stage of an inverse transform of the same radix on them, in registers
+    template <typename Scale>
+    __device__ __forceinline__ void scale_inverse(int j, Scale f) {
+        static_assert(NS * R == N && SIGN == 1, "scale_inverse: last forward stage only");
+#pragma unroll
+        for (int it = 0; it < iters; ++it) {
+            const int jj = j + it * JT;
+            if ((it + 1) * JT <= m || jj < m) {
+#pragma unroll
+                for (int t = 0; t < R; ++t) v[it][t] = f(jj + t * m, v[it][t]);
+                Dft<T, R, -1>::run(v[it]);
+            }
+        }
+    }
+    // outputs of a first stage (stride 1): butterfly jj -> positions jj*R + t
+    template <typename Out>
+    __device__ __forceinline__ void put_first(int j, Out out) const {
+#pragma unroll
+        for (int it = 0; it < iters; ++it) {
+            const int jj = j + it * JT;
+            if ((it + 1) * JT <= m || jj < m) {
+#pragma unroll
+                for (int t = 0; t < R; ++t) out(jj * R + t, v[it][t]);
+            }
         }
     }
     template <typename Out>
@@ -114,42 +146,42 @@ __device__ __forceinline__ void build_twiddles(cx<T>* tw2, cx<T>* tw3, const cx<
     }
 }
 
-// full line FFT through the rotating buffers: ld0 (tile, possibly pre-processed) -> a -> c -> last(pos, v),
-// two stages when R3 == 1 (ld0 -> a -> last). `c` may alias the buffer ld0 reads: stage 1 is complete at
-// the first barrier. All threads of the block must call (barriers inside); `live` masks the tile's tail lines.
-template <typename T, int R1, int R2, int R3, int SIGN, int JT, typename Ld0, typename StA, typename LdA, typename StC, typename LdC,
-          typename Last>
-__device__ __forceinline__ void fft_rotate(int j, bool live, const cx<T>* __restrict__ tw2, const cx<T>* __restrict__ tw3, Ld0 ld0, StA stA,
-                                           LdA ldA, StC stC, LdC ldC, Last last) {
+// remaining stages (2, and 3 when R3 > 1) of a line FFT whose stage-1 output sits in buffer A:
+// the middle stage of a three-stage transform exchanges in place in A, the last stage hands its outputs to
+// `last`; LAST_INPLACE (last writes A again) puts a barrier between the last stage's reads and writes.
+template <typename T, int R1, int R2, int R3, int SIGN, int JT, bool LAST_INPLACE, typename LdA, typename StA, typename Last>
+__device__ __forceinline__ void fft_tail(int j, bool live, const cx<T>* __restrict__ tw2, const cx<T>* __restrict__ tw3, LdA ldA, StA stA,
+                                         Last last) {
     constexpr int N = R1 * R2 * R3;
-    if (live) {
-        FStage<T, R1, SIGN, N, 1, JT> s;
-        s.run(j, nullptr, ld0);
-        s.put(j, stA);
-    }
-    __syncthreads();
     if (R3 == 1) {
-        if (live) {
-            FStage<T, R2, SIGN, N, R1, JT> s;
-            s.run(j, tw2, ldA);
-            s.put(j, last);
-        }
+        FStage<T, R2, SIGN, N, R1, JT> s;
+        if (live) s.run(j, tw2, ldA);
+        if (LAST_INPLACE) __syncthreads();
+        if (live) s.put(j, last);
     } else {
-        if (live) {
+        {
             FStage<T, R2, SIGN, N, R1, JT> s;
-            s.run(j, tw2, ldA);
-            s.put(j, stC);
+            if (live) s.run(j, tw2, ldA);
+            __syncthreads();
+            if (live) s.put(j, stA);
+            __syncthreads();
         }
-        __syncthreads();
-        if (live) {
-            constexpr int R3e = R3 > 1 ? R3 : 2;
-            FStage<T, R3e, SIGN, N, R1 * R2, JT> s;
-            s.run(j, tw3, ldC);
-            s.put(j, last);
-        }
+        constexpr int R3e = R3 > 1 ? R3 : 2;
+        FStage<T, R3e, SIGN, N, R1 * R2, JT> s;
+        if (live) s.run(j, tw3, ldA);
+        if (LAST_INPLACE) __syncthreads();
+        if (live) s.put(j, last);
     }
 }
-
+// stage 1: src -> dst (different buffers; no barrier inside)
+template <typename T, int R1, int R2, int R3, int SIGN, int JT, typename Ld, typename St>
+__device__ __forceinline__ void fft_head(int j, bool live, Ld ld, St st) {
+    if (live) {
+        FStage<T, R1, SIGN, R1 * R2 * R3, 1, JT> s;
+        s.run(j, nullptr, ld);
+        s.put(j, st);
+    }
+}
 // ------------------------------------------------------------------------------------------ strided passes (Y, X)
 template <typename T, int N, int TL, int JT>
 __device__ __forceinline__ void issue_tile(const StrideGeom& g, int tile, const cx<T>* __restrict__ spec, cx<T>* dst, int l, int j) {
@@ -165,37 +197,34 @@ __device__ __forceinline__ void issue_tile(const StrideGeom& g, int tile, const 
 }
 
 template <typename T, int R1, int R2, int R3, int SIGN, int TL, int JT>
-__global__ void __launch_bounds__(TL* JT)
+__global__ void __launch_bounds__(TL* JT, MinBlocks<TL * JT, R3>::value)
 fast_strided_kernel(StrideGeom g, int ntiles, cx<T>* __restrict__ spec, const cx<T>* __restrict__ gtw) {
     constexpr int N = R1 * R2 * R3, TILE = N * TL, NT = TL * JT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cx<T>* I0 = reinterpret_cast<cx<T>*>(smem_raw);
-    cx<T>* I1 = I0 + TILE;
-    cx<T>* A = I1 + TILE;
+    cx<T>* I = reinterpret_cast<cx<T>*>(smem_raw);
+    cx<T>* A = I + TILE;
     cx<T>* tw2 = A + TILE;
     cx<T>* tw3 = tw2 + TwGeom<R1, R2, R3>::N2;
     const int l = threadIdx.x % TL, j = threadIdx.x / TL;
     int tile = blockIdx.x;
-    if (tile < ntiles) issue_tile<T, N, TL, JT>(g, tile, spec, I0, l, j);
+    if (tile < ntiles) issue_tile<T, N, TL, JT>(g, tile, spec, I, l, j);
     build_twiddles<T, R1, R2, R3, 1>(tw2, tw3, gtw, NT);
-    for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
-        cx<T>* cur = (it & 1) ? I1 : I0;
-        cx<T>* nxt = (it & 1) ? I0 : I1;
+    cx<T>* a = A + l;
+    cx<T>* c = I + l;
+    for (; tile < ntiles; tile += gridDim.x) {
         cp_async_wait_all();
-        __syncthreads();
-        if (tile + (int)gridDim.x < ntiles) issue_tile<T, N, TL, JT>(g, tile + gridDim.x, spec, nxt, l, j);
+        __syncthreads();                       // tile landed in I; A free (previous tile's last stage has read it)
         const int o = tile / g.tiles, t = tile - o * g.tiles;
         const int c0 = t * TL;
         const bool live = l < g.n_inner - c0;
         cx<T>* out = spec + (size_t)o * g.outer_stride + c0 + l;
         const size_t ls = g.line_stride;
-        cx<T>* a = A + l;
-        cx<T>* c = cur + l;
-        fft_rotate<T, R1, R2, R3, SIGN, JT>(
-            j, live, tw2, tw3,
-            [&](int pos) { return c[pos * TL]; }, [&](int pos, cx<T> v) { a[pos * TL] = v; },
-            [&](int pos) { return a[pos * TL]; }, [&](int pos, cx<T> v) { c[pos * TL] = v; },
-            [&](int pos) { return c[pos * TL]; }, [&](int pos, cx<T> v) { out[(size_t)pos * ls] = v; });
+        fft_head<T, R1, R2, R3, SIGN, JT>(j, live, [&](int pos) { return c[pos * TL]; }, [&](int pos, cx<T> v) { a[pos * TL] = v; });
+        __syncthreads();                       // I consumed
+        if (tile + (int)gridDim.x < ntiles) issue_tile<T, N, TL, JT>(g, tile + gridDim.x, spec, I, l, j);
+        fft_tail<T, R1, R2, R3, SIGN, JT, false>(j, live, tw2, tw3, [&](int pos) { return a[pos * TL]; },
+                                                 [&](int pos, cx<T> v) { a[pos * TL] = v; },
+                                                 [&](int pos, cx<T> v) { out[(size_t)pos * ls] = v; });
     }
 }
 
@@ -222,25 +251,29 @@ __device__ __noinline__ double influence_general(const BoxInfo* Bp, const ConvTa
 // tables of conv_tables_kernel + one reciprocal per point when the cell is orthorhombic (device flag),
 // inline exp otherwise; !QUICK = any kind / virial sums through influence_general.
 template <typename T, int R1, int R2, int R3, int TL, int JT, bool QUICK>
-__global__ void __launch_bounds__(TL* JT)
+__global__ void __launch_bounds__(TL* JT, MinBlocks<TL * JT, R3>::value)
 fast_x_conv_kernel(StrideGeom g, int ntiles, const BoxInfo* __restrict__ Bp, T kappa, int kind, ConvTables tb, cx<T>* __restrict__ spec,
                    const cx<T>* __restrict__ gtw, double* __restrict__ scalars, int want_vir) {
     constexpr int N = R1 * R2 * R3, TILE = N * TL, NT = TL * JT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[7 * ((NT + 31) / 32)];
-    cx<T>* I0 = reinterpret_cast<cx<T>*>(smem_raw);
-    cx<T>* I1 = I0 + TILE;
-    cx<T>* A = I1 + TILE;
+    cx<T>* I = reinterpret_cast<cx<T>*>(smem_raw);
+    cx<T>* A = I + TILE;
     cx<T>* tw2 = A + TILE;
     cx<T>* tw3 = tw2 + TwGeom<R1, R2, R3>::N2;
-    double* sek = reinterpret_cast<double*>(tw3 + TwGeom<R1, R2, R3>::N3);     // exp(-k1^2/4kappa^2)/theta_1^2  (ortho) | 1/theta_1^2
+    // the inverse runs with the radices in reverse order (see the loop), so it needs its own twiddle tables
+    constexpr int Q1 = R3 > 1 ? R3 : R2, Q2 = R3 > 1 ? R2 : R1, Q3 = R3 > 1 ? R1 : 1;
+    cx<T>* itw2 = tw3 + TwGeom<R1, R2, R3>::N3;
+    cx<T>* itw3 = itw2 + TwGeom<Q1, Q2, Q3>::N2;
+    double* sek = reinterpret_cast<double*>(itw3 + TwGeom<Q1, Q2, Q3>::N3);    // exp(-k1^2/4kappa^2)/theta_1^2  (ortho) | 1/theta_1^2
     double* sk2 = sek + N;                                                    // k1^2 (ortho) | signed index m1
     const BoxInfo& B = *Bp;
     const int l = threadIdx.x % TL, j = threadIdx.x / TL;
     int tile = blockIdx.x;
-    if (tile < ntiles) issue_tile<T, N, TL, JT>(g, tile, spec, I0, l, j);
+    if (tile < ntiles) issue_tile<T, N, TL, JT>(g, tile, spec, I, l, j);
     const bool ortho = (*tb.ortho != 0);
     build_twiddles<T, R1, R2, R3, 1>(tw2, tw3, gtw, NT);
+    build_twiddles<T, Q1, Q2, Q3, 1>(itw2, itw3, gtw, NT);
     if (QUICK) {
         for (int i = threadIdx.x; i < N; i += NT) {
             sek[i] = ortho ? tb.ek[0][i] : tb.bt[0][i];
@@ -253,12 +286,15 @@ fast_x_conv_kernel(StrideGeom g, int ntiles, const BoxInfo* __restrict__ Bp, T k
     const double pref = 2.0 * scale * 6.283185307179586 / B.vol;
     const double q4k = -1.0 / (4.0 * kap * kap);
     double acc_e = 0.0, acc_t[6] = {0, 0, 0, 0, 0, 0};
-    for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
-        cx<T>* cur = (it & 1) ? I1 : I0;
-        cx<T>* nxt = (it & 1) ? I0 : I1;
+    cx<T>* a = A + l;
+    cx<T>* c = I + l;
+    // Per tile: stage 1 moves I -> A and the next tile is fetched into I; everything else happens in A.
+    // The forward transform's last stage leaves thread jj with the points {jj + t*N/R}: exactly the inputs of a
+    // first inverse stage of the same radix, so the scaling and that inverse stage run in registers (no
+    // exchange through shared memory, no barrier) and the inverse continues with the radices in reverse order.
+    for (; tile < ntiles; tile += gridDim.x) {
         cp_async_wait_all();
         __syncthreads();
-        if (tile + (int)gridDim.x < ntiles) issue_tile<T, N, TL, JT>(g, tile + gridDim.x, spec, nxt, l, j);
         const int c0 = tile * TL;
         const bool live = l < g.n_inner - c0;
         const int cl = live ? c0 + l : 0;
@@ -281,12 +317,7 @@ fast_x_conv_kernel(StrideGeom g, int ntiles, const BoxInfo* __restrict__ Bp, T k
         double acc_line = 0.0;
         cx<T>* out = spec + c0 + l;
         const size_t ls = g.line_stride;
-        cx<T>* a = A + l;
-        cx<T>* c = cur + l;
-        // the scaled spectrum goes to the buffer the forward transform's last stage is not reading
-        cx<T>* sx = (R3 == 1) ? c : a;
-        cx<T>* sy = (R3 == 1) ? a : c;
-        auto scale_point = [&](int i1, cx<T> s) {
+        auto scale_point = [&](int i1, cx<T> s) -> cx<T> {
             const double s2 = (double)s.x * s.x + (double)s.y * s.y;
             double gg;                                        // 2*scale*C_k/theta_k^2
             if (QUICK) {
@@ -305,20 +336,33 @@ fast_x_conv_kernel(StrideGeom g, int ntiles, const BoxInfo* __restrict__ Bp, T k
             }
             acc_line = fma(gg, s2, acc_line);
             const T gt = (T)gg;
-            sx[i1 * TL] = {s.x * gt, s.y * gt};
+            return {s.x * gt, s.y * gt};
         };
-        fft_rotate<T, R1, R2, R3, 1, JT>(
-            j, live, tw2, tw3,
-            [&](int pos) { return c[pos * TL]; }, [&](int pos, cx<T> v) { a[pos * TL] = v; },
-            [&](int pos) { return a[pos * TL]; }, [&](int pos, cx<T> v) { c[pos * TL] = v; },
-            [&](int pos) { return c[pos * TL]; }, scale_point);
+        auto ldA = [&](int pos) { return a[pos * TL]; };
+        auto stA = [&](int pos, cx<T> v) { a[pos * TL] = v; };
+        fft_head<T, R1, R2, R3, 1, JT>(j, live, [&](int pos) { return c[pos * TL]; }, stA);
+        __syncthreads();                       // I consumed: fetch the next tile while this one is transformed
+        if (tile + (int)gridDim.x < ntiles) issue_tile<T, N, TL, JT>(g, tile + gridDim.x, spec, I, l, j);
+        if (R3 > 1) {                          // middle forward stage, in place in A
+            FStage<T, R2, 1, N, R1, JT> s;
+            if (live) s.run(j, tw2, ldA);
+            __syncthreads();
+            if (live) s.put(j, stA);
+            __syncthreads();
+        }
+        {
+            // last forward stage (radix Q1, stride N/Q1) + scaling + first inverse stage (radix Q1), in registers
+            FStage<T, Q1, 1, N, N / Q1, JT> s;
+            if (live) {
+                s.run(j, R3 > 1 ? tw3 : tw2, ldA);
+                s.scale_inverse(j, scale_point);
+            }
+            __syncthreads();
+            if (live) s.put_first(j, stA);
+            __syncthreads();
+        }
         acc_e = fma(0.5 * wgt, acc_line, acc_e);              // E = scale * sum wgt g |S|^2 = sum wgt/2 * gg |S|^2
-        __syncthreads();
-        fft_rotate<T, R1, R2, R3, -1, JT>(
-            j, live, tw2, tw3,
-            [&](int pos) { return sx[pos * TL]; }, [&](int pos, cx<T> v) { sy[pos * TL] = v; },
-            [&](int pos) { return sy[pos * TL]; }, [&](int pos, cx<T> v) { sx[pos * TL] = v; },
-            [&](int pos) { return sx[pos * TL]; }, [&](int pos, cx<T> v) { out[(size_t)pos * ls] = v; });
+        fft_tail<T, Q1, Q2, Q3, -1, JT, false>(j, live, itw2, itw3, ldA, stA, [&](int pos, cx<T> v) { out[(size_t)pos * ls] = v; });
     }
     double e1[1] = {acc_e};
     block_accumulate<1>(e1, red, scalars + ADMP_S_E_RECIP);
@@ -333,56 +377,50 @@ template <int M> struct ZGeom {
 
 // forward: K3 reals per line -> K3/2+1 complex (packed real FFT, tools/fft_model.py r2c)
 template <typename T, int R1, int R2, int R3, int TL, int JT>
-__global__ void __launch_bounds__(TL* JT)
+__global__ void __launch_bounds__(TL* JT, MinBlocks<TL * JT, R3>::value)
 fast_z_fwd_kernel(int nlines, int ntiles, const T* __restrict__ mesh, cx<T>* __restrict__ spec, const cx<T>* __restrict__ gtw) {
     constexpr int M = R1 * R2 * R3, K3 = 2 * M, K3h = M + 1, LS = ZGeom<M>::LS, TILE = TL * LS, NT = TL * JT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cx<T>* I0 = reinterpret_cast<cx<T>*>(smem_raw);
-    cx<T>* I1 = I0 + TILE;
-    cx<T>* A = I1 + TILE;
+    cx<T>* I = reinterpret_cast<cx<T>*>(smem_raw);
+    cx<T>* A = I + TILE;
     cx<T>* tw2 = A + TILE;
     cx<T>* tw3 = tw2 + TwGeom<R1, R2, R3>::N2;
     cx<T>* zt = tw3 + TwGeom<R1, R2, R3>::N3;       // M+1 entries: exp(-2 pi i k / K3)
     const int j = threadIdx.x % JT, l = threadIdx.x / JT;
-    auto issue = [&](int tile, cx<T>* dst) {
+    auto issue = [&](int tile) {
         const int L0 = tile * TL;
         const int nl = min(TL, nlines - L0);
         const cx<T>* src = reinterpret_cast<const cx<T>*>(mesh + (size_t)L0 * K3);
         for (int e = threadIdx.x; e < nl * M; e += NT) {
             const int ll = e / M, pos = e - ll * M;
-            cp_async<sizeof(cx<T>)>(dst + ll * LS + pos, src + e);
+            cp_async<sizeof(cx<T>)>(I + ll * LS + pos, src + e);
         }
         cp_async_commit();
     };
     int tile = blockIdx.x;
-    if (tile < ntiles) issue(tile, I0);
+    if (tile < ntiles) issue(tile);
     build_twiddles<T, R1, R2, R3, 2>(tw2, tw3, gtw, NT);
     for (int i = threadIdx.x; i < K3h; i += NT) zt[i] = gtw[i];
-    for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
-        cx<T>* cur = (it & 1) ? I1 : I0;
-        cx<T>* nxt = (it & 1) ? I0 : I1;
+    cx<T>* a = A + l * LS;
+    cx<T>* c = I + l * LS;
+    for (; tile < ntiles; tile += gridDim.x) {
         cp_async_wait_all();
         __syncthreads();
-        if (tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x, nxt);
         const int L0 = tile * TL;
         const int nl = min(TL, nlines - L0);
         const bool live = l < nl;
-        cx<T>* a = A + l * LS;
-        cx<T>* c = cur + l * LS;
-        // the transformed line Z ends in A for three stages, in cur for two
-        cx<T>* z = (R3 == 1) ? c : a;
-        fft_rotate<T, R1, R2, R3, 1, JT>(
-            j, live, tw2, tw3,
-            [&](int pos) { return c[pos]; }, [&](int pos, cx<T> v) { a[pos] = v; },
-            [&](int pos) { return a[pos]; }, [&](int pos, cx<T> v) { c[pos] = v; },
-            [&](int pos) { return c[pos]; }, [&](int pos, cx<T> v) { z[pos] = v; });
+        fft_head<T, R1, R2, R3, 1, JT>(j, live, [&](int pos) { return c[pos]; }, [&](int pos, cx<T> v) { a[pos] = v; });
         __syncthreads();
-        const cx<T>* Z = (R3 == 1) ? cur : A;
+        if (tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x);
+        auto ldA = [&](int pos) { return a[pos]; };
+        auto stA = [&](int pos, cx<T> v) { a[pos] = v; };
+        fft_tail<T, R1, R2, R3, 1, JT, true>(j, live, tw2, tw3, ldA, stA, stA);
+        __syncthreads();
         cx<T>* dst = spec + (size_t)L0 * K3h;
         for (int e = threadIdx.x; e < nl * K3h; e += NT) {
             const int ll = e / K3h, k = e - ll * K3h;
-            const cx<T> zk = Z[ll * LS + (k == M ? 0 : k)];
-            cx<T> zc = Z[ll * LS + ((k == 0 || k == M) ? 0 : M - k)];
+            const cx<T> zk = A[ll * LS + (k == M ? 0 : k)];
+            cx<T> zc = A[ll * LS + ((k == 0 || k == M) ? 0 : M - k)];
             zc.y = -zc.y;
             const cx<T> s = {(T)0.5 * (zk.x + zc.x), (T)0.5 * (zk.y + zc.y)}, d = {(T)0.5 * (zk.x - zc.x), (T)0.5 * (zk.y - zc.y)};
             const cx<T> tw = zt[k];                                   // (cos phi, -sin phi), phi = 2 pi k / K3
@@ -394,44 +432,40 @@ fast_z_fwd_kernel(int nlines, int ntiles, const T* __restrict__ mesh, cx<T>* __r
 
 // inverse: K3/2+1 complex -> K3 reals, unnormalised (tools/fft_model.py c2r)
 template <typename T, int R1, int R2, int R3, int TL, int JT>
-__global__ void __launch_bounds__(TL* JT)
+__global__ void __launch_bounds__(TL* JT, MinBlocks<TL * JT, R3>::value)
 fast_z_inv_kernel(int nlines, int ntiles, const cx<T>* __restrict__ spec, T* __restrict__ mesh, const cx<T>* __restrict__ gtw) {
     constexpr int M = R1 * R2 * R3, K3 = 2 * M, K3h = M + 1, LS = ZGeom<M>::LS, TILE = TL * LS, NT = TL * JT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cx<T>* I0 = reinterpret_cast<cx<T>*>(smem_raw);
-    cx<T>* I1 = I0 + TILE;
-    cx<T>* A = I1 + TILE;
+    cx<T>* I = reinterpret_cast<cx<T>*>(smem_raw);
+    cx<T>* A = I + TILE;
     cx<T>* tw2 = A + TILE;
     cx<T>* tw3 = tw2 + TwGeom<R1, R2, R3>::N2;
     cx<T>* zt = tw3 + TwGeom<R1, R2, R3>::N3;
     const int j = threadIdx.x % JT, l = threadIdx.x / JT;
-    auto issue = [&](int tile, cx<T>* dst) {
+    auto issue = [&](int tile) {
         const int L0 = tile * TL;
         const int nl = min(TL, nlines - L0);
         const cx<T>* src = spec + (size_t)L0 * K3h;
         for (int e = threadIdx.x; e < nl * K3h; e += NT) {
             const int ll = e / K3h, k = e - ll * K3h;
-            cp_async<sizeof(cx<T>)>(dst + ll * LS + k, src + e);
+            cp_async<sizeof(cx<T>)>(I + ll * LS + k, src + e);
         }
         cp_async_commit();
     };
     int tile = blockIdx.x;
-    if (tile < ntiles) issue(tile, I0);
+    if (tile < ntiles) issue(tile);
     build_twiddles<T, R1, R2, R3, 2>(tw2, tw3, gtw, NT);
     for (int i = threadIdx.x; i < K3h; i += NT) zt[i] = gtw[i];
-    for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
-        cx<T>* cur = (it & 1) ? I1 : I0;
-        cx<T>* nxt = (it & 1) ? I0 : I1;
+    cx<T>* a = A + l * LS;
+    cx<T>* c = I + l * LS;
+    for (; tile < ntiles; tile += gridDim.x) {
         cp_async_wait_all();
         __syncthreads();
-        if (tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x, nxt);
         const int L0 = tile * TL;
         const bool live = l < nlines - L0;
-        cx<T>* a = A + l * LS;
-        cx<T>* c = cur + l * LS;
         cx<T>* line = reinterpret_cast<cx<T>*>(mesh + (size_t)(L0 + l) * K3);
-        fft_rotate<T, R1, R2, R3, -1, JT>(
-            j, live, tw2, tw3,
+        fft_head<T, R1, R2, R3, -1, JT>(
+            j, live,
             [&](int k) {
                 const cx<T> xk = c[k];
                 cx<T> xc = c[M - k];
@@ -441,16 +475,18 @@ fast_z_inv_kernel(int nlines, int ntiles, const cx<T>* __restrict__ spec, T* __r
                 const cx<T> f = {tw.y, tw.x};                         // Z = s + (-sin phi + i cos phi) d
                 return s + cmul(f, d);
             },
-            [&](int pos, cx<T> v) { a[pos] = v; },
-            [&](int pos) { return a[pos]; }, [&](int pos, cx<T> v) { c[pos] = v; },
-            [&](int pos) { return c[pos]; }, [&](int pos, cx<T> v) { line[pos] = v; });
+            [&](int pos, cx<T> v) { a[pos] = v; });
+        __syncthreads();
+        if (tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x);
+        fft_tail<T, R1, R2, R3, -1, JT, false>(j, live, tw2, tw3, [&](int pos) { return a[pos]; }, [&](int pos, cx<T> v) { a[pos] = v; },
+                                               [&](int pos, cx<T> v) { line[pos] = v; });
     }
 }
 
 // ------------------------------------------------------------------------------------------ configuration table
 // (R1, R2, R3 | strided: TL, JT | z (when the size is K3/2): TL, JT); line counts are for double, float doubles TL.
 // Two tile widths for the large sizes: the wide one keeps 128-byte global segments, the narrow one lets
-// more blocks share an SM (shared memory: 3 * N * TL * 16 B). `pick` selects (ADMP_FFT_WIDE=1 -> wide).
+// more blocks share an SM (shared memory: 2 * N * TL * 16 B). `pick` selects (ADMP_FFT_WIDE=1 -> wide).
 #define ADMP_FAST_LIST(X)            \
     X(0, 11, 7, 1, 8, 7, 16, 7)      \
     X(1, 11, 14, 1, 8, 14, 8, 14)    \
@@ -458,7 +494,7 @@ fast_z_inv_kernel(int nlines, int ntiles, const cx<T>* __restrict__ spec, T* __r
     X(3, 11, 7, 4, 8, 28, 8, 28)     \
     X(4, 11, 7, 8, 2, 56, 2, 56)     \
     X(5, 11, 7, 8, 4, 56, 4, 56)     \
-    X(6, 11, 14, 8, 2, 56, 2, 56)
+    X(6, 11, 14, 8, 2, 112, 2, 112)
 
 struct FastOps {
     int N, TL, threads, zTL, zthreads;
@@ -484,6 +520,10 @@ template <typename T, int R1, int R2, int R3, int TLd, int JT, int ZTLd, int ZJT
 struct FastImpl {
     static constexpr int N = R1 * R2 * R3;
     static constexpr int TL = TLd * (sizeof(T) == 4 ? 2 : 1), ZTL = ZTLd * (sizeof(T) == 4 ? 2 : 1);
+    static size_t smem_x_bytes() {
+        constexpr int Q1 = R3 > 1 ? R3 : R2, Q2 = R3 > 1 ? R2 : R1, Q3 = R3 > 1 ? R1 : 1;
+        return (size_t)(2 * N * TL + TwGeom<R1, R2, R3>::TOTAL + TwGeom<Q1, Q2, Q3>::TOTAL) * sizeof(cx<T>) + 2 * N * sizeof(double);
+    }
     static void prepare(FastOps& o) {
         o.occ[0] = prep_kernel(fast_strided_kernel<T, R1, R2, R3, 1, TL, JT>, o.threads, o.smem);
         o.occ[1] = prep_kernel(fast_strided_kernel<T, R1, R2, R3, -1, TL, JT>, o.threads, o.smem);
@@ -493,13 +533,13 @@ struct FastImpl {
         o.occ[4] = prep_kernel(fast_z_inv_kernel<T, R1, R2, R3, ZTL, ZJT>, o.zthreads, o.zsmem);
     }
     static void strided(cudaStream_t st, int sign, const StrideGeom& g, int ntiles, int grid, void* spec, const void* tw) {
-        const size_t smem = (size_t)(3 * N * TL + TwGeom<R1, R2, R3>::TOTAL) * sizeof(cx<T>);
+        const size_t smem = (size_t)(2 * N * TL + TwGeom<R1, R2, R3>::TOTAL) * sizeof(cx<T>);
         if (sign > 0) fast_strided_kernel<T, R1, R2, R3, 1, TL, JT><<<grid, TL * JT, smem, st>>>(g, ntiles, (cx<T>*)spec, (const cx<T>*)tw);
         else fast_strided_kernel<T, R1, R2, R3, -1, TL, JT><<<grid, TL * JT, smem, st>>>(g, ntiles, (cx<T>*)spec, (const cx<T>*)tw);
     }
     static void xconv(cudaStream_t st, const StrideGeom& g, int ntiles, int grid, const BoxInfo* B, double kappa, int kind,
                       const ConvTables& tb, void* spec, const void* tw, double* scalars, int want_vir) {
-        const size_t smem = (size_t)(3 * N * TL + TwGeom<R1, R2, R3>::TOTAL) * sizeof(cx<T>) + 2 * N * sizeof(double);
+        const size_t smem = smem_x_bytes();
         if (kind == ADMP_CK_COULOMB && !want_vir)
             fast_x_conv_kernel<T, R1, R2, R3, TL, JT, true><<<grid, TL * JT, smem, st>>>(g, ntiles, B, (T)kappa, kind, tb, (cx<T>*)spec,
                                                                                         (const cx<T>*)tw, scalars, want_vir);
@@ -508,19 +548,19 @@ struct FastImpl {
                                                                                          (const cx<T>*)tw, scalars, want_vir);
     }
     static void zfwd(cudaStream_t st, int nlines, int ntiles, int grid, const void* mesh, void* spec, const void* tw) {
-        const size_t smem = (size_t)(3 * ZTL * ZGeom<N>::LS + TwGeom<R1, R2, R3>::TOTAL + N + 1) * sizeof(cx<T>);
+        const size_t smem = (size_t)(2 * ZTL * ZGeom<N>::LS + TwGeom<R1, R2, R3>::TOTAL + N + 1) * sizeof(cx<T>);
         fast_z_fwd_kernel<T, R1, R2, R3, ZTL, ZJT><<<grid, ZTL * ZJT, smem, st>>>(nlines, ntiles, (const T*)mesh, (cx<T>*)spec, (const cx<T>*)tw);
     }
     static void zinv(cudaStream_t st, int nlines, int ntiles, int grid, const void* spec, void* mesh, const void* tw) {
-        const size_t smem = (size_t)(3 * ZTL * ZGeom<N>::LS + TwGeom<R1, R2, R3>::TOTAL + N + 1) * sizeof(cx<T>);
+        const size_t smem = (size_t)(2 * ZTL * ZGeom<N>::LS + TwGeom<R1, R2, R3>::TOTAL + N + 1) * sizeof(cx<T>);
         fast_z_inv_kernel<T, R1, R2, R3, ZTL, ZJT><<<grid, ZTL * ZJT, smem, st>>>(nlines, ntiles, (const cx<T>*)spec, (T*)mesh, (const cx<T>*)tw);
     }
     static FastOps ops() {
         FastOps o = {};
         o.N = N; o.TL = TL; o.threads = TL * JT; o.zTL = ZTL; o.zthreads = ZTL * ZJT;
-        o.smem = (size_t)(3 * N * TL + TwGeom<R1, R2, R3>::TOTAL) * sizeof(cx<T>);
-        o.smem_x = o.smem + 2 * N * sizeof(double);
-        o.zsmem = (size_t)(3 * ZTL * ZGeom<N>::LS + TwGeom<R1, R2, R3>::TOTAL + N + 1) * sizeof(cx<T>);
+        o.smem = (size_t)(2 * N * TL + TwGeom<R1, R2, R3>::TOTAL) * sizeof(cx<T>);
+        o.smem_x = smem_x_bytes();
+        o.zsmem = (size_t)(2 * ZTL * ZGeom<N>::LS + TwGeom<R1, R2, R3>::TOTAL + N + 1) * sizeof(cx<T>);
         o.prepare = &prepare; o.strided = &strided; o.xconv = &xconv; o.zfwd = &zfwd; o.zinv = &zinv;
         return o;
     }
