@@ -30,6 +30,30 @@ __device__ __forceinline__ void cp_async(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
+// Programmatic dependent launch (PDL): a kernel lets its successor in the stream start launching as soon as
+// all of its own blocks are resident (launch_dependents), and waits for its predecessor to complete and flush
+// before touching dependent data (wait). The successor's blocks fill the SM slots freed by the predecessor's
+// finished blocks and run their prologue (twiddle tables) in the predecessor's tail. Both are no-ops when the
+// kernel is launched without the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+    static const bool enabled = [] { const char* e = getenv("ADMP_PDL"); return !(e && atoi(e) == 0); }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = enabled ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // 1/x to ~1 ulp from the SFU approximation and two Newton steps (x normal, positive; x = 0 gives NaN:
 // callers select around it). Replaces the ~20-instruction IEEE division in the per-point influence function.
 __device__ __forceinline__ double fast_rcp(double x) {
@@ -207,8 +231,10 @@ fast_strided_kernel(StrideGeom g, int ntiles, cx<T>* __restrict__ spec, const cx
     cx<T>* tw3 = tw2 + TwGeom<R1, R2, R3>::N2;
     const int l = threadIdx.x % TL, j = threadIdx.x / TL;
     int tile = blockIdx.x;
-    if (tile < ntiles) issue_tile<T, N, TL, JT>(g, tile, spec, I, l, j);
+    pdl_launch_dependents();
     build_twiddles<T, R1, R2, R3, 1>(tw2, tw3, gtw, NT);
+    pdl_wait();
+    if (tile < ntiles) issue_tile<T, N, TL, JT>(g, tile, spec, I, l, j);
     cx<T>* a = A + l;
     cx<T>* c = I + l;
     for (; tile < ntiles; tile += gridDim.x) {
@@ -270,10 +296,12 @@ fast_x_conv_kernel(StrideGeom g, int ntiles, const BoxInfo* __restrict__ Bp, T k
     const BoxInfo& B = *Bp;
     const int l = threadIdx.x % TL, j = threadIdx.x / TL;
     int tile = blockIdx.x;
-    if (tile < ntiles) issue_tile<T, N, TL, JT>(g, tile, spec, I, l, j);
-    const bool ortho = (*tb.ortho != 0);
+    pdl_launch_dependents();
     build_twiddles<T, R1, R2, R3, 1>(tw2, tw3, gtw, NT);
     build_twiddles<T, Q1, Q2, Q3, 1>(itw2, itw3, gtw, NT);
+    pdl_wait();
+    if (tile < ntiles) issue_tile<T, N, TL, JT>(g, tile, spec, I, l, j);
+    const bool ortho = (*tb.ortho != 0);
     if (QUICK) {
         for (int i = threadIdx.x; i < N; i += NT) {
             sek[i] = ortho ? tb.ek[0][i] : tb.bt[0][i];
@@ -398,9 +426,11 @@ fast_z_fwd_kernel(int nlines, int ntiles, const T* __restrict__ mesh, cx<T>* __r
         cp_async_commit();
     };
     int tile = blockIdx.x;
-    if (tile < ntiles) issue(tile);
+    pdl_launch_dependents();
     build_twiddles<T, R1, R2, R3, 2>(tw2, tw3, gtw, NT);
     for (int i = threadIdx.x; i < K3h; i += NT) zt[i] = gtw[i];
+    pdl_wait();
+    if (tile < ntiles) issue(tile);
     cx<T>* a = A + l * LS;
     cx<T>* c = I + l * LS;
     for (; tile < ntiles; tile += gridDim.x) {
@@ -453,9 +483,11 @@ fast_z_inv_kernel(int nlines, int ntiles, const cx<T>* __restrict__ spec, T* __r
         cp_async_commit();
     };
     int tile = blockIdx.x;
-    if (tile < ntiles) issue(tile);
+    pdl_launch_dependents();
     build_twiddles<T, R1, R2, R3, 2>(tw2, tw3, gtw, NT);
     for (int i = threadIdx.x; i < K3h; i += NT) zt[i] = gtw[i];
+    pdl_wait();
+    if (tile < ntiles) issue(tile);
     cx<T>* a = A + l * LS;
     cx<T>* c = I + l * LS;
     for (; tile < ntiles; tile += gridDim.x) {
@@ -534,26 +566,26 @@ struct FastImpl {
     }
     static void strided(cudaStream_t st, int sign, const StrideGeom& g, int ntiles, int grid, void* spec, const void* tw) {
         const size_t smem = (size_t)(2 * N * TL + TwGeom<R1, R2, R3>::TOTAL) * sizeof(cx<T>);
-        if (sign > 0) fast_strided_kernel<T, R1, R2, R3, 1, TL, JT><<<grid, TL * JT, smem, st>>>(g, ntiles, (cx<T>*)spec, (const cx<T>*)tw);
-        else fast_strided_kernel<T, R1, R2, R3, -1, TL, JT><<<grid, TL * JT, smem, st>>>(g, ntiles, (cx<T>*)spec, (const cx<T>*)tw);
+        if (sign > 0) launch_pdl(fast_strided_kernel<T, R1, R2, R3, 1, TL, JT>, grid, TL * JT, smem, st, g, ntiles, (cx<T>*)spec, (const cx<T>*)tw);
+        else launch_pdl(fast_strided_kernel<T, R1, R2, R3, -1, TL, JT>, grid, TL * JT, smem, st, g, ntiles, (cx<T>*)spec, (const cx<T>*)tw);
     }
     static void xconv(cudaStream_t st, const StrideGeom& g, int ntiles, int grid, const BoxInfo* B, double kappa, int kind,
                       const ConvTables& tb, void* spec, const void* tw, double* scalars, int want_vir) {
         const size_t smem = smem_x_bytes();
         if (kind == ADMP_CK_COULOMB && !want_vir)
-            fast_x_conv_kernel<T, R1, R2, R3, TL, JT, true><<<grid, TL * JT, smem, st>>>(g, ntiles, B, (T)kappa, kind, tb, (cx<T>*)spec,
-                                                                                        (const cx<T>*)tw, scalars, want_vir);
+            launch_pdl(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, true>, grid, TL * JT, smem, st, g, ntiles, B, (T)kappa, kind, tb, (cx<T>*)spec,
+                       (const cx<T>*)tw, scalars, want_vir);
         else
-            fast_x_conv_kernel<T, R1, R2, R3, TL, JT, false><<<grid, TL * JT, smem, st>>>(g, ntiles, B, (T)kappa, kind, tb, (cx<T>*)spec,
-                                                                                         (const cx<T>*)tw, scalars, want_vir);
+            launch_pdl(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, false>, grid, TL * JT, smem, st, g, ntiles, B, (T)kappa, kind, tb, (cx<T>*)spec,
+                       (const cx<T>*)tw, scalars, want_vir);
     }
     static void zfwd(cudaStream_t st, int nlines, int ntiles, int grid, const void* mesh, void* spec, const void* tw) {
         const size_t smem = (size_t)(2 * ZTL * ZGeom<N>::LS + TwGeom<R1, R2, R3>::TOTAL + N + 1) * sizeof(cx<T>);
-        fast_z_fwd_kernel<T, R1, R2, R3, ZTL, ZJT><<<grid, ZTL * ZJT, smem, st>>>(nlines, ntiles, (const T*)mesh, (cx<T>*)spec, (const cx<T>*)tw);
+        launch_pdl(fast_z_fwd_kernel<T, R1, R2, R3, ZTL, ZJT>, grid, ZTL * ZJT, smem, st, nlines, ntiles, (const T*)mesh, (cx<T>*)spec, (const cx<T>*)tw);
     }
     static void zinv(cudaStream_t st, int nlines, int ntiles, int grid, const void* spec, void* mesh, const void* tw) {
         const size_t smem = (size_t)(2 * ZTL * ZGeom<N>::LS + TwGeom<R1, R2, R3>::TOTAL + N + 1) * sizeof(cx<T>);
-        fast_z_inv_kernel<T, R1, R2, R3, ZTL, ZJT><<<grid, ZTL * ZJT, smem, st>>>(nlines, ntiles, (const cx<T>*)spec, (T*)mesh, (const cx<T>*)tw);
+        launch_pdl(fast_z_inv_kernel<T, R1, R2, R3, ZTL, ZJT>, grid, ZTL * ZJT, smem, st, nlines, ntiles, (const cx<T>*)spec, (T*)mesh, (const cx<T>*)tw);
     }
     static FastOps ops() {
         FastOps o = {};

@@ -44,6 +44,30 @@ def timed(name, fn):
                                                            cx.lib.admp_ctx_fft_backend(cx.handle)))
 
 
+def warm(name, fn, reps=20):
+    """back-to-back launches, no L2 flush in between (the in-loop regime of the SCF cycle)"""
+    _lib.check(fn())
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        _lib.check(fn())
+    b.record()
+    b.synchronize()
+    print('%-28s %9.4f ms warm (back to back x%d)' % (name, a.elapsed_time(b) / reps, reps))
+
+
+if os.environ.get('PROF_WARM'):
+    warm('spread (zero + scatter)', lambda: cx.lib.admp_pme_spread(cx.handle, sp(), p(pos), p(box), p(M), 10, 10, None))
+    warm('fused roundtrip', lambda: cx.lib.admp_pme_fft_convolve(cx.handle, sp(), _lib.CK_COULOMB, 0, p(scal)))
+    for k, nm in enumerate(['pass z_fwd', 'pass y_fwd', 'pass x_conv', 'pass y_inv', 'pass z_inv']):
+        warm(nm, lambda k=k: cx.lib.admp_pme_fft_pass(cx.handle, sp(), k, _lib.CK_COULOMB, p(scal)))
+    Fs = torch.zeros((n, 3), dtype=dt, device=dev)
+    warm('gather (field only)', lambda: cx.lib.admp_pme_gather(cx.handle, sp(), p(pos), p(M), 10, 10, None, 1, 0, None, None, 10, p(Fs), p(scal)))
+    warm('gather (full)', lambda: cx.lib.admp_pme_gather(cx.handle, sp(), p(pos), p(M), 10, 10, None, 0, _lib.WANT_GRAD, p(dpos), p(G), 10,
+                                                       None, p(scal)))
+    torch.cuda.synchronize()
+    sys.exit(0)
+
 timed('spread (zero + scatter)', lambda: cx.lib.admp_pme_spread(cx.handle, sp(), p(pos), p(box), p(M), 10, 10, None))
 if cx.lib.admp_ctx_fft_backend(cx.handle):
     timed('fused fft+convolve roundtrip', lambda: cx.lib.admp_pme_fft_convolve(cx.handle, sp(), _lib.CK_COULOMB, 0, p(scal)))
