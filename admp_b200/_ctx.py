@@ -74,6 +74,23 @@ class Context:
         self.n_atoms = int(n_atoms)
         del keep
 
+    def mesh_view(self, K):
+        """Zero-copy torch view (K1, K2, K3) of the context's real mesh (the buffer admp_pme_spread_range
+        accumulates into and the FFT passes read): lets torch.distributed all-reduce it in place."""
+        self.lib.admp_ctx_buffer.restype = ctypes.c_void_p
+        ptr = self.lib.admp_ctx_buffer(self.handle, 0)
+        if not ptr:
+            raise _lib.AdmpLibraryError('admp_ctx_set_pme has not been called')
+
+        class _Raw:
+            pass
+        raw = _Raw()
+        raw.__cuda_array_interface__ = dict(shape=tuple(int(k) for k in K), typestr='<f8' if self.dtype == torch.float64 else '<f4',
+                                            data=(int(ptr), False), version=2)
+        t = torch.as_tensor(raw, device=self.device)
+        t._admp_ctx_keepalive = self            # the view must not outlive the context's allocation
+        return t
+
     @property
     def workspace_bytes(self):
         return int(self.lib.admp_ctx_workspace_bytes(self.handle))

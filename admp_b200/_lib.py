@@ -76,7 +76,7 @@ def load():
     lib.admp_pme_gather_range.argtypes = [vp, vp, vp, vp, i32, i32, vp, i32, u32, vp, vp, i32, vp, vp, i32, i32]
     lib.admp_pme_self_range.argtypes = [vp, vp, vp, vp, vp, u32, vp, vp, vp, vp, i32, i32]
     lib.admp_frames_bwd_range.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32]
-    lib.admp_scf_step.argtypes = [vp, vp, vp, vp, vp, vp, i32, dbl, vp, vp]
+    lib.admp_scf_step.argtypes = [vp, vp, vp, vp, vp, vp, i32, dbl, u32, vp, vp]
     lib.admp_virial_finalize.argtypes = [vp, vp, vp]
     lib.admp_ctx_fft_backend.argtypes = [vp]
     lib.admp_ctx_set_fft_backend.argtypes = [vp, i32]

@@ -571,14 +571,14 @@ extern "C" int admp_frames_bwd_range(admp_ctx* c, void* stream, const void* pos,
  * self/penalty part, reduces max|F|, tests, updates U (admp/pme.py:133-138). state: int32[8] device,
  * zeroed by the caller before the first cycle; state[5] = continue flag. */
 extern "C" int admp_scf_step(admp_ctx* c, void* stream, const void* M, void* U, const void* pol, void* F, int maxiter, double thresh,
-                             int32_t* state, double* scalars) {
+                             uint32_t flags, int32_t* state, double* scalars) {
     if (need(c, false, true)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     cudaGraphConditionalHandle none;
     memset(&none, 0, sizeof(none));
     CK(cudaMemsetAsync(scalars + ADMP_S_MAXFIELD, 0, sizeof(double), st));
     DISPATCH(c, launch_scf_field, st, c->n_atoms, c->kappa, M, U, pol, F, scalars);
-    launch_scf_decide(st, state, scalars, maxiter, thresh, 1, none, 0);
+    launch_scf_decide(st, state, scalars, maxiter, thresh, (flags & ADMP_WANT_VIRIAL) ? 0 : 1, none, 0);
     DISPATCH(c, launch_scf_update, st, c->n_atoms, state, F, pol, U, 0);
     CKLAUNCH();
     return 0;

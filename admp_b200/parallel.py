@@ -108,7 +108,7 @@ def evaluate_frames(calc, frames, box, pairs, Q_local, pol=None, tholes=None, mS
                 acc['dpScales'] += r.scalars[_lib.S_DPSCALE:_lib.S_DPSCALE + 5]
                 acc['dtholes'] += r.dtholes
                 acc['dpol'] += r.dpol
-    if param_grads:
+    if param_grads and world > 1:
         allreduce_sum_(list(acc.values()), group)
     return dict(frames=mine, energies=torch.stack(energies) if energies else torch.zeros(0, dtype=torch.float64, device=dev),
                 dpos=grads, param_grads=acc if param_grads else None)
@@ -130,7 +130,7 @@ class AtomBlockPme:
         self.mine = [rank] if emulate_blocks is None else list(range(self.nblocks))
         self._mesh = None
 
-    # the mesh all-reduce goes through a torch buffer (NCCL operates on torch tensors)
+    # the mesh all-reduce runs in place on a zero-copy torch view of the context's mesh
     def _allreduce_mesh(self):
         import torch.distributed as dist
         if self.world == 1:
@@ -138,11 +138,8 @@ class AtomBlockPme:
         c = self.calc._ctx
         K = (self.calc.K1, self.calc.K2, self.calc.K3)
         if self._mesh is None or tuple(self._mesh.shape) != K:
-            self._mesh = torch.empty(K, dtype=c.dtype, device=c.device)
-        nb = self._mesh.numel() * self._mesh.element_size()
-        _lib.check(c.lib.admp_ctx_buffer_io(c.handle, _lib.stream_ptr(), 0, _lib.ptr(self._mesh), nb, 0))
+            self._mesh = c.mesh_view(K)
         dist.all_reduce(self._mesh, op=dist.ReduceOp.SUM, group=self.group)
-        _lib.check(c.lib.admp_ctx_buffer_io(c.handle, _lib.stream_ptr(), 0, _lib.ptr(self._mesh), nb, 1))
 
     def evaluate(self, positions, box, pairs, Q_local, pol=None, tholes=None, mScales=None, pScales=None, U_init=None,
                  want_virial=True, maxiter=None, thresh=None):
@@ -178,7 +175,7 @@ class AtomBlockPme:
             state = torch.zeros(8, dtype=torch.int32, device=dev)
             for _ in range(maxiter + 1):
                 scal.zero_()
-                self._recip(pos, M, U, blocks, scal, vir)
+                self._recip(pos, M, U, blocks, scal, 0)          # SCF cycles: energy-only (quick) X pass
                 F.zero_()
                 for a0, ac, my_pairs, rc in blocks:
                     _lib.check(lib.admp_pme_gather_range(c.handle, sp(), p(pos), p(M), 10, 10, p(U), 1, 0, None, None, 10, p(F), p(scal),
@@ -188,11 +185,17 @@ class AtomBlockPme:
                         _lib.check(lib.admp_pme_real(c.handle, sp(), p(pos), p(box), p(my_pairs), rc, p(M), p(U), p(polt), p(th), p(mS),
                                                      p(pS), 1, 0, None, None, p(F), None, None, p(scal)))
                 allreduce_sum_([F], self.group)
-                _lib.check(lib.admp_scf_step(c.handle, sp(), p(M), p(U), p(polt), p(F), int(maxiter), float(thresh), p(state), p(scal)))
+                _lib.check(lib.admp_scf_step(c.handle, sp(), p(M), p(U), p(polt), p(F), int(maxiter), float(thresh), vir, p(state),
+                                             p(scal)))
                 st = state.cpu()
                 if not int(st[5]):
                     n_cycle, conv = int(st[3]), bool(st[4])
                     break
+            if want_virial:
+                # final reciprocal pass on the final U with the k-space virial sums (also the refresh pass
+                # after the last allowed update), as in admp_pme_eval
+                scal.zero_()
+                self._recip(pos, M, U, blocks, scal, vir)
         else:
             self._recip(pos, M, None, blocks, scal, vir)
         # final evaluation at fixed U; phi of the last round trip is in the context's mesh

@@ -168,9 +168,11 @@ int admp_frames_bwd_range(admp_ctx* ctx, void* stream, const void* pos, const vo
                           int count);
 /* one optimize_Uind cycle on an assembled field (admp/pme.py:133-138): adds the self/penalty part to F,
  * tests max|F| < thresh over pol > 0.001 sites BEFORE updating U. state: device int32[8], zero before the
- * first cycle; state[0]=cycle, [3]=n_cycle, [4]=converged, [5]=continue. */
+ * first cycle; state[0]=cycle, [3]=n_cycle, [4]=converged, [5]=continue. flags & ADMP_WANT_VIRIAL: the
+ * caller runs its own final reciprocal pass (with the k-space virial sums) after the loop, so the loop
+ * does not add a refresh pass after the last allowed update. */
 int admp_scf_step(admp_ctx* ctx, void* stream, const void* M, void* U, const void* pol, void* F,
-                  int maxiter, double thresh, int32_t* state, double* scalars);
+                  int maxiter, double thresh, uint32_t flags, int32_t* state, double* scalars);
 /* folds the reciprocal-space accumulators of `scalars` into dE/dbox (ADMP_S_DBOX) */
 int admp_virial_finalize(admp_ctx* ctx, void* stream, double* scalars);
 

@@ -51,14 +51,18 @@ def main():
         frames = [s.jitter(1000 + f).numpy() for f in range(6)]
         res = evaluate_frames(calc, frames, s.box, pairs, s.Q_local, s.pol, s.tholes, s.mScales, s.pScales, rank=rank, world=world)
         one = evaluate_frames(calc, frames, s.box, pairs, s.Q_local, s.pol, s.tholes, s.mScales, s.pScales, rank=0, world=1)
+        ferr = {}
         for k in res['param_grads']:
-            ok = ok and rel(res['param_grads'][k], one['param_grads'][k]) < 1e-10
-        for j, f in enumerate(res['frames']):
-            ok = ok and abs(res['energies'][j].item() - one['energies'][f].item()) < 1e-10 * abs(one['energies'][f].item())
+            ferr[k] = rel(res['param_grads'][k], one['param_grads'][k])
+        ferr['E'] = max(abs(res['energies'][j].item() - one['energies'][f].item()) / abs(one['energies'][f].item())
+                        for j, f in enumerate(res['frames']))
+        # atomics make the summation order run-dependent: 1e-9 relative is the reproducibility floor asserted here
+        ok = ok and all(v < 1e-9 for v in ferr.values())
         flag = torch.tensor([1.0 if ok else 0.0], device='cuda')
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if rank == 0:
             print('atom-block errors', errs)
+            print('frame-sharding errors', ferr)
             print('MULTIGPU CHECK OK' if flag.item() > 0 else 'MULTIGPU CHECK FAILED')
         dist.barrier()
         dist.destroy_process_group()
