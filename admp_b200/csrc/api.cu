@@ -67,6 +67,7 @@ struct admp_ctx {
     void *M = nullptr, *G = nullptr, *Fscf = nullptr;
     void *s_pos = nullptr, *s_U = nullptr, *s_pol = nullptr, *s_th = nullptr, *s_mS = nullptr, *s_pS = nullptr, *s_box = nullptr;
     int32_t* s_pairs = nullptr;
+    int8_t* s_sidx = nullptr;       // scale index per staged pair row (-1: row not evaluated)
     int64_t pairs_cap = 0;
     double* scal = nullptr;
     int32_t* state = nullptr;
@@ -152,7 +153,7 @@ extern "C" int admp_ctx_destroy(admp_ctx* c) {
     drop_graph(c);
     free_recip(c);
     free_atoms(c);
-    dfree(c->s_pairs); dfree(c->box); dfree(c->scal); dfree(c->state); dfree(c->s_mS); dfree(c->s_pS); dfree(c->s_box);
+    dfree(c->s_pairs); dfree(c->s_sidx); dfree(c->box); dfree(c->scal); dfree(c->state); dfree(c->s_mS); dfree(c->s_pS); dfree(c->s_box);
     dfree(c->nb.cell_of); dfree(c->nb.cell_count); dfree(c->nb.cell_start); dfree(c->nb.sorted); dfree(c->nb.nbr_count); dfree(c->nb.nbr_start);
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
@@ -390,7 +391,7 @@ extern "C" int admp_pme_real(admp_ctx* c, void* stream, const void* pos, const v
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(c->device));
     DISPATCH(c, launch_box_setup, st, box, c->box, c->K[0], c->K[1], c->K[2]);
-    DISPATCH(c, launch_pme_pair, st, n_rows, c->n_atoms, c->box, c->kappa, pos, pairs, c->cov_off, c->cov_idx, c->cov_nb, M, U, pol,
+    DISPATCH(c, launch_pme_pair, st, n_rows, c->n_atoms, c->box, c->kappa, pos, pairs, nullptr, c->cov_off, c->cov_idx, c->cov_nb, M, U, pol,
              tholes, mScales, pScales, mode, flags, dpos, G, F, dpol, dtholes, scalars);
     CKLAUNCH();
     return 0;
@@ -602,7 +603,7 @@ static int scf_body(admp_ctx* c, cudaStream_t st, int maxiter, double thresh, ui
     const int refresh_in_loop = (flags & ADMP_WANT_VIRIAL) ? 0 : 1;
     CK(cudaEventRecord(c->ev_fork, st));
     CK(cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
-    DISPATCH(c, launch_pme_pair, c->side_stream, c->pairs_cap, c->n_atoms, c->box, c->kappa, c->s_pos, c->s_pairs, c->cov_off, c->cov_idx,
+    DISPATCH(c, launch_pme_pair, c->side_stream, c->pairs_cap, c->n_atoms, c->box, c->kappa, c->s_pos, c->s_pairs, c->s_sidx, c->cov_off, c->cov_idx,
              c->cov_nb, c->M, c->s_U, c->s_pol, c->s_th, c->s_mS, c->s_pS, 1, 0u, nullptr, nullptr, c->Fscf, nullptr, nullptr, c->scal);
     CK(cudaEventRecord(c->ev_join, c->side_stream));
     if (recip_field(c, st, c->s_pos, c->M, 10, 10, c->s_U, ADMP_CK_COULOMB, c->scal, 0, false)) return 1;
@@ -674,8 +675,10 @@ static int ensure_pairs(admp_ctx* c, int64_t n_rows) {
     if (n_rows <= c->pairs_cap) return 0;
     drop_graph(c);
     dfree(c->s_pairs);
+    dfree(c->s_sidx);
     int64_t cap = n_rows + n_rows / 4 + 1024;
     CK(cudaMalloc(&c->s_pairs, sizeof(int32_t) * 2 * cap));
+    CK(cudaMalloc(&c->s_sidx, (size_t)cap));
     c->pairs_cap = cap;
     return 0;
 }
@@ -701,6 +704,7 @@ extern "C" int admp_pme_eval(admp_ctx* c, void* stream, const void* pos, const v
     CK(cudaMemcpyAsync(c->s_box, box, 9 * w, cudaMemcpyDeviceToDevice, st));
     CK(cudaMemsetAsync(c->s_pairs, 0, sizeof(int32_t) * 2 * c->pairs_cap, st));        // (0,0) rows are skipped (i<j fails)
     if (n_rows > 0) CK(cudaMemcpyAsync(c->s_pairs, pairs, sizeof(int32_t) * 2 * n_rows, cudaMemcpyDeviceToDevice, st));
+    launch_pair_scale(st, c->pairs_cap, n, c->s_pairs, c->cov_off, c->cov_idx, c->cov_nb, c->s_sidx);
     CK(cudaMemcpyAsync(c->s_mS, mScales, 5 * w, cudaMemcpyDeviceToDevice, st));
     if (polz) {
         CK(cudaMemcpyAsync(c->s_U, U_io, (size_t)n * 3 * w, cudaMemcpyDeviceToDevice, st));
@@ -739,7 +743,7 @@ extern "C" int admp_pme_eval(admp_ctx* c, void* stream, const void* pos, const v
     if (flags & ADMP_WANT_GRAD) {
         DISPATCH(c, launch_gather, st, n, c->box, c->s_pos, c->M, 10, 10, Uf, c->mesh, 0, f, dpos, c->G, 10, polz ? F : nullptr, c->scal);
     }
-    DISPATCH(c, launch_pme_pair, st, c->pairs_cap, n, c->box, c->kappa, c->s_pos, c->s_pairs, c->cov_off, c->cov_idx, c->cov_nb, c->M, Uf,
+    DISPATCH(c, launch_pme_pair, st, c->pairs_cap, n, c->box, c->kappa, c->s_pos, c->s_pairs, c->s_sidx, c->cov_off, c->cov_idx, c->cov_nb, c->M, Uf,
              polz ? c->s_pol : nullptr, polz ? c->s_th : nullptr, c->s_mS, polz ? c->s_pS : nullptr, 0, f, dpos, c->G, F, dpol, dtholes, c->scal);
     DISPATCH(c, launch_self, st, n, c->kappa, c->M, Uf, polz ? c->s_pol : nullptr, f, c->G, F, dpol, c->scal);
     if (flags & ADMP_WANT_GRAD) {

@@ -468,8 +468,10 @@ static StrideGeom geom_x(const Fft3dImpl* f, int TL) {
 // every block gets the same number of tiles (no block does one tile more than the rest: on the L2-resident
 // 154^3 mesh a pass is only 2-3 tiles per block, so an uneven deal costs a third of the pass)
 static int persistent_grid(const Fft3dImpl* f, int occ, int ntiles) {
+    static const bool balanced = [] { const char* e = getenv("ADMP_FFT_BALANCED"); return e && atoi(e) > 0; }();
     const long long cap = (long long)f->n_sm * (occ > 0 ? occ : 1);
     if (ntiles <= cap) return ntiles;
+    if (!balanced) return (int)cap;
     const long long waves = (ntiles + cap - 1) / cap;
     return (int)((ntiles + waves - 1) / waves);
 }

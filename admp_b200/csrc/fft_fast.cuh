@@ -50,7 +50,11 @@ static void launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem,
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = enabled ? 1 : 0;
+    // measured on B200: +12 % on back-to-back stream launches, -3 % inside the captured SCF graph (the early
+    // blocks of the successor hold SM slots while they wait) - so only outside stream capture
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    cfg.numAttrs = (enabled && cs == cudaStreamCaptureStatusNone) ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 

@@ -17,9 +17,11 @@ void launch_frames_bwd(cudaStream_t st, int n, int lmax, const BoxInfo* B, const
 template <typename T> void launch_rotate(cudaStream_t st, int64_t n, int lmax, int to_local, const void* Q, const void* Fr, void* out);
 
 // pair.cu
+void launch_pair_scale(cudaStream_t st, int64_t n_rows, int n_atoms, const int32_t* pairs, const int32_t* cov_off,
+                       const int32_t* cov_idx, const int8_t* cov_nb, int8_t* sidx);
 template <typename T>
 void launch_pme_pair(cudaStream_t st, int64_t n_rows, int n_atoms, const BoxInfo* B, double kappa, const void* pos,
-                     const int32_t* pairs, const int32_t* cov_off, const int32_t* cov_idx, const int8_t* cov_nb,
+                     const int32_t* pairs, const int8_t* sidx, const int32_t* cov_off, const int32_t* cov_idx, const int8_t* cov_nb,
                      const void* M, const void* U, const void* pol, const void* tholes, const void* mS, const void* pS,
                      int mode, uint32_t flags, void* dpos, void* G, void* F, void* dpol, void* dth, double* scalars);
 template <typename T>
