@@ -81,6 +81,9 @@ struct admp_ctx {
     double g_thresh = -1.0;
     uint32_t g_flags = 0;
     bool graph_failed = false;
+    // x-slab decomposition over the GPUs of one NVLink domain (admp_ctx_set_peers)
+    int peer_rank = 0, peer_n = 0;
+    PeerTab mesh_peers = {}, spec_peers = {};
     // neighbour list
     NbWork nb = {};
     size_t ws_bytes = 0;
@@ -140,6 +143,7 @@ static void free_recip(admp_ctx* c) {
     dfree(c->ek); dfree(c->k2); dfree(c->ortho);
     if (c->fft) { fft3d_destroy(c->fft); c->fft = nullptr; }
     c->use_custom_fft = false;
+    c->peer_n = 0;
 }
 
 static void free_atoms(admp_ctx* c) {
@@ -568,6 +572,96 @@ extern "C" int admp_frames_bwd_range(admp_ctx* c, void* stream, const void* pos,
     CKLAUNCH();
     return 0;
 }
+// ------------------------------------------------------------------------------------------ x-slab stages
+// Multi-GPU reciprocal space without a replicated mesh: rank r owns the x planes [r*K1/n, (r+1)*K1/n) of the
+// real mesh and of the half spectrum (every rank keeps full-size buffers so the element offsets are the
+// single-GPU ones; only the own planes are ever touched locally). Spread and gather address the owner of each
+// stencil plane through the peer table (NVLink peer atomics / loads for stencils that cross a slab boundary);
+// the Z and Y passes run on the own planes; the fused X pass transforms this rank's share of the (y, kz)
+// columns straight out of / into all ranks' planes. The caller (admp_b200/parallel.py) orders the stages with
+// stream-ordered cross-rank barriers.
+extern "C" int admp_ipc_export(const void* devptr, void* handle64) {
+    if (!devptr || !handle64) return fail("admp_ipc_export: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, const_cast<void*>(devptr)));
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+extern "C" int admp_ipc_open(const void* handle64, void** out) {
+    if (!handle64 || !out) return fail("admp_ipc_open: null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    CK(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+extern "C" int admp_ipc_close(void* devptr) {
+    if (devptr) CK(cudaIpcCloseMemHandle(devptr));
+    return 0;
+}
+extern "C" int admp_ctx_set_peers(admp_ctx* c, int rank, int nranks, void* const* mesh_ptrs, void* const* spec_ptrs) {
+    if (need(c, true, false)) return 1;
+    if (nranks == 0) { c->peer_n = 0; return 0; }
+    if (nranks < 1 || nranks > ADMP_MAX_PEERS) return fail("admp_ctx_set_peers: %d ranks (1..%d supported)", nranks, ADMP_MAX_PEERS);
+    if (rank < 0 || rank >= nranks) return fail("admp_ctx_set_peers: rank %d outside [0,%d)", rank, nranks);
+    if (c->K[0] % nranks) return fail("admp_ctx_set_peers: K1 = %d is not a multiple of %d ranks", c->K[0], nranks);
+    if (!c->fft || !fft3d_slab_supported(c->fft))
+        return fail("admp_ctx_set_peers: the x-slab passes need the register-blocked FFT kernels (mesh family 154*2^n); %s", c->fft_note.c_str());
+    if (!mesh_ptrs || !spec_ptrs) return fail("admp_ctx_set_peers: null pointer tables");
+    if (mesh_ptrs[rank] != c->mesh || spec_ptrs[rank] != c->spec) return fail("admp_ctx_set_peers: entry %d must be this context's own buffers", rank);
+    for (int r = 0; r < ADMP_MAX_PEERS; ++r) {
+        c->mesh_peers.base[r] = r < nranks ? mesh_ptrs[r] : nullptr;
+        c->spec_peers.base[r] = r < nranks ? spec_ptrs[r] : nullptr;
+        if (r < nranks && (!mesh_ptrs[r] || !spec_ptrs[r])) return fail("admp_ctx_set_peers: null buffer for rank %d", r);
+    }
+    c->mesh_peers.slab = c->spec_peers.slab = c->K[0] / nranks;
+    c->mesh_peers.n = c->spec_peers.n = nranks;
+    c->peer_rank = rank;
+    c->peer_n = nranks;
+    return 0;
+}
+static int need_peers(admp_ctx* c) {
+    if (need(c, true, false)) return 1;
+    if (c->peer_n < 1) return fail("admp_ctx_set_peers has not been called");
+    return 0;
+}
+/* zero the own planes of the mesh */
+extern "C" int admp_slab_zero(admp_ctx* c, void* stream) {
+    if (need_peers(c)) return 1;
+    const size_t plane = (size_t)c->K[1] * c->K[2] * c->w;
+    CK(cudaMemsetAsync((char*)c->mesh + plane * c->mesh_peers.slab * c->peer_rank, 0, plane * c->mesh_peers.slab, (cudaStream_t)stream));
+    return 0;
+}
+/* spread `count` atoms (compact arrays) onto the decomposed mesh */
+extern "C" int admp_slab_spread(admp_ctx* c, void* stream, const void* pos, const void* M, int M_cols, int M_stride, const void* U,
+                                int count) {
+    if (need_peers(c)) return 1;
+    if (count < 0) return fail("admp_slab_spread: negative count");
+    DISPATCH(c, launch_spread, (cudaStream_t)stream, count, c->box, pos, M, M_cols, M_stride, U, c->mesh, &c->mesh_peers);
+    CKLAUNCH();
+    return 0;
+}
+/* phase 0: Z-forward + Y-forward (own planes); 1: fused X pass on the own column share (peer access);
+ * 2: Y-inverse + Z-inverse (own planes). E_recip / virial sums accumulate this rank's share only. */
+extern "C" int admp_slab_fft(admp_ctx* c, void* stream, int phase, int kind, uint32_t flags, double* scalars) {
+    if (need_peers(c)) return 1;
+    if (phase < 0 || phase > 2) return fail("admp_slab_fft: phase %d", phase);
+    fft3d_slab_phase(c->fft, (cudaStream_t)stream, phase, c->peer_rank, c->mesh, c->spec, c->spec_peers, c->box, c->kappa, kind, c->tb,
+                     scalars, (flags & ADMP_WANT_VIRIAL) ? 1 : 0);
+    CKLAUNCH();
+    return 0;
+}
+/* gather for `count` atoms (compact arrays) from the decomposed potential mesh */
+extern "C" int admp_slab_gather(admp_ctx* c, void* stream, const void* pos, const void* M, int M_cols, int M_stride, const void* U,
+                                int mode, uint32_t flags, void* dpos, void* G, int G_stride, void* F, double* scalars, int count) {
+    if (need_peers(c)) return 1;
+    if (count < 0) return fail("admp_slab_gather: negative count");
+    DISPATCH(c, launch_gather, (cudaStream_t)stream, count, c->box, pos, M, M_cols, M_stride, U, c->mesh, mode, flags, dpos, G, G_stride, F,
+             scalars, &c->mesh_peers);
+    CKLAUNCH();
+    return 0;
+}
+
 /* one Jacobi decision on an already-assembled field F (pair + reciprocal parts, all atoms): adds the
  * self/penalty part, reduces max|F|, tests, updates U (admp/pme.py:133-138). state: int32[8] device,
  * zeroed by the caller before the first cycle; state[5] = continue flag. */

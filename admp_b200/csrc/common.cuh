@@ -23,6 +23,16 @@ struct BoxInfo {
     int K[3];
 };
 
+// x-slab decomposition of the mesh / half spectrum over the GPUs of one NVLink domain: plane i1 of the
+// (K1, K2, K3) array lives at the usual offset ((i1*K2 + i2)*K3 + i3) inside base[i1 / slab], where base[r] is
+// rank r's buffer mapped into this process (cudaIpc peer mapping, or a plain pointer for r == own rank).
+constexpr int ADMP_MAX_PEERS = 8;
+struct PeerTab {
+    void* base[ADMP_MAX_PEERS];
+    int slab;      // planes per rank (K1 / n)
+    int n;         // ranks
+};
+
 template <typename T> __device__ __forceinline__ T ldg(const T* p) { return __ldg(p); }
 
 __device__ __forceinline__ double warp_sum(double v) {

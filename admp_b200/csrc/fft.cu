@@ -476,10 +476,14 @@ static int persistent_grid(const Fft3dImpl* f, int occ, int ntiles) {
     return (int)((ntiles + waves - 1) / waves);
 }
 
+// x0 / nx: restrict the pass to the planes [x0, x0 + nx) of the buffers (x-slab decomposition); nx < 0 = all
 template <typename T>
-static void run_z(Fft3dImpl* f, cudaStream_t st, void* mesh, void* spec, int sign) {
+static void run_z(Fft3dImpl* f, cudaStream_t st, void* mesh, void* spec, int sign, int x0 = 0, int nx = -1) {
     const int K3 = f->K[2];
-    const int nlines = f->K[0] * f->K[1];
+    if (nx < 0) nx = f->K[0];
+    const int nlines = nx * f->K[1];
+    mesh = (char*)mesh + (size_t)x0 * f->K[1] * K3 * sizeof(T);
+    spec = (char*)spec + (size_t)x0 * f->K[1] * (K3 / 2 + 1) * sizeof(cx<T>);
     const FftDimCfg& c = f->z;
     const cx<T>* tw = (const cx<T>*)f->tw[2];
     if (c.fast) {
@@ -494,11 +498,15 @@ static void run_z(Fft3dImpl* f, cudaStream_t st, void* mesh, void* spec, int sig
 }
 
 template <typename T>
-static void run_strided(Fft3dImpl* f, cudaStream_t st, void* spec, int dim, int sign) {
+static void run_strided(Fft3dImpl* f, cudaStream_t st, void* spec, int dim, int sign, int x0 = 0, int nx = -1) {
     const FftDimCfg& c = dim == 1 ? f->y : f->x;
     const cx<T>* tw = (const cx<T>*)f->tw[dim == 1 ? 1 : 0];
     if (c.fast) {
-        const StrideGeom g = dim == 1 ? geom_y(f, c.ops.TL) : geom_x(f, c.ops.TL);
+        StrideGeom g = dim == 1 ? geom_y(f, c.ops.TL) : geom_x(f, c.ops.TL);
+        if (dim == 1 && nx >= 0) {
+            g.n_outer = nx;
+            spec = (char*)spec + (size_t)x0 * g.outer_stride * sizeof(cx<T>);
+        }
         const int ntiles = g.n_outer * g.tiles;
         c.ops.strided(st, sign, g, ntiles, persistent_grid(f, c.ops.occ[sign > 0 ? 0 : 1], ntiles), spec, tw);
         return;
@@ -521,6 +529,41 @@ static void run_x_conv(Fft3dImpl* f, cudaStream_t st, void* spec, const BoxInfo*
     }
     const StrideGeom g = geom_x(f, c.TL);
     fft_x_conv_kernel<T><<<g.tiles, 256, c.smem, st>>>(c.P, c.TL, c.LS, g, B, (T)kappa, kind, tb, (cx<T>*)spec, tw, scalars, want_vir);
+}
+
+// ---- x-slab decomposed round trip over several GPUs (each rank owns K1/n consecutive x planes of mesh and
+// spectrum; buffers keep the full-size indexing). phase 0: Z-forward + Y-forward on the own planes;
+// phase 1: fused X pass (forward, influence function, inverse) on this rank's share of the (y, kz) columns,
+// reading and writing all ranks' planes through the peer table; phase 2: Y-inverse + Z-inverse on the own planes.
+// The caller places a cross-rank barrier between the phases.
+bool fft3d_slab_supported(const Fft3d* p) {
+    const Fft3dImpl* f = reinterpret_cast<const Fft3dImpl*>(p);
+    return f && f->z.fast && f->y.fast && f->x.fast && f->x.ops.occ_peer[0] > 0 && f->x.ops.occ_peer[1] > 0;
+}
+template <typename T>
+static void slab_phase(Fft3dImpl* f, cudaStream_t st, int phase, int rank, void* mesh, void* spec, const PeerTab& peers, const BoxInfo* B,
+                       double kappa, int kind, const ConvTables& tb, double* scalars, int want_vir) {
+    const int x0 = rank * peers.slab, nx = peers.slab;
+    if (phase == 0) {
+        run_z<T>(f, st, mesh, spec, 1, x0, nx);
+        run_strided<T>(f, st, spec, 1, 1, x0, nx);
+    } else if (phase == 1) {
+        const FftDimCfg& c = f->x;
+        const StrideGeom g = geom_x(f, c.ops.TL);
+        const int t0 = (int)((long long)g.tiles * rank / peers.n), t1 = (int)((long long)g.tiles * (rank + 1) / peers.n);
+        const bool quick = kind == ADMP_CK_COULOMB && !want_vir;
+        const int grid = persistent_grid(f, c.ops.occ_peer[quick ? 0 : 1], t1 - t0);
+        if (t1 > t0) c.ops.xconv_peer(st, g, t0, t1, grid, B, kappa, kind, tb, f->tw[0], scalars, want_vir, peers);
+    } else {
+        run_strided<T>(f, st, spec, 1, -1, x0, nx);
+        run_z<T>(f, st, mesh, spec, -1, x0, nx);
+    }
+}
+void fft3d_slab_phase(Fft3d* p, cudaStream_t st, int phase, int rank, void* mesh, void* spec, const PeerTab& peers, const BoxInfo* B,
+                      double kappa, int kind, const ConvTables& tb, double* scalars, int want_vir) {
+    Fft3dImpl* f = reinterpret_cast<Fft3dImpl*>(p);
+    if (f->esz == 8) slab_phase<double>(f, st, phase, rank, mesh, spec, peers, B, kappa, kind, tb, scalars, want_vir);
+    else slab_phase<float>(f, st, phase, rank, mesh, spec, peers, B, kappa, kind, tb, scalars, want_vir);
 }
 
 // plain transforms (same conventions as cuFFT D2Z / Z2D: unnormalised)

@@ -224,6 +224,19 @@ __device__ __forceinline__ void issue_tile(const StrideGeom& g, int tile, const 
     cp_async_commit();
 }
 
+// X pass over an x-slab decomposed spectrum (PeerTab): point `pos` of every line lives in the buffer of rank
+// pos / slab; `sbase[pos]` (shared memory) holds that buffer's base pointer, element offsets are unchanged.
+template <typename T, int N, int TL, int JT>
+__device__ __forceinline__ void issue_tile_peer(const StrideGeom& g, int tile, cx<T>* const* sbase, cx<T>* dst, int l, int j) {
+    const int c0 = tile * TL;
+    const int nl = min(TL, g.n_inner - c0);
+    if (l < nl) {
+#pragma unroll 4
+        for (int pos = j; pos < N; pos += JT) cp_async<sizeof(cx<T>)>(dst + pos * TL + l, sbase[pos] + (size_t)pos * g.line_stride + c0 + l);
+    }
+    cp_async_commit();
+}
+
 template <typename T, int R1, int R2, int R3, int SIGN, int TL, int JT>
 __global__ void __launch_bounds__(TL* JT, MinBlocks<TL * JT, R3>::value)
 fast_strided_kernel(StrideGeom g, int ntiles, cx<T>* __restrict__ spec, const cx<T>* __restrict__ gtw) {
@@ -280,10 +293,13 @@ __device__ __noinline__ double influence_general(const BoxInfo* Bp, const ConvTa
 // (admp/recip.py:410-426 fused with its adjoint). QUICK = Coulomb energy only (every SCF cycle): separable
 // tables of conv_tables_kernel + one reciprocal per point when the cell is orthorhombic (device flag),
 // inline exp otherwise; !QUICK = any kind / virial sums through influence_general.
-template <typename T, int R1, int R2, int R3, int TL, int JT, bool QUICK>
+// PEER: the spectrum is x-slab decomposed over the GPUs of the NVLink domain; this rank transforms the lines
+// of tiles [tile0, ntiles) by loading / storing every point from / to the rank that owns its x plane (cp.async
+// and stores on peer-mapped memory): the all-to-all transposes of a slab FFT are fused into the X pass.
+template <typename T, int R1, int R2, int R3, int TL, int JT, bool QUICK, bool PEER>
 __global__ void __launch_bounds__(TL* JT, MinBlocks<TL * JT, R3>::value)
-fast_x_conv_kernel(StrideGeom g, int ntiles, const BoxInfo* __restrict__ Bp, T kappa, int kind, ConvTables tb, cx<T>* __restrict__ spec,
-                   const cx<T>* __restrict__ gtw, double* __restrict__ scalars, int want_vir) {
+fast_x_conv_kernel(StrideGeom g, int tile0, int ntiles, const BoxInfo* __restrict__ Bp, T kappa, int kind, ConvTables tb,
+                   cx<T>* __restrict__ spec, const cx<T>* __restrict__ gtw, double* __restrict__ scalars, int want_vir, PeerTab peers) {
     constexpr int N = R1 * R2 * R3, TILE = N * TL, NT = TL * JT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[7 * ((NT + 31) / 32)];
@@ -297,14 +313,23 @@ fast_x_conv_kernel(StrideGeom g, int ntiles, const BoxInfo* __restrict__ Bp, T k
     cx<T>* itw3 = itw2 + TwGeom<Q1, Q2, Q3>::N2;
     double* sek = reinterpret_cast<double*>(itw3 + TwGeom<Q1, Q2, Q3>::N3);    // exp(-k1^2/4kappa^2)/theta_1^2  (ortho) | 1/theta_1^2
     double* sk2 = sek + N;                                                    // k1^2 (ortho) | signed index m1
+    cx<T>** sbase = reinterpret_cast<cx<T>**>(sk2 + N);                       // PEER only: owner buffer of x plane pos
     const BoxInfo& B = *Bp;
     const int l = threadIdx.x % TL, j = threadIdx.x / TL;
-    int tile = blockIdx.x;
+    int tile = tile0 + blockIdx.x;
     pdl_launch_dependents();
     build_twiddles<T, R1, R2, R3, 1>(tw2, tw3, gtw, NT);
     build_twiddles<T, Q1, Q2, Q3, 1>(itw2, itw3, gtw, NT);
+    if (PEER) {
+        for (int i = threadIdx.x; i < N; i += NT) sbase[i] = reinterpret_cast<cx<T>*>(peers.base[i / peers.slab]);
+        __syncthreads();
+    }
     pdl_wait();
-    if (tile < ntiles) issue_tile<T, N, TL, JT>(g, tile, spec, I, l, j);
+    auto issue = [&](int t) {
+        if (PEER) issue_tile_peer<T, N, TL, JT>(g, t, sbase, I, l, j);
+        else issue_tile<T, N, TL, JT>(g, t, spec, I, l, j);
+    };
+    if (tile < ntiles) issue(tile);
     const bool ortho = (*tb.ortho != 0);
     if (QUICK) {
         for (int i = threadIdx.x; i < N; i += NT) {
@@ -374,7 +399,7 @@ fast_x_conv_kernel(StrideGeom g, int ntiles, const BoxInfo* __restrict__ Bp, T k
         auto stA = [&](int pos, cx<T> v) { a[pos * TL] = v; };
         fft_head<T, R1, R2, R3, 1, JT>(j, live, [&](int pos) { return c[pos * TL]; }, stA);
         __syncthreads();                       // I consumed: fetch the next tile while this one is transformed
-        if (tile + (int)gridDim.x < ntiles) issue_tile<T, N, TL, JT>(g, tile + gridDim.x, spec, I, l, j);
+        if (tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x);
         if (R3 > 1) {                          // middle forward stage, in place in A
             FStage<T, R2, 1, N, R1, JT> s;
             if (live) s.run(j, tw2, ldA);
@@ -394,7 +419,13 @@ fast_x_conv_kernel(StrideGeom g, int ntiles, const BoxInfo* __restrict__ Bp, T k
             __syncthreads();
         }
         acc_e = fma(0.5 * wgt, acc_line, acc_e);              // E = scale * sum wgt g |S|^2 = sum wgt/2 * gg |S|^2
-        fft_tail<T, Q1, Q2, Q3, -1, JT, false>(j, live, itw2, itw3, ldA, stA, [&](int pos, cx<T> v) { out[(size_t)pos * ls] = v; });
+        if (PEER) {
+            const size_t col = (size_t)c0 + l;
+            fft_tail<T, Q1, Q2, Q3, -1, JT, false>(j, live, itw2, itw3, ldA, stA,
+                                                   [&](int pos, cx<T> v) { sbase[pos][(size_t)pos * ls + col] = v; });
+        } else {
+            fft_tail<T, Q1, Q2, Q3, -1, JT, false>(j, live, itw2, itw3, ldA, stA, [&](int pos, cx<T> v) { out[(size_t)pos * ls] = v; });
+        }
     }
     double e1[1] = {acc_e};
     block_accumulate<1>(e1, red, scalars + ADMP_S_E_RECIP);
@@ -540,6 +571,11 @@ struct FastOps {
     void (*strided)(cudaStream_t, int sign, const StrideGeom&, int ntiles, int grid, void* spec, const void* tw);
     void (*xconv)(cudaStream_t, const StrideGeom&, int ntiles, int grid, const BoxInfo*, double kappa, int kind, const ConvTables&,
                   void* spec, const void* tw, double* scalars, int want_vir);
+    // x-slab decomposed spectrum: tiles [tile0, tile1) of the X pass on peer-mapped buffers
+    void (*xconv_peer)(cudaStream_t, const StrideGeom&, int tile0, int tile1, int grid, const BoxInfo*, double kappa, int kind,
+                       const ConvTables&, const void* tw, double* scalars, int want_vir, const PeerTab&);
+    size_t smem_xp;
+    int occ_peer[2];  // x conv on peers: quick, general
     void (*zfwd)(cudaStream_t, int nlines, int ntiles, int grid, const void* mesh, void* spec, const void* tw);
     void (*zinv)(cudaStream_t, int nlines, int ntiles, int grid, const void* spec, void* mesh, const void* tw);
 };
@@ -556,15 +592,18 @@ template <typename T, int R1, int R2, int R3, int TLd, int JT, int ZTLd, int ZJT
 struct FastImpl {
     static constexpr int N = R1 * R2 * R3;
     static constexpr int TL = TLd * (sizeof(T) == 4 ? 2 : 1), ZTL = ZTLd * (sizeof(T) == 4 ? 2 : 1);
-    static size_t smem_x_bytes() {
+    static size_t smem_x_bytes(bool peer = false) {
         constexpr int Q1 = R3 > 1 ? R3 : R2, Q2 = R3 > 1 ? R2 : R1, Q3 = R3 > 1 ? R1 : 1;
-        return (size_t)(2 * N * TL + TwGeom<R1, R2, R3>::TOTAL + TwGeom<Q1, Q2, Q3>::TOTAL) * sizeof(cx<T>) + 2 * N * sizeof(double);
+        return (size_t)(2 * N * TL + TwGeom<R1, R2, R3>::TOTAL + TwGeom<Q1, Q2, Q3>::TOTAL) * sizeof(cx<T>) + 2 * N * sizeof(double) +
+               (peer ? N * sizeof(void*) : 0);
     }
     static void prepare(FastOps& o) {
         o.occ[0] = prep_kernel(fast_strided_kernel<T, R1, R2, R3, 1, TL, JT>, o.threads, o.smem);
         o.occ[1] = prep_kernel(fast_strided_kernel<T, R1, R2, R3, -1, TL, JT>, o.threads, o.smem);
-        o.occ[2] = prep_kernel(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, true>, o.threads, o.smem_x);
-        o.occ[5] = prep_kernel(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, false>, o.threads, o.smem_x);
+        o.occ[2] = prep_kernel(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, true, false>, o.threads, o.smem_x);
+        o.occ[5] = prep_kernel(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, false, false>, o.threads, o.smem_x);
+        o.occ_peer[0] = prep_kernel(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, true, true>, o.threads, o.smem_xp);
+        o.occ_peer[1] = prep_kernel(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, false, true>, o.threads, o.smem_xp);
         o.occ[3] = prep_kernel(fast_z_fwd_kernel<T, R1, R2, R3, ZTL, ZJT>, o.zthreads, o.zsmem);
         o.occ[4] = prep_kernel(fast_z_inv_kernel<T, R1, R2, R3, ZTL, ZJT>, o.zthreads, o.zsmem);
     }
@@ -577,11 +616,21 @@ struct FastImpl {
                       const ConvTables& tb, void* spec, const void* tw, double* scalars, int want_vir) {
         const size_t smem = smem_x_bytes();
         if (kind == ADMP_CK_COULOMB && !want_vir)
-            launch_pdl(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, true>, grid, TL * JT, smem, st, g, ntiles, B, (T)kappa, kind, tb, (cx<T>*)spec,
-                       (const cx<T>*)tw, scalars, want_vir);
+            launch_pdl(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, true, false>, grid, TL * JT, smem, st, g, 0, ntiles, B, (T)kappa, kind, tb,
+                       (cx<T>*)spec, (const cx<T>*)tw, scalars, want_vir, PeerTab{});
         else
-            launch_pdl(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, false>, grid, TL * JT, smem, st, g, ntiles, B, (T)kappa, kind, tb, (cx<T>*)spec,
-                       (const cx<T>*)tw, scalars, want_vir);
+            launch_pdl(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, false, false>, grid, TL * JT, smem, st, g, 0, ntiles, B, (T)kappa, kind, tb,
+                       (cx<T>*)spec, (const cx<T>*)tw, scalars, want_vir, PeerTab{});
+    }
+    static void xconv_peer(cudaStream_t st, const StrideGeom& g, int tile0, int tile1, int grid, const BoxInfo* B, double kappa, int kind,
+                           const ConvTables& tb, const void* tw, double* scalars, int want_vir, const PeerTab& peers) {
+        const size_t smem = smem_x_bytes(true);
+        if (kind == ADMP_CK_COULOMB && !want_vir)
+            fast_x_conv_kernel<T, R1, R2, R3, TL, JT, true, true><<<grid, TL * JT, smem, st>>>(g, tile0, tile1, B, (T)kappa, kind, tb, nullptr,
+                                                                                             (const cx<T>*)tw, scalars, want_vir, peers);
+        else
+            fast_x_conv_kernel<T, R1, R2, R3, TL, JT, false, true><<<grid, TL * JT, smem, st>>>(g, tile0, tile1, B, (T)kappa, kind, tb, nullptr,
+                                                                                              (const cx<T>*)tw, scalars, want_vir, peers);
     }
     static void zfwd(cudaStream_t st, int nlines, int ntiles, int grid, const void* mesh, void* spec, const void* tw) {
         const size_t smem = (size_t)(2 * ZTL * ZGeom<N>::LS + TwGeom<R1, R2, R3>::TOTAL + N + 1) * sizeof(cx<T>);
@@ -596,8 +645,9 @@ struct FastImpl {
         o.N = N; o.TL = TL; o.threads = TL * JT; o.zTL = ZTL; o.zthreads = ZTL * ZJT;
         o.smem = (size_t)(2 * N * TL + TwGeom<R1, R2, R3>::TOTAL) * sizeof(cx<T>);
         o.smem_x = smem_x_bytes();
+        o.smem_xp = smem_x_bytes(true);
         o.zsmem = (size_t)(2 * ZTL * ZGeom<N>::LS + TwGeom<R1, R2, R3>::TOTAL + N + 1) * sizeof(cx<T>);
-        o.prepare = &prepare; o.strided = &strided; o.xconv = &xconv; o.zfwd = &zfwd; o.zinv = &zinv;
+        o.prepare = &prepare; o.strided = &strided; o.xconv = &xconv; o.xconv_peer = &xconv_peer; o.zfwd = &zfwd; o.zinv = &zinv;
         return o;
     }
 };

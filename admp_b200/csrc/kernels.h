@@ -36,7 +36,7 @@ void launch_tt_pair(cudaStream_t st, int64_t n_rows, int n_atoms, const BoxInfo*
 // recip.cu
 template <typename T>
 void launch_spread(cudaStream_t st, int n, const BoxInfo* B, const void* pos, const void* M, int m_cols, int m_stride,
-                   const void* U, void* mesh);
+                   const void* U, void* mesh, const PeerTab* peers = nullptr);
 template <typename T>
 void launch_convolve(cudaStream_t st, const BoxInfo* B, size_t n_half, int n_sm, double kappa, int kind, const ConvTables& tb,
                      void* S, double* scalars, int want_vir);
@@ -44,7 +44,8 @@ void launch_conv_tables(cudaStream_t st, const BoxInfo* B, double kappa, const d
                         double* ek, double* k2, int* ortho, int maxK);
 template <typename T>
 void launch_gather(cudaStream_t st, int n, const BoxInfo* B, const void* pos, const void* M, int m_cols, int m_stride, const void* U,
-                   const void* phi, int mode, uint32_t flags, void* dpos, void* G, int g_stride, void* F, double* scalars);
+                   const void* phi, int mode, uint32_t flags, void* dpos, void* G, int g_stride, void* F, double* scalars,
+                   const PeerTab* peers = nullptr);
 
 // fft.cu - hand-written 3-D real FFT fused with the influence-function convolution
 struct Fft3d;
@@ -56,6 +57,10 @@ void fft3d_single_pass(Fft3d* f, cudaStream_t st, int which, void* mesh, void* s
                        const ConvTables& tb, double* scalars);
 void fft3d_convolve_roundtrip(Fft3d* f, cudaStream_t st, void* mesh, void* spec, const BoxInfo* B, double kappa, int kind,
                               const ConvTables& tb, double* scalars, int want_vir);
+
+bool fft3d_slab_supported(const Fft3d* f);
+void fft3d_slab_phase(Fft3d* f, cudaStream_t st, int phase, int rank, void* mesh, void* spec, const PeerTab& spec_peers,
+                      const BoxInfo* B, double kappa, int kind, const ConvTables& tb, double* scalars, int want_vir);
 
 // site.cu
 template <typename T> void launch_box_setup(cudaStream_t st, const void* box, BoxInfo* B, int K1, int K2, int K3);

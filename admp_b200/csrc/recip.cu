@@ -68,10 +68,12 @@ __device__ __forceinline__ void mesh_anchor(const BoxInfo& B, double rx, double 
 constexpr int SPREAD_WARPS = 4;
 
 // One warp per atom; lanes stride the 216 stencil points (z fastest => 6 contiguous reals).
-template <typename T, bool MULTIPOLE>
+// PEER: the mesh is x-slab decomposed over several GPUs (PeerTab): the atomics of a stencil plane go to the
+// buffer of the rank that owns the plane (NVLink peer atomics for the few planes that cross a slab boundary).
+template <typename T, bool MULTIPOLE, bool PEER>
 __global__ void __launch_bounds__(SPREAD_WARPS * 32)
 spread_kernel(int n, const BoxInfo* __restrict__ Bp, const T* __restrict__ pos, const T* __restrict__ M, int m_stride,
-              const T* __restrict__ U, T* __restrict__ mesh) {
+              const T* __restrict__ U, T* __restrict__ mesh, PeerTab peers) {
     __shared__ T sw[SPREAD_WARPS][3][18];
     __shared__ int si[SPREAD_WARPS][3];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -128,7 +130,8 @@ spread_kernel(int n, const BoxInfo* __restrict__ Bp, const T* __restrict__ pos, 
         int gi = i0 + ia; if (gi >= K1) gi -= K1;
         int gj = j0 + ib; if (gj >= K2) gj -= K2;
         int gk = k0 + ic; if (gk >= K3) gk -= K3;
-        atomicAdd(mesh + ((size_t)gi * K2 + gj) * K3 + gk, val);
+        T* base = PEER ? reinterpret_cast<T*>(peers.base[gi / peers.slab]) : mesh;
+        atomicAdd(base + ((size_t)gi * K2 + gj) * K3 + gk, val);
     }
 }
 
@@ -217,11 +220,11 @@ constexpr int GATHER_APB = 128 / GATHER_LPA;        // atoms per 128-thread bloc
 //   S_p3 = sum_ic phi[ia, ib, ic] * d^p3 M6(z)[ic] ;  P[p1 p2 p3] += d^p1 M6(x)[ia] * d^p2 M6(y)[ib] * S_p3
 // (54 FMA-class operations per column instead of ~50 per mesh point), then two shuffle steps reduce the
 // 20 (4 in field mode) partial sums over the four lanes and lane 0 of the group does the per-atom algebra.
-template <typename T, bool MULTIPOLE, int MODE>
+template <typename T, bool MULTIPOLE, int MODE, bool PEER>
 __global__ void __launch_bounds__(128)
 gather_kernel(int n, const BoxInfo* __restrict__ Bp, const T* __restrict__ pos, const T* __restrict__ M, int m_stride,
               const T* __restrict__ U, const T* __restrict__ phi, uint32_t flags, T* __restrict__ dpos, T* __restrict__ G,
-              int g_stride, T* __restrict__ F, double* __restrict__ scalars) {
+              int g_stride, T* __restrict__ F, double* __restrict__ scalars, PeerTab peers) {
     constexpr int NP = (MODE == 1) ? 2 : (MULTIPOLE ? 4 : 2);
     __shared__ T sw[GATHER_APB][3][6 * NP];
     __shared__ int si[GATHER_APB][3];
@@ -259,7 +262,7 @@ gather_kernel(int n, const BoxInfo* __restrict__ Bp, const T* __restrict__ pos, 
             const int ia = col / 6, ib = col - 6 * ia;
             int gi = i0 + ia; if (gi >= K1) gi -= K1;
             int gj = j0 + ib; if (gj >= K2) gj -= K2;
-            const T* line = phi + ((size_t)gi * K2 + gj) * K3;
+            const T* line = (PEER ? reinterpret_cast<const T*>(peers.base[gi / peers.slab]) : phi) + ((size_t)gi * K2 + gj) * K3;
             T ph[6];
             if (!wrap) {
 #pragma unroll
@@ -402,11 +405,19 @@ gather_kernel(int n, const BoxInfo* __restrict__ Bp, const T* __restrict__ pos, 
 // ---------------------------------------------------------------------------- launchers
 template <typename T>
 void launch_spread(cudaStream_t st, int n, const BoxInfo* B, const void* pos, const void* M, int m_cols, int m_stride,
-                   const void* U, void* mesh) {
+                   const void* U, void* mesh, const PeerTab* peers) {
     if (n <= 0) return;
     const unsigned grid = (n + SPREAD_WARPS - 1) / SPREAD_WARPS;
-    if (m_cols >= 10) spread_kernel<T, true><<<grid, SPREAD_WARPS * 32, 0, st>>>(n, B, (const T*)pos, (const T*)M, m_stride, (const T*)U, (T*)mesh);
-    else spread_kernel<T, false><<<grid, SPREAD_WARPS * 32, 0, st>>>(n, B, (const T*)pos, (const T*)M, m_stride, nullptr, (T*)mesh);
+    const PeerTab pt = peers ? *peers : PeerTab{};
+#define ADMP_S_ARGS(u) n, B, (const T*)pos, (const T*)M, m_stride, u, (T*)mesh, pt
+    if (peers) {
+        if (m_cols >= 10) spread_kernel<T, true, true><<<grid, SPREAD_WARPS * 32, 0, st>>>(ADMP_S_ARGS((const T*)U));
+        else spread_kernel<T, false, true><<<grid, SPREAD_WARPS * 32, 0, st>>>(ADMP_S_ARGS(nullptr));
+    } else {
+        if (m_cols >= 10) spread_kernel<T, true, false><<<grid, SPREAD_WARPS * 32, 0, st>>>(ADMP_S_ARGS((const T*)U));
+        else spread_kernel<T, false, false><<<grid, SPREAD_WARPS * 32, 0, st>>>(ADMP_S_ARGS(nullptr));
+    }
+#undef ADMP_S_ARGS
 }
 template <typename T>
 void launch_convolve(cudaStream_t st, const BoxInfo* B, size_t n_half, int n_sm, double kappa, int kind, const ConvTables& tb,
@@ -422,21 +433,30 @@ void launch_conv_tables(cudaStream_t st, const BoxInfo* B, double kappa, const d
 }
 template <typename T>
 void launch_gather(cudaStream_t st, int n, const BoxInfo* B, const void* pos, const void* M, int m_cols, int m_stride, const void* U,
-                   const void* phi, int mode, uint32_t flags, void* dpos, void* G, int g_stride, void* F, double* scalars) {
+                   const void* phi, int mode, uint32_t flags, void* dpos, void* G, int g_stride, void* F, double* scalars,
+                   const PeerTab* peers) {
     if (n <= 0) return;
     const unsigned grid = (n + GATHER_APB - 1) / GATHER_APB;
-#define ADMP_G_ARGS n, B, (const T*)pos, (const T*)M, m_stride, (const T*)U, (const T*)phi, flags, (T*)dpos, (T*)G, g_stride, (T*)F, scalars
-    if (mode == 1) gather_kernel<T, true, 1><<<grid, 128, 0, st>>>(ADMP_G_ARGS);
-    else if (m_cols >= 10) gather_kernel<T, true, 0><<<grid, 128, 0, st>>>(ADMP_G_ARGS);
-    else gather_kernel<T, false, 0><<<grid, 128, 0, st>>>(ADMP_G_ARGS);
+    const PeerTab pt = peers ? *peers : PeerTab{};
+#define ADMP_G_ARGS n, B, (const T*)pos, (const T*)M, m_stride, (const T*)U, (const T*)phi, flags, (T*)dpos, (T*)G, g_stride, (T*)F, scalars, pt
+    if (peers) {
+        if (mode == 1) gather_kernel<T, true, 1, true><<<grid, 128, 0, st>>>(ADMP_G_ARGS);
+        else if (m_cols >= 10) gather_kernel<T, true, 0, true><<<grid, 128, 0, st>>>(ADMP_G_ARGS);
+        else gather_kernel<T, false, 0, true><<<grid, 128, 0, st>>>(ADMP_G_ARGS);
+    } else {
+        if (mode == 1) gather_kernel<T, true, 1, false><<<grid, 128, 0, st>>>(ADMP_G_ARGS);
+        else if (m_cols >= 10) gather_kernel<T, true, 0, false><<<grid, 128, 0, st>>>(ADMP_G_ARGS);
+        else gather_kernel<T, false, 0, false><<<grid, 128, 0, st>>>(ADMP_G_ARGS);
+    }
 #undef ADMP_G_ARGS
 }
 #define ADMP_INST(T)                                                                                                              \
-    template void launch_spread<T>(cudaStream_t, int, const BoxInfo*, const void*, const void*, int, int, const void*, void*);    \
+    template void launch_spread<T>(cudaStream_t, int, const BoxInfo*, const void*, const void*, int, int, const void*, void*,     \
+                                   const PeerTab*);                                                                               \
     template void launch_convolve<T>(cudaStream_t, const BoxInfo*, size_t, int, double, int, const ConvTables&, void*, double*,   \
                                      int);                                                                                        \
     template void launch_gather<T>(cudaStream_t, int, const BoxInfo*, const void*, const void*, int, int, const void*, const void*, \
-                                   int, uint32_t, void*, void*, int, void*, double*);
+                                   int, uint32_t, void*, void*, int, void*, double*, const PeerTab*);
 ADMP_INST(double)
 ADMP_INST(float)
 #undef ADMP_INST

@@ -13,6 +13,8 @@ Two shardings, both prescribed by the north star; neither exists in the referenc
   gather own atoms; pair kernel on own rows; per-atom results (field, dE/dM, dE/dr) are all-reduced.
   The replicated mesh and its all-reduce are the scaling limiter; reported as measured.
 """
+import ctypes
+
 import numpy as np
 import torch
 
@@ -240,3 +242,241 @@ class AtomBlockPme:
             _lib.check(lib.admp_pme_fft(c.handle, sp(), 0))
             _lib.check(lib.admp_pme_convolve(c.handle, sp(), _lib.CK_COULOMB, vir, p(scal)))
             _lib.check(lib.admp_pme_fft(c.handle, sp(), 1))
+
+
+# ----------------------------------------------------------------------------------- x-slab reciprocal space (C5)
+def partition_atoms_by_slab(positions, box, world):
+    """Spatial ownership for the x-slab scheme: atom a belongs to the rank whose x planes contain its fractional
+    x coordinate (so nearly all of its 6x6x6 stencil is local). Returns a list of sorted int64 index arrays."""
+    pos = np.asarray(positions, dtype=np.float64)
+    inv = np.linalg.inv(np.asarray(box, dtype=np.float64))
+    sx = (pos @ inv)[:, 0]
+    sx = sx - np.floor(sx)
+    owner = np.minimum((sx * world).astype(np.int64), world - 1)
+    return [np.nonzero(owner == r)[0] for r in range(world)]
+
+
+class SlabPme:
+    """Polarizable / non-polarizable PME evaluation with reciprocal space decomposed into x slabs over the GPUs
+    of one NVLink domain (include/admp_b200.h, "x-slab decomposition"): no replicated FFT, no mesh all-reduce.
+
+    Rank r owns K1/P x planes of the mesh and of the half spectrum, the atoms whose fractional x lies in its slab
+    (spread / gather), a contiguous slice of the pair rows and a contiguous atom block for the per-site stages.
+    Positions, multipoles and induced dipoles stay replicated (<= 100 MB at C5); per cycle the only collectives
+    are the all-reduce of the field (Na x 3) and five stream-ordered barriers; the spectrum transposes of the
+    distributed FFT happen inside the fused X-pass kernel over peer-mapped memory.
+
+    emulate_ranks=P (world == 1) walks all P ranks in one process on one device, each with its own context
+    (mesh + spectrum), stage by stage: the single-GPU check of the decomposition.
+    """
+
+    def __init__(self, calc, rank=0, world=1, group=None, granule=3, emulate_ranks=None):
+        self.calc, self.rank, self.world, self.group = calc, rank, world, group
+        if emulate_ranks is not None and world != 1:
+            raise ValueError('emulate_ranks needs world == 1')
+        self.P = world if emulate_ranks is None else int(emulate_ranks)
+        self.mine = [rank] if emulate_ranks is None else list(range(self.P))
+        self.atoms = partition_atoms(calc.n_atoms, self.P, granule)
+        self._ctxs = {}
+        self._opened = []
+        self._key = None
+        self._tok = None
+
+    # ---- contexts and peer tables
+    def _own_buffers(self, c):
+        lib = c.lib
+        lib.admp_ctx_buffer.restype = ctypes.c_void_p
+        return int(lib.admp_ctx_buffer(c.handle, 0)), int(lib.admp_ctx_buffer(c.handle, 1))
+
+    def _setup(self):
+        from ._ctx import Context
+        calc = self.calc
+        main = calc._ctx
+        key = (self._own_buffers(main), calc.K1, calc.K2, calc.K3, calc.kappa)
+        if key == self._key:
+            return
+        self.close()
+        self._key = key
+        lib = main.lib
+        if calc.K1 % self.P:
+            raise ValueError('x-slab decomposition needs K1 (%d) to be a multiple of the number of ranks (%d)' % (calc.K1, self.P))
+        if self.world > 1:
+            import torch.distributed as dist
+            self._ctxs = {self.rank: main}
+            hm, hs = (ctypes.create_string_buffer(64) for _ in range(2))
+            mp, spp = self._own_buffers(main)
+            _lib.check(lib.admp_ipc_export(ctypes.c_void_p(mp), hm))
+            _lib.check(lib.admp_ipc_export(ctypes.c_void_p(spp), hs))
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, (hm.raw, hs.raw), group=self.group)
+            mesh_ptrs, spec_ptrs = [], []
+            for r, (a, b) in enumerate(gathered):
+                if r == self.rank:
+                    mesh_ptrs.append(mp)
+                    spec_ptrs.append(spp)
+                    continue
+                out = []
+                for h in (a, b):
+                    pv = ctypes.c_void_p()
+                    _lib.check(lib.admp_ipc_open(ctypes.create_string_buffer(h, 64), ctypes.byref(pv)))
+                    self._opened.append(pv.value)
+                    out.append(pv.value)
+                mesh_ptrs.append(out[0])
+                spec_ptrs.append(out[1])
+            self._set_peers(main, self.rank, mesh_ptrs, spec_ptrs)
+            self._tok = torch.zeros(1, dtype=torch.float32, device=main.device)
+        else:
+            self._ctxs = {0: main}
+            for r in range(1, self.P):
+                c = Context()
+                c.set_topology(calc.n_atoms, calc.axis_type, calc.axis_indices, calc.covalent_map)
+                c.set_pme(calc.kappa, calc.K1, calc.K2, calc.K3, calc.lmax)
+                self._ctxs[r] = c
+            bufs = [self._own_buffers(self._ctxs[r]) for r in range(self.P)]
+            for r in range(self.P):
+                self._set_peers(self._ctxs[r], r, [b[0] for b in bufs], [b[1] for b in bufs])
+
+    def _set_peers(self, c, rank, mesh_ptrs, spec_ptrs):
+        arr = ctypes.c_void_p * self.P
+        _lib.check(c.lib.admp_ctx_set_peers(c.handle, rank, self.P, arr(*mesh_ptrs), arr(*spec_ptrs)))
+
+    def close(self):
+        lib = self.calc._ctx.lib
+        for c in self._ctxs.values():
+            try:
+                lib.admp_ctx_set_peers(c.handle, 0, 0, None, None)
+            except Exception:                                        # noqa: BLE001
+                pass
+        for pv in self._opened:
+            lib.admp_ipc_close(ctypes.c_void_p(pv))
+        self._opened = []
+        for r, c in list(self._ctxs.items()):
+            if c is not self.calc._ctx:
+                c.close()
+        self._ctxs = {}
+        self._key = None
+
+    def _barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self._tok, group=self.group)
+
+    # ---- evaluation
+    def evaluate(self, positions, box, pairs, Q_local, pol=None, tholes=None, mScales=None, pScales=None, U_init=None,
+                 want_virial=True, maxiter=None, thresh=None):
+        """Same contract as AtomBlockPme.evaluate: every rank passes the same full inputs and receives the same
+        full outputs: dict(E, dpos, dbox, dQ_local, U, F, n_cycle, converged, scalars)."""
+        from ._ctx import pairs_to_dev
+        calc = self.calc
+        self._setup()
+        c, lib = calc._ctx, calc._ctx.lib
+        p, sp = _lib.ptr, _lib.stream_ptr
+        dev, dt = c.device, c.dtype
+        n, nh = calc.n_atoms, (calc.lmax + 1) ** 2
+        polz = pol is not None
+        prep = calc._prep
+        pos, box_d, Ql, mS = prep(positions).detach(), prep(box).detach(), prep(Q_local).detach(), prep(mScales).detach()
+        pr = pairs_to_dev(pairs, dev)
+        rows = partition_rows(int(pr.shape[0]), self.P)
+        maxiter = settings.MAX_N_POL if maxiter is None else maxiter
+        thresh = settings.POL_CONV if thresh is None else thresh
+        fl = _lib.WANT_GRAD | (_lib.WANT_VIRIAL if want_virial else 0)
+        vir = _lib.WANT_VIRIAL if want_virial else 0
+
+        for r in self.mine:
+            _lib.check(lib.admp_set_box(self._ctxs[r].handle, sp(), p(box_d)))
+        M = torch.empty((n, 10), dtype=dt, device=dev)
+        _lib.check(lib.admp_frames_fwd(c.handle, sp(), p(pos), p(box_d), p(Ql), p(M), None, None))
+        owned = partition_atoms_by_slab(pos.cpu().numpy(), box_d.cpu().numpy(), self.P)
+        # per owned rank: spatial atom set (compact copies), pair-row slice, per-site atom block
+        work = []
+        for r in self.mine:
+            idx = torch.as_tensor(owned[r], dtype=torch.int64, device=dev)
+            work.append(dict(r=r, ctx=self._ctxs[r], idx=idx, cnt=int(idx.numel()), pos=pos.index_select(0, idx).contiguous(),
+                             M=M.index_select(0, idx).contiguous(), pairs=pr[rows[r][0]:rows[r][0] + rows[r][1]].contiguous(),
+                             nrows=rows[r][1], a0=self.atoms[r][0], ac=self.atoms[r][1]))
+        scal = torch.zeros(_lib.S_COUNT, dtype=torch.float64, device=dev)
+        U = F = None
+        n_cycle, conv = 0, True
+        if polz:
+            polt, th, pS = prep(pol).detach(), prep(tholes).detach(), prep(pScales).detach()
+            U = torch.zeros((n, 3), dtype=dt, device=dev) if U_init is None else prep(U_init).detach().clone()
+            F = torch.zeros((n, 3), dtype=dt, device=dev)
+            state = torch.zeros(8, dtype=torch.int32, device=dev)
+            for _ in range(maxiter + 1):
+                scal.zero_()
+                self._recip(work, U, scal, 0)
+                F.zero_()
+                for wk in work:
+                    Fr = torch.zeros((wk['cnt'], 3), dtype=dt, device=dev)
+                    _lib.check(lib.admp_slab_gather(wk['ctx'].handle, sp(), p(wk['pos']), p(wk['M']), 10, 10, p(wk['U']), 1, 0, None, None, 10,
+                                                    p(Fr), p(scal), wk['cnt']))
+                    F.index_add_(0, wk['idx'], Fr)
+                for wk in work:
+                    if wk['nrows'] > 0:
+                        _lib.check(lib.admp_pme_real(c.handle, sp(), p(pos), p(box_d), p(wk['pairs']), wk['nrows'], p(M), p(U), p(polt), p(th),
+                                                     p(mS), p(pS), 1, 0, None, None, p(F), None, None, p(scal)))
+                allreduce_sum_([F], self.group)          # also orders this cycle's gathers before the next slab_zero
+                _lib.check(lib.admp_scf_step(c.handle, sp(), p(M), p(U), p(polt), p(F), int(maxiter), float(thresh), vir, p(state),
+                                             p(scal)))
+                st = state.cpu()
+                if not int(st[5]):
+                    n_cycle, conv = int(st[3]), bool(st[4])
+                    break
+            if want_virial:
+                scal.zero_()
+                self._recip(work, U, scal, vir)
+        else:
+            self._recip(work, None, scal, vir)
+        # final evaluation at fixed U; phi of the last round trip sits in the slabs
+        e_recip = scal[_lib.S_E_RECIP].clone()
+        tk = scal[_lib.S_TK:_lib.S_TK + 6].clone()
+        scal.zero_()
+        scal[_lib.S_E_RECIP] = e_recip                     # this rank's share of the k sum: summed over ranks below
+        scal[_lib.S_TK:_lib.S_TK + 6] = tk
+        G = torch.zeros((n, 10), dtype=dt, device=dev)
+        dpos = torch.zeros((n, 3), dtype=dt, device=dev)
+        dQ = torch.zeros((n, nh), dtype=dt, device=dev)
+        Fo = torch.zeros((n, 3), dtype=dt, device=dev) if polz else None
+        for wk in work:
+            cnt = wk['cnt']
+            dr, Gr = torch.zeros((cnt, 3), dtype=dt, device=dev), torch.zeros((cnt, 10), dtype=dt, device=dev)
+            Fr = torch.zeros((cnt, 3), dtype=dt, device=dev) if polz else None
+            _lib.check(lib.admp_slab_gather(wk['ctx'].handle, sp(), p(wk['pos']), p(wk['M']), 10, 10, p(wk['U']) if polz else None, 0, fl,
+                                            p(dr), p(Gr), 10, p(Fr), p(scal), cnt))
+            dpos.index_add_(0, wk['idx'], dr)
+            G.index_add_(0, wk['idx'], Gr)
+            if polz:
+                Fo.index_add_(0, wk['idx'], Fr)
+            if wk['nrows'] > 0:
+                _lib.check(lib.admp_pme_real(c.handle, sp(), p(pos), p(box_d), p(wk['pairs']), wk['nrows'], p(M), p(U),
+                                             p(polt) if polz else None, p(th) if polz else None, p(mS), p(pS) if polz else None, 0, fl,
+                                             p(dpos), p(G), p(Fo), None, None, p(scal)))
+            _lib.check(lib.admp_pme_self_range(c.handle, sp(), p(M), p(U), p(polt) if polz else None, fl, p(G), p(Fo), None, p(scal),
+                                               wk['a0'], wk['ac']))
+        allreduce_sum_([G], self.group)
+        for wk in work:
+            _lib.check(lib.admp_frames_bwd_range(c.handle, sp(), p(pos), p(Ql), p(G), p(dQ), p(dpos), p(scal), wk['a0'], wk['ac']))
+        allreduce_sum_([dpos, dQ, Fo, scal], self.group)
+        if want_virial:
+            _lib.check(lib.admp_virial_finalize(c.handle, sp(), p(scal)))
+        E = scal[_lib.S_E_REAL] + scal[_lib.S_E_RECIP] + scal[_lib.S_E_SELF] + scal[_lib.S_E_PEN]
+        return dict(E=E, dpos=dpos, dbox=scal[_lib.S_DBOX:_lib.S_DBOX + 9].reshape(3, 3).clone(), dQ_local=dQ, U=U, F=Fo,
+                    n_cycle=n_cycle, converged=conv, scalars=scal)
+
+    def _recip(self, work, U, scal, vir):
+        """zero | spread | Z,Y forward | fused X pass over peer memory | Y,Z inverse, with a cross-rank barrier
+        between the stages; leaves phi = dE/dmesh in the slabs."""
+        lib = self.calc._ctx.lib
+        p, sp = _lib.ptr, _lib.stream_ptr
+        for wk in work:
+            wk['U'] = U.index_select(0, wk['idx']).contiguous() if U is not None else None
+            _lib.check(lib.admp_slab_zero(wk['ctx'].handle, sp()))
+        self._barrier()
+        for wk in work:
+            _lib.check(lib.admp_slab_spread(wk['ctx'].handle, sp(), p(wk['pos']), p(wk['M']), 10, 10, p(wk['U']), wk['cnt']))
+        self._barrier()
+        for phase in range(3):
+            for wk in work:
+                _lib.check(lib.admp_slab_fft(wk['ctx'].handle, sp(), phase, _lib.CK_COULOMB, vir, p(scal)))
+            self._barrier()

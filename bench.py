@@ -36,7 +36,7 @@ WORKLOAD = 'C2 examples/water_pol_1024: 1024 waters (3072 atoms), 50 A box, rc 4
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -109,30 +109,85 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
-        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+    """SM clock + throttle reasons sampled every ~5 ms through NVML in a background thread (nvidia-smi as the
+    fallback); only samples taken between mark_start() and mark_stop() (the timed regions) are reported."""
+    BAD = (('hw_slowdown', 0x8), ('hw_thermal_slowdown', 0x40), ('sw_thermal_slowdown', 0x20), ('sw_power_cap', 0x4))
 
     def __init__(self, index):
-        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        import threading
+        self.samples = []                 # (t, sm_mhz, reasons bitmask)
+        self.windows = []
+        self.max_mhz = None
+        self.err = None
+        self._stop = threading.Event()
+        self._smi = None
         try:
-            self.p = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
-                                       '-lms', '100'], stdout=self.f, stderr=subprocess.DEVNULL)
-        except Exception:
-            self.p = None
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(vis.split(',')[index]) if vis and vis.split(',')[index].isdigit() else index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self._thr = threading.Thread(target=self._run_nvml, daemon=True)
+            self._thr.start()
+        except Exception as e:                                       # noqa: BLE001
+            self.err = 'nvml: %r' % (e,)
+            self._nv = None
+            self._start_smi(index)
+
+    def _run_nvml(self):
+        nv, h = self._nv, self._h
+        get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                self.samples.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(get_reasons(h))))
+            except Exception as e:                                   # noqa: BLE001
+                self.err = 'nvml: %r' % (e,)
+                return
+            time.sleep(0.004)
+
+    def _start_smi(self, index):
+        q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+        try:
+            self._f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+            self._smi = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + q, '--format=csv,noheader,nounits', '-lms', '20'],
+                                         stdout=self._f, stderr=subprocess.DEVNULL)
+        except Exception as e:                                       # noqa: BLE001
+            self.err = (self.err or '') + ' nvidia-smi: %r' % (e,)
+
+    def mark_start(self):
+        self.windows.append([time.perf_counter(), None])
+
+    def mark_stop(self):
+        self.windows[-1][1] = time.perf_counter()
 
     def stop(self):
-        if self.p is None:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
-        self.p.terminate()
+        self._stop.set()
+        reasons = set()
+        if self._nv is not None:
+            self._thr.join(timeout=2)
+            inside = [s for s in self.samples if any(a <= s[0] <= (b or 1e30) for a, b in self.windows)]
+            use = inside if inside else self.samples
+            sm = [s[1] for s in use]
+            for s in use:
+                for nm, bit in self.BAD:
+                    if s[2] & bit:
+                        reasons.add(nm)
+            return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=self.max_mhz, reasons=sorted(reasons),
+                        samples=len(use), samples_in_timed_regions=len(inside), source='nvml, 4 ms period')
+        if self._smi is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['clock sampling unavailable: %s' % self.err], samples=0)
+        self._smi.terminate()
         try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for line in self.f.read().splitlines():
+            self._smi.wait(timeout=5)
+        except Exception:                                            # noqa: BLE001
+            self._smi.kill()
+        self._f.flush()
+        self._f.seek(0)
+        sm, mx = [], []
+        for line in self._f.read().splitlines():
             c = [x.strip() for x in line.split(',')]
             if len(c) < 6:
                 continue
@@ -140,12 +195,12 @@ class ClockSampler:
                 sm.append(float(c[0])); mx.append(float(c[1]))
             except ValueError:
                 continue
-            for k, nm in enumerate(names):
+            for k, (nm, _) in enumerate(self.BAD):
                 if c[2 + k].lower().startswith('active'):
                     reasons.add(nm)
-        os.unlink(self.f.name)
-        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+        os.unlink(self._f.name)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons),
+                    samples=len(sm), source='nvidia-smi -lms 20 (whole run)')
 
 
 # ----------------------------------------------------------------------------------- GPU arm
@@ -226,6 +281,96 @@ def kernel_rooflines(torch, _lib, reps, peak, flush, n_launch=10):
     return out
 
 
+def dense_rooflines(torch, _lib, peak_hbm, flush, n_side=32, rc=8.0, n_launch=5):
+    """Pair / spread / gather kernels on the liquid-density box of SURVEY 8(d) ("dense-256k" recipe at
+    n_side^3 waters, rc 8 A): the BASELINE configs are gas-like (8 neighbours per atom), so the pair kernel's
+    FP-pipe utilisation is only visible here. Pair kernel: algorithmic 1 719 flop per polarizable pair
+    (energy + all adjoints) against the live FP64 FMA peak (admp_fp_peak)."""
+    import ctypes
+    import numpy as np
+    from admp_b200 import workloads
+    from admp_b200._ctx import Context, to_dev
+    from admp_b200.neighbor import neighbor_list
+    w = workloads.dense_water(n_side)
+    L = float(w.box[0, 0])
+    kappa = float(np.sqrt(-np.log(2e-4)) / rc)
+    K = 154 * max(1, int(round(L / 99.3)))
+    cx = Context()
+    cx.set_topology(w.n_atoms, w.axis_type, w.axis_indices, w.covalent_map)
+    cx.set_pme(kappa, K, K, K, 2)
+    dt, dev = cx.dtype, cx.device
+    pos, box, Ql, pol, th, mS, pS = (to_dev(x, dt, dev) for x in (w.positions, w.box, w.Q_local, w.pol, w.tholes, w.mScales, w.pScales))
+    n = w.n_atoms
+    nb = neighbor_list(w.box, rc).allocate(w.positions)
+    pairs, npairs = nb.pairs, int(nb.n_pairs)
+    rows = int(pairs.shape[0])
+    p, sp = _lib.ptr, _lib.stream_ptr
+    M = torch.empty((n, 10), dtype=dt, device=dev)
+    _lib.check(cx.lib.admp_frames_fwd(cx.handle, sp(), p(pos), p(box), p(Ql), p(M), None, None))
+    g = torch.Generator(device='cuda').manual_seed(1)
+    U = 0.01 * torch.randn((n, 3), dtype=dt, device=dev, generator=g)
+    scal = torch.zeros(_lib.S_COUNT, dtype=torch.float64, device=dev)
+    dpos = torch.zeros((n, 3), dtype=dt, device=dev)
+    G = torch.zeros((n, 10), dtype=dt, device=dev)
+    F = torch.zeros((n, 3), dtype=dt, device=dev)
+    tf = ctypes.c_double(0.0)
+    _lib.check(cx.lib.admp_fp_peak(sp(), _lib.F64, ctypes.byref(tf)))
+    fp_peak = tf.value
+
+    def time_stage(fn):
+        ts = []
+        for it in range(n_launch + 2):
+            flush()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            _lib.check(fn())
+            b.record()
+            b.synchronize()
+            if it >= 2:
+                ts.append(a.elapsed_time(b))
+        return statistics.mean(ts)
+
+    fl = _lib.WANT_GRAD | _lib.WANT_VIRIAL
+    out = {}
+    desc = 'dense water %d^3 (%d atoms, L %.2f A, rc %.1f A, %d pairs, %.1f neighbours/atom), mesh %d^3' % (
+        n_side, n, L, rc, npairs, 2.0 * npairs / n, K)
+    for name, mode, flags, flop in (('pme_pair_kernel (E + all adjoints, polarizable)', 0, fl, 1719),
+                                    ('pme_pair_kernel (SCF field only)', 1, 0, None)):
+        ms = time_stage(lambda: cx.lib.admp_pme_real(cx.handle, sp(), p(pos), p(box), p(pairs), rows, p(M), p(U), p(pol), p(th), p(mS), p(pS),
+                                                     mode, flags, p(dpos) if mode == 0 else None, p(G) if mode == 0 else None, p(F), None, None,
+                                                     p(scal)))
+        d = dict(ms=round(ms, 4), gpairs_per_s=round(npairs / ms / 1e6, 3), n_pairs=npairs)
+        if flop:
+            ach = npairs * flop / (ms * 1e-3) / 1e12
+            d.update(bound='fp64', achieved=round(ach, 3), peak=round(fp_peak, 2), unit='TFLOP/s', frac=round(ach / fp_peak, 4),
+                     algorithmic_flop_per_pair=flop, peak_source='admp_fp_peak (FP64 FMA chain, measured in this run)')
+        out[name] = d
+    wb = 8
+    ms = time_stage(lambda: cx.lib.admp_pme_spread(cx.handle, sp(), p(pos), p(box), p(M), 10, 10, None))
+    nbytes = wb * K ** 3 + 216 * 2 * wb * n + 13 * wb * n
+    out['spread (zero-fill + spread_kernel)'] = dict(bound='hbm', achieved=round(nbytes / ms / 1e6, 1), peak=peak_hbm, unit='GB/s',
+                                                     frac=round(nbytes / ms / 1e6 / peak_hbm, 4), ms=round(ms, 4), algorithmic_bytes=nbytes)
+    _lib.check(cx.lib.admp_pme_fft_convolve(cx.handle, sp(), _lib.CK_COULOMB, 0, p(scal)))
+    ms = time_stage(lambda: cx.lib.admp_pme_gather(cx.handle, sp(), p(pos), p(M), 10, 10, None, 0, _lib.WANT_GRAD, p(dpos), p(G), 10, None,
+                                                   p(scal)))
+    nbytes = min(wb * K ** 3, 216 * wb * n) + 23 * wb * n
+    out['gather_kernel'] = dict(bound='hbm', achieved=round(nbytes / ms / 1e6, 1), peak=peak_hbm, unit='GB/s',
+                                frac=round(nbytes / ms / 1e6 / peak_hbm, 4), ms=round(ms, 4), algorithmic_bytes=nbytes)
+    out['workload'] = desc
+    cx.close()
+    return out
+
+
+def ncu_traffic():
+    """DRAM bytes per launch from the committed `ncu --set full` captures (profiles/ncu_traffic.json:
+    {kernel name: {mesh: bytes}}); None when a kernel / mesh has no capture."""
+    p = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    try:
+        return json.load(open(p))
+    except Exception:                                                # noqa: BLE001
+        return {}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -267,21 +412,24 @@ def run_ours(args):
     def step(pos):
         return calc._eval(pos, box, pairs, Ql, None, pol, th, mS, pS, flags, True)
 
+    sampler = ClockSampler(local) if rank == 0 else None
     for f in range(args.warmup):
         r = step(frames[f])
     barrier()
     n_cycle, conv = [int(x) for x in r.scf.cpu()]
     bodies = n_cycle + 1 + (0 if conv or n_cycle < 29 else 1)
-    sampler = ClockSampler(local) if rank == 0 else None
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    if sampler:
+        sampler.mark_start()
     for k in range(args.steps):
         flush()
         ev[k][0].record()
         r = step(frames[args.warmup + k])
         ev[k][1].record()
     barrier()
-    clocks = sampler.stop() if sampler else None
+    if sampler:
+        sampler.mark_stop()
     t_ms = sum(a.elapsed_time(b) for a, b in ev)
     tt = torch.tensor([t_ms], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -310,11 +458,17 @@ def run_ours(args):
     for k in range(args.warmup):
         e2e_step(k)
     barrier()
+    if sampler:
+        sampler.mark_start()
     t0 = time.perf_counter()
     for k in range(args.steps):
         e2e_step(args.warmup + k)
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
+    clocks = None
+    if sampler:
+        sampler.mark_stop()
+        clocks = sampler.stop()
     te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -332,9 +486,16 @@ def run_ours(args):
     roof_small = kernel_rooflines(torch, _lib, (1, 1, 1), peak, flush)
     roof_large = None if args.no_large else kernel_rooflines(torch, _lib, (2, 4, 4), peak, flush, n_launch=5)
     dominant = next((k for k in roof_small if k.startswith('fft_x_conv')), 'convolve_kernel')
+    traffic = ncu_traffic()
+    for tab in (roof_small, roof_large or {}):
+        for name, d in tab.items():
+            t = traffic.get(name, {}).get(d.get('mesh'))
+            if t is not None:
+                d['traffic'] = t
     roofline = dict(roof_small[dominant])
     roofline['kernel'] = dominant
     roofline['peak_source'] = peak_src
+    roof_dense = None if args.no_large else dense_rooflines(torch, _lib, peak, flush)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu, _ = cpu_oracle_sample(n_iter=3)
@@ -347,7 +508,7 @@ def run_ours(args):
                                     '(reproduced iteration for iteration)', scf_graph=calc._ctx.scf_graph_active, energy=E_last),
                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
                gpu_launches=args.steps * (2 + 8 * bodies + 5), clocks=clocks, roofline=roofline,
-               kernels=dict(C2=roof_small, C3=roof_large), cpu_baseline=cpu)
+               kernels=dict(C2=roof_small, C3=roof_large, dense=roof_dense), cpu_baseline=cpu)
     print(json.dumps(out))
     if dist is not None:
         dist.barrier()

@@ -203,6 +203,33 @@ int admp_tt_pair(admp_ctx* ctx, void* stream, const void* pos, const void* box,
 int admp_nblist_build(admp_ctx* ctx, void* stream, const void* pos, const void* box, int n_atoms,
                       double rc, int32_t* pairs, int64_t capacity, int32_t* info);
 
+/* ---- x-slab decomposition of reciprocal space over the GPUs of one NVLink domain (no reference counterpart;
+ * north-star config "256k-water box at 1/2/4/8 B200"). Rank r owns the x planes [r*K1/n, (r+1)*K1/n) of the mesh
+ * and of the half spectrum; every rank maps the other ranks' buffers (cudaIpc) and the kernels address the owner
+ * of each plane directly over NVLink: spread / gather for stencils crossing a slab boundary, and the fused X pass,
+ * which reads and writes all ranks' planes (the transposes of a distributed FFT happen inside the kernel).
+ * The caller orders the stages with stream-ordered cross-rank barriers:
+ *   slab_zero | barrier | slab_spread | barrier | slab_fft 0 | barrier | slab_fft 1 | barrier | slab_fft 2 |
+ *   barrier | slab_gather | (collective on the gathered field = barrier) */
+int admp_ipc_export(const void* devptr, void* handle64);          /* cudaIpcGetMemHandle */
+int admp_ipc_open(const void* handle64, void** devptr);           /* cudaIpcOpenMemHandle (peer access enabled) */
+int admp_ipc_close(void* devptr);
+/* mesh_ptrs / spec_ptrs: host arrays of nranks device pointers (entry `rank` = admp_ctx_buffer(ctx, 0 / 1)).
+ * nranks = 0 clears the table. Needs K1 % nranks == 0 and the register-blocked FFT kernels. */
+int admp_ctx_set_peers(admp_ctx* ctx, int rank, int nranks, void* const* mesh_ptrs, void* const* spec_ptrs);
+int admp_slab_zero(admp_ctx* ctx, void* stream);
+int admp_slab_spread(admp_ctx* ctx, void* stream, const void* pos, const void* M, int M_cols, int M_stride,
+                     const void* U, int count);
+int admp_slab_fft(admp_ctx* ctx, void* stream, int phase, int kind, uint32_t flags, double* scalars);
+int admp_slab_gather(admp_ctx* ctx, void* stream, const void* pos, const void* M, int M_cols, int M_stride,
+                     const void* U, int mode, uint32_t flags, void* dpos, void* G, int G_stride, void* F,
+                     double* scalars, int count);
+
+/* Measurement helper (no reference counterpart): dense FMA throughput of the FP64 (dtype ADMP_F64) or FP32
+ * CUDA-core pipe of the current device in TFLOP/s - the roofline denominator of the pair kernel. Allocates
+ * and synchronises; not a compute entry point. */
+int admp_fp_peak(void* stream, int dtype, double* tflops);
+
 #ifdef __cplusplus
 }
 #endif

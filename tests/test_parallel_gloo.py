@@ -27,6 +27,21 @@ def test_partitions_cover_everything():
         parallel.partition_atoms(10, 2, 3)
 
 
+def test_slab_ownership_is_a_partition_by_fractional_x():
+    rng = np.random.default_rng(3)
+    box = np.diag([40.0, 50.0, 60.0])
+    pos = rng.uniform(-80.0, 120.0, size=(999, 3))            # unwrapped positions are fine (admp/recip.py:324 wraps)
+    for world in (1, 2, 8):
+        owned = parallel.partition_atoms_by_slab(pos, box, world)
+        allidx = np.concatenate(owned)
+        assert len(owned) == world and sorted(allidx.tolist()) == list(range(999))
+        for r, idx in enumerate(owned):
+            sx = pos[idx, 0] / 40.0
+            sx -= np.floor(sx)
+            assert np.all(sx >= r / world - 1e-12) and np.all(sx < (r + 1) / world + 1e-12)
+            assert np.all(np.diff(idx) > 0)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(('127.0.0.1', 0))

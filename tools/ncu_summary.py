@@ -12,7 +12,7 @@ WANT = [
     ('gpu__time_duration.sum', 'dur'),
     ('dram__bytes_read.sum', 'dram_rd'),
     ('dram__bytes_write.sum', 'dram_wr'),
-    ('dram__throughput.avg.pct_of_peak_sustained_elapsed', 'dram%'),
+    ('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'dram%'),
     ('lts__throughput.avg.pct_of_peak_sustained_elapsed', 'l2%'),
     ('sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm%'),
     ('sm__warps_active.avg.pct_of_peak_sustained_active', 'occ%'),

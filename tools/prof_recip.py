@@ -56,6 +56,15 @@ def warm(name, fn, reps=20):
     print('%-28s %9.4f ms warm (back to back x%d)' % (name, a.elapsed_time(b) / reps, reps))
 
 
+if os.environ.get('PROF_ONCE'):
+    # one launch of every reciprocal-space kernel (for `ncu --set full`): spread, the five FFT passes, gather
+    _lib.check(cx.lib.admp_pme_spread(cx.handle, sp(), p(pos), p(box), p(M), 10, 10, None))
+    _lib.check(cx.lib.admp_pme_fft_convolve(cx.handle, sp(), _lib.CK_COULOMB, 0, p(scal)))
+    _lib.check(cx.lib.admp_pme_gather(cx.handle, sp(), p(pos), p(M), 10, 10, None, 0, _lib.WANT_GRAD, p(dpos), p(G), 10, None, p(scal)))
+    torch.cuda.synchronize()
+    print('one launch per kernel on mesh %dx%dx%d' % tuple(w.K))
+    sys.exit(0)
+
 if os.environ.get('PROF_WARM'):
     warm('spread (zero + scatter)', lambda: cx.lib.admp_pme_spread(cx.handle, sp(), p(pos), p(box), p(M), 10, 10, None))
     warm('fused roundtrip', lambda: cx.lib.admp_pme_fft_convolve(cx.handle, sp(), _lib.CK_COULOMB, 0, p(scal)))
