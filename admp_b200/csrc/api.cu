@@ -64,7 +64,9 @@ struct admp_ctx {
     bool use_custom_fft = false;
     std::string fft_note;
     // per-atom workspaces and staged inputs of admp_pme_eval
-    void *M = nullptr, *G = nullptr, *Fscf = nullptr;
+    void *M = nullptr, *G = nullptr, *Fscf = nullptr, *rec = nullptr;
+    int8_t* r_sidx = nullptr;       // scale index per row for admp_pme_real (caller-owned pair list)
+    int64_t r_sidx_cap = 0;
     void *s_pos = nullptr, *s_U = nullptr, *s_pol = nullptr, *s_th = nullptr, *s_mS = nullptr, *s_pS = nullptr, *s_box = nullptr;
     int32_t* s_pairs = nullptr;
     int8_t* s_sidx = nullptr;       // scale index per staged pair row (-1: row not evaluated)
@@ -84,6 +86,7 @@ struct admp_ctx {
     // x-slab decomposition over the GPUs of one NVLink domain (admp_ctx_set_peers)
     int peer_rank = 0, peer_n = 0;
     PeerTab mesh_peers = {}, spec_peers = {};
+    SlabAux slab_aux = {};
     // neighbour list
     NbWork nb = {};
     size_t ws_bytes = 0;
@@ -147,7 +150,7 @@ static void free_recip(admp_ctx* c) {
 }
 
 static void free_atoms(admp_ctx* c) {
-    dfree(c->M); dfree(c->G); dfree(c->Fscf); dfree(c->s_pos); dfree(c->s_U); dfree(c->s_pol); dfree(c->s_th);
+    dfree(c->M); dfree(c->G); dfree(c->Fscf); dfree(c->rec); dfree(c->s_pos); dfree(c->s_U); dfree(c->s_pol); dfree(c->s_th);
     dfree(c->axis_type); dfree(c->axis_idx); dfree(c->cov_off); dfree(c->cov_idx); dfree(c->cov_nb);
 }
 
@@ -157,13 +160,18 @@ extern "C" int admp_ctx_destroy(admp_ctx* c) {
     drop_graph(c);
     free_recip(c);
     free_atoms(c);
-    dfree(c->s_pairs); dfree(c->s_sidx); dfree(c->box); dfree(c->scal); dfree(c->state); dfree(c->s_mS); dfree(c->s_pS); dfree(c->s_box);
+    dfree(c->s_pairs); dfree(c->s_sidx); dfree(c->r_sidx); dfree(c->box); dfree(c->scal); dfree(c->state); dfree(c->s_mS); dfree(c->s_pS); dfree(c->s_box);
     dfree(c->nb.cell_of); dfree(c->nb.cell_count); dfree(c->nb.cell_start); dfree(c->nb.sorted); dfree(c->nb.nbr_count); dfree(c->nb.nbr_start);
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
     if (c->side_stream) cudaStreamDestroy(c->side_stream);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->slab_aux.copy_stream) {
+        cudaStreamDestroy(c->slab_aux.copy_stream);
+        cudaEventDestroy(c->slab_aux.fork);
+        for (int k = 0; k < SLAB_CHUNKS; ++k) cudaEventDestroy(c->slab_aux.chunk[k]);
+    }
     delete c;
     return 0;
 }
@@ -263,6 +271,7 @@ extern "C" int admp_ctx_set_topology(admp_ctx* c, int n, const int32_t* axis_typ
     CK(cudaMalloc(&c->M, (size_t)n * 10 * w));
     CK(cudaMalloc(&c->G, (size_t)n * 10 * w));
     CK(cudaMalloc(&c->Fscf, (size_t)n * 3 * w));
+    CK(cudaMalloc(&c->rec, (size_t)n * pair_record_bytes((int)w)));
     CK(cudaMalloc(&c->s_pos, (size_t)n * 3 * w));
     CK(cudaMalloc(&c->s_U, (size_t)n * 3 * w));
     CK(cudaMalloc(&c->s_pol, (size_t)n * w));
@@ -395,8 +404,15 @@ extern "C" int admp_pme_real(admp_ctx* c, void* stream, const void* pos, const v
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(c->device));
     DISPATCH(c, launch_box_setup, st, box, c->box, c->K[0], c->K[1], c->K[2]);
-    DISPATCH(c, launch_pme_pair, st, n_rows, c->n_atoms, c->box, c->kappa, pos, pairs, nullptr, c->cov_off, c->cov_idx, c->cov_nb, M, U, pol,
-             tholes, mScales, pScales, mode, flags, dpos, G, F, dpol, dtholes, scalars);
+    // scale index per row once per call (one byte per row) instead of a covalent-CSR walk inside the pair loop
+    if (n_rows > c->r_sidx_cap) {
+        dfree(c->r_sidx);
+        c->r_sidx_cap = n_rows + n_rows / 4 + 1024;
+        CK(cudaMalloc(&c->r_sidx, (size_t)c->r_sidx_cap));
+    }
+    launch_pair_scale(st, n_rows, c->n_atoms, pairs, c->cov_off, c->cov_idx, c->cov_nb, c->r_sidx);
+    DISPATCH(c, launch_pme_pair, st, n_rows, c->n_atoms, c->box, c->kappa, pos, pairs, c->r_sidx, c->cov_off, c->cov_idx, c->cov_nb, M, U, pol,
+             tholes, mScales, pScales, mode, flags, dpos, G, F, dpol, dtholes, scalars, c->rec);
     CKLAUNCH();
     return 0;
 }
@@ -614,6 +630,12 @@ extern "C" int admp_ctx_set_peers(admp_ctx* c, int rank, int nranks, void* const
         c->spec_peers.base[r] = r < nranks ? spec_ptrs[r] : nullptr;
         if (r < nranks && (!mesh_ptrs[r] || !spec_ptrs[r])) return fail("admp_ctx_set_peers: null buffer for rank %d", r);
     }
+    if (!c->slab_aux.copy_stream) {
+        CK(cudaStreamCreateWithFlags(&c->slab_aux.copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c->slab_aux.fork, cudaEventDisableTiming));
+        for (int k = 0; k < SLAB_CHUNKS; ++k) CK(cudaEventCreateWithFlags(&c->slab_aux.chunk[k], cudaEventDisableTiming));
+        c->slab_aux.n_events = SLAB_CHUNKS;
+    }
     c->mesh_peers.slab = c->spec_peers.slab = c->K[0] / nranks;
     c->mesh_peers.n = c->spec_peers.n = nranks;
     c->peer_rank = rank;
@@ -647,7 +669,7 @@ extern "C" int admp_slab_fft(admp_ctx* c, void* stream, int phase, int kind, uin
     if (need_peers(c)) return 1;
     if (phase < 0 || phase > 2) return fail("admp_slab_fft: phase %d", phase);
     fft3d_slab_phase(c->fft, (cudaStream_t)stream, phase, c->peer_rank, c->mesh, c->spec, c->spec_peers, c->box, c->kappa, kind, c->tb,
-                     scalars, (flags & ADMP_WANT_VIRIAL) ? 1 : 0);
+                     scalars, (flags & ADMP_WANT_VIRIAL) ? 1 : 0, &c->slab_aux);
     CKLAUNCH();
     return 0;
 }
@@ -698,7 +720,7 @@ static int scf_body(admp_ctx* c, cudaStream_t st, int maxiter, double thresh, ui
     CK(cudaEventRecord(c->ev_fork, st));
     CK(cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
     DISPATCH(c, launch_pme_pair, c->side_stream, c->pairs_cap, c->n_atoms, c->box, c->kappa, c->s_pos, c->s_pairs, c->s_sidx, c->cov_off, c->cov_idx,
-             c->cov_nb, c->M, c->s_U, c->s_pol, c->s_th, c->s_mS, c->s_pS, 1, 0u, nullptr, nullptr, c->Fscf, nullptr, nullptr, c->scal);
+             c->cov_nb, c->M, c->s_U, c->s_pol, c->s_th, c->s_mS, c->s_pS, 1, 0u, nullptr, nullptr, c->Fscf, nullptr, nullptr, c->scal, c->rec);
     CK(cudaEventRecord(c->ev_join, c->side_stream));
     if (recip_field(c, st, c->s_pos, c->M, 10, 10, c->s_U, ADMP_CK_COULOMB, c->scal, 0, false)) return 1;
     DISPATCH(c, launch_gather, st, c->n_atoms, c->box, c->s_pos, c->M, 10, 10, c->s_U, c->mesh, 1, 0u, nullptr, nullptr, 10, c->Fscf, c->scal);
@@ -838,7 +860,8 @@ extern "C" int admp_pme_eval(admp_ctx* c, void* stream, const void* pos, const v
         DISPATCH(c, launch_gather, st, n, c->box, c->s_pos, c->M, 10, 10, Uf, c->mesh, 0, f, dpos, c->G, 10, polz ? F : nullptr, c->scal);
     }
     DISPATCH(c, launch_pme_pair, st, c->pairs_cap, n, c->box, c->kappa, c->s_pos, c->s_pairs, c->s_sidx, c->cov_off, c->cov_idx, c->cov_nb, c->M, Uf,
-             polz ? c->s_pol : nullptr, polz ? c->s_th : nullptr, c->s_mS, polz ? c->s_pS : nullptr, 0, f, dpos, c->G, F, dpol, dtholes, c->scal);
+             polz ? c->s_pol : nullptr, polz ? c->s_th : nullptr, c->s_mS, polz ? c->s_pS : nullptr, 0, f, dpos, c->G, F, dpol, dtholes, c->scal,
+             c->rec);
     DISPATCH(c, launch_self, st, n, c->kappa, c->M, Uf, polz ? c->s_pol : nullptr, f, c->G, F, dpol, c->scal);
     if (flags & ADMP_WANT_GRAD) {
         DISPATCH(c, launch_frames_bwd, st, n, c->lmax, c->box, c->s_pos, c->axis_type, c->axis_idx, Ql, c->G, dQl, dpos, c->scal, want_vir);

@@ -16,6 +16,7 @@
 // so every global access is a TL*sizeof(complex) contiguous segment. Line stride in shared memory is
 // odd (in complex units) to keep the transposing loads bank-conflict free.
 // Index math validated by tools/fft_model.py (tests/test_fft_model.py).
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -540,9 +541,14 @@ bool fft3d_slab_supported(const Fft3d* p) {
     const Fft3dImpl* f = reinterpret_cast<const Fft3dImpl*>(p);
     return f && f->z.fast && f->y.fast && f->x.fast && f->x.ops.occ_peer[0] > 0 && f->x.ops.occ_peer[1] > 0;
 }
+// phase 1 pipeline (SlabAux non-null, n > 1): the peers' planes of this rank's columns are pulled into the own
+// spectrum buffer chunk by chunk with strided peer copies on a copy stream (DMA engines over NVLink, large
+// contiguous rows), the fused X pass of chunk k runs as soon as its pull has landed and stores its results
+// straight to the owners' planes (peer stores, fire and forget): pull(k+1) | transform(k) | push(k) overlap.
+// ADMP_SLAB_PULL=0 selects the fully in-kernel variant (peer loads through cp.async as well).
 template <typename T>
 static void slab_phase(Fft3dImpl* f, cudaStream_t st, int phase, int rank, void* mesh, void* spec, const PeerTab& peers, const BoxInfo* B,
-                       double kappa, int kind, const ConvTables& tb, double* scalars, int want_vir) {
+                       double kappa, int kind, const ConvTables& tb, double* scalars, int want_vir, const SlabAux* aux) {
     const int x0 = rank * peers.slab, nx = peers.slab;
     if (phase == 0) {
         run_z<T>(f, st, mesh, spec, 1, x0, nx);
@@ -551,19 +557,47 @@ static void slab_phase(Fft3dImpl* f, cudaStream_t st, int phase, int rank, void*
         const FftDimCfg& c = f->x;
         const StrideGeom g = geom_x(f, c.ops.TL);
         const int t0 = (int)((long long)g.tiles * rank / peers.n), t1 = (int)((long long)g.tiles * (rank + 1) / peers.n);
+        if (t1 <= t0) return;
         const bool quick = kind == ADMP_CK_COULOMB && !want_vir;
-        const int grid = persistent_grid(f, c.ops.occ_peer[quick ? 0 : 1], t1 - t0);
-        if (t1 > t0) c.ops.xconv_peer(st, g, t0, t1, grid, B, kappa, kind, tb, f->tw[0], scalars, want_vir, peers);
+        const int occ = c.ops.occ_peer[quick ? 0 : 1];
+        static const bool pull = [] { const char* e = getenv("ADMP_SLAB_PULL"); return !(e && atoi(e) == 0); }();
+        if (!pull || !aux || peers.n == 1) {
+            c.ops.xconv_peer(st, g, t0, t1, persistent_grid(f, occ, t1 - t0), B, kappa, kind, tb, spec, f->tw[0], scalars, want_vir, peers, 0);
+            return;
+        }
+        static const int want_chunks = [] { const char* e = getenv("ADMP_SLAB_CHUNKS"); return e ? atoi(e) : 4; }();
+        static const int debug_skip = [] { const char* e = getenv("ADMP_SLAB_SKIP"); return e ? atoi(e) : 0; }();   // 1: no copies, 2: no kernels (timing only)
+        const int nchunk = std::max(1, std::min(aux->n_events, std::min(want_chunks, t1 - t0)));
+        const size_t pitch = (size_t)g.n_inner * sizeof(cx<T>);
+        cudaEventRecord(aux->fork, st);
+        cudaStreamWaitEvent(aux->copy_stream, aux->fork, 0);
+        for (int k = 0; k < nchunk; ++k) {
+            const int a = t0 + (int)((long long)(t1 - t0) * k / nchunk), b = t0 + (int)((long long)(t1 - t0) * (k + 1) / nchunk);
+            const size_t col0 = (size_t)a * c.ops.TL, col1 = std::min((size_t)b * c.ops.TL, (size_t)g.n_inner);
+            for (int q = 0; q < peers.n; ++q) {
+                if (q == rank || col1 <= col0 || debug_skip == 1) continue;
+                const size_t off = ((size_t)q * peers.slab * g.n_inner + col0) * sizeof(cx<T>);
+                cudaMemcpy2DAsync((char*)spec + off, pitch, (const char*)peers.base[q] + off, pitch, (col1 - col0) * sizeof(cx<T>),
+                                  (size_t)peers.slab, cudaMemcpyDefault, aux->copy_stream);
+            }
+            cudaEventRecord(aux->chunk[k], aux->copy_stream);
+        }
+        for (int k = 0; k < nchunk; ++k) {
+            const int a = t0 + (int)((long long)(t1 - t0) * k / nchunk), b = t0 + (int)((long long)(t1 - t0) * (k + 1) / nchunk);
+            cudaStreamWaitEvent(st, aux->chunk[k], 0);
+            if (b > a && debug_skip != 2)
+                c.ops.xconv_peer(st, g, a, b, persistent_grid(f, occ, b - a), B, kappa, kind, tb, spec, f->tw[0], scalars, want_vir, peers, 1);
+        }
     } else {
         run_strided<T>(f, st, spec, 1, -1, x0, nx);
         run_z<T>(f, st, mesh, spec, -1, x0, nx);
     }
 }
 void fft3d_slab_phase(Fft3d* p, cudaStream_t st, int phase, int rank, void* mesh, void* spec, const PeerTab& peers, const BoxInfo* B,
-                      double kappa, int kind, const ConvTables& tb, double* scalars, int want_vir) {
+                      double kappa, int kind, const ConvTables& tb, double* scalars, int want_vir, const SlabAux* aux) {
     Fft3dImpl* f = reinterpret_cast<Fft3dImpl*>(p);
-    if (f->esz == 8) slab_phase<double>(f, st, phase, rank, mesh, spec, peers, B, kappa, kind, tb, scalars, want_vir);
-    else slab_phase<float>(f, st, phase, rank, mesh, spec, peers, B, kappa, kind, tb, scalars, want_vir);
+    if (f->esz == 8) slab_phase<double>(f, st, phase, rank, mesh, spec, peers, B, kappa, kind, tb, scalars, want_vir, aux);
+    else slab_phase<float>(f, st, phase, rank, mesh, spec, peers, B, kappa, kind, tb, scalars, want_vir, aux);
 }
 
 // plain transforms (same conventions as cuFFT D2Z / Z2D: unnormalised)

@@ -299,7 +299,8 @@ __device__ __noinline__ double influence_general(const BoxInfo* Bp, const ConvTa
 template <typename T, int R1, int R2, int R3, int TL, int JT, bool QUICK, bool PEER>
 __global__ void __launch_bounds__(TL* JT, MinBlocks<TL * JT, R3>::value)
 fast_x_conv_kernel(StrideGeom g, int tile0, int ntiles, const BoxInfo* __restrict__ Bp, T kappa, int kind, ConvTables tb,
-                   cx<T>* __restrict__ spec, const cx<T>* __restrict__ gtw, double* __restrict__ scalars, int want_vir, PeerTab peers) {
+                   cx<T>* __restrict__ spec, const cx<T>* __restrict__ gtw, double* __restrict__ scalars, int want_vir, PeerTab peers,
+                   int local_reads) {
     constexpr int N = R1 * R2 * R3, TILE = N * TL, NT = TL * JT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[7 * ((NT + 31) / 32)];
@@ -325,8 +326,10 @@ fast_x_conv_kernel(StrideGeom g, int tile0, int ntiles, const BoxInfo* __restric
         __syncthreads();
     }
     pdl_wait();
+    // local_reads: the peers' planes of this rank's columns were pulled into `spec` beforehand (bulk copies over
+    // NVLink, pipelined by the host side): loads are local, only the stores go to the owners
     auto issue = [&](int t) {
-        if (PEER) issue_tile_peer<T, N, TL, JT>(g, t, sbase, I, l, j);
+        if (PEER && !local_reads) issue_tile_peer<T, N, TL, JT>(g, t, sbase, I, l, j);
         else issue_tile<T, N, TL, JT>(g, t, spec, I, l, j);
     };
     if (tile < ntiles) issue(tile);
@@ -573,7 +576,7 @@ struct FastOps {
                   void* spec, const void* tw, double* scalars, int want_vir);
     // x-slab decomposed spectrum: tiles [tile0, tile1) of the X pass on peer-mapped buffers
     void (*xconv_peer)(cudaStream_t, const StrideGeom&, int tile0, int tile1, int grid, const BoxInfo*, double kappa, int kind,
-                       const ConvTables&, const void* tw, double* scalars, int want_vir, const PeerTab&);
+                       const ConvTables&, void* spec, const void* tw, double* scalars, int want_vir, const PeerTab&, int local_reads);
     size_t smem_xp;
     int occ_peer[2];  // x conv on peers: quick, general
     void (*zfwd)(cudaStream_t, int nlines, int ntiles, int grid, const void* mesh, void* spec, const void* tw);
@@ -617,20 +620,21 @@ struct FastImpl {
         const size_t smem = smem_x_bytes();
         if (kind == ADMP_CK_COULOMB && !want_vir)
             launch_pdl(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, true, false>, grid, TL * JT, smem, st, g, 0, ntiles, B, (T)kappa, kind, tb,
-                       (cx<T>*)spec, (const cx<T>*)tw, scalars, want_vir, PeerTab{});
+                       (cx<T>*)spec, (const cx<T>*)tw, scalars, want_vir, PeerTab{}, 0);
         else
             launch_pdl(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, false, false>, grid, TL * JT, smem, st, g, 0, ntiles, B, (T)kappa, kind, tb,
-                       (cx<T>*)spec, (const cx<T>*)tw, scalars, want_vir, PeerTab{});
+                       (cx<T>*)spec, (const cx<T>*)tw, scalars, want_vir, PeerTab{}, 0);
     }
     static void xconv_peer(cudaStream_t st, const StrideGeom& g, int tile0, int tile1, int grid, const BoxInfo* B, double kappa, int kind,
-                           const ConvTables& tb, const void* tw, double* scalars, int want_vir, const PeerTab& peers) {
+                           const ConvTables& tb, void* spec, const void* tw, double* scalars, int want_vir, const PeerTab& peers,
+                           int local_reads) {
         const size_t smem = smem_x_bytes(true);
         if (kind == ADMP_CK_COULOMB && !want_vir)
-            fast_x_conv_kernel<T, R1, R2, R3, TL, JT, true, true><<<grid, TL * JT, smem, st>>>(g, tile0, tile1, B, (T)kappa, kind, tb, nullptr,
-                                                                                             (const cx<T>*)tw, scalars, want_vir, peers);
+            fast_x_conv_kernel<T, R1, R2, R3, TL, JT, true, true><<<grid, TL * JT, smem, st>>>(g, tile0, tile1, B, (T)kappa, kind, tb, (cx<T>*)spec,
+                                                                                             (const cx<T>*)tw, scalars, want_vir, peers, local_reads);
         else
-            fast_x_conv_kernel<T, R1, R2, R3, TL, JT, false, true><<<grid, TL * JT, smem, st>>>(g, tile0, tile1, B, (T)kappa, kind, tb, nullptr,
-                                                                                              (const cx<T>*)tw, scalars, want_vir, peers);
+            fast_x_conv_kernel<T, R1, R2, R3, TL, JT, false, true><<<grid, TL * JT, smem, st>>>(g, tile0, tile1, B, (T)kappa, kind, tb, (cx<T>*)spec,
+                                                                                              (const cx<T>*)tw, scalars, want_vir, peers, local_reads);
     }
     static void zfwd(cudaStream_t st, int nlines, int ntiles, int grid, const void* mesh, void* spec, const void* tw) {
         const size_t smem = (size_t)(2 * ZTL * ZGeom<N>::LS + TwGeom<R1, R2, R3>::TOTAL + N + 1) * sizeof(cx<T>);

@@ -23,7 +23,8 @@ template <typename T>
 void launch_pme_pair(cudaStream_t st, int64_t n_rows, int n_atoms, const BoxInfo* B, double kappa, const void* pos,
                      const int32_t* pairs, const int8_t* sidx, const int32_t* cov_off, const int32_t* cov_idx, const int8_t* cov_nb,
                      const void* M, const void* U, const void* pol, const void* tholes, const void* mS, const void* pS,
-                     int mode, uint32_t flags, void* dpos, void* G, void* F, void* dpol, void* dth, double* scalars);
+                     int mode, uint32_t flags, void* dpos, void* G, void* F, void* dpol, void* dth, double* scalars, void* rec);
+size_t pair_record_bytes(int dtype_bytes);        // per-atom record of the staged pair kernel (workspace `rec`)
 template <typename T>
 void launch_disp_pair(cudaStream_t st, int64_t n_rows, int n_atoms, const BoxInfo* B, double kappa, int pmax, const void* pos,
                       const int32_t* pairs, const int32_t* cov_off, const int32_t* cov_idx, const int8_t* cov_nb,
@@ -59,8 +60,16 @@ void fft3d_convolve_roundtrip(Fft3d* f, cudaStream_t st, void* mesh, void* spec,
                               const ConvTables& tb, double* scalars, int want_vir);
 
 bool fft3d_slab_supported(const Fft3d* f);
+constexpr int SLAB_CHUNKS = 16;       // maximum pipeline depth of the pulled X pass (ADMP_SLAB_CHUNKS, default 4)
+struct SlabAux {                      // copy stream + events of the pull pipeline (owned by the context)
+    cudaStream_t copy_stream;
+    cudaEvent_t fork;
+    cudaEvent_t chunk[SLAB_CHUNKS];
+    int n_events;
+};
 void fft3d_slab_phase(Fft3d* f, cudaStream_t st, int phase, int rank, void* mesh, void* spec, const PeerTab& spec_peers,
-                      const BoxInfo* B, double kappa, int kind, const ConvTables& tb, double* scalars, int want_vir);
+                      const BoxInfo* B, double kappa, int kind, const ConvTables& tb, double* scalars, int want_vir,
+                      const SlabAux* aux);
 
 // site.cu
 template <typename T> void launch_box_setup(cudaStream_t st, const void* box, BoxInfo* B, int K1, int K2, int K3);

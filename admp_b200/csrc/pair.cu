@@ -225,14 +225,48 @@ void launch_pair_scale(cudaStream_t st, int64_t n_rows, int n_atoms, const int32
 //    of 16 atomics per lane; any other ordering falls back to per-lane atomics (correct for every list).
 //  * MODE 0: energy + all adjoints. MODE 1: dE/dU only (the SCF field).
 constexpr int PAIR_TILE = 128;
-template <bool POL> struct PairFields { static constexpr int N = POL ? 18 : 13; };   // pos 3, M 10, [U 3, pol, thole]
+// Packed per-atom record the staged (MODE 0) kernel gathers: position 3, Cartesian multipoles 10, induced dipole 3,
+// polarizability, Thole width = 18 reals, padded to whole 16-byte chunks (double: 18 = 9 chunks; float: 20 = 5
+// chunks). One record = 9 (5) LDGSTS.128 + 9 (5) LDS.128 per pair end instead of 18 + 18 eight-byte ones: the
+// pair loop is bound by the load/store unit (cp.async + shared loads + 32 reductions per pair), not by DRAM.
+template <typename T> struct PairRec {
+    static constexpr int EPC = 16 / sizeof(T);                 // elements per 16-byte chunk
+    static constexpr int STRIDE = sizeof(T) == 8 ? 18 : 20;    // elements per record
+    static constexpr int chunks(bool pol) { return ((pol ? 18 : 13) + EPC - 1) / EPC; }
+};
+template <typename T> struct alignas(16) PairChunk { T v[16 / sizeof(T)]; };
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
 
 template <typename T>
-__device__ __forceinline__ void cp_async_real(T* smem, const T* gmem) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    if (sizeof(T) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem) : "memory");
-    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem) : "memory");
+__global__ void __launch_bounds__(256)
+pair_pack_kernel(int n, const T* __restrict__ pos, const T* __restrict__ M, const T* __restrict__ U, const T* __restrict__ pol,
+                 const T* __restrict__ tholes, T* __restrict__ rec) {
+    constexpr int S = PairRec<T>::STRIDE;
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)n * S) return;
+    const int a = (int)(e / S), f = (int)(e - (int64_t)a * S);
+    T v = (T)0;
+    if (f < 3) v = pos[3 * (size_t)a + f];
+    else if (f < 13) v = M[10 * (size_t)a + (f - 3)];
+    else if (f < 16) v = U ? U[3 * (size_t)a + (f - 13)] : (T)0;
+    else if (f == 16) v = pol ? pol[a] : (T)0;
+    else if (f == 17) v = tholes ? tholes[a] : (T)0;
+    rec[e] = v;
 }
+template <typename T>
+void launch_pair_pack(cudaStream_t st, int n, const void* pos, const void* M, const void* U, const void* pol, const void* tholes, void* rec) {
+    if (n <= 0) return;
+    const int64_t tot = (int64_t)n * PairRec<T>::STRIDE;
+    pair_pack_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(n, (const T*)pos, (const T*)M, (const T*)U, (const T*)pol,
+                                                                        (const T*)tholes, (T*)rec);
+}
+template void launch_pair_pack<double>(cudaStream_t, int, const void*, const void*, const void*, const void*, const void*, void*);
+template void launch_pair_pack<float>(cudaStream_t, int, const void*, const void*, const void*, const void*, const void*, void*);
+size_t pair_record_bytes(int dtype_bytes) { return dtype_bytes == 8 ? PairRec<double>::STRIDE * 8 : PairRec<float>::STRIDE * 4; }
 
 // sum of 16 per-lane values over the warp: after the call lane L holds the total of value
 // (L >> 1) & 15 (both lanes of a pair hold the same total). 16 shuffles instead of 80.
@@ -269,8 +303,8 @@ pme_pair_kernel(int64_t n_rows, int n_atoms, const BoxInfo* __restrict__ Bp, T k
                 const T* __restrict__ M, const T* __restrict__ U, const T* __restrict__ pol, const T* __restrict__ tholes,
                 const T* __restrict__ mScales, const T* __restrict__ pScales, uint32_t flags,
                 T* __restrict__ dpos, T* __restrict__ G, T* __restrict__ F, T* __restrict__ dpol, T* __restrict__ dth,
-                double* __restrict__ scalars) {
-    constexpr int NF = PairFields<POL>::N;
+                double* __restrict__ scalars, const T* __restrict__ rec) {
+    constexpr int NCH = PairRec<T>::chunks(POL), EPC = PairRec<T>::EPC, REC = PairRec<T>::STRIDE;
     // the field-only SCF kernel does ~200 FP64 operations per pair: staging 36 values per pair through shared
     // memory costs more than it hides there, so MODE 1 gathers straight from global memory (L2-resident arrays)
     constexpr bool STAGED = (MODE == 0);
@@ -278,7 +312,7 @@ pme_pair_kernel(int64_t n_rows, int n_atoms, const BoxInfo* __restrict__ Bp, T k
     __shared__ double red[10 * 4];
     __shared__ BoxInfo sB;                                      // cell + scale tables: shared-memory reads in the pair loop
     __shared__ T sScale[10];
-    T* stage_base = reinterpret_cast<T*>(pair_smem);            // [2 stages][2 ends][NF][PAIR_TILE]
+    PairChunk<T>* stage_base = reinterpret_cast<PairChunk<T>*>(pair_smem);   // [2 stages][2 ends][NCH][PAIR_TILE] 16-byte chunks
     const int tid = threadIdx.x, lane = tid & 31;
     if (tid < (int)(sizeof(BoxInfo) / sizeof(double))) reinterpret_cast<double*>(&sB)[tid] = reinterpret_cast<const double*>(Bp)[tid];
     if (tid < 5) { sScale[tid] = mScales[tid]; sScale[5 + tid] = POL ? pScales[tid] : (T)0; }
@@ -304,23 +338,17 @@ pme_pair_kernel(int64_t n_rows, int n_atoms, const BoxInfo* __restrict__ Bp, T k
         }
         return r;
     };
-    auto field = [&](int stage, int end, int f) -> T* { return stage_base + ((size_t)((stage * 2 + end) * NF + f)) * PAIR_TILE + tid; };
+    auto slot = [&](int stage, int end, int ch) -> PairChunk<T>* {
+        return stage_base + ((size_t)((stage * 2 + end) * NCH + ch)) * PAIR_TILE + tid;
+    };
     auto issue = [&](const Row& r, int stage) {
         if (!STAGED) return;
         if (r.s >= 0) {
 #pragma unroll
             for (int end = 0; end < 2; ++end) {
-                const size_t a = end == 0 ? r.i : r.j;
+                const PairChunk<T>* src = reinterpret_cast<const PairChunk<T>*>(rec + (size_t)(end == 0 ? r.i : r.j) * REC);
 #pragma unroll
-                for (int k = 0; k < 3; ++k) cp_async_real(field(stage, end, k), pos + 3 * a + k);
-#pragma unroll
-                for (int k = 0; k < 10; ++k) cp_async_real(field(stage, end, 3 + k), M + 10 * a + k);
-                if (POL) {
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) cp_async_real(field(stage, end, 13 + k), U + 3 * a + k);
-                    cp_async_real(field(stage, end, 16), pol + a);
-                    cp_async_real(field(stage, end, 17), tholes + a);
-                }
+                for (int ch = 0; ch < NCH; ++ch) cp_async16(slot(stage, end, ch), src + ch);
             }
         }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
@@ -342,8 +370,19 @@ pme_pair_kernel(int64_t n_rows, int n_atoms, const BoxInfo* __restrict__ Bp, T k
 #pragma unroll
         for (int k = 0; k < 16; ++k) gj[k] = (T)0;
         // field f of pair end `end`: 0-2 position, 3-12 multipoles, 13-15 induced dipole, 16 polarizability, 17 Thole width
+        T ra[2][STAGED ? NCH * EPC : 1];          // staged records of both ends (registers after unrolling)
+        if (STAGED && live) {
+#pragma unroll
+            for (int end = 0; end < 2; ++end)
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    const PairChunk<T> c = *slot(stage, end, ch);
+#pragma unroll
+                    for (int e = 0; e < EPC; ++e) ra[end][ch * EPC + e] = c.v[e];
+                }
+        }
         auto rd = [&](int end, int f) -> T {
-            if (STAGED) return *field(stage, end, f);
+            if (STAGED) return ra[end][f];
             const size_t a = end == 0 ? i : j;
             if (f < 3) return pos[3 * a + f];
             if (f < 13) return M[10 * a + (f - 3)];
@@ -544,9 +583,9 @@ template <typename T, bool POL, int MODE>
 static void launch_pme_pair_t(cudaStream_t st, int64_t n_rows, int n_atoms, const BoxInfo* B, double kappa, const void* pos,
                               const int32_t* pairs, const int8_t* sidx, const int32_t* cov_off, const int32_t* cov_idx, const int8_t* cov_nb,
                               const void* M, const void* U, const void* pol, const void* tholes, const void* mS, const void* pS,
-                              uint32_t flags, void* dpos, void* G, void* F, void* dpol, void* dth, double* scalars) {
+                              uint32_t flags, void* dpos, void* G, void* F, void* dpol, void* dth, double* scalars, const void* rec) {
     static int grid_cap = 0;
-    const size_t smem = MODE == 0 ? (size_t)2 * 2 * PairFields<POL>::N * PAIR_TILE * sizeof(T) : 0;
+    const size_t smem = MODE == 0 ? (size_t)2 * 2 * PairRec<T>::chunks(POL) * PAIR_TILE * 16 : 0;
     auto kern = pme_pair_kernel<T, POL, MODE>;
     if (grid_cap == 0) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -560,18 +599,20 @@ static void launch_pme_pair_t(cudaStream_t st, int64_t n_rows, int n_atoms, cons
     const unsigned grid = (unsigned)(ntiles < grid_cap ? ntiles : grid_cap);
     kern<<<grid, PAIR_TILE, smem, st>>>(n_rows, n_atoms, B, (T)kappa, (const T*)pos, pairs, sidx, cov_off, cov_idx, cov_nb, (const T*)M,
                                         (const T*)U, (const T*)pol, (const T*)tholes, (const T*)mS, (const T*)pS, flags, (T*)dpos, (T*)G,
-                                        (T*)F, (T*)dpol, (T*)dth, scalars);
+                                        (T*)F, (T*)dpol, (T*)dth, scalars, (const T*)rec);
 }
 
 template <typename T>
 void launch_pme_pair(cudaStream_t st, int64_t n_rows, int n_atoms, const BoxInfo* B, double kappa, const void* pos,
                      const int32_t* pairs, const int8_t* sidx, const int32_t* cov_off, const int32_t* cov_idx, const int8_t* cov_nb,
                      const void* M, const void* U, const void* pol, const void* tholes, const void* mS, const void* pS,
-                     int mode, uint32_t flags, void* dpos, void* G, void* F, void* dpol, void* dth, double* scalars) {
+                     int mode, uint32_t flags, void* dpos, void* G, void* F, void* dpol, void* dth, double* scalars, void* rec) {
     if (n_rows <= 0) return;
     const bool polz = (U != nullptr);
+    // mode 0 gathers packed per-atom records (rec: n_atoms * pair_record_bytes workspace, filled here)
+    if (mode != 1) launch_pair_pack<T>(st, n_atoms, pos, M, U, pol, tholes, rec);
 #define ADMP_PAIR_ARGS st, n_rows, n_atoms, B, kappa, pos, pairs, sidx, cov_off, cov_idx, cov_nb, M, U, pol, tholes, mS, pS, flags, dpos, G, F, \
-    dpol, dth, scalars
+    dpol, dth, scalars, rec
     if (mode == 1) {
         if (polz) launch_pme_pair_t<T, true, 1>(ADMP_PAIR_ARGS);
     } else if (polz) {
@@ -583,10 +624,10 @@ void launch_pme_pair(cudaStream_t st, int64_t n_rows, int n_atoms, const BoxInfo
 }
 template void launch_pme_pair<double>(cudaStream_t, int64_t, int, const BoxInfo*, double, const void*, const int32_t*, const int8_t*,
                                       const int32_t*, const int32_t*, const int8_t*, const void*, const void*, const void*, const void*,
-                                      const void*, const void*, int, uint32_t, void*, void*, void*, void*, void*, double*);
+                                      const void*, const void*, int, uint32_t, void*, void*, void*, void*, void*, double*, void*);
 template void launch_pme_pair<float>(cudaStream_t, int64_t, int, const BoxInfo*, double, const void*, const int32_t*, const int8_t*,
                                      const int32_t*, const int32_t*, const int8_t*, const void*, const void*, const void*, const void*,
-                                     const void*, const void*, int, uint32_t, void*, void*, void*, void*, void*, double*);
+                                     const void*, const void*, int, uint32_t, void*, void*, void*, void*, void*, double*, void*);
 
 // ------------------------------------------------------------------------------------------
 // Dispersion real space: admp/disp_pme.py:126-251.  E = sum_p (m + g_p(x^2) - 1) ci cj / r^p.

@@ -281,6 +281,8 @@ class SlabPme:
         self._opened = []
         self._key = None
         self._tok = None
+        self.profile = False
+        self._spans = []
 
     # ---- contexts and peer tables
     def _own_buffers(self, c):
@@ -359,7 +361,35 @@ class SlabPme:
     def _barrier(self):
         if self.world > 1:
             import torch.distributed as dist
-            dist.all_reduce(self._tok, group=self.group)
+            with self._timed('barrier'):
+                dist.all_reduce(self._tok, group=self.group)
+
+    # optional per-stage device timing (profile=True): CUDA events on the current stream, summed per stage name
+    class _Span:
+        def __init__(self, owner, name):
+            self.o, self.name = owner, name
+
+        def __enter__(self):
+            if self.o.profile:
+                self.a = torch.cuda.Event(enable_timing=True)
+                self.a.record()
+
+        def __exit__(self, *exc):
+            if self.o.profile:
+                b = torch.cuda.Event(enable_timing=True)
+                b.record()
+                self.o._spans.append((self.name, self.a, b))
+
+    def _timed(self, name):
+        return SlabPme._Span(self, name)
+
+    def stage_times(self):
+        """{stage: milliseconds} of the last evaluate() when profile=True (synchronises)."""
+        torch.cuda.synchronize()
+        out = {}
+        for name, a, b in self._spans:
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return out
 
     # ---- evaluation
     def evaluate(self, positions, box, pairs, Q_local, pol=None, tholes=None, mScales=None, pScales=None, U_init=None,
@@ -369,6 +399,7 @@ class SlabPme:
         from ._ctx import pairs_to_dev
         calc = self.calc
         self._setup()
+        self._spans = []
         c, lib = calc._ctx, calc._ctx.lib
         p, sp = _lib.ptr, _lib.stream_ptr
         dev, dt = c.device, c.dtype
@@ -383,18 +414,26 @@ class SlabPme:
         fl = _lib.WANT_GRAD | (_lib.WANT_VIRIAL if want_virial else 0)
         vir = _lib.WANT_VIRIAL if want_virial else 0
 
+        span_setup = self._timed('setup')
+        span_setup.__enter__()
         for r in self.mine:
             _lib.check(lib.admp_set_box(self._ctxs[r].handle, sp(), p(box_d)))
         M = torch.empty((n, 10), dtype=dt, device=dev)
         _lib.check(lib.admp_frames_fwd(c.handle, sp(), p(pos), p(box_d), p(Ql), p(M), None, None))
-        owned = partition_atoms_by_slab(pos.cpu().numpy(), box_d.cpu().numpy(), self.P)
+        # spatial ownership (same rule as partition_atoms_by_slab, evaluated on the device in float64)
+        sx = (pos.to(torch.float64) @ torch.linalg.inv(box_d.to(torch.float64)))[:, 0]
+        sx = sx - torch.floor(sx)
+        owner = torch.clamp((sx * self.P).to(torch.int64), max=self.P - 1)
         # per owned rank: spatial atom set (compact copies), pair-row slice, per-site atom block
         work = []
         for r in self.mine:
-            idx = torch.as_tensor(owned[r], dtype=torch.int64, device=dev)
-            work.append(dict(r=r, ctx=self._ctxs[r], idx=idx, cnt=int(idx.numel()), pos=pos.index_select(0, idx).contiguous(),
+            idx = torch.nonzero(owner == r).reshape(-1)
+            cnt = int(idx.numel())
+            work.append(dict(r=r, ctx=self._ctxs[r], idx=idx, cnt=cnt, pos=pos.index_select(0, idx).contiguous(),
                              M=M.index_select(0, idx).contiguous(), pairs=pr[rows[r][0]:rows[r][0] + rows[r][1]].contiguous(),
-                             nrows=rows[r][1], a0=self.atoms[r][0], ac=self.atoms[r][1]))
+                             nrows=rows[r][1], a0=self.atoms[r][0], ac=self.atoms[r][1],
+                             Fr=torch.empty((cnt, 3), dtype=dt, device=dev)))
+        span_setup.__exit__()
         scal = torch.zeros(_lib.S_COUNT, dtype=torch.float64, device=dev)
         U = F = None
         n_cycle, conv = 0, True
@@ -407,19 +446,23 @@ class SlabPme:
                 scal.zero_()
                 self._recip(work, U, scal, 0)
                 F.zero_()
-                for wk in work:
-                    Fr = torch.zeros((wk['cnt'], 3), dtype=dt, device=dev)
-                    _lib.check(lib.admp_slab_gather(wk['ctx'].handle, sp(), p(wk['pos']), p(wk['M']), 10, 10, p(wk['U']), 1, 0, None, None, 10,
-                                                    p(Fr), p(scal), wk['cnt']))
-                    F.index_add_(0, wk['idx'], Fr)
-                for wk in work:
-                    if wk['nrows'] > 0:
-                        _lib.check(lib.admp_pme_real(c.handle, sp(), p(pos), p(box_d), p(wk['pairs']), wk['nrows'], p(M), p(U), p(polt), p(th),
-                                                     p(mS), p(pS), 1, 0, None, None, p(F), None, None, p(scal)))
-                allreduce_sum_([F], self.group)          # also orders this cycle's gathers before the next slab_zero
-                _lib.check(lib.admp_scf_step(c.handle, sp(), p(M), p(U), p(polt), p(F), int(maxiter), float(thresh), vir, p(state),
-                                             p(scal)))
-                st = state.cpu()
+                with self._timed('gather'):
+                    for wk in work:
+                        Fr = wk['Fr'].zero_()
+                        _lib.check(lib.admp_slab_gather(wk['ctx'].handle, sp(), p(wk['pos']), p(wk['M']), 10, 10, p(wk['U']), 1, 0, None, None,
+                                                        10, p(Fr), p(scal), wk['cnt']))
+                        F.index_add_(0, wk['idx'], Fr)
+                with self._timed('pair'):
+                    for wk in work:
+                        if wk['nrows'] > 0:
+                            _lib.check(lib.admp_pme_real(c.handle, sp(), p(pos), p(box_d), p(wk['pairs']), wk['nrows'], p(M), p(U), p(polt),
+                                                         p(th), p(mS), p(pS), 1, 0, None, None, p(F), None, None, p(scal)))
+                with self._timed('allreduce_F'):
+                    allreduce_sum_([F], self.group)      # also orders this cycle's gathers before the next slab_zero
+                with self._timed('scf_step'):
+                    _lib.check(lib.admp_scf_step(c.handle, sp(), p(M), p(U), p(polt), p(F), int(maxiter), float(thresh), vir, p(state),
+                                                 p(scal)))
+                    st = state.cpu()
                 if not int(st[5]):
                     n_cycle, conv = int(st[3]), bool(st[4])
                     break
@@ -429,6 +472,8 @@ class SlabPme:
         else:
             self._recip(work, None, scal, vir)
         # final evaluation at fixed U; phi of the last round trip sits in the slabs
+        span_final = self._timed('final')
+        span_final.__enter__()
         e_recip = scal[_lib.S_E_RECIP].clone()
         tk = scal[_lib.S_TK:_lib.S_TK + 6].clone()
         scal.zero_()
@@ -461,6 +506,7 @@ class SlabPme:
         if want_virial:
             _lib.check(lib.admp_virial_finalize(c.handle, sp(), p(scal)))
         E = scal[_lib.S_E_REAL] + scal[_lib.S_E_RECIP] + scal[_lib.S_E_SELF] + scal[_lib.S_E_PEN]
+        span_final.__exit__()
         return dict(E=E, dpos=dpos, dbox=scal[_lib.S_DBOX:_lib.S_DBOX + 9].reshape(3, 3).clone(), dQ_local=dQ, U=U, F=Fo,
                     n_cycle=n_cycle, converged=conv, scalars=scal)
 
@@ -469,14 +515,17 @@ class SlabPme:
         between the stages; leaves phi = dE/dmesh in the slabs."""
         lib = self.calc._ctx.lib
         p, sp = _lib.ptr, _lib.stream_ptr
-        for wk in work:
-            wk['U'] = U.index_select(0, wk['idx']).contiguous() if U is not None else None
-            _lib.check(lib.admp_slab_zero(wk['ctx'].handle, sp()))
+        with self._timed('zero'):
+            for wk in work:
+                wk['U'] = U.index_select(0, wk['idx']).contiguous() if U is not None else None
+                _lib.check(lib.admp_slab_zero(wk['ctx'].handle, sp()))
         self._barrier()
-        for wk in work:
-            _lib.check(lib.admp_slab_spread(wk['ctx'].handle, sp(), p(wk['pos']), p(wk['M']), 10, 10, p(wk['U']), wk['cnt']))
+        with self._timed('spread'):
+            for wk in work:
+                _lib.check(lib.admp_slab_spread(wk['ctx'].handle, sp(), p(wk['pos']), p(wk['M']), 10, 10, p(wk['U']), wk['cnt']))
         self._barrier()
         for phase in range(3):
-            for wk in work:
-                _lib.check(lib.admp_slab_fft(wk['ctx'].handle, sp(), phase, _lib.CK_COULOMB, vir, p(scal)))
+            with self._timed(('fft_zy_fwd', 'fft_x_peer', 'fft_yz_inv')[phase]):
+                for wk in work:
+                    _lib.check(lib.admp_slab_fft(wk['ctx'].handle, sp(), phase, _lib.CK_COULOMB, vir, p(scal)))
             self._barrier()

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Multi-rank driver (launch with torchrun, one rank per GPU):
     torchrun --nproc-per-node N tools/run_multigpu.py --check          # parity of both shardings vs 1 rank
-    torchrun --nproc-per-node N tools/run_multigpu.py --config C5      # atom-block timing on a big box
+    torchrun --nproc-per-node N tools/run_multigpu.py --config C5      # x-slab timing on a big box
+    torchrun --nproc-per-node N tools/run_multigpu.py --config C5 --scheme blocks    # replicated-mesh atom blocks
 """
 import argparse
 import os
@@ -13,7 +14,7 @@ import numpy as np                                  # noqa: E402
 import torch                                        # noqa: E402
 import torch.distributed as dist                    # noqa: E402
 from admp_b200 import _lib, workloads               # noqa: E402
-from admp_b200.parallel import AtomBlockPme, evaluate_frames   # noqa: E402
+from admp_b200.parallel import AtomBlockPme, SlabPme, evaluate_frames   # noqa: E402
 from admp_b200.pme import ADMPPmeForce              # noqa: E402
 from admp_b200.neighbor import neighbor_list        # noqa: E402
 
@@ -29,6 +30,8 @@ def main():
     ap.add_argument('--check', action='store_true')
     ap.add_argument('--config', default='C3')
     ap.add_argument('--steps', type=int, default=2)
+    ap.add_argument('--scheme', default='slab', choices=['slab', 'blocks'])
+    ap.add_argument('--profile', action='store_true', help='per-stage device times of the x-slab scheme (rank 0)')
     a = ap.parse_args()
     rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
     torch.cuda.set_device(local)
@@ -47,6 +50,23 @@ def main():
         errs = dict(E=abs(out['E'].item() - ref.energy.item()) / abs(ref.energy.item()), dpos=rel(out['dpos'], ref.dpos),
                     U=rel(out['U'], ref.U), dbox=rel(out['dbox'], ref.dbox), dQ=rel(out['dQ_local'], ref.dQ))
         ok = ok and all(v < 1e-9 for v in errs.values())
+        # x-slab reciprocal space over peer memory on the base water box (mesh 154^3), 4 Jacobi cycles
+        serr = {}
+        if 154 % world == 0:
+            w = workloads.water_box((1, 1, 1), polarizable=True)
+            calc2 = ADMPPmeForce(w.box, w.axis_type, w.axis_indices, w.covalent_map, w.rc, w.ethresh, 2, lpol=True)
+            calc2.update_env('kappa', w.kappa)
+            pairs2 = neighbor_list(w.box, w.rc).allocate(w.positions).pairs
+            sl = SlabPme(calc2, rank, world)
+            o2 = sl.evaluate(w.positions, w.box, pairs2, w.Q_local, w.pol, w.tholes, w.mScales, w.pScales, maxiter=4)
+            a2 = [calc2._prep(x) for x in (w.positions, w.box, w.Q_local, w.pol, w.tholes, w.mScales, w.pScales)]
+            r2 = calc2._eval(a2[0], a2[1], pairs2, a2[2], None, a2[3], a2[4], a2[5], a2[6],
+                             _lib.WANT_GRAD | _lib.WANT_VIRIAL, True, maxiter=4, cache_scf=False)
+            ok = ok and [o2['n_cycle'], int(o2['converged'])] == r2.scf.cpu().tolist()
+            serr = dict(E=abs(o2['E'].item() - r2.energy.item()) / abs(r2.energy.item()), dpos=rel(o2['dpos'], r2.dpos),
+                        U=rel(o2['U'], r2.U), dbox=rel(o2['dbox'], r2.dbox), dQ=rel(o2['dQ_local'], r2.dQ))
+            ok = ok and all(v < 1e-9 for v in serr.values())
+            sl.close()
         # frames: 6 jittered frames, parameter gradients all-reduced
         frames = [s.jitter(1000 + f).numpy() for f in range(6)]
         res = evaluate_frames(calc, frames, s.box, pairs, s.Q_local, s.pol, s.tholes, s.mScales, s.pScales, rank=rank, world=world)
@@ -62,6 +82,7 @@ def main():
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if rank == 0:
             print('atom-block errors', errs)
+            print('x-slab errors', serr)
             print('frame-sharding errors', ferr)
             print('MULTIGPU CHECK OK' if flag.item() > 0 else 'MULTIGPU CHECK FAILED')
         dist.barrier()
@@ -74,22 +95,34 @@ def main():
     for d in range(3):
         calc.update_env('K%d' % (d + 1), w.K[d])
     pairs = neighbor_list(w.box, w.rc).allocate(w.positions).pairs
-    ab = AtomBlockPme(calc, rank, world)
+    ab = SlabPme(calc, rank, world) if a.scheme == 'slab' else AtomBlockPme(calc, rank, world)
+    if a.profile and a.scheme == 'slab':
+        ab.profile = True
     ts = []
     for k in range(a.steps + 1):
         dist.barrier()
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         out = ab.evaluate(w.positions, w.box, pairs, w.Q_local, w.pol, w.tholes, w.mScales, w.pScales)
+        e1.record()
         torch.cuda.synchronize()
         dist.barrier()
         if k:
-            ts.append(time.perf_counter() - t0)
+            ts.append(1e-3 * e0.elapsed_time(e1))       # device time (CUDA events); max over ranks below
     t = torch.tensor([np.mean(ts)], device='cuda')
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print('%s atom-block on %d GPU(s): %.1f ms/eval (%.3f evals/s), E = %.6f, scf [%d, %s]' % (
-            a.config, world, 1e3 * t.item(), 1.0 / t.item(), out['E'].item(), out['n_cycle'], out['converged']))
+        print('%s %s on %d GPU(s): %.1f ms/eval (%.3f evals/s), E = %.6f, scf [%d, %s]' % (
+            a.config, 'x-slab' if a.scheme == 'slab' else 'atom-block', world, 1e3 * t.item(), 1.0 / t.item(), out['E'].item(),
+            out['n_cycle'], out['converged']))
+    if a.profile and a.scheme == 'slab':
+        st = ab.stage_times()
+        if rank == 0:
+            tot = sum(st.values())
+            print('stage times of the last eval on rank 0 (ms, CUDA events; a barrier span includes waiting for the slowest rank):')
+            for k, v in sorted(st.items(), key=lambda kv: -kv[1]):
+                print('  %-12s %9.2f  %5.1f %%' % (k, v, 100 * v / tot))
     dist.barrier()
     dist.destroy_process_group()
 
