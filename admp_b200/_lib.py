@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libadmp_b200.so')
+# ADMP_LIB: alternative build of the same library (kernel A/B measurements); never a different implementation
+LIB_PATH = os.environ.get('ADMP_LIB') or os.path.join(_HERE, 'lib', 'libadmp_b200.so')
 
 F64, F32 = 0, 1
 CK_COULOMB, CK_DISP6, CK_DISP8, CK_DISP10 = 1, 6, 8, 10

@@ -167,10 +167,11 @@ extern "C" int admp_ctx_destroy(admp_ctx* c) {
     if (c->side_stream) cudaStreamDestroy(c->side_stream);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
-    if (c->slab_aux.copy_stream) {
-        cudaStreamDestroy(c->slab_aux.copy_stream);
+    if (c->slab_aux.ready) {
+        for (int s = 0; s < SLAB_STREAMS; ++s) cudaStreamDestroy(c->slab_aux.copy_stream[s]);
         cudaEventDestroy(c->slab_aux.fork);
-        for (int k = 0; k < SLAB_CHUNKS; ++k) cudaEventDestroy(c->slab_aux.chunk[k]);
+        for (int k = 0; k < SLAB_CHUNKS; ++k)
+            for (int s = 0; s < SLAB_STREAMS; ++s) cudaEventDestroy(c->slab_aux.chunk[k][s]);
     }
     delete c;
     return 0;
@@ -630,11 +631,12 @@ extern "C" int admp_ctx_set_peers(admp_ctx* c, int rank, int nranks, void* const
         c->spec_peers.base[r] = r < nranks ? spec_ptrs[r] : nullptr;
         if (r < nranks && (!mesh_ptrs[r] || !spec_ptrs[r])) return fail("admp_ctx_set_peers: null buffer for rank %d", r);
     }
-    if (!c->slab_aux.copy_stream) {
-        CK(cudaStreamCreateWithFlags(&c->slab_aux.copy_stream, cudaStreamNonBlocking));
+    if (!c->slab_aux.ready) {
+        for (int s = 0; s < SLAB_STREAMS; ++s) CK(cudaStreamCreateWithFlags(&c->slab_aux.copy_stream[s], cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&c->slab_aux.fork, cudaEventDisableTiming));
-        for (int k = 0; k < SLAB_CHUNKS; ++k) CK(cudaEventCreateWithFlags(&c->slab_aux.chunk[k], cudaEventDisableTiming));
-        c->slab_aux.n_events = SLAB_CHUNKS;
+        for (int k = 0; k < SLAB_CHUNKS; ++k)
+            for (int s = 0; s < SLAB_STREAMS; ++s) CK(cudaEventCreateWithFlags(&c->slab_aux.chunk[k][s], cudaEventDisableTiming));
+        c->slab_aux.ready = 1;
     }
     c->mesh_peers.slab = c->spec_peers.slab = c->K[0] / nranks;
     c->mesh_peers.n = c->spec_peers.n = nranks;

@@ -567,24 +567,37 @@ static void slab_phase(Fft3dImpl* f, cudaStream_t st, int phase, int rank, void*
         }
         static const int want_chunks = [] { const char* e = getenv("ADMP_SLAB_CHUNKS"); return e ? atoi(e) : 4; }();
         static const int debug_skip = [] { const char* e = getenv("ADMP_SLAB_SKIP"); return e ? atoi(e) : 0; }();   // 1: no copies, 2: no kernels (timing only)
-        const int nchunk = std::max(1, std::min(aux->n_events, std::min(want_chunks, t1 - t0)));
+        const int nchunk = std::max(1, std::min(SLAB_CHUNKS, std::min(want_chunks, t1 - t0)));
         const size_t pitch = (size_t)g.n_inner * sizeof(cx<T>);
+        // copies of one chunk: one per peer (two row halves per peer when there is a single peer), dealt over the
+        // copy streams; staggered source order: at step s every rank pulls from rank + s, so each source feeds
+        // exactly one reader at a time
+        // measured on B200 / NVSwitch: ONE copy stream is fastest (P = 2: 7.3 vs 7.8 ms per pass, P = 4: 5.5 vs 6.2 ms
+        // with four); ADMP_SLAB_STREAMS spreads the pulls of a chunk over more streams for experiments
+        static const int want_streams = [] { const char* e = getenv("ADMP_SLAB_STREAMS"); return e ? atoi(e) : 1; }();
+        const int halves = (peers.n == 2 && want_streams > 1) ? 2 : 1;
+        const int nstreams = std::max(1, std::min(std::min(SLAB_STREAMS, want_streams), (peers.n - 1) * halves));
         cudaEventRecord(aux->fork, st);
-        cudaStreamWaitEvent(aux->copy_stream, aux->fork, 0);
+        for (int s = 0; s < nstreams; ++s) cudaStreamWaitEvent(aux->copy_stream[s], aux->fork, 0);
         for (int k = 0; k < nchunk; ++k) {
             const int a = t0 + (int)((long long)(t1 - t0) * k / nchunk), b = t0 + (int)((long long)(t1 - t0) * (k + 1) / nchunk);
             const size_t col0 = (size_t)a * c.ops.TL, col1 = std::min((size_t)b * c.ops.TL, (size_t)g.n_inner);
-            for (int q = 0; q < peers.n; ++q) {
-                if (q == rank || col1 <= col0 || debug_skip == 1) continue;
-                const size_t off = ((size_t)q * peers.slab * g.n_inner + col0) * sizeof(cx<T>);
-                cudaMemcpy2DAsync((char*)spec + off, pitch, (const char*)peers.base[q] + off, pitch, (col1 - col0) * sizeof(cx<T>),
-                                  (size_t)peers.slab, cudaMemcpyDefault, aux->copy_stream);
+            int item = 0;
+            for (int s = 1; s < peers.n; ++s) {
+                const int q = (rank + s) % peers.n;
+                for (int h = 0; h < halves; ++h, ++item) {
+                    if (col1 <= col0 || debug_skip == 1) continue;
+                    const int r0 = peers.slab * h / halves, r1 = peers.slab * (h + 1) / halves;
+                    const size_t off = (((size_t)q * peers.slab + r0) * g.n_inner + col0) * sizeof(cx<T>);
+                    cudaMemcpy2DAsync((char*)spec + off, pitch, (const char*)peers.base[q] + off, pitch, (col1 - col0) * sizeof(cx<T>),
+                                      (size_t)(r1 - r0), cudaMemcpyDefault, aux->copy_stream[item % nstreams]);
+                }
             }
-            cudaEventRecord(aux->chunk[k], aux->copy_stream);
+            for (int s = 0; s < nstreams; ++s) cudaEventRecord(aux->chunk[k][s], aux->copy_stream[s]);
         }
         for (int k = 0; k < nchunk; ++k) {
             const int a = t0 + (int)((long long)(t1 - t0) * k / nchunk), b = t0 + (int)((long long)(t1 - t0) * (k + 1) / nchunk);
-            cudaStreamWaitEvent(st, aux->chunk[k], 0);
+            for (int s = 0; s < nstreams; ++s) cudaStreamWaitEvent(st, aux->chunk[k][s], 0);
             if (b > a && debug_skip != 2)
                 c.ops.xconv_peer(st, g, a, b, persistent_grid(f, occ, b - a), B, kappa, kind, tb, spec, f->tw[0], scalars, want_vir, peers, 1);
         }

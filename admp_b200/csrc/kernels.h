@@ -60,12 +60,13 @@ void fft3d_convolve_roundtrip(Fft3d* f, cudaStream_t st, void* mesh, void* spec,
                               const ConvTables& tb, double* scalars, int want_vir);
 
 bool fft3d_slab_supported(const Fft3d* f);
-constexpr int SLAB_CHUNKS = 16;       // maximum pipeline depth of the pulled X pass (ADMP_SLAB_CHUNKS, default 4)
-struct SlabAux {                      // copy stream + events of the pull pipeline (owned by the context)
-    cudaStream_t copy_stream;
+constexpr int SLAB_CHUNKS = 8;        // maximum pipeline depth of the pulled X pass (ADMP_SLAB_CHUNKS, default 4)
+constexpr int SLAB_STREAMS = 4;       // copy streams the peer pulls of one chunk are spread over (several DMA engines)
+struct SlabAux {                      // copy streams + events of the pull pipeline (owned by the context)
+    cudaStream_t copy_stream[SLAB_STREAMS];
     cudaEvent_t fork;
-    cudaEvent_t chunk[SLAB_CHUNKS];
-    int n_events;
+    cudaEvent_t chunk[SLAB_CHUNKS][SLAB_STREAMS];
+    int ready;
 };
 void fft3d_slab_phase(Fft3d* f, cudaStream_t st, int phase, int rank, void* mesh, void* spec, const PeerTab& spec_peers,
                       const BoxInfo* B, double kappa, int kind, const ConvTables& tb, double* scalars, int want_vir,

@@ -225,6 +225,9 @@ void launch_pair_scale(cudaStream_t st, int64_t n_rows, int n_atoms, const int32
 //    of 16 atomics per lane; any other ordering falls back to per-lane atomics (correct for every list).
 //  * MODE 0: energy + all adjoints. MODE 1: dE/dU only (the SCF field).
 constexpr int PAIR_TILE = 128;
+#ifndef ADMP_PAIR_MINBLOCKS
+#define ADMP_PAIR_MINBLOCKS 2     // resident blocks per SM of the float64 energy + adjoint kernel (252 registers)
+#endif
 // Packed per-atom record the staged (MODE 0) kernel gathers: position 3, Cartesian multipoles 10, induced dipole 3,
 // polarizability, Thole width = 18 reals, padded to whole 16-byte chunks (double: 18 = 9 chunks; float: 20 = 5
 // chunks). One record = 9 (5) LDGSTS.128 + 9 (5) LDS.128 per pair end instead of 18 + 18 eight-byte ones: the
@@ -296,7 +299,7 @@ __device__ __forceinline__ T warp_reduce_scatter16(T (&v)[16], int lane) {
 }
 
 template <typename T, bool POL, int MODE>
-__global__ void __launch_bounds__(PAIR_TILE, (MODE == 1 || sizeof(T) == 4) ? 4 : 2)
+__global__ void __launch_bounds__(PAIR_TILE, (MODE == 1 || sizeof(T) == 4) ? 4 : ADMP_PAIR_MINBLOCKS)
 pme_pair_kernel(int64_t n_rows, int n_atoms, const BoxInfo* __restrict__ Bp, T kappa,
                 const T* __restrict__ pos, const int32_t* __restrict__ pairs, const int8_t* __restrict__ sidx_rows,
                 const int32_t* __restrict__ cov_off, const int32_t* __restrict__ cov_idx, const int8_t* __restrict__ cov_nb,
@@ -322,6 +325,8 @@ pme_pair_kernel(int64_t n_rows, int n_atoms, const BoxInfo* __restrict__ Bp, T k
     double acc_ms[5] = {0, 0, 0, 0, 0}, acc_ps[5] = {0, 0, 0, 0, 0};
     const bool want_grad = (flags & ADMP_WANT_GRAD) != 0, want_vir = (flags & ADMP_WANT_VIRIAL) != 0,
                want_pg = (flags & ADMP_WANT_PGRAD) != 0;
+    // measurement switch (tools/pair_roofline.py): drop the per-pair i-side reductions to see what they cost
+    const bool iside = (flags & 0x40000000u) == 0;
     const BoxInfo& B = sB;
     const int64_t ntiles = (n_rows + PAIR_TILE - 1) / PAIR_TILE;
 
@@ -425,7 +430,7 @@ pme_pair_kernel(int64_t n_rows, int n_atoms, const BoxInfo* __restrict__ Bp, T k
                 const T e_pJ = B1 * qI + B2 * dI + B5 * tI + C2 * pI;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                    atomicAdd(F + (size_t)i * 3 + k, e_pI * n[k] + B3 * muJ[k] - B6 * vJ[k] + C3 * uJ[k]);
+                    if (iside) atomicAdd(F + (size_t)i * 3 + k, e_pI * n[k] + B3 * muJ[k] - B6 * vJ[k] + C3 * uJ[k]);
                     gj[13 + k] = e_pJ * n[k] + B3 * muI[k] + B6 * vI[k] + C3 * uI[k];
                 }
             } else {
@@ -487,7 +492,7 @@ pme_pair_kernel(int64_t n_rows, int n_atoms, const BoxInfo* __restrict__ Bp, T k
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
                         fv[k] = dEdr * n[k] + (gn[k] - gnn * n[k]) * rinv;
-                        atomicAdd(dpos + (size_t)i * 3 + k, fv[k]);
+                        if (iside) atomicAdd(dpos + (size_t)i * 3 + k, fv[k]);
                         gj[k] = -fv[k];
                     }
                     if (want_vir) {
@@ -498,10 +503,11 @@ pme_pair_kernel(int64_t n_rows, int n_atoms, const BoxInfo* __restrict__ Bp, T k
                     }
                     // dE/dM
                     T* Gi = G + (size_t)i * 10;
-                    atomicAdd(Gi, g_qI); gj[3] = g_qJ;
+                    if (iside) atomicAdd(Gi, g_qI);
+                    gj[3] = g_qJ;
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
-                        atomicAdd(Gi + 1 + k, e_dI * n[k] + A[3] * muJ[k] - A[6] * vJ[k] + B3 * uJ[k]);
+                        if (iside) atomicAdd(Gi + 1 + k, e_dI * n[k] + A[3] * muJ[k] - A[6] * vJ[k] + B3 * uJ[k]);
                         gj[4 + k] = e_dJ * n[k] + A[3] * muI[k] + A[6] * vI[k] + B3 * uI[k];
                     }
                     // quadrupole gradient: e_t n n^T + w n^T (symmetrised into the 6-comp layout) + A9 T_other
@@ -518,13 +524,13 @@ pme_pair_kernel(int64_t n_rows, int n_atoms, const BoxInfo* __restrict__ Bp, T k
                         const T mult = (a == b) ? (T)1 : (T)2;
                         T gI = e_tI * n[a] * n[b] * mult + ((a == b) ? wI[a] * n[a] : wI[a] * n[b] + wI[b] * n[a]) + A[9] * TJ[k] * mult;
                         T gJ = e_tJ * n[a] * n[b] * mult + ((a == b) ? wJ[a] * n[a] : wJ[a] * n[b] + wJ[b] * n[a]) + A[9] * TI[k] * mult;
-                        atomicAdd(Gi + 4 + k, gI);
+                        if (iside) atomicAdd(Gi + 4 + k, gI);
                         gj[7 + k] = gJ;
                     }
                     if (POL) {
 #pragma unroll
                         for (int k = 0; k < 3; ++k) {
-                            atomicAdd(F + (size_t)i * 3 + k, e_pI * n[k] + B3 * muJ[k] - B6 * vJ[k] + C3 * uJ[k]);
+                            if (iside) atomicAdd(F + (size_t)i * 3 + k, e_pI * n[k] + B3 * muJ[k] - B6 * vJ[k] + C3 * uJ[k]);
                             gj[13 + k] = e_pJ * n[k] + B3 * muI[k] + B6 * vI[k] + C3 * uI[k];
                         }
                     }
