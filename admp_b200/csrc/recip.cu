@@ -12,6 +12,8 @@
 //   u_d = m0_d - Nstar[d].r + 3 + s ; w_d^p[k] = d^p M6/du^p at f_d + k
 //   mesh(g) += q W000 + sum_d muf_d W[e_d] + sum_de Tf_de W[e_d+e_e]
 //   muf_d = -sum_c Nstar[d][c] mu_c ; Tf_de = sum_ab Nstar[d][a] Nstar[e][b] T_ab / 3
+#include <cstdlib>
+
 #include "kernels.h"
 #include "influence.cuh"
 
@@ -211,8 +213,10 @@ convolve_kernel(const BoxInfo* __restrict__ Bp, T kappa, int kind, ConvTables tb
 }
 
 // ---------------------------------------------------------------------------- gather
-constexpr int GATHER_LPA = 4;                       // lanes per atom: 36 (x, y) stencil columns = 9 per lane
-constexpr int GATHER_APB = 128 / GATHER_LPA;        // atoms per 128-thread block
+// lanes per atom (LPA): the 36 (x, y) stencil columns are dealt over 4 lanes (9 columns each: least total work,
+// large systems) or 16 lanes (2-3 columns each: a 4x shorter dependent chain per thread and 4x more blocks; the
+// 3 072-atom boxes are latency-bound and fill only 96 blocks with 4 lanes per atom)
+constexpr int GATHER_SMALL_N = 32768;               // below this many atoms: 16 lanes per atom
 
 // MODE 0: everything (dE/dM, dE/dr, dE/dNstar).  MODE 1: field only (dE/dmu accumulated into F).
 // Four lanes per atom, each lane owns 9 of the 36 (ia, ib) stencil columns. A column is 6 consecutive mesh
@@ -220,12 +224,13 @@ constexpr int GATHER_APB = 128 / GATHER_LPA;        // atoms per 128-thread bloc
 //   S_p3 = sum_ic phi[ia, ib, ic] * d^p3 M6(z)[ic] ;  P[p1 p2 p3] += d^p1 M6(x)[ia] * d^p2 M6(y)[ib] * S_p3
 // (54 FMA-class operations per column instead of ~50 per mesh point), then two shuffle steps reduce the
 // 20 (4 in field mode) partial sums over the four lanes and lane 0 of the group does the per-atom algebra.
-template <typename T, bool MULTIPOLE, int MODE, bool PEER>
+template <typename T, bool MULTIPOLE, int MODE, bool PEER, int LPA>
 __global__ void __launch_bounds__(128)
 gather_kernel(int n, const BoxInfo* __restrict__ Bp, const T* __restrict__ pos, const T* __restrict__ M, int m_stride,
               const T* __restrict__ U, const T* __restrict__ phi, uint32_t flags, T* __restrict__ dpos, T* __restrict__ G,
               int g_stride, T* __restrict__ F, double* __restrict__ scalars, PeerTab peers) {
     constexpr int NP = (MODE == 1) ? 2 : (MULTIPOLE ? 4 : 2);
+    constexpr int GATHER_LPA = LPA, GATHER_APB = 128 / LPA;
     __shared__ T sw[GATHER_APB][3][6 * NP];
     __shared__ int si[GATHER_APB][3];
     __shared__ double red[9 * 4];
@@ -257,8 +262,9 @@ gather_kernel(int n, const BoxInfo* __restrict__ Bp, const T* __restrict__ pos, 
         const int i0 = si[slot][0], j0 = si[slot][1], k0 = si[slot][2];
         const bool wrap = k0 + 5 >= K3;
 #pragma unroll
-        for (int c = 0; c < 36 / GATHER_LPA; ++c) {
+        for (int c = 0; c < (36 + GATHER_LPA - 1) / GATHER_LPA; ++c) {
             const int col = sub + GATHER_LPA * c;
+            if (36 % GATHER_LPA != 0 && col >= 36) break;
             const int ia = col / 6, ib = col - 6 * ia;
             int gi = i0 + ia; if (gi >= K1) gi -= K1;
             int gj = j0 + ib; if (gj >= K2) gj -= K2;
@@ -299,8 +305,8 @@ gather_kernel(int n, const BoxInfo* __restrict__ Bp, const T* __restrict__ pos, 
     }
 #pragma unroll
     for (int k = 0; k < NC; ++k) {
-        P[k] += __shfl_xor_sync(0xffffffffu, P[k], 1);
-        P[k] += __shfl_xor_sync(0xffffffffu, P[k], 2);
+#pragma unroll
+        for (int o = 1; o < GATHER_LPA; o <<= 1) P[k] += __shfl_xor_sync(0xffffffffu, P[k], o);
     }
     if (valid && sub == 0) {
         T N[9];
@@ -436,18 +442,24 @@ void launch_gather(cudaStream_t st, int n, const BoxInfo* B, const void* pos, co
                    const void* phi, int mode, uint32_t flags, void* dpos, void* G, int g_stride, void* F, double* scalars,
                    const PeerTab* peers) {
     if (n <= 0) return;
-    const unsigned grid = (n + GATHER_APB - 1) / GATHER_APB;
+    static const int force_lpa = [] { const char* e = getenv("ADMP_GATHER_LPA"); return e ? atoi(e) : 0; }();
+    const bool wide = force_lpa ? force_lpa == 16 : n < GATHER_SMALL_N;
+    const int apb = 128 / (wide ? 16 : 4);
+    const unsigned grid = (n + apb - 1) / apb;
     const PeerTab pt = peers ? *peers : PeerTab{};
 #define ADMP_G_ARGS n, B, (const T*)pos, (const T*)M, m_stride, (const T*)U, (const T*)phi, flags, (T*)dpos, (T*)G, g_stride, (T*)F, scalars, pt
+#define ADMP_G_LAUNCH(PEER, LPA)                                                                         \
+    do {                                                                                                 \
+        if (mode == 1) gather_kernel<T, true, 1, PEER, LPA><<<grid, 128, 0, st>>>(ADMP_G_ARGS);          \
+        else if (m_cols >= 10) gather_kernel<T, true, 0, PEER, LPA><<<grid, 128, 0, st>>>(ADMP_G_ARGS);  \
+        else gather_kernel<T, false, 0, PEER, LPA><<<grid, 128, 0, st>>>(ADMP_G_ARGS);                   \
+    } while (0)
     if (peers) {
-        if (mode == 1) gather_kernel<T, true, 1, true><<<grid, 128, 0, st>>>(ADMP_G_ARGS);
-        else if (m_cols >= 10) gather_kernel<T, true, 0, true><<<grid, 128, 0, st>>>(ADMP_G_ARGS);
-        else gather_kernel<T, false, 0, true><<<grid, 128, 0, st>>>(ADMP_G_ARGS);
+        if (wide) ADMP_G_LAUNCH(true, 16); else ADMP_G_LAUNCH(true, 4);
     } else {
-        if (mode == 1) gather_kernel<T, true, 1, false><<<grid, 128, 0, st>>>(ADMP_G_ARGS);
-        else if (m_cols >= 10) gather_kernel<T, true, 0, false><<<grid, 128, 0, st>>>(ADMP_G_ARGS);
-        else gather_kernel<T, false, 0, false><<<grid, 128, 0, st>>>(ADMP_G_ARGS);
+        if (wide) ADMP_G_LAUNCH(false, 16); else ADMP_G_LAUNCH(false, 4);
     }
+#undef ADMP_G_LAUNCH
 #undef ADMP_G_ARGS
 }
 #define ADMP_INST(T)                                                                                                              \

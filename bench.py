@@ -496,6 +496,27 @@ def run_ours(args):
     roofline['kernel'] = dominant
     roofline['peak_source'] = peak_src
     roof_dense = None if args.no_large else dense_rooflines(torch, _lib, peak, flush)
+    # ---- config C4 on one GPU: a batch of independent frames (E + dE/dr + parameter gradients per frame), one frame
+    # at a time and with several frames in flight (one context + stream per lane): device time, CUDA events
+    c4 = None
+    if world == 1 and not args.no_large:
+        from admp_b200.parallel import evaluate_frames
+        nbatch = 48
+        bframes = [workloads.jitter_frame(w, 5000 + f) for f in range(nbatch)]
+        nl = neighbor_list(w.box, w.rc)
+        bpairs = [nl.allocate(bf).pairs for bf in bframes]
+        c4 = dict(frames=nbatch, what='E + dE/dr + dE/d(Q_local, mScales, pScales, tholes, pol) per frame, pair lists prebuilt; '
+                                     'device time of the whole batch (CUDA events)')
+        for lanes in (1, 2, 3):
+            evaluate_frames(calc, bframes[:2 * lanes], w.box, lambda f: bpairs[f], w.Q_local, w.pol, w.tholes, w.mScales, w.pScales,
+                            in_flight=lanes)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            evaluate_frames(calc, bframes, w.box, lambda f: bpairs[f], w.Q_local, w.pol, w.tholes, w.mScales, w.pScales, in_flight=lanes)
+            b.record()
+            b.synchronize()
+            c4['evals_per_s_in_flight_%d' % lanes] = round(nbatch / (a.elapsed_time(b) * 1e-3), 1)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu, _ = cpu_oracle_sample(n_iter=3)
@@ -508,7 +529,7 @@ def run_ours(args):
                                     '(reproduced iteration for iteration)', scf_graph=calc._ctx.scf_graph_active, energy=E_last),
                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
                gpu_launches=args.steps * (2 + 8 * bodies + 5), clocks=clocks, roofline=roofline,
-               kernels=dict(C2=roof_small, C3=roof_large, dense=roof_dense), cpu_baseline=cpu)
+               kernels=dict(C2=roof_small, C3=roof_large, dense=roof_dense), c4_batch_one_gpu=c4, cpu_baseline=cpu)
     print(json.dumps(out))
     if dist is not None:
         dist.barrier()
