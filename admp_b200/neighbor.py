@@ -71,7 +71,19 @@ class NeighborListFn:
         return self._build(positions, max(capacity, 1))
 
     def update(self, positions, nbr):
-        """Rebuild into a buffer of the same capacity (check ``did_buffer_overflow``)."""
+        """jax_md semantics: with a skin (dr_threshold > 0) the list is kept while no atom has moved further than
+        dr_threshold / 2 from the positions it was built on (it was built with rc + dr_threshold, so it still holds
+        every pair inside rc; like the reference, the energy functions evaluate every listed pair); otherwise it is
+        rebuilt into a buffer of the same capacity (check ``did_buffer_overflow``). The test costs one device
+        reduction and a scalar read."""
+        if self.dr_threshold > 0.0:
+            cx = self._ctx
+            pos = to_dev(positions, cx.dtype, cx.device).detach()
+            ref = nbr.reference_position
+            if ref.shape == pos.shape:
+                moved = (pos - ref).pow(2).sum(dim=1).max()
+                if float(moved.item()) < (0.5 * self.dr_threshold) ** 2:
+                    return nbr
         return self._build(positions, int(nbr.pairs.shape[0]))
 
 

@@ -254,6 +254,32 @@ def test_reference_example_water_1024_nonpol():
     assert rel(F, go) < RTOL
 
 
+def test_neighbor_list_skin_update_semantics():
+    """jax_md's allocate / update contract: a list built with a skin is reused while no atom
+    moved further than dr_threshold / 2 and still contains every pair inside rc; a larger move rebuilds it and the
+    rebuilt pair set is again bit-exact against the oracle's predicate."""
+    from admp_b200.neighbor import neighbor_list
+    s = fixtures.water1024().nonpol()
+    rc, skin = 4.0, 0.6
+    fn = neighbor_list(s.box, rc, dr_threshold=skin)
+    nbr = fn.allocate(s.positions)
+    pairs_skin, n_skin = pairlist.build_pairs(s.positions.numpy(), s.box.numpy(), rc + skin)
+    assert nbr.n_pairs == n_skin and np.array_equal(nbr.pairs[:n_skin].cpu().numpy(), pairs_skin[:n_skin])
+    rng = np.random.default_rng(5)
+    small = s.positions.numpy() + rng.uniform(-0.1, 0.1, size=s.positions.shape)        # |dr| <= 0.173 < skin / 2
+    same = nbr.update(small)
+    assert same is nbr
+    exact, n_exact = pairlist.build_pairs(small, s.box.numpy(), rc)
+    listed = set(map(tuple, nbr.pairs[:n_skin].cpu().numpy().tolist()))
+    assert all(tuple(p) in listed for p in exact[:n_exact].tolist()), 'the skinned list lost a pair inside rc'
+    big = small.copy()
+    big[7] += np.array([0.0, 0.5, 0.0])                                                  # one atom beyond skin / 2
+    rebuilt = nbr.update(big)
+    assert rebuilt is not nbr and not rebuilt.did_buffer_overflow
+    ref, n_ref = pairlist.build_pairs(big, s.box.numpy(), rc + skin)
+    assert rebuilt.n_pairs == n_ref and np.array_equal(rebuilt.pairs[:n_ref].cpu().numpy(), ref[:n_ref])
+
+
 def test_replica_invariance_polarizable(lattice):
     """with K scaled by the replication factors, E(replicated) = n_rep * E and forces and
     induced dipoles replicate - the parity check at sizes the reference could never run."""
