@@ -177,6 +177,52 @@ def test_polarizable_energy_fn_and_all_gradients(carved):
     assert rel(calc.grad_pos_fn(*[vals[0], vals[1], pairs, vals[2], vals[3], vals[4], vals[5], mS0, pS0, dS0]), go[0]) < RTOL
 
 
+@pytest.mark.parametrize('lmax', [0, 1])
+def test_lower_multipole_orders_nonpol(carved, lmax):
+    """lmax = 0 (charges only; admp/pme.py:224-231 skips the frames) and lmax = 1 (charges + dipoles): Q_local has
+    (lmax+1)^2 columns, energy and every gradient against the oracle."""
+    from admp_b200.pme import ADMPPmeForce
+    s, pairs = carved
+    nh = (lmax + 1) ** 2
+    Ql = _perturbed(s)[0][:, :nh].copy()
+    calc = ADMPPmeForce(s.box, s.axis_type, s.axis_indices, s.covalent_map, 6.0, 1e-4, lmax)
+    ref = orc.OraclePmeForce(s.box, s.axis_type, s.axis_indices, s.covalent_map, 6.0, 1e-4, lmax)
+    mS0 = [0.1, 0.3, 0.0, 0.7, 1.0]
+    tp, tb, tQ, tm = _t(s.positions), _t(s.box), _t(Ql), _t(mS0)
+    Eo = ref.get_energy(tp, tb, pairs, tQ, tm)
+    go = torch.autograd.grad(Eo, [tp, tb, tQ, tm])
+    p, b, q, m = (torch.tensor(np.asarray(x), device='cuda', dtype=torch.float64, requires_grad=True)
+                  for x in (s.positions, s.box, Ql, mS0))
+    E = calc.get_energy(p, b, pairs, q, m)
+    g = torch.autograd.grad(E, [p, b, q, m])
+    assert g[2].shape == (s.n_atoms, nh)
+    assert abs(E.item() - Eo.item()) < RTOL * abs(Eo.item()), (E.item(), Eo.item())
+    assert rel(g[0], go[0]) < RTOL and rel(g[2], go[2]) < RTOL and rel(g[3], go[3]) < RTOL
+    assert rel(torch.diagonal(g[1]), torch.diagonal(go[1])) < RTOL
+
+
+def test_dipole_order_polarizable(carved):
+    """lmax = 1 with induced dipoles: energy_fn and its gradients (positions, Q_local, U, pol, tholes, scales)."""
+    from admp_b200.pme import ADMPPmeForce
+    s, pairs = carved
+    Ql, U, pol, th = _perturbed(s)
+    Ql = Ql[:, :4].copy()
+    calc = ADMPPmeForce(s.box, s.axis_type, s.axis_indices, s.covalent_map, 6.0, 1e-4, 1, lpol=True)
+    ref = orc.OraclePmeForce(s.box, s.axis_type, s.axis_indices, s.covalent_map, 6.0, 1e-4, 1, lpol=True)
+    mS0, pS0, dS0 = [0.1, 0.3, 0.0, 0.7, 1.0], [0.0, 0.4, 0.0, 1.0, 1.0], [0.0, 0.0, 0.0, 1.0, 1.0]
+    vals = [s.positions, s.box, Ql, U, pol, th, mS0, pS0]
+    to = [_t(v) for v in vals]
+    Eo = ref.energy_fn(to[0], to[1], pairs, to[2], to[3], to[4], to[5], to[6], to[7], _t(dS0, False))
+    go = torch.autograd.grad(Eo, to)
+    tg = [torch.tensor(np.asarray(v), device='cuda', dtype=torch.float64, requires_grad=True) for v in vals]
+    E = calc.energy_fn(tg[0], tg[1], pairs, tg[2], tg[3], tg[4], tg[5], tg[6], tg[7], dS0)
+    g = torch.autograd.grad(E, tg)
+    assert abs(E.item() - Eo.item()) < RTOL * abs(Eo.item())
+    for k in (0, 2, 3, 4, 5, 6, 7):
+        assert rel(g[k], go[k]) < RTOL, (k, rel(g[k], go[k]))
+    assert rel(torch.diagonal(g[1]), torch.diagonal(go[1])) < RTOL
+
+
 def test_scf_converging_system_matches_oracle_iteration_for_iteration(lattice):
     from admp_b200.pme import ADMPPmeForce
     s, pairs = lattice
