@@ -517,6 +517,25 @@ def run_ours(args):
             b.record()
             b.synchronize()
             c4['evals_per_s_in_flight_%d' % lanes] = round(nbatch / (a.elapsed_time(b) * 1e-3), 1)
+    # ---- config C1 (examples/water_1024, non-polarizable: one reciprocal round trip, no SCF), device-timed
+    c1 = None
+    if world == 1:
+        w1 = workloads.water_box((1, 1, 1), polarizable=False)
+        calc1 = ADMPPmeForce(w1.box, w1.axis_type, w1.axis_indices, w1.covalent_map, w1.rc, w1.ethresh, 2)
+        calc1.update_env('kappa', w1.kappa)
+        a1 = [calc1._prep(x) for x in (w1.positions, w1.box, w1.Q_local, w1.mScales)]
+        for _ in range(10):
+            r1 = calc1._eval(a1[0], a1[1], pairs, a1[2], None, None, None, a1[3], None, flags, False)
+        torch.cuda.synchronize()
+        n1 = 200
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        for _ in range(n1):
+            r1 = calc1._eval(a1[0], a1[1], pairs, a1[2], None, None, None, a1[3], None, flags, False)
+        eb.record()
+        eb.synchronize()
+        c1 = dict(workload='C1 examples/water_1024 non-polarizable, E + dE/dr + dE/dbox', evals_per_s=round(n1 / (ea.elapsed_time(eb) * 1e-3), 1),
+                  ms_per_eval=round(ea.elapsed_time(eb) / n1, 4), energy=r1.energy.item(), timing='CUDA events around 200 back-to-back evaluations')
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu, _ = cpu_oracle_sample(n_iter=3)
@@ -529,7 +548,7 @@ def run_ours(args):
                                     '(reproduced iteration for iteration)', scf_graph=calc._ctx.scf_graph_active, energy=E_last),
                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
                gpu_launches=args.steps * (2 + 8 * bodies + 5), clocks=clocks, roofline=roofline,
-               kernels=dict(C2=roof_small, C3=roof_large, dense=roof_dense), c4_batch_one_gpu=c4, cpu_baseline=cpu)
+               kernels=dict(C2=roof_small, C3=roof_large, dense=roof_dense), c4_batch_one_gpu=c4, c1_nonpol_one_gpu=c1, cpu_baseline=cpu)
     print(json.dumps(out))
     if dist is not None:
         dist.barrier()
