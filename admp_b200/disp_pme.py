@@ -104,3 +104,67 @@ class ADMPDispPmeForce:
         positions, box, c_list, mScales = (self._prep(x).detach() for x in (positions, box, c_list, mScales))
         scal, dpos, _ = self._eval(positions, box, pairs_to_dev(pairs, self._ctx.device), c_list, mScales, _lib.WANT_GRAD)
         return (scal[_lib.S_E_REAL] + scal[_lib.S_E_RECIP] + scal[_lib.S_E_SELF]).to(self._dtype), dpos
+
+    def generate_get_energy(self):
+        """admp/disp_pme.py:44-50"""
+        self.refresh_calculators()
+        return self.get_energy
+
+
+# ---------------------------------------------------------------------- module-level functions of admp/disp_pme.py
+def g_p(x2, pmax):
+    """admp/disp_pme.py:219-252: g_p(x^2) = exp(-x^2) sum_{k < p/2} x^(2k) / k!, stacked for p = 6, 8, 10 (<= pmax)."""
+    x2 = x2 if isinstance(x2, torch.Tensor) else torch.as_tensor(x2, dtype=torch.float64)
+    x4 = x2 * x2
+    g = [1 + x2 + 0.5 * x4]
+    if pmax >= 8:
+        g.append(g[0] + x4 * x2 / 6)
+    if pmax >= 10:
+        g.append(g[1] + x4 * x4 / 24)
+    return torch.stack(g) * torch.exp(-x2)
+
+
+def disp_pme_self(c_list, kappa, pmax):
+    """admp/disp_pme.py:255-279: -kappa^6/12 sum c6^2 - kappa^8/48 sum c8^2 - kappa^10/240 sum c10^2."""
+    c = c_list if isinstance(c_list, torch.Tensor) else torch.as_tensor(c_list, dtype=torch.float64)
+    E = -kappa ** 6 / 12 * torch.sum(c[:, 0] ** 2)
+    if pmax >= 8:
+        E = E - kappa ** 8 / 48 * torch.sum(c[:, 1] ** 2)
+    if pmax >= 10:
+        E = E - kappa ** 10 / 240 * torch.sum(c[:, 2] ** 2)
+    return E
+
+
+_disp_cache = {}
+
+
+def _disp_calc(box, covalent_map, kappa, K1, K2, K3, pmax):
+    from . import settings
+    key = (id(covalent_map), int(K1), int(K2), int(K3), int(pmax), settings.PRECISION)
+    calc = _disp_cache.get(key)
+    if calc is None:
+        import numpy as np
+        calc = ADMPDispPmeForce(np.eye(3) * 20.0, covalent_map, 4.0, 1e-4, pmax)
+        calc.K1, calc.K2, calc.K3 = int(K1), int(K2), int(K3)
+        calc.kappa = float(kappa)
+        calc.refresh_calculators()
+        _disp_cache[key] = calc
+    if calc.kappa != float(kappa):
+        calc.update_env('kappa', float(kappa))
+    return calc
+
+
+def energy_disp_pme(positions, box, pairs, c_list, mScales, covalent_map, kappa, K1, K2, K3, pmax,
+                    recip_fn6=None, recip_fn8=None, recip_fn10=None):
+    """admp/disp_pme.py:80-123, the top-level dispersion-PME energy (the recip_fn* arguments are accepted for
+    signature compatibility; the fused kernels of the calculator are used). Differentiable like get_energy."""
+    return _disp_calc(box, covalent_map, kappa, K1, K2, K3, pmax).get_energy(positions, box, pairs, c_list, mScales)
+
+
+def disp_pme_real(positions, box, pairs, c_list, mScales, covalent_map, kappa, pmax):
+    """admp/disp_pme.py:126-178: the real-space part alone. The pair kernel is fused into admp_disp_eval, so this runs
+    one evaluation on the smallest mesh and returns its real-space slot (no gradient; use ADMPDispPmeForce for those)."""
+    calc = _disp_calc(box, covalent_map, kappa, 6, 6, 6, pmax)
+    args = [calc._prep(x).detach() for x in (positions, box, c_list, mScales)]
+    scal, _, _ = calc._eval(args[0], args[1], pairs_to_dev(pairs, calc._ctx.device), args[2], args[3], 0)
+    return scal[_lib.S_E_REAL].to(calc._dtype)

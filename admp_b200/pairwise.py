@@ -12,6 +12,24 @@ from . import _lib
 from ._ctx import Context, to_dev, pairs_to_dev
 
 
+# admp/pairwise.py:21-42: per-pair gathers of per-atom arrays (vmapped indexing upstream). The device kernels gather
+# inside the pair loop, so these are only kept for callers that use them directly.
+def distribute_scalar(params, index):
+    return params[index]
+
+
+def distribute_v3(pos, index):
+    return pos[index]
+
+
+def distribute_multipoles(multipoles, index):
+    return multipoles[index]
+
+
+def distribute_dispcoeff(c_list, index):
+    return c_list[index]
+
+
 class PairKernel:
     """Marker naming a device pair kernel and its per-atom parameter list."""
 

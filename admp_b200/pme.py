@@ -297,3 +297,147 @@ class ADMPPmeForce:
         _lib.check(c.lib.admp_frames_fwd(c.handle, _lib.stream_ptr(), _lib.ptr(positions), _lib.ptr(box), _lib.ptr(dummy),
                                          None, None, _lib.ptr(fr)))
         return fr
+
+
+    def generate_get_energy(self):
+        """admp/pme.py:58-87 builds the closures; here they are bound methods selected by refresh_calculators."""
+        self.refresh_calculators()
+        return self.get_energy
+
+
+# ---------------------------------------------------------------------- module-level functions of admp/pme.py
+# The reference exposes its building blocks as free functions; callers that use them directly keep working.
+# energy_pme / pme_real run the same kernels as the calculator (cached contexts); pme_self / pol_penalty are
+# per-site closed forms evaluated with tensor arithmetic on whatever device their inputs live on.
+_L_OF_HARM = [0, 1, 1, 1, 2, 2, 2, 2, 2]
+_FAC2 = [1, 3, 3, 3, 15, 15, 15, 15, 15]
+
+
+def _as_tensor(x, like=None):
+    if isinstance(x, torch.Tensor):
+        return x
+    t = torch.as_tensor(np.asarray(x, dtype=np.float64))
+    return t.to(like.device) if like is not None else t
+
+
+def pme_self(Q_h, kappa, lmax=2):
+    """admp/pme.py:738-757: -DIELECTRIC * sum_l kappa/sqrt(pi) (2 kappa^2)^l / (2l+1)!! * Q_lm^2."""
+    Q_h = _as_tensor(Q_h)
+    nh = (lmax + 1) ** 2
+    fac = torch.tensor([kappa / math.sqrt(math.pi) * (2 * kappa ** 2) ** _L_OF_HARM[k] / _FAC2[k] for k in range(nh)],
+                       dtype=Q_h.dtype, device=Q_h.device)
+    return -torch.sum(fac[None, :] * Q_h[:, :nh] ** 2) * DIELECTRIC
+
+
+def trim_val_0(x, thresh=1e-8):
+    """admp/pme.py:351-361: x where x > thresh, thresh otherwise (keeps 1/pol finite for pol = 0)."""
+    x = _as_tensor(x)
+    return torch.where(x > thresh, x, torch.full_like(x, thresh))
+
+
+def pol_penalty(U_ind, pol):
+    """admp/pme.py:760-774: DIELECTRIC * sum U^2 / (2 max(pol, 1e-8))."""
+    U_ind = _as_tensor(U_ind)
+    pol = _as_tensor(pol, U_ind).to(U_ind.dtype)
+    return torch.sum(0.5 / trim_val_0(pol)[:, None] * U_ind ** 2) * DIELECTRIC
+
+
+def get_pair_dmp(pol1, pol2):
+    """admp/pme.py:732-735."""
+    return (_as_tensor(pol1) * _as_tensor(pol2)) ** (1.0 / 6.0)
+
+
+_energy_pme_cache = {}
+
+
+def energy_pme(positions, box, pairs, Q_local, Uind_global, pol, tholes, mScales, pScales, dScales, covalent_map,
+               construct_local_frame_fn, pme_recip_fn, kappa, K1, K2, K3, lmax, lpol):
+    """admp/pme.py:176-254, the top-level energy function. The local-frame definition is taken from the
+    ``axis_types`` / ``axis_indices`` attributes of ``construct_local_frame_fn`` (set by
+    admp_b200.spatial.generate_construct_local_frames); ``pme_recip_fn`` is accepted for signature compatibility (the
+    fused reciprocal kernels of the calculator are used). Differentiable like ADMPPmeForce.energy_fn."""
+    at = getattr(construct_local_frame_fn, 'axis_types', None)
+    ai = getattr(construct_local_frame_fn, 'axis_indices', None)
+    if lmax > 0 and (at is None or ai is None):
+        raise TypeError('energy_pme needs a construct_local_frame_fn made by admp_b200.spatial.generate_construct_local_frames')
+    key = (id(covalent_map), id(construct_local_frame_fn), int(K1), int(K2), int(K3), int(lmax), bool(lpol), settings.PRECISION)
+    calc = _energy_pme_cache.get(key)
+    if calc is None:
+        n = int(covalent_map.shape[0])
+        if at is None:
+            at, ai = np.full(n, 5), np.zeros((n, 3), dtype=np.int64)
+        calc = ADMPPmeForce(np.eye(3) * 20.0, at, ai, covalent_map, 4.0, 1e-4, lmax, lpol)
+        calc.K1, calc.K2, calc.K3 = int(K1), int(K2), int(K3)
+        calc.kappa = float(kappa)
+        calc.refresh_calculators()
+        _energy_pme_cache[key] = calc
+    if calc.kappa != float(kappa):
+        calc.update_env('kappa', float(kappa))
+    if lpol:
+        return calc.energy_fn(positions, box, pairs, Q_local, Uind_global, pol, tholes, mScales, pScales, dScales)
+    return calc.get_energy(positions, box, pairs, Q_local, mScales)
+
+
+def _harm_to_cart_matrix(dtype, device):
+    """(10, 9): Cartesian site record (q, mu_x, mu_y, mu_z, T_xx, T_xy, T_xz, T_yy, T_yz, T_zz) from the harmonic
+    components (00, 10, 11c, 11s, 20, 21c, 21s, 22c, 22s); admp/multipole.py:17-33 (C1_h2c, C2_h2c)."""
+    from .multipole import C1_h2c, C2_h2c
+    H = np.zeros((10, 9))
+    H[0, 0] = 1.0
+    H[1:4, 1:4] = C1_h2c                                   # (x, y, z) <- (10, 11c, 11s)
+    c2 = C2_h2c                                            # rows xx, yy, zz, xy, xz, yz <- (20, 21c, 21s, 22c, 22s)
+    for row, src in zip((4, 7, 9, 5, 6, 8), range(6)):     # record order xx, xy, xz, yy, yz, zz
+        H[row, 4:9] = c2[src]
+    return torch.tensor(H, dtype=dtype, device=device)
+
+
+class _PmeRealFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cx, pairs, lmax, positions, box, Q_global, U_h, pol, tholes, mScales, pScales):
+        n, dt, dev = positions.shape[0], positions.dtype, positions.device
+        nh = (lmax + 1) ** 2
+        H = _harm_to_cart_matrix(dt, dev)
+        M = (Q_global[:, :nh] @ H[:, :nh].T).contiguous()
+        polz = U_h is not None
+        U = U_h[:, [1, 2, 0]].contiguous() if polz else None          # harmonic (z, x, y) -> Cartesian (x, y, z)
+        scal = torch.zeros(_lib.S_COUNT, dtype=torch.float64, device=dev)
+        dpos = torch.zeros((n, 3), dtype=dt, device=dev)
+        G = torch.zeros((n, 10), dtype=dt, device=dev)
+        F = torch.zeros((n, 3), dtype=dt, device=dev) if polz else None
+        p = _lib.ptr
+        _lib.check(cx.lib.admp_pme_real(cx.handle, _lib.stream_ptr(), p(positions), p(box), p(pairs), int(pairs.shape[0]), p(M), p(U),
+                                        p(pol), p(tholes), p(mScales), p(pScales), 0, _lib.WANT_GRAD, p(dpos), p(G), p(F), None, None,
+                                        p(scal)))
+        ctx.saved = (dpos, (G @ H)[:, :Q_global.shape[1]], F[:, [2, 0, 1]] if polz else None)
+        return scal[_lib.S_E_REAL].to(dt)
+
+    @staticmethod
+    def backward(ctx, g):
+        dpos, dQ, dU = ctx.saved
+        n = ctx.needs_input_grad
+        return (None, None, None, g * dpos if n[3] else None, None, g * dQ if n[5] else None,
+                (g * dU if (dU is not None and n[6]) else None), None, None, None, None)
+
+
+_pme_real_ctx = {}
+
+
+def pme_real(positions, box, pairs, Q_global, Uind_global, pol, tholes, mScales, pScales, dScales, covalent_map, kappa, lmax, lpol):
+    """admp/pme.py:628-729: real-space energy of the listed pairs (rows with pairs[:,0] < pairs[:,1]) from GLOBAL-frame
+    harmonic multipoles and harmonic-order (z, x, y) induced dipoles. One launch of the pair kernel; differentiable
+    with respect to positions, Q_global and Uind_global (use ADMPPmeForce for the other derivatives)."""
+    key = (id(covalent_map), settings.PRECISION)
+    cx = _pme_real_ctx.get(key)
+    n = int(covalent_map.shape[0])
+    if cx is None:
+        cx = Context()
+        cx.set_topology(n, None, None, covalent_map)
+        _pme_real_ctx[key] = cx
+    cx.set_pme(float(kappa), 6, 6, 6, max(int(lmax), 0))      # the pair kernel only needs kappa; the mesh is not used
+    dt, dev = cx.dtype, cx.device
+    prep = lambda x: None if x is None else to_dev(x, dt, dev)                  # noqa: E731
+    pairs = pairs_to_dev(pairs, dev)
+    Uh = prep(Uind_global) if lpol else None
+    return _PmeRealFunction.apply(cx, pairs, int(lmax), prep(positions), prep(box), prep(Q_global), Uh,
+                                  prep(pol) if lpol else None, prep(tholes) if lpol else None, prep(mScales),
+                                  prep(pScales) if lpol else None)

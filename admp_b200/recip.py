@@ -10,6 +10,8 @@ import torch
 from . import _lib
 from ._ctx import Context, to_dev
 
+sqrt_pi = 1.7724538509055159     # admp/recip.py:19
+
 
 class InfluenceFunction:
     def __init__(self, name, kind, gamma):

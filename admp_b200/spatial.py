@@ -25,6 +25,12 @@ def pbc_shift(drvecs, box, box_inv):
     return ds @ box
 
 
+def normalize(matrix, axis=1, ord=2):
+    '''admp/spatial.py:36-41: normalise a matrix along one dimension'''
+    m = _t(matrix)
+    return m / torch.linalg.norm(m, ord=ord, dim=axis, keepdim=True)
+
+
 v_pbc_shift = pbc_shift          # admp/spatial.py:34 (vmap over rows; the matrix form is already row-wise)
 
 
@@ -65,4 +71,6 @@ def generate_construct_local_frames(axis_types, axis_indices):
         return fr
 
     construct_local_frames._ctx = cx
+    construct_local_frames.axis_types = axis_types            # read back by admp_b200.pme.energy_pme
+    construct_local_frames.axis_indices = axis_indices
     return construct_local_frames

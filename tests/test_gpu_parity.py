@@ -471,3 +471,66 @@ def test_neighbor_list_capacity_overflow_and_skin(lattice):
     pm, nm = pairlist.build_pairs(moved.numpy(), s.box.numpy(), 5.0)
     upd = nbr.update(moved)
     assert upd.n_pairs == nm and np.array_equal(upd.pairs[:nm].cpu().numpy(), pm[:nm])
+
+
+# ------------------------------------------------------------------------------------------ module-level surface
+def test_module_level_functions_of_the_reference_surface(carved):
+    """admp/pme.py and admp/disp_pme.py expose their building blocks as free functions (energy_pme, pme_real,
+    pme_self, pol_penalty, energy_disp_pme, disp_pme_real, disp_pme_self, g_p): same names, argument order and
+    values here, against the oracle's restatements."""
+    from admp_b200 import pme as P, disp_pme as D
+    from admp_b200.spatial import generate_construct_local_frames
+    from oracle.frames import construct_local_frames as o_frames
+    from oracle.harmonics import rot_local2global as o_l2g, cart_dipole_to_harm
+    from oracle import dispersion as odisp
+    s, pairs = carved
+    Ql, U, pol, th = _perturbed(s)
+    mS0, pS0, dS0 = [0.1, 0.3, 0.0, 0.7, 1.0], [0.0, 0.4, 0.0, 1.0, 1.0], [0.0, 0.0, 0.0, 1.0, 1.0]
+    kappa, K = 0.41, 30
+    # energy_pme, polarizable and not, with its position gradient
+    fn = generate_construct_local_frames(s.axis_type, s.axis_indices)
+    to = [_t(v) for v in (s.positions, s.box, Ql, U, pol, th, mS0, pS0)]
+    Eo = orc.energy_pme(to[0], to[1], pairs, to[2], to[3], to[4], to[5], to[6], to[7], _t(dS0, False), s.covalent_map,
+                        s.axis_type, s.axis_indices, kappa, K, K, K, 2, True)
+    go = torch.autograd.grad(Eo, to[0])[0]
+    pos = torch.tensor(s.positions.numpy(), device='cuda', requires_grad=True)
+    E = P.energy_pme(pos, s.box, pairs, Ql, U, pol, th, mS0, pS0, dS0, s.covalent_map, fn, None, kappa, K, K, K, 2, True)
+    assert abs(E.item() - Eo.item()) < RTOL * abs(Eo.item())
+    assert rel(torch.autograd.grad(E, pos)[0], go) < RTOL
+    En = P.energy_pme(s.positions, s.box, pairs, Ql, None, None, None, mS0, None, None, s.covalent_map, fn, None, kappa, K, K, K, 2, False)
+    Eno = orc.energy_pme(to[0], to[1], pairs, to[2], None, None, None, to[6], None, None, s.covalent_map,
+                         s.axis_type, s.axis_indices, kappa, K, K, K, 2, False)
+    assert abs(En.item() - Eno.item()) < RTOL * abs(Eno.item())
+    # pme_real from global-frame harmonic multipoles and harmonic-order induced dipoles
+    Qg = o_l2g(_t(Ql, False), o_frames(s.positions, s.box, s.axis_type, s.axis_indices), 2)
+    Uh = cart_dipole_to_harm(_t(U, False))
+    qg, uh, tp = Qg.clone().requires_grad_(True), Uh.clone().requires_grad_(True), _t(s.positions)
+    Ero = orc.pme_real(tp, _t(s.box, False), pairs, qg, uh, _t(pol, False), _t(th, False), _t(mS0, False), _t(pS0, False), _t(dS0, False),
+                       s.covalent_map, kappa, 2, True)
+    gro = torch.autograd.grad(Ero, [tp, qg, uh])
+    a = [torch.tensor(x.detach().numpy(), device='cuda', requires_grad=True) for x in (tp, qg, uh)]
+    Er = P.pme_real(a[0], s.box, pairs, a[1], a[2], pol, th, mS0, pS0, dS0, s.covalent_map, kappa, 2, True)
+    gr = torch.autograd.grad(Er, a)
+    assert abs(Er.item() - Ero.item()) < RTOL * abs(Ero.item())
+    for k in range(3):
+        assert rel(gr[k], gro[k]) < RTOL, k
+    # closed forms
+    assert abs(P.pme_self(Qg, kappa, 2).item() - orc.pme_self(Qg, kappa, 2).item()) < 1e-12 * abs(orc.pme_self(Qg, kappa, 2).item())
+    assert abs(P.pol_penalty(Uh, _t(pol, False)).item() - orc.pol_penalty(Uh, _t(pol, False)).item()) < 1e-9 * orc.pol_penalty(Uh, _t(pol, False)).item()
+    # dispersion
+    for pmax in (6, 10):
+        Ed = D.energy_disp_pme(s.positions, s.box, pairs, s.c_list, mS0, s.covalent_map, kappa, K, K, K, pmax)
+        Edo = odisp.energy_disp_pme(s.positions, s.box, pairs, s.c_list, _t(mS0, False), s.covalent_map, kappa, K, K, K, pmax)
+        assert abs(Ed.item() - Edo.item()) < RTOL * abs(Edo.item())
+    x2 = torch.tensor([0.3, 1.7, 4.0], dtype=torch.float64)
+    g = D.g_p(x2, 10)
+    ref = torch.exp(-x2) * torch.stack([1 + x2 + x2 ** 2 / 2, 1 + x2 + x2 ** 2 / 2 + x2 ** 3 / 6,
+                                        1 + x2 + x2 ** 2 / 2 + x2 ** 3 / 6 + x2 ** 4 / 24])
+    assert torch.allclose(g, ref, rtol=1e-14)
+    Eself = D.disp_pme_self(s.c_list, kappa, 10).item()
+    c = s.c_list
+    assert abs(Eself - (-kappa ** 6 / 12 * (c[:, 0] ** 2).sum() - kappa ** 8 / 48 * (c[:, 1] ** 2).sum()
+                        - kappa ** 10 / 240 * (c[:, 2] ** 2).sum()).item()) < 1e-12 * abs(Eself)
+    Edr = D.disp_pme_real(s.positions, s.box, pairs, s.c_list, mS0, s.covalent_map, kappa, 10)
+    Edro = odisp.disp_pme_real(s.positions, s.box, pairs, s.c_list, _t(mS0, False), s.covalent_map, kappa, 10)
+    assert abs(Edr.item() - Edro.item()) < RTOL * abs(Edro.item())
