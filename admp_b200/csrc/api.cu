@@ -1,4 +1,5 @@
-// C ABI of libadmp_b200.so: context, cuFFT plans, stage entry points and the fused
+// C ABI of libadmp_b200.so: context, FFT set-up (hand-written passes; cuFFT plans are created lazily, only when the
+// library backend is selected or the mesh sizes are outside the hand-written family), stage entry points and the fused
 // evaluation (energy_pme + optimize_Uind + all adjoints) - see include/admp_b200.h.
 #include <cufft.h>
 
@@ -149,6 +150,28 @@ static void free_recip(admp_ctx* c) {
     c->peer_n = 0;
 }
 
+// cuFFT plans + work area of the library backend: created on first use (the hand-written passes need none of it;
+// at 616x1232x1232 the work area alone is 7.5 GB and the two plans take seconds to build)
+static int ensure_cufft(admp_ctx* c) {
+    if (c->plans) return 0;
+    if (!c->mesh) return fail("admp_ctx_set_pme has not been called");
+    size_t ws1 = 0, ws2 = 0;
+    CKFFT(cufftCreate(&c->plan_fwd));
+    CKFFT(cufftCreate(&c->plan_inv));
+    c->plans = true;
+    CKFFT(cufftSetAutoAllocation(c->plan_fwd, 0));
+    CKFFT(cufftSetAutoAllocation(c->plan_inv, 0));
+    CKFFT(cufftMakePlan3d(c->plan_fwd, c->K[0], c->K[1], c->K[2], c->dtype == ADMP_F64 ? CUFFT_D2Z : CUFFT_R2C, &ws1));
+    CKFFT(cufftMakePlan3d(c->plan_inv, c->K[0], c->K[1], c->K[2], c->dtype == ADMP_F64 ? CUFFT_Z2D : CUFFT_C2R, &ws2));
+    c->fftwork_bytes = ws1 > ws2 ? ws1 : ws2;
+    if (c->fftwork_bytes == 0) c->fftwork_bytes = 256;
+    CK(cudaMalloc(&c->fftwork, c->fftwork_bytes));        // one work area shared by both directions
+    CKFFT(cufftSetWorkArea(c->plan_fwd, c->fftwork));
+    CKFFT(cufftSetWorkArea(c->plan_inv, c->fftwork));
+    c->ws_bytes += c->fftwork_bytes;
+    return 0;
+}
+
 static void free_atoms(admp_ctx* c) {
     dfree(c->M); dfree(c->G); dfree(c->Fscf); dfree(c->rec); dfree(c->s_pos); dfree(c->s_U); dfree(c->s_pol); dfree(c->s_th);
     dfree(c->axis_type); dfree(c->axis_idx); dfree(c->cov_off); dfree(c->cov_idx); dfree(c->cov_nb);
@@ -202,7 +225,7 @@ extern "C" int admp_ctx_set_pme(admp_ctx* c, double kappa, int K1, int K2, int K
     c->kappa = kappa;
     c->lmax = lmax;
     drop_graph(c);
-    if (c->plans && c->K[0] == K1 && c->K[1] == K2 && c->K[2] == K3) return 0;
+    if (c->mesh && c->K[0] == K1 && c->K[1] == K2 && c->K[2] == K3) return 0;
     free_recip(c);
     c->K[0] = K1; c->K[1] = K2; c->K[2] = K3;
     const size_t G = (size_t)K1 * K2 * K3, Gh = (size_t)K1 * K2 * (K3 / 2 + 1);
@@ -210,19 +233,6 @@ extern "C" int admp_ctx_set_pme(admp_ctx* c, double kappa, int K1, int K2, int K
     c->spec_bytes = Gh * 2 * c->w;
     CK(cudaMalloc(&c->mesh, c->mesh_bytes));
     CK(cudaMalloc(&c->spec, c->spec_bytes));
-    size_t ws1 = 0, ws2 = 0;
-    CKFFT(cufftCreate(&c->plan_fwd));
-    CKFFT(cufftCreate(&c->plan_inv));
-    c->plans = true;
-    CKFFT(cufftSetAutoAllocation(c->plan_fwd, 0));
-    CKFFT(cufftSetAutoAllocation(c->plan_inv, 0));
-    CKFFT(cufftMakePlan3d(c->plan_fwd, K1, K2, K3, c->dtype == ADMP_F64 ? CUFFT_D2Z : CUFFT_R2C, &ws1));
-    CKFFT(cufftMakePlan3d(c->plan_inv, K1, K2, K3, c->dtype == ADMP_F64 ? CUFFT_Z2D : CUFFT_C2R, &ws2));
-    c->fftwork_bytes = ws1 > ws2 ? ws1 : ws2;
-    if (c->fftwork_bytes == 0) c->fftwork_bytes = 256;
-    CK(cudaMalloc(&c->fftwork, c->fftwork_bytes));        // one work area shared by both directions
-    CKFFT(cufftSetWorkArea(c->plan_fwd, c->fftwork));
-    CKFFT(cufftSetWorkArea(c->plan_inv, c->fftwork));
     const int cnt[3] = {K1, K2, K3 / 2 + 1};
     for (int d = 0; d < 3; ++d) {
         std::vector<double> t = theta_inv2(c->K[d], cnt[d]);
@@ -246,7 +256,8 @@ extern "C" int admp_ctx_set_pme(admp_ctx* c, double kappa, int K1, int K2, int K
     c->use_custom_fft = (c->fft != nullptr) && !(env && strcmp(env, "cufft") == 0);
     c->fft_note = c->fft ? "" : why;
     cudaGetLastError();
-    c->ws_bytes += c->mesh_bytes + c->spec_bytes + c->fftwork_bytes;
+    c->ws_bytes += c->mesh_bytes + c->spec_bytes;
+    if (!c->use_custom_fft && ensure_cufft(c)) return 1;
     return 0;
 }
 
@@ -255,6 +266,7 @@ extern "C" int admp_ctx_fft_backend(const admp_ctx* c) { return (c && c->use_cus
 extern "C" int admp_ctx_set_fft_backend(admp_ctx* c, int custom) {
     if (!c) return fail("null ctx");
     if (custom && !c->fft) return fail("hand-written FFT unavailable for this mesh: %s", c->fft_note.c_str());
+    if (!custom && ensure_cufft(c)) return 1;           // plan creation allocates: never inside a stream capture
     c->use_custom_fft = custom != 0;
     drop_graph(c);
     return 0;
@@ -318,18 +330,20 @@ extern "C" int admp_ctx_set_topology(admp_ctx* c, int n, const int32_t* axis_typ
 
 static int need(admp_ctx* c, bool recip, bool atoms) {
     if (!c) return fail("null ctx");
-    if (recip && !c->plans) return fail("admp_ctx_set_pme has not been called");
+    if (recip && !c->mesh) return fail("admp_ctx_set_pme has not been called");
     if (atoms && c->n_atoms <= 0) return fail("admp_ctx_set_topology has not been called");
     return 0;
 }
 
 static int fft_fwd(admp_ctx* c, cudaStream_t st) {
+    if (ensure_cufft(c)) return 1;
     CKFFT(cufftSetStream(c->plan_fwd, st));
     if (c->dtype == ADMP_F64) CKFFT(cufftExecD2Z(c->plan_fwd, (cufftDoubleReal*)c->mesh, (cufftDoubleComplex*)c->spec));
     else CKFFT(cufftExecR2C(c->plan_fwd, (cufftReal*)c->mesh, (cufftComplex*)c->spec));
     return 0;
 }
 static int fft_inv(admp_ctx* c, cudaStream_t st) {
+    if (ensure_cufft(c)) return 1;
     CKFFT(cufftSetStream(c->plan_inv, st));
     if (c->dtype == ADMP_F64) CKFFT(cufftExecZ2D(c->plan_inv, (cufftDoubleComplex*)c->spec, (cufftDoubleReal*)c->mesh));
     else CKFFT(cufftExecC2R(c->plan_inv, (cufftComplex*)c->spec, (cufftReal*)c->mesh));
