@@ -195,6 +195,8 @@ extern "C" int admp_ctx_destroy(admp_ctx* c) {
         cudaEventDestroy(c->slab_aux.fork);
         for (int k = 0; k < SLAB_CHUNKS; ++k)
             for (int s = 0; s < SLAB_STREAMS; ++s) cudaEventDestroy(c->slab_aux.chunk[k][s]);
+        for (int k = 0; k < SLAB_CHUNKS; ++k) cudaEventDestroy(c->slab_aux.done[k]);
+        cudaEventDestroy(c->slab_aux.pushed);
     }
     delete c;
     return 0;
@@ -650,6 +652,8 @@ extern "C" int admp_ctx_set_peers(admp_ctx* c, int rank, int nranks, void* const
         CK(cudaEventCreateWithFlags(&c->slab_aux.fork, cudaEventDisableTiming));
         for (int k = 0; k < SLAB_CHUNKS; ++k)
             for (int s = 0; s < SLAB_STREAMS; ++s) CK(cudaEventCreateWithFlags(&c->slab_aux.chunk[k][s], cudaEventDisableTiming));
+        for (int k = 0; k < SLAB_CHUNKS; ++k) CK(cudaEventCreateWithFlags(&c->slab_aux.done[k], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->slab_aux.pushed, cudaEventDisableTiming));
         c->slab_aux.ready = 1;
     }
     c->mesh_peers.slab = c->spec_peers.slab = c->K[0] / nranks;

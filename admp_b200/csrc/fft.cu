@@ -525,7 +525,7 @@ static void run_x_conv(Fft3dImpl* f, cudaStream_t st, void* spec, const BoxInfo*
     const cx<T>* tw = (const cx<T>*)f->tw[0];
     if (c.fast) {
         const StrideGeom g = geom_x(f, c.ops.TL);
-        c.ops.xconv(st, g, g.tiles, persistent_grid(f, c.ops.occ[(kind == ADMP_CK_COULOMB && !want_vir) ? 2 : 5], g.tiles), B, kappa, kind, tb, spec, tw, scalars, want_vir);
+        c.ops.xconv(st, g, 0, g.tiles, persistent_grid(f, c.ops.occ[(kind == ADMP_CK_COULOMB && !want_vir) ? 2 : 5], g.tiles), B, kappa, kind, tb, spec, tw, scalars, want_vir);
         return;
     }
     const StrideGeom g = geom_x(f, c.TL);
@@ -595,11 +595,35 @@ static void slab_phase(Fft3dImpl* f, cudaStream_t st, int phase, int rank, void*
             }
             for (int s = 0; s < nstreams; ++s) cudaEventRecord(aux->chunk[k][s], aux->copy_stream[s]);
         }
+        // results go back to the owners as peer stores from inside the kernel (default) or, with ADMP_SLAB_PUSH=dma, as
+        // strided peer copies on a second copy stream behind a purely local transform (pull(k+1) | transform(k) |
+        // push(k-1) on three engines). Measured on B200 / NVSwitch: both are bound by the NVLink ingress of a rank
+        // (its pulls + its peers' pushes, ~500 GB/s aggregate): 5.7 (kernel) vs 6.2 ms (dma) per pass at 4 ranks.
+        static const bool dma_push = [] { const char* e = getenv("ADMP_SLAB_PUSH"); return e && strcmp(e, "dma") == 0; }();
+        cudaStream_t push_stream = aux->copy_stream[SLAB_STREAMS - 1];
+        const int occ_local = c.ops.occ[quick ? 2 : 5];
         for (int k = 0; k < nchunk; ++k) {
             const int a = t0 + (int)((long long)(t1 - t0) * k / nchunk), b = t0 + (int)((long long)(t1 - t0) * (k + 1) / nchunk);
             for (int s = 0; s < nstreams; ++s) cudaStreamWaitEvent(st, aux->chunk[k][s], 0);
-            if (b > a && debug_skip != 2)
+            if (b <= a || debug_skip == 2) continue;
+            if (!dma_push) {
                 c.ops.xconv_peer(st, g, a, b, persistent_grid(f, occ, b - a), B, kappa, kind, tb, spec, f->tw[0], scalars, want_vir, peers, 1);
+                continue;
+            }
+            c.ops.xconv(st, g, a, b, persistent_grid(f, occ_local, b - a), B, kappa, kind, tb, spec, f->tw[0], scalars, want_vir);
+            cudaEventRecord(aux->done[k], st);
+            cudaStreamWaitEvent(push_stream, aux->done[k], 0);
+            const size_t col0 = (size_t)a * c.ops.TL, col1 = std::min((size_t)b * c.ops.TL, (size_t)g.n_inner);
+            for (int s = 1; s < peers.n; ++s) {
+                const int q = (rank + s) % peers.n;
+                const size_t off = ((size_t)q * peers.slab * g.n_inner + col0) * sizeof(cx<T>);
+                cudaMemcpy2DAsync((char*)peers.base[q] + off, pitch, (const char*)spec + off, pitch, (col1 - col0) * sizeof(cx<T>),
+                                  (size_t)peers.slab, cudaMemcpyDefault, push_stream);
+            }
+        }
+        if (dma_push) {
+            cudaEventRecord(aux->pushed, push_stream);
+            cudaStreamWaitEvent(st, aux->pushed, 0);
         }
     } else {
         run_strided<T>(f, st, spec, 1, -1, x0, nx);

@@ -572,8 +572,8 @@ struct FastOps {
     int occ[6];      // strided fwd, strided inv, x conv (quick), z fwd, z inv, x conv (general)
     void (*prepare)(FastOps&);
     void (*strided)(cudaStream_t, int sign, const StrideGeom&, int ntiles, int grid, void* spec, const void* tw);
-    void (*xconv)(cudaStream_t, const StrideGeom&, int ntiles, int grid, const BoxInfo*, double kappa, int kind, const ConvTables&,
-                  void* spec, const void* tw, double* scalars, int want_vir);
+    void (*xconv)(cudaStream_t, const StrideGeom&, int tile0, int tile1, int grid, const BoxInfo*, double kappa, int kind,
+                  const ConvTables&, void* spec, const void* tw, double* scalars, int want_vir);
     // x-slab decomposed spectrum: tiles [tile0, tile1) of the X pass on peer-mapped buffers
     void (*xconv_peer)(cudaStream_t, const StrideGeom&, int tile0, int tile1, int grid, const BoxInfo*, double kappa, int kind,
                        const ConvTables&, void* spec, const void* tw, double* scalars, int want_vir, const PeerTab&, int local_reads);
@@ -615,14 +615,14 @@ struct FastImpl {
         if (sign > 0) launch_pdl(fast_strided_kernel<T, R1, R2, R3, 1, TL, JT>, grid, TL * JT, smem, st, g, ntiles, (cx<T>*)spec, (const cx<T>*)tw);
         else launch_pdl(fast_strided_kernel<T, R1, R2, R3, -1, TL, JT>, grid, TL * JT, smem, st, g, ntiles, (cx<T>*)spec, (const cx<T>*)tw);
     }
-    static void xconv(cudaStream_t st, const StrideGeom& g, int ntiles, int grid, const BoxInfo* B, double kappa, int kind,
+    static void xconv(cudaStream_t st, const StrideGeom& g, int tile0, int ntiles, int grid, const BoxInfo* B, double kappa, int kind,
                       const ConvTables& tb, void* spec, const void* tw, double* scalars, int want_vir) {
         const size_t smem = smem_x_bytes();
         if (kind == ADMP_CK_COULOMB && !want_vir)
-            launch_pdl(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, true, false>, grid, TL * JT, smem, st, g, 0, ntiles, B, (T)kappa, kind, tb,
+            launch_pdl(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, true, false>, grid, TL * JT, smem, st, g, tile0, ntiles, B, (T)kappa, kind, tb,
                        (cx<T>*)spec, (const cx<T>*)tw, scalars, want_vir, PeerTab{}, 0);
         else
-            launch_pdl(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, false, false>, grid, TL * JT, smem, st, g, 0, ntiles, B, (T)kappa, kind, tb,
+            launch_pdl(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, false, false>, grid, TL * JT, smem, st, g, tile0, ntiles, B, (T)kappa, kind, tb,
                        (cx<T>*)spec, (const cx<T>*)tw, scalars, want_vir, PeerTab{}, 0);
     }
     static void xconv_peer(cudaStream_t st, const StrideGeom& g, int tile0, int tile1, int grid, const BoxInfo* B, double kappa, int kind,

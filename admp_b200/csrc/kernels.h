@@ -66,6 +66,8 @@ struct SlabAux {                      // copy streams + events of the pull pipel
     cudaStream_t copy_stream[SLAB_STREAMS];
     cudaEvent_t fork;
     cudaEvent_t chunk[SLAB_CHUNKS][SLAB_STREAMS];
+    cudaEvent_t done[SLAB_CHUNKS];      // transform of chunk k finished (its push may start)
+    cudaEvent_t pushed;                 // all pushes of the pass issued behind this event
     int ready;
 };
 void fft3d_slab_phase(Fft3d* f, cudaStream_t st, int phase, int rank, void* mesh, void* spec, const PeerTab& spec_peers,
