@@ -98,7 +98,9 @@ def evaluate_frames(calc, frames, box, pairs, Q_local, pol=None, tholes=None, mS
 
     in_flight > 1 keeps that many frames in flight on one GPU (one calculator context + CUDA stream per lane):
     a 1024-water evaluation is latency-bound (a 30-cycle SCF of ~8 small dependent kernels per cycle leaves most
-    of the 148 SMs idle), so independent frames overlap almost for free."""
+    of the 148 SMs idle), so independent frames overlap: measured 312 / 375 / 420 evals/s with 1 / 2 / 4 lanes (saturated: every
+    FFT pass of one frame already occupies all resident-block slots). Run with CUDA_DEVICE_MAX_CONNECTIONS=32 (set before CUDA
+    initialises): each lane uses three streams and with the default 8 hardware queues some lane counts serialise."""
     mine = shard_frames(len(frames), rank, world)
     dev, dt = calc._ctx.device, calc._dtype
     prep = calc._prep
