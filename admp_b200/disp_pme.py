@@ -141,14 +141,15 @@ _disp_cache = {}
 def _disp_calc(box, covalent_map, kappa, K1, K2, K3, pmax):
     from . import settings
     key = (id(covalent_map), int(K1), int(K2), int(K3), int(pmax), settings.PRECISION)
-    calc = _disp_cache.get(key)
+    hit = _disp_cache.get(key)
+    calc = hit[0] if (hit is not None and hit[1] is covalent_map) else None    # id() key: identity-checked
     if calc is None:
         import numpy as np
         calc = ADMPDispPmeForce(np.eye(3) * 20.0, covalent_map, 4.0, 1e-4, pmax)
         calc.K1, calc.K2, calc.K3 = int(K1), int(K2), int(K3)
         calc.kappa = float(kappa)
         calc.refresh_calculators()
-        _disp_cache[key] = calc
+        _disp_cache[key] = (calc, covalent_map)
     if calc.kappa != float(kappa):
         calc.update_env('kappa', float(kappa))
     return calc

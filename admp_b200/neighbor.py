@@ -87,7 +87,39 @@ class NeighborListFn:
         return self._build(positions, int(nbr.pairs.shape[0]))
 
 
-def neighbor_list(box, r_cutoff, dr_threshold=0.0, capacity_multiplier=1.25, **_ignored):
-    """Factory with jax_md's argument order minus the displacement function (the periodic
-    general displacement is implied by ``box``)."""
+def neighbor_list(box, r_cutoff, dr_threshold=0.0, capacity_multiplier=1.25, *extra, **_ignored):
+    """Factory with jax_md's argument order minus the displacement function (the periodic general displacement is
+    implied by ``box``). The reference scripts' own call, ``partition.neighbor_list(displacement_fn, box, rc, 0,
+    format=partition.OrderedSparse)`` (examples/water_1024/run_admp.py:110-111), is accepted as well: a callable first
+    argument is dropped."""
+    if callable(box):
+        box, r_cutoff, dr_threshold = r_cutoff, dr_threshold, (capacity_multiplier if extra or capacity_multiplier != 1.25 else 0.0)
+        capacity_multiplier = extra[0] if extra else 1.25
     return NeighborListFn(box, r_cutoff, dr_threshold, capacity_multiplier)
+
+
+class _Space:
+    """``jax_md.space`` stand-in for the two lines the reference scripts use (run_admp.py:109)."""
+
+    @staticmethod
+    def periodic_general(box, fractional_coordinates=False):
+        import torch as _torch
+        b = box if isinstance(box, _torch.Tensor) else _torch.as_tensor(np.asarray(box, dtype=np.float64))
+
+        def displacement_fn(ra, rb):
+            from .spatial import pbc_shift
+            return pbc_shift((ra - rb).reshape(-1, 3), b, _torch.linalg.inv(b)).reshape(ra.shape)
+
+        def shift_fn(r, dr):
+            return r + dr
+        return displacement_fn, shift_fn
+
+
+class _Partition:
+    """``jax_md.partition`` stand-in: ``neighbor_list`` and the format marker."""
+    OrderedSparse = 'OrderedSparse'
+    neighbor_list = staticmethod(neighbor_list)
+
+
+space = _Space()
+partition = _Partition()

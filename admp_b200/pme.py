@@ -361,7 +361,9 @@ def energy_pme(positions, box, pairs, Q_local, Uind_global, pol, tholes, mScales
     if lmax > 0 and (at is None or ai is None):
         raise TypeError('energy_pme needs a construct_local_frame_fn made by admp_b200.spatial.generate_construct_local_frames')
     key = (id(covalent_map), id(construct_local_frame_fn), int(K1), int(K2), int(K3), int(lmax), bool(lpol), settings.PRECISION)
-    calc = _energy_pme_cache.get(key)
+    hit = _energy_pme_cache.get(key)
+    # the key uses id(): keep the keyed objects alive in the entry and check identity, so a recycled id can never alias
+    calc = hit[0] if (hit is not None and hit[1] is covalent_map and hit[2] is construct_local_frame_fn) else None
     if calc is None:
         n = int(covalent_map.shape[0])
         if at is None:
@@ -370,7 +372,7 @@ def energy_pme(positions, box, pairs, Q_local, Uind_global, pol, tholes, mScales
         calc.K1, calc.K2, calc.K3 = int(K1), int(K2), int(K3)
         calc.kappa = float(kappa)
         calc.refresh_calculators()
-        _energy_pme_cache[key] = calc
+        _energy_pme_cache[key] = (calc, covalent_map, construct_local_frame_fn)
     if calc.kappa != float(kappa):
         calc.update_env('kappa', float(kappa))
     if lpol:
@@ -427,12 +429,13 @@ def pme_real(positions, box, pairs, Q_global, Uind_global, pol, tholes, mScales,
     harmonic multipoles and harmonic-order (z, x, y) induced dipoles. One launch of the pair kernel; differentiable
     with respect to positions, Q_global and Uind_global (use ADMPPmeForce for the other derivatives)."""
     key = (id(covalent_map), settings.PRECISION)
-    cx = _pme_real_ctx.get(key)
+    hit = _pme_real_ctx.get(key)
+    cx = hit[0] if (hit is not None and hit[1] is covalent_map) else None      # id() keys: identity-checked, see energy_pme
     n = int(covalent_map.shape[0])
     if cx is None:
         cx = Context()
         cx.set_topology(n, None, None, covalent_map)
-        _pme_real_ctx[key] = cx
+        _pme_real_ctx[key] = (cx, covalent_map)
     cx.set_pme(float(kappa), 6, 6, 6, max(int(lmax), 0))      # the pair kernel only needs kappa; the mesh is not used
     dt, dev = cx.dtype, cx.device
     prep = lambda x: None if x is None else to_dev(x, dt, dev)                  # noqa: E731

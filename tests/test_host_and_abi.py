@@ -90,3 +90,18 @@ def test_convert_cart2harm_numpy_and_tensor():
     assert qt.shape == (1, 4) and float(qt[0, 1]) == pytest.approx(-0.23671684)
     with pytest.raises(NotImplementedError):
         convert_cart2harm(th, 3)
+
+
+def test_neighbor_list_accepts_the_reference_scripts_call(monkeypatch):
+    """examples/water_1024/run_admp.py:109-111: space.periodic_general(box) + partition.neighbor_list(displacement_fn,
+    box, rc, 0, format=partition.OrderedSparse) keep working with `from admp_b200.neighbor import space, partition`."""
+    import admp_b200.neighbor as nb
+    calls = []
+    monkeypatch.setattr(nb, 'NeighborListFn', lambda *a: calls.append(a))
+    box = np.eye(3) * 50.0
+    disp, shift = nb.space.periodic_general(box, fractional_coordinates=False)
+    nb.partition.neighbor_list(disp, box, 4.0, 0, format=nb.partition.OrderedSparse)
+    nb.neighbor_list(box, 4.0, 0.6)
+    assert [(c[1], c[2], c[3]) for c in calls] == [(4.0, 0, 1.25), (4.0, 0.6, 1.25)] and all(c[0] is box for c in calls)
+    d = disp(torch.tensor([[49.0, 0.0, 26.0]], dtype=torch.float64), torch.tensor([[1.0, 0.0, 1.0]], dtype=torch.float64))
+    assert torch.allclose(d, torch.tensor([[-2.0, 0.0, -25.0]], dtype=torch.float64))      # +L/2 maps to -L/2 (A14)
