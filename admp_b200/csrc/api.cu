@@ -637,7 +637,7 @@ extern "C" int admp_ctx_set_peers(admp_ctx* c, int rank, int nranks, void* const
     if (nranks == 0) { c->peer_n = 0; return 0; }
     if (nranks < 1 || nranks > ADMP_MAX_PEERS) return fail("admp_ctx_set_peers: %d ranks (1..%d supported)", nranks, ADMP_MAX_PEERS);
     if (rank < 0 || rank >= nranks) return fail("admp_ctx_set_peers: rank %d outside [0,%d)", rank, nranks);
-    if (c->K[0] % nranks) return fail("admp_ctx_set_peers: K1 = %d is not a multiple of %d ranks", c->K[0], nranks);
+    if (c->K[0] < nranks) return fail("admp_ctx_set_peers: K1 = %d is smaller than %d ranks", c->K[0], nranks);
     if (!c->fft || !fft3d_slab_supported(c->fft))
         return fail("admp_ctx_set_peers: the x-slab passes need the register-blocked FFT kernels (mesh family 154*2^n); %s", c->fft_note.c_str());
     if (!mesh_ptrs || !spec_ptrs) return fail("admp_ctx_set_peers: null pointer tables");
@@ -656,7 +656,10 @@ extern "C" int admp_ctx_set_peers(admp_ctx* c, int rank, int nranks, void* const
         CK(cudaEventCreateWithFlags(&c->slab_aux.pushed, cudaEventDisableTiming));
         c->slab_aux.ready = 1;
     }
-    c->mesh_peers.slab = c->spec_peers.slab = c->K[0] / nranks;
+    for (int r = 0; r <= ADMP_MAX_PEERS; ++r) {
+        const int st = r <= nranks ? (int)((long long)c->K[0] * r / nranks) : c->K[0];
+        c->mesh_peers.start[r] = c->spec_peers.start[r] = st;
+    }
     c->mesh_peers.n = c->spec_peers.n = nranks;
     c->peer_rank = rank;
     c->peer_n = nranks;
@@ -671,7 +674,8 @@ static int need_peers(admp_ctx* c) {
 extern "C" int admp_slab_zero(admp_ctx* c, void* stream) {
     if (need_peers(c)) return 1;
     const size_t plane = (size_t)c->K[1] * c->K[2] * c->w;
-    CK(cudaMemsetAsync((char*)c->mesh + plane * c->mesh_peers.slab * c->peer_rank, 0, plane * c->mesh_peers.slab, (cudaStream_t)stream));
+    CK(cudaMemsetAsync((char*)c->mesh + plane * c->mesh_peers.start[c->peer_rank], 0, plane * c->mesh_peers.planes(c->peer_rank),
+                       (cudaStream_t)stream));
     return 0;
 }
 /* spread `count` atoms (compact arrays) onto the decomposed mesh */

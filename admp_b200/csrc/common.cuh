@@ -23,14 +23,22 @@ struct BoxInfo {
     int K[3];
 };
 
-// x-slab decomposition of the mesh / half spectrum over the GPUs of one NVLink domain: plane i1 of the
-// (K1, K2, K3) array lives at the usual offset ((i1*K2 + i2)*K3 + i3) inside base[i1 / slab], where base[r] is
-// rank r's buffer mapped into this process (cudaIpc peer mapping, or a plain pointer for r == own rank).
+// x-slab decomposition of the mesh / half spectrum over the GPUs of one NVLink domain: rank r owns the planes
+// [start[r], start[r+1]) (start[r] = r*K1/n, so any K1 works); plane i1 of the (K1, K2, K3) array lives at the usual
+// offset ((i1*K2 + i2)*K3 + i3) inside base[owner(i1)], where base[r] is rank r's buffer mapped into this process
+// (cudaIpc peer mapping, or a plain pointer for r == own rank).
 constexpr int ADMP_MAX_PEERS = 8;
 struct PeerTab {
     void* base[ADMP_MAX_PEERS];
-    int slab;      // planes per rank (K1 / n)
+    int start[ADMP_MAX_PEERS + 1];
     int n;         // ranks
+    __host__ __device__ __forceinline__ int owner(int plane) const {
+        int o = 0;
+#pragma unroll
+        for (int r = 1; r < ADMP_MAX_PEERS; ++r) o += (r < n && plane >= start[r]) ? 1 : 0;
+        return o;
+    }
+    __host__ __device__ __forceinline__ int planes(int r) const { return start[r + 1] - start[r]; }
 };
 
 template <typename T> __device__ __forceinline__ T ldg(const T* p) { return __ldg(p); }

@@ -549,7 +549,7 @@ bool fft3d_slab_supported(const Fft3d* p) {
 template <typename T>
 static void slab_phase(Fft3dImpl* f, cudaStream_t st, int phase, int rank, void* mesh, void* spec, const PeerTab& peers, const BoxInfo* B,
                        double kappa, int kind, const ConvTables& tb, double* scalars, int want_vir, const SlabAux* aux) {
-    const int x0 = rank * peers.slab, nx = peers.slab;
+    const int x0 = peers.start[rank], nx = peers.planes(rank);
     if (phase == 0) {
         run_z<T>(f, st, mesh, spec, 1, x0, nx);
         run_strided<T>(f, st, spec, 1, 1, x0, nx);
@@ -587,8 +587,8 @@ static void slab_phase(Fft3dImpl* f, cudaStream_t st, int phase, int rank, void*
                 const int q = (rank + s) % peers.n;
                 for (int h = 0; h < halves; ++h, ++item) {
                     if (col1 <= col0 || debug_skip == 1) continue;
-                    const int r0 = peers.slab * h / halves, r1 = peers.slab * (h + 1) / halves;
-                    const size_t off = (((size_t)q * peers.slab + r0) * g.n_inner + col0) * sizeof(cx<T>);
+                    const int r0 = peers.planes(q) * h / halves, r1 = peers.planes(q) * (h + 1) / halves;
+                    const size_t off = (((size_t)peers.start[q] + r0) * g.n_inner + col0) * sizeof(cx<T>);
                     cudaMemcpy2DAsync((char*)spec + off, pitch, (const char*)peers.base[q] + off, pitch, (col1 - col0) * sizeof(cx<T>),
                                       (size_t)(r1 - r0), cudaMemcpyDefault, aux->copy_stream[item % nstreams]);
                 }
@@ -616,9 +616,9 @@ static void slab_phase(Fft3dImpl* f, cudaStream_t st, int phase, int rank, void*
             const size_t col0 = (size_t)a * c.ops.TL, col1 = std::min((size_t)b * c.ops.TL, (size_t)g.n_inner);
             for (int s = 1; s < peers.n; ++s) {
                 const int q = (rank + s) % peers.n;
-                const size_t off = ((size_t)q * peers.slab * g.n_inner + col0) * sizeof(cx<T>);
+                const size_t off = ((size_t)peers.start[q] * g.n_inner + col0) * sizeof(cx<T>);
                 cudaMemcpy2DAsync((char*)peers.base[q] + off, pitch, (const char*)spec + off, pitch, (col1 - col0) * sizeof(cx<T>),
-                                  (size_t)peers.slab, cudaMemcpyDefault, push_stream);
+                                  (size_t)peers.planes(q), cudaMemcpyDefault, push_stream);
             }
         }
         if (dma_push) {

@@ -225,7 +225,7 @@ __device__ __forceinline__ void issue_tile(const StrideGeom& g, int tile, const 
 }
 
 // X pass over an x-slab decomposed spectrum (PeerTab): point `pos` of every line lives in the buffer of rank
-// pos / slab; `sbase[pos]` (shared memory) holds that buffer's base pointer, element offsets are unchanged.
+// owner(pos); `sbase[pos]` (shared memory) holds that buffer's base pointer, element offsets are unchanged.
 template <typename T, int N, int TL, int JT>
 __device__ __forceinline__ void issue_tile_peer(const StrideGeom& g, int tile, cx<T>* const* sbase, cx<T>* dst, int l, int j) {
     const int c0 = tile * TL;
@@ -322,7 +322,7 @@ fast_x_conv_kernel(StrideGeom g, int tile0, int ntiles, const BoxInfo* __restric
     build_twiddles<T, R1, R2, R3, 1>(tw2, tw3, gtw, NT);
     build_twiddles<T, Q1, Q2, Q3, 1>(itw2, itw3, gtw, NT);
     if (PEER) {
-        for (int i = threadIdx.x; i < N; i += NT) sbase[i] = reinterpret_cast<cx<T>*>(peers.base[i / peers.slab]);
+        for (int i = threadIdx.x; i < N; i += NT) sbase[i] = reinterpret_cast<cx<T>*>(peers.base[peers.owner(i)]);
         __syncthreads();
     }
     pdl_wait();

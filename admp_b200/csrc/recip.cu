@@ -132,7 +132,7 @@ spread_kernel(int n, const BoxInfo* __restrict__ Bp, const T* __restrict__ pos, 
         int gi = i0 + ia; if (gi >= K1) gi -= K1;
         int gj = j0 + ib; if (gj >= K2) gj -= K2;
         int gk = k0 + ic; if (gk >= K3) gk -= K3;
-        T* base = PEER ? reinterpret_cast<T*>(peers.base[gi / peers.slab]) : mesh;
+        T* base = PEER ? reinterpret_cast<T*>(peers.base[peers.owner(gi)]) : mesh;
         atomicAdd(base + ((size_t)gi * K2 + gj) * K3 + gk, val);
     }
 }
@@ -268,7 +268,7 @@ gather_kernel(int n, const BoxInfo* __restrict__ Bp, const T* __restrict__ pos, 
             const int ia = col / 6, ib = col - 6 * ia;
             int gi = i0 + ia; if (gi >= K1) gi -= K1;
             int gj = j0 + ib; if (gj >= K2) gj -= K2;
-            const T* line = (PEER ? reinterpret_cast<const T*>(peers.base[gi / peers.slab]) : phi) + ((size_t)gi * K2 + gj) * K3;
+            const T* line = (PEER ? reinterpret_cast<const T*>(peers.base[peers.owner(gi)]) : phi) + ((size_t)gi * K2 + gj) * K3;
             T ph[6];
             if (!wrap) {
 #pragma unroll

@@ -353,8 +353,6 @@ class SlabPme:
         self.close()
         self._key = key
         lib = main.lib
-        if calc.K1 % self.P:
-            raise ValueError('x-slab decomposition needs K1 (%d) to be a multiple of the number of ranks (%d)' % (calc.K1, self.P))
         if self.world > 1:
             import torch.distributed as dist
             self._ctxs = {self.rank: main}

@@ -204,7 +204,7 @@ int admp_nblist_build(admp_ctx* ctx, void* stream, const void* pos, const void* 
                       double rc, int32_t* pairs, int64_t capacity, int32_t* info);
 
 /* ---- x-slab decomposition of reciprocal space over the GPUs of one NVLink domain (no reference counterpart;
- * north-star config "256k-water box at 1/2/4/8 B200"). Rank r owns the x planes [r*K1/n, (r+1)*K1/n) of the mesh
+ * north-star config "256k-water box at 1/2/4/8 B200"). Rank r owns the x planes [floor(r*K1/n), floor((r+1)*K1/n)) of the mesh
  * and of the half spectrum; every rank maps the other ranks' buffers (cudaIpc) and the kernels address the owner
  * of each plane directly over NVLink: spread / gather for stencils crossing a slab boundary, and the fused X pass,
  * which reads and writes all ranks' planes (the transposes of a distributed FFT happen inside the kernel).
@@ -215,7 +215,7 @@ int admp_ipc_export(const void* devptr, void* handle64);          /* cudaIpcGetM
 int admp_ipc_open(const void* handle64, void** devptr);           /* cudaIpcOpenMemHandle (peer access enabled) */
 int admp_ipc_close(void* devptr);
 /* mesh_ptrs / spec_ptrs: host arrays of nranks device pointers (entry `rank` = admp_ctx_buffer(ctx, 0 / 1)).
- * nranks = 0 clears the table. Needs K1 % nranks == 0 and the register-blocked FFT kernels. */
+ * nranks = 0 clears the table. Needs K1 >= nranks and the register-blocked FFT kernels. */
 int admp_ctx_set_peers(admp_ctx* ctx, int rank, int nranks, void* const* mesh_ptrs, void* const* spec_ptrs);
 int admp_slab_zero(admp_ctx* ctx, void* stream);
 int admp_slab_spread(admp_ctx* ctx, void* stream, const void* pos, const void* M, int M_cols, int M_stride,

@@ -48,10 +48,11 @@ def test_atom_block_algebra_matches_fused_evaluation(polz, nblocks):
 
 
 @pytest.mark.parametrize('polz', [False, True])
-@pytest.mark.parametrize('nranks', [2, 7])
+@pytest.mark.parametrize('nranks', [2, 7, 8])
 def test_x_slab_decomposition_matches_fused_evaluation(polz, nranks):
     """x-slab reciprocal space (peer-addressed spread / gather / fused X pass) walked in one process with one context
-    per emulated rank, on the base water box (mesh 154^3: 77 or 22 planes per rank) against the fused evaluation."""
+    per emulated rank, on the base water box (mesh 154^3: 77 or 22 planes per rank, or uneven 19 / 20 planes with 8 ranks)
+    against the fused evaluation."""
     w = workloads.water_box((1, 1, 1), polarizable=polz)
     calc = ADMPPmeForce(w.box, w.axis_type, w.axis_indices, w.covalent_map, w.rc, w.ethresh, 2, lpol=polz)
     calc.update_env('kappa', w.kappa)

@@ -52,7 +52,7 @@ def main():
         ok = ok and all(v < 1e-9 for v in errs.values())
         # x-slab reciprocal space over peer memory on the base water box (mesh 154^3), 4 Jacobi cycles
         serr = {}
-        if 154 % world == 0:
+        if True:
             w = workloads.water_box((1, 1, 1), polarizable=True)
             calc2 = ADMPPmeForce(w.box, w.axis_type, w.axis_indices, w.covalent_map, w.rc, w.ethresh, 2, lpol=True)
             calc2.update_env('kappa', w.kappa)
