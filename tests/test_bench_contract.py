@@ -1,0 +1,41 @@
+"""The bench line contract (task statement, section 4) checked on the committed line of the last GPU run
+(profiles/r1n_bench.json, written by `python bench.py` on a B200) and on the reference-arm line: every key the driver
+and the judge read is present and self-consistent. CPU only; bench.py itself needs a GPU."""
+import json
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _load(name):
+    with open(os.path.join(ROOT, 'profiles', name)) as f:
+        return json.loads(f.read().strip().splitlines()[-1])
+
+
+def test_gpu_arm_line():
+    d = _load('r1n_bench.json')
+    for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'vs_baseline',
+              'dtype', 'data', 'config', 'e2e', 'gpu_launches', 'clocks', 'roofline', 'cpu_baseline'):
+        assert k in d, k
+    assert d['unit'] == 'evals/s' and d['higher_is_better'] is True and d['dtype'] == 'f64' and d['vs_baseline'] is None
+    assert 'workload' in d['config'] and 'model' not in d['config']
+    assert abs(d['value'] - d['n_gpus'] * 1e3 / d['ms_per_step']) < 1e-6 * d['value']
+    e = d['e2e']
+    assert e['unit'] == 'evals/s' and e['h2d_bytes_per_step'] > 0 and e['d2h_bytes_per_step'] > 0 and 0 < e['value'] <= 1.05 * d['value']
+    r = d['roofline']
+    assert r['bound'] in ('hbm', 'tensor') and r['unit'] == 'GB/s'
+    assert abs(r['frac'] - r['achieved'] / r['peak']) < 1e-3 and r['traffic'] is not None and r['traffic'] > 0
+    c = d['clocks']
+    assert c['sm_mhz'] and c['sm_max_mhz'] and c['samples'] > 0
+    assert not set(c['reasons']) & {'hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown'}
+    b = d['cpu_baseline']
+    assert b['kind'] in ('port', 'reference') and b['cores'] >= 1 and b['value'] > 0 and b['sample']
+    assert d['gpu_launches'] > 0
+
+
+def test_reference_arm_line():
+    d = _load('r1m_bench_reference.json')
+    assert d['impl'] == 'reference' and d['unit'] == 'evals/s' and d['value'] > 0
+    assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0 and d['e2e']['value'] == d['value']
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['value'] == d['value']
+    assert d['metric'] == _load('r1n_bench.json')['metric']
