@@ -53,7 +53,9 @@ def _cartesian_multipoles(s, pos=None):
 
 def _ladder(r, kappa, kind):
     """B_n, n = 0..4, with B_0 = f(r), B_{n+1} = -(1/r) dB_n/dr for f = erfc(kappa r)/r ('erfc'),
-    erf(kappa r)/r ('erf') or 1/r ('coul')."""
+    erf(kappa r)/r ('erf') or 1/r ('coul'); `kind` may also be a precomputed list [B_0 .. B_4]."""
+    if isinstance(kind, (list, tuple)):
+        return kind
     r2 = r * r
     coul = [1.0 / r]
     for n in range(1, 5):
@@ -117,9 +119,11 @@ def _pair_energy_autodiff(d, Mi, Mj, kappa):
     return torch.stack(out)
 
 
-def _exact_ewald(s, kappa, r_images, m_max, pos=None):
+def _exact_ewald(s, kappa, r_images, m_max, pos=None, extra_dipole=None):
     pos = s.positions if pos is None else pos
     q, mu, Th = _cartesian_multipoles(s, pos)
+    if extra_dipole is not None:
+        mu = mu + extra_dipole
     L = torch.diagonal(s.box)
     n = s.n_atoms
     mol = torch.arange(n) // 3
@@ -222,3 +226,69 @@ def test_oracle_forces_converge_to_exact_multipolar_ewald(small):
         errs.append((g_pme - g_exact).abs().max().item() / g_exact.abs().max().item())
     assert errs[1] < 2e-4 and errs[0] < 6e-4, errs
     assert errs[0] / errs[1] > 2.8, errs                       # (96 / 64)^3 = 3.4
+
+
+# ------------------------------------------------------------------------------------------ Thole-damped polarization
+def _radial_ladder_autodiff(f, r):
+    """[B_0 .. B_4] of an arbitrary radial function by automatic differentiation: B_{n+1} = -(1/r) dB_n/dr."""
+    r = r.clone().requires_grad_(True)
+    B = [f(r)]
+    for _ in range(4):
+        (g,) = torch.autograd.grad(B[-1].sum(), r, create_graph=True)
+        B.append(-g / r)
+    return [b.detach() for b in B]
+
+
+def test_oracle_polarizable_energy_matches_exact_ewald_with_thole_damping(small):
+    """energy_fn(U) of the polarizable model (admp/pme.py:176-254 with calc_e_ind, :379-475) against an independent
+    statement of the same physics: exact Ewald sum of the TOTAL multipoles (permanent + induced dipoles), plus, for the
+    listed pairs, the replacement of the bare 1/r kernel by the Thole-damped one in the permanent-induced and
+    induced-induced interactions, plus the polarization penalty sum U^2 / (2 alpha).
+
+    The Thole model behind thole_c/d0/d1/q0/q1 is the exponential charge smearing whose potential is
+    g(r) = [1 - (1 + au/2) exp(-au)] / r, u = r / (alpha_i alpha_j)^(1/6), a = thole_i + thole_j (0.3 for pairs whose
+    pScale is 0): lambda3, lambda5, lambda7 are its radial derivatives, so every damped multipole-dipole interaction is
+    L_i L_j g - obtained here by differentiating g automatically instead of using the reference's closed forms."""
+    s = small
+    n = s.n_atoms
+    rng = np.random.default_rng(11)
+    pol = torch.tensor(rng.uniform(0.5, 1.0, n))
+    th = torch.tensor(rng.uniform(2.5, 3.5, n))
+    U = torch.tensor(rng.normal(0.0, 0.05, (n, 3)))
+    kappa_pme, rc, K = 1.25, 3.45, 96
+    pairs, npairs = pairlist.build_pairs(s.positions.numpy(), s.box.numpy(), rc)
+    parts = {}
+    E_pme = orc.energy_pme(s.positions, s.box, pairs, s.Q_local, U, pol, th, s.mScales, s.pScales, s.dScales, s.covalent_map,
+                           s.axis_type, s.axis_indices, kappa_pme, K, K, K, 2, True, parts=parts).item()
+
+    # exact Ewald of the total multipoles; intramolecular pairs carry no interaction at all in it
+    E = _exact_ewald(s, 0.55, r_images=11.5, m_max=9, extra_dipole=U)
+    q, mu, Th = _cartesian_multipoles(s)
+    zero_q, zero_T = torch.zeros(n, dtype=torch.float64), torch.zeros(n, 3, 3, dtype=torch.float64)
+    pr = torch.as_tensor(np.asarray(pairs[:npairs]), dtype=torch.int64)
+    i, j = pr[:, 0], pr[:, 1]
+    L = torch.diagonal(s.box)
+    d = s.positions[i] - s.positions[j]
+    d = d - torch.round(d / L) * L                                     # the listed pairs are minimum-image pairs
+    r = torch.sqrt((d * d).sum(1))
+    same = (i // 3) == (j // 3)
+    dmp = (pol[i] * pol[j]) ** (1.0 / 6.0)
+    a = torch.where(same, torch.full_like(r, 0.3), th[i] + th[j])      # pScale 0 inside a molecule -> default width
+
+    def h(x):                                                         # damped minus bare kernel
+        au = a * x / dmp
+        return -(1.0 + 0.5 * au) * torch.exp(-au) / x
+
+    Bh = _radial_ladder_autodiff(h, r)
+    perm_i, perm_j = (q[i], mu[i], Th[i]), (q[j], mu[j], Th[j])
+    ind_i, ind_j = (zero_q[i], U[i], zero_T[i]), (zero_q[j], U[j], zero_T[j])
+    inter = ~same
+    # intermolecular listed pairs: permanent-induced (both ways) and induced-induced with g instead of 1/r
+    dE = (_pair_energy(d, perm_i, ind_j, None, Bh) + _pair_energy(d, ind_i, perm_j, None, Bh) + _pair_energy(d, ind_i, ind_j, None, Bh))[inter].sum()
+    # intramolecular pairs: only the induced-induced interaction exists (uscale = 1), fully damped with a = 0.3
+    Bc = _ladder(r, None, 'coul')
+    uu = _pair_energy(d, ind_i, ind_j, None, Bc) + _pair_energy(d, ind_i, ind_j, None, Bh)
+    dE = dE + uu[same].sum()
+    E_exact = (E + DIEL * dE + DIEL * (0.5 * (U * U).sum(1) / pol).sum()).item()
+    assert abs(dE.item() * DIEL) > 1e-4 * abs(E_exact)                 # the damping terms are 300x the tolerance below
+    assert abs(E_pme - E_exact) < 2e-6 * abs(E_exact), (E_pme, E_exact, parts)
