@@ -18,9 +18,15 @@ Parity pin status (see DESIGN.md "Oracle"):
     the reference's ``examples/water_pol_1024/ref_out`` induced dipoles
     (ADMP column and MPID column) - see ``tests/test_oracle_pins.py``;
   * energies / forces / virial / parameter gradients have NO fixture in the
-    reference ("parity unpinned" beyond the restatement): they are pinned by the
-    restatement plus finite-difference, replica- and Ewald-parameter-invariance
-    self checks (``tests/test_oracle_selfchecks.py``);
+    reference. Energies (permanent multipoles, and the polarizable energy_fn(U)
+    with Thole damping) and forces are pinned instead against an independent
+    formulation of the same physics - exact multipolar Ewald summation in
+    Cartesian-tensor form with automatically differentiated kernels
+    (``tests/test_oracle_independent_ewald.py``: 6e-8 / 1.6e-7 on the energies,
+    forces converging as h^3); virial and parameter gradients remain "parity
+    unpinned" beyond the restatement and are covered by finite-difference,
+    replica- and Ewald-parameter-invariance self checks
+    (``tests/test_oracle_selfchecks.py``);
   * the neighbour pair *set* (third-party jax_md, version unpinned in the
     reference) is "parity unpinned": only the set predicate is restated.
 """
