@@ -32,10 +32,10 @@ DIEL = 1389.35455846          # admp/pme.py:16
 torch.set_num_threads(4)
 
 
-def _cartesian_multipoles(s, pos=None):
+def _cartesian_multipoles(s, pos=None, box=None):
     """(q, mu, Theta) in the global frame from the oracle's own rotated harmonic multipoles (Stone's traceless
     Theta; harmonic order 00,10,11c,11s,20,21c,21s,22c,22s; dipoles (z, x, y))."""
-    frames = construct_local_frames(s.positions if pos is None else pos, s.box, s.axis_type, s.axis_indices)
+    frames = construct_local_frames(s.positions if pos is None else pos, s.box if box is None else box, s.axis_type, s.axis_indices)
     Q = rot_local2global(s.Q_local, frames, 2)
     q = Q[:, 0]
     mu = torch.stack([Q[:, 2], Q[:, 3], Q[:, 1]], dim=1)
@@ -119,12 +119,12 @@ def _pair_energy_autodiff(d, Mi, Mj, kappa):
     return torch.stack(out)
 
 
-def _exact_ewald(s, kappa, r_images, m_max, pos=None, extra_dipole=None):
+def _exact_ewald(s, kappa, r_images, m_max, pos=None, extra_dipole=None, box=None):
     pos = s.positions if pos is None else pos
-    q, mu, Th = _cartesian_multipoles(s, pos)
+    q, mu, Th = _cartesian_multipoles(s, pos, box)
     if extra_dipole is not None:
         mu = mu + extra_dipole
-    L = torch.diagonal(s.box)
+    L = torch.diagonal(s.box if box is None else box)
     n = s.n_atoms
     mol = torch.arange(n) // 3
     # --- reciprocal space: explicit k sum (k != 0)
@@ -141,7 +141,7 @@ def _exact_ewald(s, kappa, r_images, m_max, pos=None, extra_dipole=None):
     V = torch.prod(L)
     e_recip = (2.0 * math.pi / V) * (torch.exp(-k2 / (4 * kappa * kappa)) / k2 * S2).sum()
     # --- real space: every image inside the sphere, non-excluded pairs (different molecules, or any image n != 0)
-    nmax = int(math.ceil(r_images / float(L.min()))) + 1
+    nmax = int(math.ceil(r_images / float(L.detach().min()))) + 1
     sh = torch.arange(-nmax, nmax + 1, dtype=torch.float64)
     shifts = torch.stack(torch.meshgrid(sh, sh, sh, indexing='ij'), -1).reshape(-1, 3)
     ii, jj = torch.meshgrid(torch.arange(n), torch.arange(n), indexing='ij')
@@ -226,6 +226,28 @@ def test_oracle_forces_converge_to_exact_multipolar_ewald(small):
         errs.append((g_pme - g_exact).abs().max().item() / g_exact.abs().max().item())
     assert errs[1] < 2e-4 and errs[0] < 6e-4, errs
     assert errs[0] / errs[1] > 2.8, errs                       # (96 / 64)^3 = 3.4
+
+
+def test_oracle_virial_diagonal_converges_to_exact_multipolar_ewald(small):
+    """dE/dbox at fixed Cartesian positions (what jax.grad(energy, argnums=1) returns; README.md:7): the diagonal of the
+    exact sum's box gradient (through the k vectors, the volume, the image shifts and the anchor displacements of the
+    local frames) against the oracle's. At fixed Cartesian positions a box change moves every atom relative to the mesh, so
+    the mesh error of dE/dbox_aa is the force error times the lever arm sum_i |x_i| (measured: 2.3e-2, 8.5e-3, 3.1e-3,
+    2.7e-3 kJ/mol/A at K = 64, 96, 128, 160 on components of size 25; no axis dependence - the residual follows the
+    configuration when the coordinates are permuted): asserted at that level, far below any convention error (a wrong
+    volume, image-shift or frame term changes the components by O(1))."""
+    s = small
+    box = s.box.clone().requires_grad_(True)
+    g_exact = torch.diagonal(torch.autograd.grad(_exact_ewald(s, 0.55, r_images=11.5, m_max=9, box=box), box)[0])
+    pairs, _ = pairlist.build_pairs(s.positions.numpy(), s.box.numpy(), 3.45)
+    errs = []
+    for K in (64, 96):
+        b2 = s.box.clone().requires_grad_(True)
+        E = orc.energy_pme(s.positions, b2, pairs, s.Q_local, None, None, None, s.mScales, None, None, s.covalent_map,
+                           s.axis_type, s.axis_indices, 1.25, K, K, K, 2, False)
+        g = torch.diagonal(torch.autograd.grad(E, b2)[0])
+        errs.append((g - g_exact).abs().max().item() / g_exact.abs().max().item())
+    assert errs[0] < 2e-3 and errs[1] < 7e-4 and errs[1] < errs[0], (errs, g_exact)
 
 
 # ------------------------------------------------------------------------------------------ Thole-damped polarization
