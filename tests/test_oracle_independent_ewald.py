@@ -294,12 +294,14 @@ def test_oracle_polarizable_energy_matches_exact_ewald_with_thole_damping(small)
     rng = np.random.default_rng(11)
     pol = torch.tensor(rng.uniform(0.5, 1.0, n))
     th = torch.tensor(rng.uniform(2.5, 3.5, n))
-    U = torch.tensor(rng.normal(0.0, 0.05, (n, 3)))
+    U = torch.tensor(rng.normal(0.0, 0.05, (n, 3)), requires_grad=True)
     kappa_pme, rc, K = 1.25, 3.45, 96
     pairs, npairs = pairlist.build_pairs(s.positions.numpy(), s.box.numpy(), rc)
     parts = {}
-    E_pme = orc.energy_pme(s.positions, s.box, pairs, s.Q_local, U, pol, th, s.mScales, s.pScales, s.dScales, s.covalent_map,
-                           s.axis_type, s.axis_indices, kappa_pme, K, K, K, 2, True, parts=parts).item()
+    E_pme_t = orc.energy_pme(s.positions, s.box, pairs, s.Q_local, U, pol, th, s.mScales, s.pScales, s.dScales, s.covalent_map,
+                             s.axis_type, s.axis_indices, kappa_pme, K, K, K, 2, True, parts=parts)
+    field_pme = torch.autograd.grad(E_pme_t, U)[0]               # dE/dU: what optimize_Uind iterates on (admp/pme.py:133)
+    E_pme = E_pme_t.item()
 
     # exact Ewald of the total multipoles; intramolecular pairs carry no interaction at all in it
     E = _exact_ewald(s, 0.55, r_images=11.5, m_max=9, extra_dipole=U)
@@ -329,6 +331,10 @@ def test_oracle_polarizable_energy_matches_exact_ewald_with_thole_damping(small)
     Bc = _ladder(r, None, 'coul')
     uu = _pair_energy(d, ind_i, ind_j, None, Bc) + _pair_energy(d, ind_i, ind_j, None, Bh)
     dE = dE + uu[same].sum()
-    E_exact = (E + DIEL * dE + DIEL * (0.5 * (U * U).sum(1) / pol).sum()).item()
+    E_exact_t = E + DIEL * dE + DIEL * (0.5 * (U * U).sum(1) / pol).sum()
+    field_exact = torch.autograd.grad(E_exact_t, U)[0]
+    E_exact = E_exact_t.item()
+    ferr = (field_pme - field_exact).abs().max().item() / field_exact.abs().max().item()
+    assert ferr < 1e-6, ferr                                           # the SCF field dE/dU
     assert abs(dE.item() * DIEL) > 1e-4 * abs(E_exact)                 # the damping terms are 300x the tolerance below
     assert abs(E_pme - E_exact) < 2e-6 * abs(E_exact), (E_pme, E_exact, parts)
