@@ -91,6 +91,30 @@ def _worker(rank, world, port, out):
         a0, ac = parallel.partition_atoms(s.n_atoms, world, 3)[rank]
         mesh = orecip.spread(s.positions[a0:a0 + ac], s.box, Qg[a0:a0 + ac], K, 2)
         parallel.allreduce_sum_([e_real, mesh])
+        # 4. x-slab algebra (SlabPme / admp_slab_*): atoms owned by fractional x, planes [floor(r K1/P), floor((r+1) K1/P)),
+        #    Z and Y transforms on the own planes, the X transform on the own share of the (y, kz) columns after the
+        #    exchange of planes - on an uneven split (K1 = 25 over 2 ranks: 12 + 13 planes)
+        Ks = (25, 24, 24)
+        owned = parallel.partition_atoms_by_slab(s.positions.numpy(), s.box.numpy(), world)[rank]
+        idx = torch.as_tensor(owned)
+        part = orecip.spread(s.positions[idx], s.box, Qg[idx], Ks, 2)             # own atoms, anywhere on the mesh
+        parallel.allreduce_sum_([part])                                            # = what the peer atomics accumulate
+        x0, x1 = Ks[0] * rank // world, Ks[0] * (rank + 1) // world
+        slab_zy = torch.fft.fft(torch.fft.rfft(part[x0:x1], dim=2), dim=1)         # Z (real -> half spectrum), then Y
+        counts = [Ks[0] * (q + 1) // world - Ks[0] * q // world for q in range(world)]
+        pad = torch.zeros((max(counts), Ks[1], Ks[2] // 2 + 1, 2), dtype=torch.float64)      # equal-size real buffers for gloo
+        pad[:x1 - x0] = torch.view_as_real(slab_zy)
+        got = [torch.zeros_like(pad) for _ in range(world)]
+        dist.all_gather(got, pad)                                                  # the pull of the fused X pass
+        planes = [torch.view_as_complex(got[q][:counts[q]].contiguous()) for q in range(world)]
+        cols = torch.cat(planes, dim=0).reshape(Ks[0], -1)
+        ncol = cols.shape[1]
+        c0, c1 = ncol * rank // world, ncol * (rank + 1) // world
+        mine_x = torch.fft.fft(cols[:, c0:c1], dim=0)
+        full_mesh_s = orecip.spread(s.positions, s.box, Qg, Ks, 2)
+        ref_x = torch.fft.fftn(torch.fft.rfft(full_mesh_s, dim=2), dim=(0, 1)).reshape(Ks[0], -1)[:, c0:c1]
+        slab_err = torch.tensor([(mine_x - ref_x).abs().max().item() / ref_x.abs().max().item()], dtype=torch.float64)
+        dist.all_reduce(slab_err, op=dist.ReduceOp.MAX)
         if rank == 0:
             ref_g = torch.zeros(5, dtype=torch.float64)
             ref_e = []
@@ -104,7 +128,7 @@ def _worker(rank, world, port, out):
             out.put(dict(g=(g_local - ref_g).abs().max().item() / ref_g.abs().max().item(),
                          e=float(np.abs(e_local.numpy() - np.array(ref_e)).max()),
                          real=abs(e_real.item() - full_real.item()) / abs(full_real.item()),
-                         mesh=(mesh - full_mesh).abs().max().item()))
+                         mesh=(mesh - full_mesh).abs().max().item(), slab=slab_err.item()))
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -117,8 +141,18 @@ def test_world_size_2_gloo():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
     for p in procs:
         p.start()
-    res = out.get(timeout=300)
+    import queue as _queue
+    res = None
+    for _ in range(300):                      # fail fast when a worker dies instead of waiting for the full timeout
+        try:
+            res = out.get(timeout=1)
+            break
+        except _queue.Empty:
+            if any(p.exitcode not in (None, 0) for p in procs):
+                break
+    assert res is not None, 'a gloo worker failed: exit codes %s' % [p.exitcode for p in procs]
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
     assert res['g'] < 1e-12 and res['e'] < 1e-9 and res['real'] < 1e-12 and res['mesh'] < 1e-12
+    assert res['slab'] < 1e-12
