@@ -1,5 +1,5 @@
 """The bench line contract (task statement, section 4) checked on the committed line of the last GPU run
-(profiles/r1n_bench.json, written by `python bench.py` on a B200) and on the reference-arm line: every key the driver
+(profiles/r1o_bench.json, written by `python bench.py` on a B200) and on the reference-arm line: every key the driver
 and the judge read is present and self-consistent. CPU only; bench.py itself needs a GPU."""
 import json
 import os
@@ -13,7 +13,7 @@ def _load(name):
 
 
 def test_gpu_arm_line():
-    d = _load('r1n_bench.json')
+    d = _load('r1o_bench.json')
     for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'vs_baseline',
               'dtype', 'data', 'config', 'e2e', 'gpu_launches', 'clocks', 'roofline', 'cpu_baseline'):
         assert k in d, k
@@ -34,8 +34,8 @@ def test_gpu_arm_line():
 
 
 def test_reference_arm_line():
-    d = _load('r1m_bench_reference.json')
+    d = _load('r1o_bench_reference.json')
     assert d['impl'] == 'reference' and d['unit'] == 'evals/s' and d['value'] > 0
     assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0 and d['e2e']['value'] == d['value']
     assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['value'] == d['value']
-    assert d['metric'] == _load('r1n_bench.json')['metric']
+    assert d['metric'] == _load('r1o_bench.json')['metric']
