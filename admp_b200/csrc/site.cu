@@ -117,10 +117,16 @@ scf_field_kernel(int n, T kappa, const T* __restrict__ M, const T* __restrict__ 
 
 // Decision step of optimize_Uind (pme.py:133-143): test BEFORE the update; converging exactly on
 // the last iteration reports flag False. state: [0]=iter, [1]=do_update, [2]=final_pass,
-// [3]=n_cycle, [4]=converged, [5]=loop condition (mirrors the graph conditional handle).
+// [3]=n_cycle, [4]=converged, [5]=loop condition (mirrors the graph conditional handle), [7]=loop ended.
 __global__ void scf_decide_kernel(int32_t* __restrict__ state, double* __restrict__ scalars, int maxiter, double thresh,
                                   cudaGraphConditionalHandle handle, int use_handle, int refresh_in_loop) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (state[7]) {                       // the loop has already ended: a speculatively enqueued extra cycle (host-driven
+        state[1] = 0;                     // multi-GPU loop, admp_b200/parallel.py) must not touch U or the result
+        state[5] = 0;
+        if (use_handle) cudaGraphSetConditional(handle, 0);
+        return;
+    }
     int cond = 0;
     if (state[2]) {                       // this pass only refreshed the field/mesh after the last update
         state[1] = 0;
@@ -143,6 +149,7 @@ __global__ void scf_decide_kernel(int32_t* __restrict__ state, double* __restric
         }
     }
     state[5] = cond;
+    if (!cond) state[7] = 1;
     if (cond) {                           // re-arm the per-cycle accumulators for the next pass
         scalars[ADMP_S_MAXFIELD] = 0.0;
         scalars[ADMP_S_E_RECIP] = 0.0;

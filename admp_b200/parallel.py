@@ -493,7 +493,17 @@ class SlabPme:
             U = torch.zeros((n, 3), dtype=dt, device=dev) if U_init is None else prep(U_init).detach().clone()
             F = torch.zeros((n, 3), dtype=dt, device=dev)
             state = torch.zeros(8, dtype=torch.int32, device=dev)
-            for _ in range(maxiter + 1):
+            # The host drives the loop but never waits for the cycle it has just enqueued: cycle c + 1 is issued before the
+            # decision of cycle c is read back (pinned snapshot + event). If cycle c ended the loop, the extra cycle is a
+            # no-op for U and the SCF status (scf_decide_kernel's `ended` guard) and only recomputes the same potential.
+            # Worth it while a cycle is short enough for the host's enqueue latency to show (measured: 32k waters on 2 GPUs
+            # 86 -> 71 ms); on the largest meshes the one wasted cycle (1/31 of the GPU time) costs more than it hides.
+            speculate = (calc.K1 * calc.K2 * calc.K3) / self.P < 2.5e8
+            snaps = [torch.zeros(8, dtype=torch.int32).pin_memory() for _ in range(2)]
+            events = [torch.cuda.Event() for _ in range(2)]
+            pending = None
+            final = None
+            for c_it in range(maxiter + 2):
                 scal.zero_()
                 self._recip(work, U, scal, 0)
                 F.zero_()
@@ -513,10 +523,21 @@ class SlabPme:
                 with self._timed('scf_step'):
                     _lib.check(lib.admp_scf_step(c.handle, sp(), p(M), p(U), p(polt), p(F), int(maxiter), float(thresh), vir, p(state),
                                                  p(scal)))
-                    st = state.cpu()
-                if not int(st[5]):
-                    n_cycle, conv = int(st[3]), bool(st[4])
-                    break
+                    k = c_it % 2
+                    snaps[k].copy_(state, non_blocking=True)
+                    events[k].record()
+                    if not speculate:
+                        pending = k
+                    if pending is not None:
+                        events[pending].synchronize()
+                        if not int(snaps[pending][5]):
+                            final = snaps[pending].clone()
+                            break
+                    pending = k
+            if final is None:
+                events[pending].synchronize()
+                final = snaps[pending].clone()
+            n_cycle, conv = int(final[3]), bool(final[4])
             if want_virial:
                 scal.zero_()
                 self._recip(work, U, scal, vir)
