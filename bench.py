@@ -27,7 +27,8 @@ import time
 # frames in flight (config C4) use one lane stream + the SCF graph's capture / side streams per frame: with the default 8
 # hardware connections distinct streams share queues and some lane counts serialise (measured: 150-200 instead of 410 evals/s
 # at 3 lanes); harmless for the single-stream headline measurement. Must be set before CUDA initialises.
-os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
+if int(os.environ.get('WORLD_SIZE', '1')) == 1:          # the frames-in-flight measurement only runs on one GPU
+    os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
