@@ -95,3 +95,26 @@ def test_dispersion_matches_direct_lattice_sum(sysm):
         r2[np.all(sh == 0, axis=1), i] = np.inf
         tot += 0.5 * np.sum(c6[i] * c6[None, :] / r2 ** 3)
     assert abs(E - tot) < 2e-3 * abs(tot)           # shell truncation of the brute-force sum
+
+
+def test_c8_and_c10_dispersion_match_direct_lattice_sums(sysm):
+    """The r^-8 and r^-10 parts of the dispersion PME (admp/disp_pme.py:80-279, Ck_8 / Ck_10 of admp/recip.py:445-462),
+    isolated as differences of pmax = 10, 8, 6 evaluations, against brute-force image sums; these converge absolutely
+    and fast (shell truncation at 4 L < 1e-6), so the comparison is tight."""
+    s, _, _ = sysm
+    pairs, _ = pairlist.build_pairs(s.positions.numpy(), s.box.numpy(), 4.94)
+    m1 = torch.ones(5, dtype=torch.float64)
+    E = {p: energy_disp_pme(s.positions, s.box, pairs, s.c_list, m1, s.covalent_map, 0.9, 40, 40, 40, p).item() for p in (6, 8, 10)}
+    pos, L = s.positions.numpy(), s.box[0, 0].item()
+    R = 4
+    sh = np.stack(np.meshgrid(*[np.arange(-R, R + 1)] * 3, indexing='ij'), -1).reshape(-1, 3) * L
+    home = np.all(sh == 0, axis=1)
+    for col, p, part in ((1, 8, E[8] - E[6]), (2, 10, E[10] - E[8])):
+        c = s.c_list[:, col].numpy()
+        tot = 0.0
+        for i in range(s.n_atoms):
+            d = pos[None, :, :] - pos[i][None, None, :] + sh[:, None, :]
+            r2 = (d ** 2).sum(-1)
+            r2[home, i] = np.inf
+            tot += 0.5 * np.sum(c[i] * c[None, :] / r2 ** (p // 2))
+        assert abs(part - tot) < 1e-5 * abs(tot), (p, part, tot)
