@@ -159,14 +159,21 @@ def _safe_sqrt_ksq(ksq):
     return ksq
 
 
-def pme_recip(positions, box, Q, kappa, K, lmax, kind=1, gamma=False, jacobian='correct',
-              korder='natural'):
+# Module-level defaults of the two documented divergences; tests flip them to 'reference' to reproduce the
+# reference's dE/dbox entry by entry (tests/test_reference_source.py).
+DEFAULTS = {'jacobian': 'correct', 'korder': 'natural'}
+
+
+def pme_recip(positions, box, Q, kappa, K, lmax, kind=1, gamma=False, jacobian=None,
+              korder=None):
     """recip.py:394-426 (the body of the generated ``pme_recip`` closure).
 
     kind: 1 (Coulomb, times DIELECTRIC, gamma point dropped) or 6/8/10 (dispersion,
     gamma point kept).  ``korder='reference'`` reproduces the meshgrid(kz,kx,ky)
     permutation of recip.py:340 (only meaningful for K1=K2=K3).
     """
+    jacobian = DEFAULTS['jacobian'] if jacobian is None else jacobian
+    korder = DEFAULTS['korder'] if korder is None else korder
     K1, K2, K3 = int(K[0]), int(K[1]), int(K[2])
     mesh = spread(positions, box, Q, (K1, K2, K3), lmax, jacobian)
     dt = positions.dtype
