@@ -54,6 +54,9 @@ class Context:
 
     def set_pme(self, kappa, K1, K2, K3, lmax):
         _lib.check(self.lib.admp_ctx_set_pme(self.handle, float(kappa), int(K1), int(K2), int(K3), int(lmax)))
+        if settings.KVEC_ORDER not in ('natural', 'reference'):
+            raise ValueError("settings.KVEC_ORDER must be 'natural' or 'reference'")
+        _lib.check(self.lib.admp_ctx_set_kvec_order(self.handle, 1 if settings.KVEC_ORDER == 'reference' else 0))
 
     def set_topology(self, n_atoms, axis_type=None, axis_indices=None, covalent_map=None):
         at = ai = off = idx = nb = None

@@ -46,6 +46,7 @@ struct admp_ctx {
     double kappa = 0.0;
     int K[3] = {0, 0, 0};
     int lmax = 2;
+    int kvec_ref = 0;               // admp_ctx_set_kvec_order
     int n_atoms = 0;
     // topology
     int32_t *axis_type = nullptr, *axis_idx = nullptr, *cov_off = nullptr, *cov_idx = nullptr;
@@ -94,7 +95,12 @@ struct admp_ctx {
 };
 
 extern "C" const char* admp_last_error(void) { return g_err.c_str(); }
-extern "C" int admp_version(void) { return 100; }
+extern "C" int admp_version(void) { return 200; }
+extern "C" int admp_ctx_set_kvec_order(admp_ctx* c, int reference) {
+    if (!c) return fail("admp_ctx_set_kvec_order: null context");
+    c->kvec_ref = reference ? 1 : 0;
+    return 0;
+}
 
 static void drop_graph(admp_ctx* c) {
     if (c->gexec) cudaGraphExecDestroy(c->gexec);
@@ -726,7 +732,7 @@ extern "C" int admp_scf_step(admp_ctx* c, void* stream, const void* M, void* U, 
 }
 extern "C" int admp_virial_finalize(admp_ctx* c, void* stream, double* scalars) {
     if (need(c, true, false)) return 1;
-    launch_virial_finalize((cudaStream_t)stream, c->box, scalars);
+    launch_virial_finalize((cudaStream_t)stream, c->box, scalars, c->kvec_ref);
     CKLAUNCH();
     return 0;
 }
@@ -890,7 +896,7 @@ extern "C" int admp_pme_eval(admp_ctx* c, void* stream, const void* pos, const v
     if (flags & ADMP_WANT_GRAD) {
         DISPATCH(c, launch_frames_bwd, st, n, c->lmax, c->box, c->s_pos, c->axis_type, c->axis_idx, Ql, c->G, dQl, dpos, c->scal, want_vir);
     }
-    if (want_vir) launch_virial_finalize(st, c->box, c->scal);
+    if (want_vir) launch_virial_finalize(st, c->box, c->scal, c->kvec_ref);
     CKLAUNCH();
     CK(cudaMemcpyAsync(scalars, c->scal, sizeof(double) * ADMP_S_COUNT, cudaMemcpyDeviceToDevice, st));
     (void)nh;
@@ -927,7 +933,7 @@ extern "C" int admp_disp_eval(admp_ctx* c, void* stream, const void* pos, const 
         }
     }
     DISPATCH(c, launch_disp_self, st, n, c->kappa, pmax, c_list, f, dc, c->scal);
-    if (f & ADMP_WANT_VIRIAL) launch_virial_finalize(st, c->box, c->scal);
+    if (f & ADMP_WANT_VIRIAL) launch_virial_finalize(st, c->box, c->scal, c->kvec_ref);
     CKLAUNCH();
     CK(cudaMemcpyAsync(scalars, c->scal, sizeof(double) * ADMP_S_COUNT, cudaMemcpyDeviceToDevice, st));
     return 0;

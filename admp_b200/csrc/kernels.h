@@ -87,7 +87,7 @@ void launch_scf_decide(cudaStream_t st, int32_t* state, double* scalars, int max
                        cudaGraphConditionalHandle handle, int use_handle);
 template <typename T>
 void launch_scf_update(cudaStream_t st, int n, const int32_t* state, void* F, const void* pol, void* U, int zero_F);
-void launch_virial_finalize(cudaStream_t st, const BoxInfo* B, double* scalars);
+void launch_virial_finalize(cudaStream_t st, const BoxInfo* B, double* scalars, int kvec_ref);
 
 // nblist.cu
 struct NbWork {

@@ -176,11 +176,19 @@ scf_update_kernel(int n, const int32_t* __restrict__ state, T* __restrict__ F, c
 
 // dE/dbox (3x3, row-major) += reciprocal-space part assembled from the accumulators:
 //   -inv^T (W^T Nstar)  [spread/gather, W = dE/dNstar]  - 2 T inv^T - E_recip inv^T  [k^2 and V in C_k]
-__global__ void virial_finalize_kernel(const BoxInfo* __restrict__ B, double* __restrict__ s) {
+__global__ void virial_finalize_kernel(const BoxInfo* __restrict__ B, double* __restrict__ s, int kvec_ref) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const double* W = s + ADMP_S_DNSTAR;
     const double* tk = s + ADMP_S_TK;
-    const double T[9] = {tk[0], tk[1], tk[2], tk[1], tk[3], tk[4], tk[2], tk[4], tk[5]};
+    const double Tn[9] = {tk[0], tk[1], tk[2], tk[1], tk[3], tk[4], tk[2], tk[4], tk[5]};
+    double T[9];
+    // kvec_ref: the reference's k table is built with meshgrid(kz, kx, ky) (admp/recip.py:339-341), which pairs
+    // k-vector component 0 with mesh axis 1 and vice versa: T_ref[a][b] = T[p(a)][p(b)], p = (1, 0, 2).
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+            const int pa = kvec_ref ? (a == 0 ? 1 : (a == 1 ? 0 : 2)) : a, pb = kvec_ref ? (b == 0 ? 1 : (b == 1 ? 0 : 2)) : b;
+            T[3 * a + b] = Tn[3 * pa + pb];
+        }
     const double E = s[ADMP_S_E_RECIP];
     double Mm[9];
     for (int c = 0; c < 3; ++c)
@@ -193,7 +201,9 @@ __global__ void virial_finalize_kernel(const BoxInfo* __restrict__ B, double* __
             s[ADMP_S_DBOX + 3 * a + b] += v;
         }
 }
-void launch_virial_finalize(cudaStream_t st, const BoxInfo* B, double* scalars) { virial_finalize_kernel<<<1, 32, 0, st>>>(B, scalars); }
+void launch_virial_finalize(cudaStream_t st, const BoxInfo* B, double* scalars, int kvec_ref) {
+    virial_finalize_kernel<<<1, 32, 0, st>>>(B, scalars, kvec_ref);
+}
 
 template <typename T>
 void launch_box_setup(cudaStream_t st, const void* box, BoxInfo* B, int K1, int K2, int K3) {

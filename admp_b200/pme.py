@@ -142,8 +142,9 @@ class ADMPPmeForce:
             self._ctx.set_topology(self.n_atoms, at, ai, self.covalent_map)
             self._topology_set = True
         if self.lpol:
-            if self.U_ind is None:
-                self.U_ind = torch.zeros((self.n_atoms, 3), dtype=self._dtype, device=self._ctx.device)
+            # admp/pme.py:79: every refresh re-creates the zeros array that is both self.U_ind and the U_init default
+            self.U_ind = torch.zeros((self.n_atoms, 3), dtype=self._dtype, device=self._ctx.device)
+            self._scf = None
             self.get_energy = self._get_energy_pol
             self.get_forces = self._get_forces_pol
         else:
@@ -177,6 +178,19 @@ class ADMPPmeForce:
         if Q_local.shape != (n, nh):
             raise ValueError('Q_local must be (%d, %d) for lmax = %d' % (n, nh, self.lmax))
         polz = pol is not None
+        if tuple(box.shape) != (3, 3):
+            raise ValueError('box must be (3, 3)')
+        if mScales.shape != (5,):
+            raise ValueError('mScales must hold exactly 5 entries (1-2 ... 1-6; the last doubles as the non-bonded scale)')
+        if polz:
+            if pol.shape != (n,) or tholes.shape != (n,):
+                raise ValueError('pol and tholes must be (%d,)' % n)
+            if pScales.shape != (5,):
+                raise ValueError('pScales must hold exactly 5 entries')
+            if U is not None and tuple(U.shape) != (n, 3):
+                raise ValueError('Uind_global / U_init must be (%d, 3)' % n)
+            if do_scf and int(settings.MAX_N_POL if maxiter is None else maxiter) < 1:
+                raise ValueError('maxiter must be >= 1')
         r = EvalResult()
         r.scalars = torch.empty(_lib.S_COUNT, dtype=torch.float64, device=dev)
         want_grad = bool(flags & _lib.WANT_GRAD)
@@ -259,7 +273,7 @@ class ADMPPmeForce:
         positions, box, Q_local, pol, tholes, mScales, pScales = map(
             self._prep, (positions, box, Q_local, pol, tholes, mScales, pScales))
         pairs = pairs_to_dev(pairs, self._ctx.device)
-        U0 = self.U_ind if U_init is None else self._prep(U_init).detach()
+        U0 = None if U_init is None else self._prep(U_init).detach()   # the default is the zeros array bound at closure creation (pme.py:79-81), never the last result
         E = _PmeFunction.apply(self, pairs, True, U0, positions, box, Q_local, None, pol, tholes, mScales, pScales)
         return E
 
@@ -267,7 +281,7 @@ class ADMPPmeForce:
         positions, box, Q_local, pol, tholes, mScales, pScales = (
             self._prep(x).detach() for x in (positions, box, Q_local, pol, tholes, mScales, pScales))
         pairs = pairs_to_dev(pairs, self._ctx.device)
-        U0 = self.U_ind if U_init is None else self._prep(U_init).detach()
+        U0 = None if U_init is None else self._prep(U_init).detach()   # the default is the zeros array bound at closure creation (pme.py:79-81), never the last result
         r = self._eval(positions, box, pairs, Q_local, U0, pol, tholes, mScales, pScales, _lib.WANT_GRAD, True)
         return r.energy.to(self._dtype), r.dpos
 
@@ -280,7 +294,7 @@ class ADMPPmeForce:
         fl = _lib.WANT_GRAD | _lib.WANT_VIRIAL
         if self.lpol:
             pol, tholes, mScales, pScales = (self._prep(x).detach() for x in rest[:4])
-            U0 = self.U_ind if U_init is None else self._prep(U_init).detach()
+            U0 = None if U_init is None else self._prep(U_init).detach()   # the default is the zeros array bound at closure creation (pme.py:79-81), never the last result
             r = self._eval(positions, box, pairs, Q_local, U0, pol, tholes, mScales, pScales, fl, True)
         else:
             mScales = self._prep(rest[0]).detach()

@@ -12,6 +12,14 @@ POL_CONV = 10.0   # gradient convergence thresh for induced dipoles
 MAX_N_POL = 30    # maximum number of cycles for optimizing induced dipoles
 
 
+# Convention of the k-space part of dE/dbox (no counterpart in admp/settings.py). 'natural': component i of a k-vector
+# belongs to mesh axis i - the chain-rule-correct virial. 'reference': the reference's k table (admp/recip.py:339-341,
+# meshgrid(kz, kx, ky)), which exchanges axes 0 and 1 in dk^2/dbox; on cubic cells with K1=K2=K3 this reproduces the
+# diagonal of the reference's jax.grad(..., argnums=box) entry by entry. Read when a calculator (re)builds its plans
+# (constructor / update_env / refresh_calculators). Energies, forces and all other gradients are unaffected.
+KVEC_ORDER = 'natural'
+
+
 def jit_condition(*args, **kwargs):
     """admp/settings.py:12-18: a decorator factory; a no-op here."""
     def deco(func):

@@ -79,6 +79,12 @@ int admp_ctx_set_pme(admp_ctx* ctx, double kappa, int K1, int K2, int K3, int lm
 int admp_ctx_set_topology(admp_ctx* ctx, int n_atoms, const int32_t* axis_type,
                           const int32_t* axis_indices, const int32_t* cov_offsets,
                           const int32_t* cov_index, const int8_t* cov_nbonds);
+/* k-vector convention of the k-space virial term. 0 (default): component i of k belongs to mesh axis i (the
+ * chain-rule-correct dE/dbox). 1: the reference's table, built with meshgrid(kz, kx, ky) (admp/recip.py:339-341),
+ * which exchanges the roles of axes 0 and 1 in dk^2/dbox; on a cubic cell with K1 = K2 = K3 (the only case in which
+ * the reference is self-consistent) this reproduces the diagonal of jax.grad(energy, argnums=box) entry by entry.
+ * Energies, forces and every other gradient do not depend on it. */
+int admp_ctx_set_kvec_order(admp_ctx* ctx, int reference);
 int64_t admp_ctx_workspace_bytes(const admp_ctx* ctx);
 /* 1 when optimize_Uind runs as the device-resident CUDA-graph WHILE loop, 0 when the
  * host-synchronised loop is in use (ADMP_SCF_HOSTSYNC or graph construction failed). */

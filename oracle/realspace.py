@@ -368,7 +368,8 @@ class OraclePmeForce:
                               self.kappa, self.K1, self.K2, self.K3, self.lmax, False, parts)
         pol, tholes, mScales, pScales, dScales = rest
         if U_init is None:
-            U_init = self.U_ind
+            # pme.py:81: the default is the zeros array bound when the closure was created, NOT the last result
+            U_init = torch.zeros(self.n_atoms, 3, dtype=torch.float64)
         self.U_ind, self.lconverg, self.n_cycle = self.optimize_Uind(
             positions, box, pairs, Q_local, pol, tholes, mScales, pScales, dScales, U_init=U_init)
         return self.energy_fn(positions, box, pairs, Q_local, self.U_ind, pol, tholes,
