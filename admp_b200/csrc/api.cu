@@ -67,8 +67,6 @@ struct admp_ctx {
     std::string fft_note;
     // per-atom workspaces and staged inputs of admp_pme_eval
     void *M = nullptr, *G = nullptr, *Fscf = nullptr, *rec = nullptr;
-    int8_t* r_sidx = nullptr;       // scale index per row for admp_pme_real (caller-owned pair list)
-    int64_t r_sidx_cap = 0;
     void *s_pos = nullptr, *s_U = nullptr, *s_pol = nullptr, *s_th = nullptr, *s_mS = nullptr, *s_pS = nullptr, *s_box = nullptr;
     int32_t* s_pairs = nullptr;
     int8_t* s_sidx = nullptr;       // scale index per staged pair row (-1: row not evaluated)
@@ -91,11 +89,29 @@ struct admp_ctx {
     SlabAux slab_aux = {};
     // neighbour list
     NbWork nb = {};
+    // cluster pair tiles (pair_cluster.cu)
+    ClusterWork cw = {};
+    int cluster_force = 0;          // ADMP_PAIR_CLUSTER: 0 auto, 1 always (when the row order allows), -1 never
     size_t ws_bytes = 0;
 };
 
 extern "C" const char* admp_last_error(void) { return g_err.c_str(); }
 extern "C" int admp_version(void) { return 200; }
+static void drop_graph(admp_ctx* c);
+extern "C" int admp_ctx_pair_cluster_active(admp_ctx* c) {
+    if (!c || !c->cw.state) return -1;
+    int32_t h[4] = {0, 0, 0, 0};
+    cudaSetDevice(c->device);
+    if (cudaMemcpy(h, c->cw.state, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;   // synchronises: tests / tools only
+    return h[2];
+}
+extern "C" int admp_ctx_set_pair_cluster(admp_ctx* c, int force, int min_rows_per_cluster) {
+    if (!c) return fail("admp_ctx_set_pair_cluster: null context");
+    c->cluster_force = force > 0 ? 1 : (force < 0 ? -1 : 0);
+    if (min_rows_per_cluster > 0) c->cw.min_rows_per_cluster = min_rows_per_cluster;
+    drop_graph(c);
+    return 0;
+}
 extern "C" int admp_ctx_set_kvec_order(admp_ctx* c, int reference) {
     if (!c) return fail("admp_ctx_set_kvec_order: null context");
     c->kvec_ref = reference ? 1 : 0;
@@ -131,6 +147,11 @@ extern "C" int admp_ctx_create(admp_ctx** out, int device, int dtype) {
     CK(cudaMalloc(&c->box, sizeof(BoxInfo)));
     CK(cudaMalloc(&c->scal, sizeof(double) * ADMP_S_COUNT));
     CK(cudaMalloc(&c->state, sizeof(int32_t) * 8));
+    CK(cudaMalloc(&c->cw.state, sizeof(int32_t) * 4));
+    CK(cudaMemset(c->cw.state, 0, sizeof(int32_t) * 4));
+    c->cw.min_rows_per_cluster = 96;
+    if (const char* e = getenv("ADMP_PAIR_CLUSTER")) c->cluster_force = atoi(e) > 0 ? 1 : (atoi(e) < 0 || e[0] == '0' ? -1 : 0);
+    if (const char* e = getenv("ADMP_PAIR_CLUSTER_MINROWS")) c->cw.min_rows_per_cluster = atoi(e);
     CK(cudaMalloc(&c->s_mS, 8 * 8));
     CK(cudaMalloc(&c->s_pS, 8 * 8));
     CK(cudaMalloc(&c->s_box, 9 * 8));
@@ -181,6 +202,8 @@ static int ensure_cufft(admp_ctx* c) {
 static void free_atoms(admp_ctx* c) {
     dfree(c->M); dfree(c->G); dfree(c->Fscf); dfree(c->rec); dfree(c->s_pos); dfree(c->s_U); dfree(c->s_pol); dfree(c->s_th);
     dfree(c->axis_type); dfree(c->axis_idx); dfree(c->cov_off); dfree(c->cov_idx); dfree(c->cov_nb);
+    dfree(c->cw.cl_of); dfree(c->cw.cl_first); dfree(c->cw.cl_size); dfree(c->cw.row_start); dfree(c->cw.cl_extra);
+    c->cw.n_clusters = 0;
 }
 
 extern "C" int admp_ctx_destroy(admp_ctx* c) {
@@ -189,7 +212,7 @@ extern "C" int admp_ctx_destroy(admp_ctx* c) {
     drop_graph(c);
     free_recip(c);
     free_atoms(c);
-    dfree(c->s_pairs); dfree(c->s_sidx); dfree(c->r_sidx); dfree(c->box); dfree(c->scal); dfree(c->state); dfree(c->s_mS); dfree(c->s_pS); dfree(c->s_box);
+    dfree(c->s_pairs); dfree(c->s_sidx); dfree(c->cw.ent_i); dfree(c->cw.ent_m); dfree(c->cw.state); dfree(c->box); dfree(c->scal); dfree(c->state); dfree(c->s_mS); dfree(c->s_pS); dfree(c->s_box);
     dfree(c->nb.cell_of); dfree(c->nb.cell_count); dfree(c->nb.cell_start); dfree(c->nb.sorted); dfree(c->nb.nbr_count); dfree(c->nb.nbr_start);
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
@@ -326,6 +349,36 @@ extern "C" int admp_ctx_set_topology(admp_ctx* c, int n, const int32_t* axis_typ
         CK(cudaMemcpy(c->cov_idx, cov_index, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c->cov_nb, cov_nbonds, nnz, cudaMemcpyHostToDevice));
     }
+    // j-clusters of the cluster pair kernel: runs of consecutive atoms (at most 4) in which every atom is covalently
+    // listed with an earlier member - a water molecule, a methyl group ... (singletons without a covalent map)
+    {
+        std::vector<int32_t> cl_of(n), cl_first, cl_size;
+        int a = 0;
+        while (a < n) {
+            int sz = 1;
+            while (sz < 4 && a + sz < n && cov_offsets && cov_index) {
+                const int b = a + sz;
+                bool bonded = false;
+                for (int k = cov_offsets[b]; k < cov_offsets[b + 1] && !bonded; ++k) bonded = (cov_index[k] >= a && cov_index[k] < b);
+                if (!bonded) break;
+                ++sz;
+            }
+            for (int k = 0; k < sz; ++k) cl_of[a + k] = (int32_t)cl_first.size();
+            cl_first.push_back(a);
+            cl_size.push_back(sz);
+            a += sz;
+        }
+        const int nc = (int)cl_first.size();
+        c->cw.n_clusters = nc;
+        CK(cudaMalloc(&c->cw.cl_of, sizeof(int32_t) * n));
+        CK(cudaMalloc(&c->cw.cl_first, sizeof(int32_t) * nc));
+        CK(cudaMalloc(&c->cw.cl_size, sizeof(int32_t) * nc));
+        CK(cudaMalloc(&c->cw.cl_extra, sizeof(int32_t) * nc));
+        CK(cudaMalloc(&c->cw.row_start, sizeof(int32_t) * ((size_t)n + 2)));
+        CK(cudaMemcpy(c->cw.cl_of, cl_of.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->cw.cl_first, cl_first.data(), sizeof(int32_t) * nc, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->cw.cl_size, cl_size.data(), sizeof(int32_t) * nc, cudaMemcpyHostToDevice));
+    }
     return 0;
 }
 
@@ -417,6 +470,7 @@ extern "C" int admp_rotate(admp_ctx* c, void* stream, int64_t n, int lmax, int t
     return 0;
 }
 
+static int ensure_pairs(admp_ctx* c, int64_t n_rows);
 extern "C" int admp_pme_real(admp_ctx* c, void* stream, const void* pos, const void* box, const int32_t* pairs, int64_t n_rows,
                              const void* M, const void* U, const void* pol, const void* tholes, const void* mScales,
                              const void* pScales, int mode, uint32_t flags, void* dpos, void* G, void* F, void* dpol,
@@ -427,15 +481,16 @@ extern "C" int admp_pme_real(admp_ctx* c, void* stream, const void* pos, const v
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(c->device));
     DISPATCH(c, launch_box_setup, st, box, c->box, c->K[0], c->K[1], c->K[2]);
-    // scale index per row once per call (one byte per row) instead of a covalent-CSR walk inside the pair loop
-    if (n_rows > c->r_sidx_cap) {
-        dfree(c->r_sidx);
-        c->r_sidx_cap = n_rows + n_rows / 4 + 1024;
-        CK(cudaMalloc(&c->r_sidx, (size_t)c->r_sidx_cap));
-    }
-    launch_pair_scale(st, n_rows, c->n_atoms, pairs, c->cov_off, c->cov_idx, c->cov_nb, c->r_sidx);
-    DISPATCH(c, launch_pme_pair, st, n_rows, c->n_atoms, c->box, c->kappa, pos, pairs, c->r_sidx, c->cov_off, c->cov_idx, c->cov_nb, M, U, pol,
-             tholes, mScales, pScales, mode, flags, dpos, G, F, dpol, dtholes, scalars, c->rec);
+    // scale index per row once per call (one byte per row) instead of a covalent-CSR walk inside the pair loop, then the
+    // cluster tiles when the list qualifies (pair_cluster.cu); exactly one of the two pair kernels does the work
+    if (ensure_pairs(c, n_rows)) return 1;
+    launch_pair_scale(st, n_rows, c->n_atoms, pairs, c->cov_off, c->cov_idx, c->cov_nb, c->s_sidx);
+    launch_cluster_prepare(st, n_rows, c->n_atoms, c->cw.n_clusters, pairs, c->s_sidx, c->cw, c->cluster_force);
+    if (mode == 1) DISPATCH(c, launch_pair_pack, st, c->n_atoms, pos, M, U, pol, tholes, c->rec);
+    DISPATCH(c, launch_pme_pair, st, n_rows, c->n_atoms, c->box, c->kappa, pos, pairs, c->s_sidx, c->cov_off, c->cov_idx, c->cov_nb, M, U, pol,
+             tholes, mScales, pScales, mode, flags, dpos, G, F, dpol, dtholes, scalars, c->rec, c->cw.state);
+    DISPATCH(c, launch_pme_cluster, st, c->cw.n_clusters, c->box, c->kappa, c->cw, c->rec, U, mScales, pScales, mode, flags, dpos, G, F, dpol,
+             dtholes, scalars);
     CKLAUNCH();
     return 0;
 }
@@ -750,7 +805,10 @@ static int scf_body(admp_ctx* c, cudaStream_t st, int maxiter, double thresh, ui
     CK(cudaEventRecord(c->ev_fork, st));
     CK(cudaStreamWaitEvent(c->side_stream, c->ev_fork, 0));
     DISPATCH(c, launch_pme_pair, c->side_stream, c->pairs_cap, c->n_atoms, c->box, c->kappa, c->s_pos, c->s_pairs, c->s_sidx, c->cov_off, c->cov_idx,
-             c->cov_nb, c->M, c->s_U, c->s_pol, c->s_th, c->s_mS, c->s_pS, 1, 0u, nullptr, nullptr, c->Fscf, nullptr, nullptr, c->scal, c->rec);
+             c->cov_nb, c->M, c->s_U, c->s_pol, c->s_th, c->s_mS, c->s_pS, 1, 0u, nullptr, nullptr, c->Fscf, nullptr, nullptr, c->scal, c->rec,
+             c->cw.state);
+    DISPATCH(c, launch_pme_cluster, c->side_stream, c->cw.n_clusters, c->box, c->kappa, c->cw, c->rec, c->s_U, c->s_mS, c->s_pS, 1, 0u, nullptr,
+             nullptr, c->Fscf, nullptr, nullptr, c->scal);
     CK(cudaEventRecord(c->ev_join, c->side_stream));
     if (recip_field(c, st, c->s_pos, c->M, 10, 10, c->s_U, ADMP_CK_COULOMB, c->scal, 0, false)) return 1;
     DISPATCH(c, launch_gather, st, c->n_atoms, c->box, c->s_pos, c->M, 10, 10, c->s_U, c->mesh, 1, 0u, nullptr, nullptr, 10, c->Fscf, c->scal);
@@ -822,9 +880,13 @@ static int ensure_pairs(admp_ctx* c, int64_t n_rows) {
     drop_graph(c);
     dfree(c->s_pairs);
     dfree(c->s_sidx);
+    dfree(c->cw.ent_i);
+    dfree(c->cw.ent_m);
     int64_t cap = n_rows + n_rows / 4 + 1024;
     CK(cudaMalloc(&c->s_pairs, sizeof(int32_t) * 2 * cap));
     CK(cudaMalloc(&c->s_sidx, (size_t)cap));
+    CK(cudaMalloc(&c->cw.ent_i, sizeof(int32_t) * cap));
+    CK(cudaMalloc(&c->cw.ent_m, sizeof(uint32_t) * cap));
     c->pairs_cap = cap;
     return 0;
 }
@@ -851,6 +913,7 @@ extern "C" int admp_pme_eval(admp_ctx* c, void* stream, const void* pos, const v
     CK(cudaMemsetAsync(c->s_pairs, 0, sizeof(int32_t) * 2 * c->pairs_cap, st));        // (0,0) rows are skipped (i<j fails)
     if (n_rows > 0) CK(cudaMemcpyAsync(c->s_pairs, pairs, sizeof(int32_t) * 2 * n_rows, cudaMemcpyDeviceToDevice, st));
     launch_pair_scale(st, c->pairs_cap, n, c->s_pairs, c->cov_off, c->cov_idx, c->cov_nb, c->s_sidx);
+    launch_cluster_prepare(st, c->pairs_cap, n, c->cw.n_clusters, c->s_pairs, c->s_sidx, c->cw, c->cluster_force);
     CK(cudaMemcpyAsync(c->s_mS, mScales, 5 * w, cudaMemcpyDeviceToDevice, st));
     if (polz) {
         CK(cudaMemcpyAsync(c->s_U, U_io, (size_t)n * 3 * w, cudaMemcpyDeviceToDevice, st));
@@ -871,6 +934,8 @@ extern "C" int admp_pme_eval(admp_ctx* c, void* stream, const void* pos, const v
     const int want_vir = (flags & ADMP_WANT_VIRIAL) ? 1 : 0;
     if (polz && (flags & ADMP_SCF)) {
         CK(cudaMemsetAsync(c->Fscf, 0, (size_t)n * 3 * w, st));
+        // packed records of the cluster field kernel (it reads the current U from s_U, everything else from here)
+        DISPATCH(c, launch_pair_pack, st, n, c->s_pos, c->M, c->s_U, c->s_pol, c->s_th, c->rec);
         if (run_scf(c, st, maxiter, thresh, flags)) return 1;
         if (want_vir) {
             // final reciprocal pass on the converged / last-updated U with the k-space virial sums
@@ -891,7 +956,9 @@ extern "C" int admp_pme_eval(admp_ctx* c, void* stream, const void* pos, const v
     }
     DISPATCH(c, launch_pme_pair, st, c->pairs_cap, n, c->box, c->kappa, c->s_pos, c->s_pairs, c->s_sidx, c->cov_off, c->cov_idx, c->cov_nb, c->M, Uf,
              polz ? c->s_pol : nullptr, polz ? c->s_th : nullptr, c->s_mS, polz ? c->s_pS : nullptr, 0, f, dpos, c->G, F, dpol, dtholes, c->scal,
-             c->rec);
+             c->rec, c->cw.state);
+    DISPATCH(c, launch_pme_cluster, st, c->cw.n_clusters, c->box, c->kappa, c->cw, c->rec, Uf, c->s_mS, polz ? c->s_pS : nullptr, 0, f, dpos, c->G,
+             F, dpol, dtholes, c->scal);
     DISPATCH(c, launch_self, st, n, c->kappa, c->M, Uf, polz ? c->s_pol : nullptr, f, c->G, F, dpol, c->scal);
     if (flags & ADMP_WANT_GRAD) {
         DISPATCH(c, launch_frames_bwd, st, n, c->lmax, c->box, c->s_pos, c->axis_type, c->axis_idx, Ql, c->G, dQl, dpos, c->scal, want_vir);

@@ -23,8 +23,28 @@ template <typename T>
 void launch_pme_pair(cudaStream_t st, int64_t n_rows, int n_atoms, const BoxInfo* B, double kappa, const void* pos,
                      const int32_t* pairs, const int8_t* sidx, const int32_t* cov_off, const int32_t* cov_idx, const int8_t* cov_nb,
                      const void* M, const void* U, const void* pol, const void* tholes, const void* mS, const void* pS,
-                     int mode, uint32_t flags, void* dpos, void* G, void* F, void* dpol, void* dth, double* scalars, void* rec);
+                     int mode, uint32_t flags, void* dpos, void* G, void* F, void* dpol, void* dth, double* scalars, void* rec,
+                     const int32_t* sel = nullptr);      // sel: cluster-kernel selector (ClusterWork::state); the kernel is a no-op when sel[2] != 0
 size_t pair_record_bytes(int dtype_bytes);        // per-atom record of the staged pair kernel (workspace `rec`)
+template <typename T>
+void launch_pair_pack(cudaStream_t st, int n, const void* pos, const void* M, const void* U, const void* pol, const void* tholes, void* rec);
+
+// pair_cluster.cu - j-cluster x i-lane tiles built from the caller's pair rows (dense, (j, i)-sorted lists)
+struct ClusterWork {
+    int32_t *cl_of, *cl_first, *cl_size;   // per atom / per cluster (host-built from the covalent map at set_topology)
+    int32_t* row_start;                    // n_atoms + 1: first row of every j
+    int32_t* ent_i;                        // pairs_cap: i atom of every tile entry
+    uint32_t* ent_m;                       // pairs_cap: 4 bits per cluster slot: listed, scale index
+    int32_t* cl_extra;                     // n_clusters: entries beyond slot 0's own list
+    int32_t* state;                        // [0] bad order, [1] live rows, [2] cluster kernel selected
+    int n_clusters, min_rows_per_cluster;
+};
+void launch_cluster_prepare(cudaStream_t st, int64_t n_rows, int n_atoms, int n_clusters, const int32_t* pairs, const int8_t* sidx,
+                            const ClusterWork& w, int force);
+template <typename T>
+void launch_pme_cluster(cudaStream_t st, int n_clusters, const BoxInfo* B, double kappa, const ClusterWork& w, const void* rec,
+                        const void* U, const void* mS, const void* pS, int mode, uint32_t flags, void* dpos, void* G, void* F,
+                        void* dpol, void* dth, double* scalars);
 template <typename T>
 void launch_disp_pair(cudaStream_t st, int64_t n_rows, int n_atoms, const BoxInfo* B, double kappa, int pmax, const void* pos,
                       const int32_t* pairs, const int32_t* cov_off, const int32_t* cov_idx, const int8_t* cov_nb,

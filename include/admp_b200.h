@@ -85,6 +85,14 @@ int admp_ctx_set_topology(admp_ctx* ctx, int n_atoms, const int32_t* axis_type,
  * the reference is self-consistent) this reproduces the diagonal of jax.grad(energy, argnums=box) entry by entry.
  * Energies, forces and every other gradient do not depend on it. */
 int admp_ctx_set_kvec_order(admp_ctx* ctx, int reference);
+/* Real-space pair traversal of admp_pme_eval. Two kernels evaluate the caller's pair rows (identical pair set, identical
+ * arithmetic): the flat one (one row per thread, any row order) and the cluster one (a warp per j-cluster = bonded group of
+ * <= 4 consecutive atoms, lanes = the union of the cluster's i neighbours; needs rows grouped by j with ascending i - the order
+ * admp_nblist_build / jax_md's OrderedSparse produce). force: 0 = choose on the device (cluster when the rows are ordered and the
+ * list holds >= min_rows_per_cluster rows per cluster, default 96), 1 = cluster whenever the order allows, -1 = flat.
+ * admp_ctx_pair_cluster_active reads back which one the last evaluation used (1 cluster, 0 flat; synchronises - tests only). */
+int admp_ctx_set_pair_cluster(admp_ctx* ctx, int force, int min_rows_per_cluster);
+int admp_ctx_pair_cluster_active(admp_ctx* ctx);
 int64_t admp_ctx_workspace_bytes(const admp_ctx* ctx);
 /* 1 when optimize_Uind runs as the device-resident CUDA-graph WHILE loop, 0 when the
  * host-synchronised loop is in use (ADMP_SCF_HOSTSYNC or graph construction failed). */

@@ -56,6 +56,17 @@ def timed(fn, reps=5):
 
 
 fl = _lib.WANT_GRAD | _lib.WANT_VIRIAL | (0x40000000 if os.environ.get('PAIR_NO_ISIDE') else 0)
+for force, label in ((-1, 'flat rows'), (1, 'cluster tiles')):
+    _lib.check(cx.lib.admp_ctx_set_pair_cluster(cx.handle, force, 0))
+    ms = timed(lambda: cx.lib.admp_pme_real(cx.handle, sp(), p(pos), p(box), p(pairs), rows, p(M), p(U), p(pol), p(th), p(mS), p(pS), 0, fl,
+                                            p(dpos), p(G), p(F), None, None, p(scal)))
+    tf = npairs * 1719 / (ms * 1e-3) / 1e12
+    print('[%s, active %d] pair pass incl. tile build (E + adjoints, polarizable): %.3f ms, %.2f Gpairs/s, %.2f TFLOP/s algorithmic = %.1f %% of the FP64 FMA peak (%.1f)'
+          % (label, cx.lib.admp_ctx_pair_cluster_active(cx.handle), ms, npairs / ms / 1e6, tf, 100 * tf / FP64_PEAK, FP64_PEAK))
+    ms = timed(lambda: cx.lib.admp_pme_real(cx.handle, sp(), p(pos), p(box), p(pairs), rows, p(M), p(U), p(pol), p(th), p(mS), p(pS), 1, 0,
+                                            None, None, p(F), None, None, p(scal)))
+    print('[%s] pair pass incl. tile build (SCF field only): %.3f ms, %.2f Gpairs/s' % (label, ms, npairs / ms / 1e6))
+_lib.check(cx.lib.admp_ctx_set_pair_cluster(cx.handle, -1 if os.environ.get('PAIR_FLAT') else 1, 0))
 ms = timed(lambda: cx.lib.admp_pme_real(cx.handle, sp(), p(pos), p(box), p(pairs), rows, p(M), p(U), p(pol), p(th), p(mS), p(pS), 0, fl,
                                         p(dpos), p(G), p(F), None, None, p(scal)))
 tf = npairs * 1719 / (ms * 1e-3) / 1e12
