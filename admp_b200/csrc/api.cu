@@ -147,8 +147,8 @@ extern "C" int admp_ctx_create(admp_ctx** out, int device, int dtype) {
     CK(cudaMalloc(&c->box, sizeof(BoxInfo)));
     CK(cudaMalloc(&c->scal, sizeof(double) * ADMP_S_COUNT));
     CK(cudaMalloc(&c->state, sizeof(int32_t) * 8));
-    CK(cudaMalloc(&c->cw.state, sizeof(int32_t) * 4));
-    CK(cudaMemset(c->cw.state, 0, sizeof(int32_t) * 4));
+    CK(cudaMalloc(&c->cw.state, sizeof(int32_t) * 8));
+    CK(cudaMemset(c->cw.state, 0, sizeof(int32_t) * 8));
     c->cw.min_rows_per_cluster = 96;
     if (const char* e = getenv("ADMP_PAIR_CLUSTER")) c->cluster_force = atoi(e) > 0 ? 1 : (atoi(e) < 0 || e[0] == '0' ? -1 : 0);
     if (const char* e = getenv("ADMP_PAIR_CLUSTER_MINROWS")) c->cw.min_rows_per_cluster = atoi(e);
@@ -483,9 +483,13 @@ extern "C" int admp_pme_real(admp_ctx* c, void* stream, const void* pos, const v
     DISPATCH(c, launch_box_setup, st, box, c->box, c->K[0], c->K[1], c->K[2]);
     // scale index per row once per call (one byte per row) instead of a covalent-CSR walk inside the pair loop, then the
     // cluster tiles when the list qualifies (pair_cluster.cu); exactly one of the two pair kernels does the work
-    if (ensure_pairs(c, n_rows)) return 1;
-    launch_pair_scale(st, n_rows, c->n_atoms, pairs, c->cov_off, c->cov_idx, c->cov_nb, c->s_sidx);
-    launch_cluster_prepare(st, n_rows, c->n_atoms, c->cw.n_clusters, pairs, c->s_sidx, c->cw, c->cluster_force);
+    if (!(flags & ADMP_REUSE_PAIR_TILES)) {
+        if (ensure_pairs(c, n_rows)) return 1;
+        launch_pair_scale(st, n_rows, c->n_atoms, pairs, c->cov_off, c->cov_idx, c->cov_nb, c->s_sidx);
+        launch_cluster_prepare(st, n_rows, c->n_atoms, c->cw.n_clusters, pairs, c->s_sidx, c->cw, c->cluster_force);
+    } else if (n_rows > c->pairs_cap) {
+        return fail("admp_pme_real: ADMP_REUSE_PAIR_TILES without a previous call on this pair list");
+    }
     if (mode == 1) DISPATCH(c, launch_pair_pack, st, c->n_atoms, pos, M, U, pol, tholes, c->rec);
     DISPATCH(c, launch_pme_pair, st, n_rows, c->n_atoms, c->box, c->kappa, pos, pairs, c->s_sidx, c->cov_off, c->cov_idx, c->cov_nb, M, U, pol,
              tholes, mScales, pScales, mode, flags, dpos, G, F, dpol, dtholes, scalars, c->rec, c->cw.state);

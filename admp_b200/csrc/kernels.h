@@ -36,7 +36,7 @@ struct ClusterWork {
     int32_t* ent_i;                        // pairs_cap: i atom of every tile entry
     uint32_t* ent_m;                       // pairs_cap: 4 bits per cluster slot: listed, scale index
     int32_t* cl_extra;                     // n_clusters: entries beyond slot 0's own list
-    int32_t* state;                        // [0] bad order, [1] live rows, [2] cluster kernel selected
+    int32_t* state;                        // int32[8]: [1] live rows, [2] cluster kernel selected, [3] group column (pair_cluster.cu)
     int n_clusters, min_rows_per_cluster;
 };
 void launch_cluster_prepare(cudaStream_t st, int64_t n_rows, int n_atoms, int n_clusters, const int32_t* pairs, const int8_t* sidx,

@@ -71,6 +71,7 @@ pair_pack_kernel(int n, const T* __restrict__ pos, const T* __restrict__ M, cons
     else if (f < 16) v = U ? U[3 * (size_t)a + (f - 13)] : (T)0;
     else if (f == 16) v = pol ? pol[a] : (T)0;
     else if (f == 17) v = tholes ? tholes[a] : (T)0;
+    else if (f == 18) v = (pol && pol[a] > (T)0) ? (T)pow((double)pol[a], 1.0 / 6.0) : (T)0;
     rec[e] = v;
 }
 template <typename T>
@@ -102,11 +103,11 @@ pme_pair_kernel(int64_t n_rows, int n_atoms, const BoxInfo* __restrict__ Bp, T k
     extern __shared__ __align__(16) unsigned char pair_smem[];
     __shared__ double red[10 * 4];
     __shared__ BoxInfo sB;                                      // cell + scale tables: shared-memory reads in the pair loop
-    __shared__ T sScale[10];
+    __shared__ T sScale[10], sW0[5];
     PairChunk<T>* stage_base = reinterpret_cast<PairChunk<T>*>(pair_smem);   // [2 stages][2 ends][NCH][PAIR_TILE] 16-byte chunks
     const int tid = threadIdx.x, lane = tid & 31;
     if (tid < (int)(sizeof(BoxInfo) / sizeof(double))) reinterpret_cast<double*>(&sB)[tid] = reinterpret_cast<const double*>(Bp)[tid];
-    if (tid < 5) { sScale[tid] = mScales[tid]; sScale[5 + tid] = POL ? pScales[tid] : (T)0; }
+    if (tid < 5) { sScale[tid] = mScales[tid]; sScale[5 + tid] = POL ? pScales[tid] : (T)0; sW0[tid] = POL ? thole_switch_w0<T>(pScales[tid]) : (T)0; }
     __syncthreads();
     double acc_e = 0.0;
     double acc_box[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -195,7 +196,7 @@ pme_pair_kernel(int64_t n_rows, int n_atoms, const BoxInfo* __restrict__ Bp, T k
             const T rinv = rsqrt(r2), r = r2 * rinv;
             const T n[3] = {d[0] * rinv, d[1] * rinv, d[2] * rinv};
             Radial<T> R;
-            radial_setup(r, kappa, R);
+            radial_setup(r, rinv, kappa, R);
             const T qI = mi[0], qJ = mj[0];
             const T *muI = mi + 1, *muJ = mj + 1, *TI = mi + 4, *TJ = mj + 4;
             T vI[3], vJ[3];
@@ -209,7 +210,7 @@ pme_pair_kernel(int64_t n_rows, int n_atoms, const BoxInfo* __restrict__ Bp, T k
                 for (int k = 0; k < 3; ++k) { uI[k] = rd(0, 13 + k); uJ[k] = rd(1, 13 + k); }
                 pI = dot3(uI, n); pJ = dot3(uJ, n);
                 polI = rd(0, 16); polJ = rd(1, 16);
-                ind_coeffs<T, MODE == 0>(R, sScale[5 + sidx], rd(0, 17), rd(1, 17), polI, polJ, C);
+                ind_coeffs<T, MODE == 0>(R, sScale[5 + sidx], sW0[sidx], rd(0, 17), rd(1, 17), polI, polJ, C);
             }
             if (MODE == 1) {
                 // dE/du only

@@ -10,8 +10,8 @@
 //   * i side: the lane's 16 components accumulate in registers over the cluster's j atoms (~2.7 pairs per lane and
 //     chunk for water) and are flushed once per chunk.
 //   * the j records sit in shared memory (uniform-address reads), the i records are gathered once per chunk.
-// The pair SET is exactly the caller's: the tiles are built from the caller's rows (i < j, grouped by j, ascending i -
-// the order admp_nblist_build and jax_md's OrderedSparse produce) with a per-entry mask of which (i, j_k) pairs are
+// The pair SET is exactly the caller's: the tiles are built from the caller's rows (i < j, strictly sorted by one column then
+// the other - the orders admp_nblist_build and jax_md's OrderedSparse produce; the sorted-by column becomes the cluster side) with a per-entry mask of which (i, j_k) pairs are
 // listed and their scale index; no pair is added or dropped. Any other row order, or a sparse list (gas-like boxes:
 // fewer than ~1 full chunk per cluster), keeps the flat kernel: a device-side flag selects which of the two kernels
 // does the work, so there is no host synchronisation and both launches are graph-capturable.
@@ -20,43 +20,54 @@
 namespace admp {
 
 // ------------------------------------------------------------------------------------------ tile construction
-// state[0] = bad order flag, state[1] = live rows, state[2] = use cluster kernel (decision)
+// state[0] = rows are NOT strictly sorted by (column 0, column 1); state[1] = live rows (they must form a prefix);
+// state[2] = use the cluster kernel (decision); state[3] = group column gc (the cluster side), the lanes take the other;
+// state[4] = rows are NOT strictly sorted by (column 1, column 0); state[5] = live rows do not form a prefix.
+// admp_nblist_build and the oracle list rows by (i, j) ascending (gc = 0); jax_md's OrderedSparse groups by the receiver.
 __global__ void __launch_bounds__(256)
-cluster_check_kernel(int64_t n_rows, int n_atoms, const int32_t* __restrict__ pairs, const int8_t* __restrict__ sidx,
-                     int32_t* __restrict__ row_start, int32_t* __restrict__ state) {
+cluster_check_kernel(int64_t n_rows, const int32_t* __restrict__ pairs, const int8_t* __restrict__ sidx, int32_t* __restrict__ state) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool live = false;
     if (p < n_rows) {
         live = sidx[p] >= 0;
-        if (live) {
-            const int i = pairs[2 * p], j = pairs[2 * p + 1];
-            int jprev = -1;
-            if (p > 0) {
-                const bool lp = sidx[p - 1] >= 0;
-                const int ip = pairs[2 * p - 2], jp = pairs[2 * p - 1];
-                // live rows must form a prefix sorted strictly by (j, i)
-                if (!lp || jp > j || (jp == j && ip >= i)) state[0] = 1;
-                jprev = lp ? jp : -1;
-            }
-            if (jprev < j) {
-                for (int jj = (jprev < 0 ? 0 : jprev + 1); jj <= j; ++jj) row_start[jj] = (int32_t)p;
-            }
-            const bool last = (p + 1 == n_rows) || (sidx[p + 1] < 0);
-            if (last)
-                for (int jj = j + 1; jj <= n_atoms; ++jj) row_start[jj] = (int32_t)(p + 1);
+        if (live && p > 0) {
+            const int a = pairs[2 * p], b = pairs[2 * p + 1];
+            const int ap = pairs[2 * p - 2], bp = pairs[2 * p - 1];
+            if (sidx[p - 1] < 0) state[5] = 1;
+            if (ap > a || (ap == a && bp >= b)) state[0] = 1;
+            if (bp > b || (bp == b && ap >= a)) state[4] = 1;
         }
     }
-    const unsigned b = __ballot_sync(0xffffffffu, live);
-    if ((threadIdx.x & 31) == 0 && b) atomicAdd(&state[1], __popc(b));
+    // the live rows must form a prefix (state[5] otherwise), so their number is the index after the last live row:
+    // one plain store instead of a same-address atomic per warp
+    if (live && (p + 1 == n_rows || sidx[p + 1] < 0)) state[1] = (int32_t)(p + 1);
 }
 
 __global__ void cluster_decide_kernel(int n_clusters, int min_rows_per_cluster, int force, int32_t* __restrict__ state) {
     // force: 0 = auto, 1 = cluster whenever the order allows, -1 = never
-    int use = 0;
-    if (force >= 0 && state[0] == 0 && n_clusters > 0) {
-        use = force > 0 ? (state[1] > 0) : ((int64_t)state[1] >= (int64_t)min_rows_per_cluster * n_clusters);
+    int use = 0, gc = 0;
+    const bool ok0 = state[0] == 0, ok1 = state[4] == 0;
+    if (force >= 0 && state[5] == 0 && (ok0 || ok1) && n_clusters > 0 && state[1] > 0) {
+        gc = ok0 ? 0 : 1;
+        use = force > 0 ? 1 : ((int64_t)state[1] >= (int64_t)min_rows_per_cluster * n_clusters);
     }
     state[2] = use;
+    state[3] = gc;
+}
+
+// first row of every atom in the group column: lower bound over the sorted live prefix (no row: the next atom's start)
+__global__ void __launch_bounds__(256)
+cluster_rowstart_kernel(int n_atoms, const int32_t* __restrict__ pairs, int32_t* __restrict__ row_start, const int32_t* __restrict__ state) {
+    if (state[2] == 0) return;
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a > n_atoms) return;
+    const int gc = state[3];
+    int lo = 0, hi = state[1];
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (pairs[2 * (int64_t)mid + gc] < a) lo = mid + 1; else hi = mid;
+    }
+    row_start[a] = lo;
 }
 
 __global__ void __launch_bounds__(256)
@@ -69,7 +80,8 @@ cluster_build_kernel(int64_t n_rows, const int32_t* __restrict__ pairs, const in
     if (p >= n_rows) return;
     const int s = sidx[p];
     if (s < 0) return;
-    const int i = pairs[2 * p], j = pairs[2 * p + 1];
+    const int gc = state[3], oc = 1 - gc;
+    const int i = pairs[2 * p + oc], j = pairs[2 * p + gc];          // j: cluster side, i: lane side
     const int c = cl_of[j], first = cl_first[c], k = j - first;
     const uint32_t bits = (uint32_t)(1 | (s << 1)) << (4 * k);       // 4 bits per slot: listed, scale index (3 bits)
     const int base = row_start[first], n0 = row_start[first + 1] - base;
@@ -82,9 +94,9 @@ cluster_build_kernel(int64_t n_rows, const int32_t* __restrict__ pairs, const in
     int lo = 0, hi = n0;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (pairs[2 * (int64_t)(base + mid)] < i) lo = mid + 1; else hi = mid;
+        if (pairs[2 * (int64_t)(base + mid) + oc] < i) lo = mid + 1; else hi = mid;
     }
-    if (lo < n0 && pairs[2 * (int64_t)(base + lo)] == i) {
+    if (lo < n0 && pairs[2 * (int64_t)(base + lo) + oc] == i) {
         atomicOr(&ent_m[base + lo], bits);
     } else {
         const int e = atomicAdd(&cl_extra[c], 1);
@@ -98,7 +110,7 @@ cluster_build_kernel(int64_t n_rows, const int32_t* __restrict__ pairs, const in
 // (0-2 position, 3-12 Cartesian multipoles, 13-15 induced dipole, 16 polarizability, 17 Thole width).
 // Accumulates the I-side gradient into gi (0-2 dE/dr, 3-12 dE/dM, 13-15 dE/dU) and RETURNS the J side in gj.
 template <typename T, bool POL, int MODE, bool PG>
-__device__ __forceinline__ void cluster_pair(const BoxInfo& B, T kappa, const T (&ir)[18], const T* __restrict__ jr, T mscale, T pscale,
+__device__ __forceinline__ void cluster_pair(const BoxInfo& B, T kappa, const T (&ir)[20], const T* __restrict__ jr, T mscale, T pscale, T w0,
                                              bool want_grad, bool want_vir, T (&gi)[16], T (&gj)[16], double& acc_e,
                                              double (&acc_box)[9], T& dm_out, T& dp_out, T& eth_out, T& edpi_out, T& edpj_out) {
     T mj[10];
@@ -112,7 +124,7 @@ __device__ __forceinline__ void cluster_pair(const BoxInfo& B, T kappa, const T 
     const T rinv = rsqrt(r2), r = r2 * rinv;
     const T n[3] = {d[0] * rinv, d[1] * rinv, d[2] * rinv};
     Radial<T> R;
-    radial_setup(r, kappa, R);
+    radial_setup(r, rinv, kappa, R);
     const T qI = mi[0], qJ = mj[0];
     const T *muI = mi + 1, *muJ = mj + 1, *TI = mi + 4, *TJ = mj + 4;
     T vI[3], vJ[3];
@@ -125,7 +137,7 @@ __device__ __forceinline__ void cluster_pair(const BoxInfo& B, T kappa, const T 
         for (int k = 0; k < 3; ++k) { uI[k] = ir[13 + k]; uJ[k] = jr[13 + k]; }
         pI = dot3(uI, n); pJ = dot3(uJ, n);
         polI = ir[16]; polJ = jr[16];
-        ind_coeffs<T, MODE == 0>(R, pscale, ir[17], jr[17], polI, polJ, C);
+        ind_coeffs<T, MODE == 0, true>(R, pscale, w0, ir[17], jr[17], ir[18], jr[18], C);
     }
     if (MODE == 1) {
         const T B1 = C.B[0], B2 = C.B[1], B3 = C.B[2], B5 = C.B[3], B6 = C.B[4], C2 = C.B[5], C3 = C.B[6];
@@ -246,14 +258,14 @@ pme_cluster_kernel(int n_clusters, const BoxInfo* __restrict__ Bp, T kappa, cons
                    T* __restrict__ dpos, T* __restrict__ G, T* __restrict__ F, T* __restrict__ dpol, T* __restrict__ dth,
                    double* __restrict__ scalars, const int32_t* __restrict__ state) {
     if (state[2] == 0) return;                                   // the flat kernel does the work
-    constexpr int REC = PairRec<T>::STRIDE, EPC = PairRec<T>::EPC, NCH = PairRec<T>::chunks(true);
+    constexpr int REC = PairRec<T>::STRIDE, EPC = PairRec<T>::EPC, NCH = PairRec<T>::chunks_all();
     __shared__ double red[10 * CL_WARPS];
     __shared__ BoxInfo sB;
-    __shared__ T sScale[10];
+    __shared__ T sScale[10], sW0[5];
     __shared__ __align__(16) T sJ[CL_WARPS][CL_MAX][NCH * EPC];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < (int)(sizeof(BoxInfo) / sizeof(double))) reinterpret_cast<double*>(&sB)[tid] = reinterpret_cast<const double*>(Bp)[tid];
-    if (tid < 5) { sScale[tid] = mScales[tid]; sScale[5 + tid] = POL ? pScales[tid] : (T)0; }
+    if (tid < 5) { sScale[tid] = mScales[tid]; sScale[5 + tid] = POL ? pScales[tid] : (T)0; sW0[tid] = POL ? thole_switch_w0<T>(pScales[tid]) : (T)0; }
     __syncthreads();
     const BoxInfo& B = sB;
     const bool want_grad = MODE == 1 || (flags & ADMP_WANT_GRAD) != 0, want_vir = (flags & ADMP_WANT_VIRIAL) != 0;
@@ -287,7 +299,7 @@ pme_cluster_kernel(int n_clusters, const BoxInfo* __restrict__ Bp, T kappa, cons
             const bool act = e < cnt;
             const int i = act ? ent_i[base + e] : first;
             const uint32_t m = act ? ent_m[base + e] : 0u;
-            T ir[18];
+            T ir[20];
             {
                 const PairChunk<T>* src = reinterpret_cast<const PairChunk<T>*>(rec + (size_t)i * REC);
 #pragma unroll
@@ -295,7 +307,7 @@ pme_cluster_kernel(int n_clusters, const BoxInfo* __restrict__ Bp, T kappa, cons
                     const PairChunk<T> v = src[ch];
 #pragma unroll
                     for (int q = 0; q < EPC; ++q)
-                        if (ch * EPC + q < 18) ir[ch * EPC + q] = v.v[q];
+                        ir[ch * EPC + q] = v.v[q];
                 }
                 if (MODE == 1) {
 #pragma unroll
@@ -306,40 +318,44 @@ pme_cluster_kernel(int n_clusters, const BoxInfo* __restrict__ Bp, T kappa, cons
 #pragma unroll
             for (int k = 0; k < 16; ++k) gi[k] = (T)0;
             T ith = 0, ipol = 0;
+            // one copy of the pair arithmetic (~3 000 instructions): the slot loop must stay rolled or the kernel outgrows
+            // the instruction cache (4 copies = 130 KB of code: "no instruction" became the top stall)
+#pragma unroll 1
+            for (int k = 0; k < csize; ++k) {
+                const uint32_t bits = (m >> (4 * k)) & 15u;
+                const bool on = bits & 1u;
+                if (!__any_sync(0xffffffffu, on)) continue;
+                T gj[16];
 #pragma unroll
-            for (int k = 0; k < CL_MAX; ++k) {
-                if (k < csize) {
-                    const uint32_t bits = (m >> (4 * k)) & 15u;
-                    const bool on = bits & 1u;
-                    if (__any_sync(0xffffffffu, on)) {
-                        T gj[16];
+                for (int q = 0; q < 16; ++q) gj[q] = (T)0;
+                T dm = 0, dp = 0, eth = 0, edpi = 0, edpj = 0;
+                if (on) {
+                    const int s = (int)(bits >> 1);
+                    cluster_pair<T, POL, MODE, PG>(B, kappa, ir, sJ[warp][k], sScale[s], sScale[5 + s], sW0[s], want_grad, want_vir, gi, gj,
+                                                   acc_e, acc_box, dm, dp, eth, edpi, edpj);
+                    if (PG) {
 #pragma unroll
-                        for (int q = 0; q < 16; ++q) gj[q] = (T)0;
-                        T dm = 0, dp = 0, eth = 0, edpi = 0, edpj = 0;
-                        if (on) {
-                            const int s = (int)(bits >> 1);
-                            cluster_pair<T, POL, MODE, PG>(B, kappa, ir, sJ[warp][k], sScale[s], sScale[5 + s], want_grad, want_vir, gi, gj,
-                                                           acc_e, acc_box, dm, dp, eth, edpi, edpj);
-                            if (PG) {
-#pragma unroll
-                                for (int q = 0; q < 5; ++q) {
-                                    acc_ms[q] += (q == s) ? (double)dm : 0.0;
-                                    acc_ps[q] += (q == s) ? (double)dp : 0.0;
-                                }
-                                ith += eth; ipol += edpi;
-                            }
+                        for (int q = 0; q < 5; ++q) {
+                            acc_ms[q] += (q == s) ? (double)dm : 0.0;
+                            acc_ps[q] += (q == s) ? (double)dp : 0.0;
                         }
-                        if (MODE == 1) {
-#pragma unroll
-                            for (int q = 0; q < 3; ++q) {
-                                const T s3 = warp_sum(gj[13 + q]);
-                                if (lane == q) jacc[k] += s3;
-                            }
-                        } else if (want_grad) {
-                            jacc[k] += warp_reduce_scatter16(gj, lane);
-                        }
-                        if (PG && POL) { jth[k] += eth; jpol[k] += edpj; }
+                        ith += eth; ipol += edpi;
                     }
+                }
+                T r = (T)0;
+                if (MODE == 1) {
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        const T s3 = warp_sum(gj[13 + q]);
+                        if (lane == q) r = s3;
+                    }
+                } else if (want_grad) {
+                    r = warp_reduce_scatter16(gj, lane);
+                }
+#pragma unroll
+                for (int q = 0; q < CL_MAX; ++q) {
+                    jacc[q] += (q == k) ? r : (T)0;
+                    if (PG && POL) { jth[q] += (q == k) ? eth : (T)0; jpol[q] += (q == k) ? edpj : (T)0; }
                 }
             }
             // i side: one flush per chunk
@@ -399,14 +415,14 @@ pme_cluster_kernel(int n_clusters, const BoxInfo* __restrict__ Bp, T kappa, cons
 // ------------------------------------------------------------------------------------------ host side
 void launch_cluster_prepare(cudaStream_t st, int64_t n_rows, int n_atoms, int n_clusters, const int32_t* pairs, const int8_t* sidx,
                             const ClusterWork& w, int force) {
-    cudaMemsetAsync(w.state, 0, sizeof(int32_t) * 4, st);
-    if (n_rows <= 0 || n_clusters <= 0) return;
-    cudaMemsetAsync(w.row_start, 0, sizeof(int32_t) * ((size_t)n_atoms + 1), st);
+    cudaMemsetAsync(w.state, 0, sizeof(int32_t) * 8, st);
+    if (n_rows <= 0 || n_clusters <= 0 || force < 0) return;
     cudaMemsetAsync(w.ent_m, 0, sizeof(uint32_t) * (size_t)n_rows, st);
     cudaMemsetAsync(w.cl_extra, 0, sizeof(int32_t) * (size_t)n_clusters, st);
     const unsigned g = (unsigned)((n_rows + 255) / 256);
-    cluster_check_kernel<<<g, 256, 0, st>>>(n_rows, n_atoms, pairs, sidx, w.row_start, w.state);
+    cluster_check_kernel<<<g, 256, 0, st>>>(n_rows, pairs, sidx, w.state);
     cluster_decide_kernel<<<1, 1, 0, st>>>(n_clusters, w.min_rows_per_cluster, force, w.state);
+    cluster_rowstart_kernel<<<(unsigned)((n_atoms + 256) / 256), 256, 0, st>>>(n_atoms, pairs, w.row_start, w.state);
     cluster_build_kernel<<<g, 256, 0, st>>>(n_rows, pairs, sidx, w.cl_of, w.cl_first, w.row_start, w.ent_i, w.ent_m, w.cl_extra, w.state);
 }
 

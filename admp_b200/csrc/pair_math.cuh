@@ -14,9 +14,8 @@ template <typename T> struct Radial {
 };
 
 template <typename T>
-__device__ __forceinline__ void radial_setup(T r, T kappa, Radial<T>& R) {
+__device__ __forceinline__ void radial_setup(T r, T rinv, T kappa, Radial<T>& R) {
     R.r = r; R.kappa = kappa;
-    const T rinv = (T)1 / r;
     R.ri[0] = (T)ADMP_DIEL;
 #pragma unroll
     for (int i = 1; i < 6; ++i) R.ri[i] = R.ri[i - 1] * rinv;
@@ -91,26 +90,34 @@ template <typename T> struct IndCoef {
     T dmp;
 };
 
-template <typename T, bool DERIV>
-__device__ __forceinline__ void ind_coeffs(const Radial<T>& R, T p, T th1, T th2, T pol1, T pol2, IndCoef<T>& C) {
+// Fermi switch of the Thole width (admp/pme.py:337-348,411): depends on the pair's pscale only, i.e. on its scale
+// index - the kernels tabulate it once per launch instead of one exp + one division per pair.
+template <typename T> __device__ __forceinline__ T thole_switch_w0(T p) {
+    T uarg = (p - (T)1e-3) * (T)1e5;
+    uarg = uarg > (T)80 ? (T)80 : uarg;
+    return (T)1 / (exp(uarg) + (T)1);
+}
+
+// SIXTH: pol1 / pol2 are pol^(1/6) per atom (packed record slot 18; 0 for pol = 0), so that the pair's
+// dmp = (pol1 pol2)^(1/6) is one product instead of a double-precision pow per pair.
+template <typename T, bool DERIV, bool SIXTH = false>
+__device__ __forceinline__ void ind_coeffs(const Radial<T>& R, T p, T w0, T th1, T th2, T pol1, T pol2, IndCoef<T>& C) {
     const T x = R.x, x2 = x * x, x3 = x2 * x, x4 = x2 * x2, x5 = x4 * x, x6 = x3 * x3, X = R.X;
     const T c23 = (T)(2 / ADMP_SQRT3), s3 = (T)ADMP_SQRT3;
     const T* ri = R.ri;
     const T rinv = ri[1] * (T)(1 / ADMP_DIEL);
     // Thole width: Fermi switch of admp/pme.py:337-348,411, piecewise constant in pscale (A7)
-    T uarg = (p - (T)1e-3) * (T)1e5;
-    uarg = uarg > (T)80 ? (T)80 : uarg;
-    const T w0 = (T)1 / (exp(uarg) + (T)1);
     const T a = w0 * (T)ADMP_THOLE_DEFAULT + ((T)1 - w0) * (th1 + th2);
     C.da_dth = (T)1 - w0;
     // dmp = trim_val_0((pol1 pol2)^(1/6)), u = trim_val_infty(r/dmp)   (pme.py:413-414,732-735)
     const double prod = (double)pol1 * (double)pol2;
-    double dmpd = prod < 1e-48 ? 0.0 : pow(prod, 1.0 / 6.0);
+    double dmpd = SIXTH ? prod : (prod < 1e-48 ? 0.0 : pow(prod, 1.0 / 6.0));
     C.trimmed = dmpd < 1e-8;
     if (C.trimmed) dmpd = 1e-8;
     const T dmp = (T)dmpd;
     C.dmp = dmp;
-    const double ud = (double)R.r / dmpd;
+    const double dinv = 1.0 / dmpd;
+    const double ud = (double)R.r * dinv;
     const bool clipped = ud >= 1e8;
     const T u = clipped ? (T)1e8 : (T)ud;
     const T au = a * u;
@@ -127,9 +134,9 @@ __device__ __forceinline__ void ind_coeffs(const Radial<T>& R, T p, T th1, T th2
         sq0 = e * (au4 - au3) * (T)(1.0 / 18);
         sq1 = e * au3 * (T)(1.0 / 6);
     }
-    const T au_r = clipped ? (T)0 : a / dmp;
+    const T au_r = clipped ? (T)0 : a * (T)dinv;
     C.au_a = u;
-    C.au_d = clipped ? (T)0 : -a * R.r / (dmp * dmp);
+    C.au_d = clipped ? (T)0 : -a * R.r * (T)(dinv * dinv);
     const T d3 = R.dxnX(3, x2, x4), d5 = R.dxnX(5, x4, x6);
     // cud/2
     const T t1 = p * tc + R.b2;
@@ -186,8 +193,9 @@ template <typename T> __device__ __forceinline__ void symv(const T* t, const T* 
 // pair loop is bound by the load/store unit (cp.async + shared loads + 32 reductions per pair), not by DRAM.
 template <typename T> struct PairRec {
     static constexpr int EPC = 16 / sizeof(T);                 // elements per 16-byte chunk
-    static constexpr int STRIDE = sizeof(T) == 8 ? 18 : 20;    // elements per record
-    static constexpr int chunks(bool pol) { return ((pol ? 18 : 13) + EPC - 1) / EPC; }
+    static constexpr int STRIDE = 20;                          // elements per record: 18 + pol^(1/6) (slot 18) + pad
+    static constexpr int chunks(bool pol) { return ((pol ? 18 : 13) + EPC - 1) / EPC; }   // what the flat kernel stages
+    static constexpr int chunks_all() { return STRIDE / EPC; }                            // incl. slot 18 (cluster kernel)
 };
 template <typename T> struct alignas(16) PairChunk { T v[16 / sizeof(T)]; };
 

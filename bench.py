@@ -287,7 +287,7 @@ def kernel_rooflines(torch, _lib, reps, peak, flush, n_launch=10):
     return out
 
 
-def dense_rooflines(torch, _lib, peak_hbm, flush, n_side=32, rc=8.0, n_launch=5):
+def dense_rooflines(torch, _lib, peak_hbm, flush, n_side=64, rc=8.0, n_launch=5):
     """Pair / spread / gather kernels on the liquid-density box of SURVEY 8(d) ("dense-256k" recipe at
     n_side^3 waters, rc 8 A): the BASELINE configs are gas-like (8 neighbours per atom), so the pair kernel's
     FP-pipe utilisation is only visible here. Pair kernel: algorithmic 1 719 flop per polarizable pair
@@ -340,17 +340,29 @@ def dense_rooflines(torch, _lib, peak_hbm, flush, n_side=32, rc=8.0, n_launch=5)
     out = {}
     desc = 'dense water %d^3 (%d atoms, L %.2f A, rc %.1f A, %d pairs, %.1f neighbours/atom), mesh %d^3' % (
         n_side, n, L, rc, npairs, 2.0 * npairs / n, K)
-    for name, mode, flags, flop in (('pme_pair_kernel (E + all adjoints, polarizable)', 0, fl, 1719),
-                                    ('pme_pair_kernel (SCF field only)', 1, 0, None)):
-        ms = time_stage(lambda: cx.lib.admp_pme_real(cx.handle, sp(), p(pos), p(box), p(pairs), rows, p(M), p(U), p(pol), p(th), p(mS), p(pS),
-                                                     mode, flags, p(dpos) if mode == 0 else None, p(G) if mode == 0 else None, p(F), None, None,
-                                                     p(scal)))
-        d = dict(ms=round(ms, 4), gpairs_per_s=round(npairs / ms / 1e6, 3), n_pairs=npairs)
-        if flop:
-            ach = npairs * flop / (ms * 1e-3) / 1e12
-            d.update(bound='fp64', achieved=round(ach, 3), peak=round(fp_peak, 2), unit='TFLOP/s', frac=round(ach / fp_peak, 4),
-                     algorithmic_flop_per_pair=flop, peak_source='admp_fp_peak (FP64 FMA chain, measured in this run)')
-        out[name] = d
+    # Two traversals of the same rows: flat (one row per thread) and cluster tiles (pair_cluster.cu; what the device picks
+    # for this list). "pass" = the pair kernel on already-built tiles / scale indices (the state of 30 of the 31 pair
+    # passes of a polarizable evaluation); "first_pass" additionally builds them (pair_scale + check + build kernels).
+    RE = _lib.REUSE_PAIR_TILES
+    for force, label in ((-1, 'flat rows, pme_pair_kernel'), (0, 'cluster tiles, pme_cluster_kernel')):
+        _lib.check(cx.lib.admp_ctx_set_pair_cluster(cx.handle, force, 0))
+        for name, mode, flags, flop in (('E + all adjoints, polarizable', 0, fl, 1719), ('SCF field only', 1, 0, None)):
+            def call(extra, mode=mode, flags=flags):
+                return cx.lib.admp_pme_real(cx.handle, sp(), p(pos), p(box), p(pairs), rows, p(M), p(U), p(pol), p(th), p(mS), p(pS),
+                                            mode, flags | extra, p(dpos) if mode == 0 else None, p(G) if mode == 0 else None, p(F),
+                                            None, None, p(scal))
+            ms_first = time_stage(lambda: call(0))
+            active = int(cx.lib.admp_ctx_pair_cluster_active(cx.handle))
+            ms = time_stage(lambda: call(RE))
+            d = dict(ms=round(ms, 4), ms_first_pass=round(ms_first, 4), gpairs_per_s=round(npairs / ms / 1e6, 3), n_pairs=npairs,
+                     cluster_kernel_active=active)
+            if flop:
+                ach = npairs * flop / (ms * 1e-3) / 1e12
+                d.update(bound='fp64', achieved=round(ach, 3), peak=round(fp_peak, 2), unit='TFLOP/s', frac=round(ach / fp_peak, 4),
+                         algorithmic_flop_per_pair=flop, peak_source='admp_fp_peak (FP64 FMA chain, measured in this run)',
+                         frac_first_pass=round(npairs * flop / (ms_first * 1e-3) / 1e12 / fp_peak, 4))
+            out['%s (%s)' % (label, name)] = d
+    _lib.check(cx.lib.admp_ctx_set_pair_cluster(cx.handle, 0, 0))
     wb = 8
     ms = time_stage(lambda: cx.lib.admp_pme_spread(cx.handle, sp(), p(pos), p(box), p(M), 10, 10, None))
     nbytes = wb * K ** 3 + 216 * 2 * wb * n + 13 * wb * n

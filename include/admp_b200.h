@@ -62,6 +62,10 @@ extern "C" {
 #define ADMP_WANT_PGRAD 4u    /* dE/dmScales, dE/dpScales, dE/dtholes, dE/dpol */
 #define ADMP_SCF 8u           /* run optimize_Uind before the final evaluation */
 #define ADMP_SCF_HOSTSYNC 16u /* debug: host-synchronised SCF loop instead of the device-resident graph */
+/* admp_pme_real only: the pair rows, topology and scales index are those of the previous admp_pme_real call on this
+ * context - reuse its per-row scale indices and cluster tiles (what admp_pme_eval does for the 31 pair passes of one
+ * polarizable evaluation) instead of rebuilding them */
+#define ADMP_REUSE_PAIR_TILES 0x20000000u
 
 typedef struct admp_ctx admp_ctx;
 

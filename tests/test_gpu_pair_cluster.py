@@ -74,21 +74,32 @@ def test_cluster_and_flat_traversals_agree_with_the_reference_and_each_other(nam
 
 
 def test_unsorted_rows_fall_back_to_the_flat_kernel_and_dense_lists_select_the_cluster_kernel():
+    from admp_b200 import _lib   # noqa: F401
     from admp_b200.pme import ADMPPmeForce
     s = fixtures.lattice_water(6, 3.1, seed=3)                    # 216 waters, 18.6 A box
     rc = 7.0
     pairs, n = pairlist.build_pairs(s.positions.numpy(), s.box.numpy(), rc)
     calc = ADMPPmeForce(s.box, s.axis_type, s.axis_indices, s.covalent_map, rc, 1e-4, 2, lpol=True)
     args = (s.Q_local, s.pol, s.tholes, s.mScales, s.pScales, s.dScales)
-    # oracle order = (i, j) lexicographic: not grouped by j -> flat kernel
+    # oracle / admp_nblist_build order: rows sorted by (i, j) -> clusters on column 0; dense list -> the device picks the cluster kernel
     E_a, F_a = calc.get_forces(s.positions, s.box, pairs, *args)
-    assert active(calc) == 0
-    # grouped by j, ascending i (admp_nblist_build / jax_md OrderedSparse order), dense: the device picks the cluster kernel
+    assert active(calc) == 1, 'dense sorted list should select the cluster kernel (%d rows, %d clusters)' % (n, s.n_atoms // 3)
+    # grouped by j, ascending i (jax_md OrderedSparse-like order) with padding rows -> clusters on column 1
     order = np.lexsort((pairs[:n, 0], pairs[:n, 1]))
     sorted_pairs = np.concatenate([pairs[:n][order], np.full((37, 2), s.n_atoms, dtype=pairs.dtype)])
     E_b, F_b = calc.get_forces(s.positions, s.box, sorted_pairs, *args)
-    assert active(calc) == 1, 'dense (j, i)-sorted list should select the cluster kernel (%d rows, %d clusters)' % (n, s.n_atoms // 3)
+    assert active(calc) == 1
     assert rel(E_a, E_b) < 1e-10 and rel(F_a, F_b) < 1e-9
+    # shuffled rows: no usable order -> flat kernel, same result
+    rng = np.random.default_rng(0)
+    shuffled = pairs[:n][rng.permutation(n)]
+    E_s, F_s = calc.get_forces(s.positions, s.box, shuffled, *args)
+    assert active(calc) == 0
+    assert rel(E_s, E_b) < 1e-10 and rel(F_s, F_b) < 1e-9
+    force_path(calc, -1)
+    E_f, F_f = calc.get_forces(s.positions, s.box, pairs, *args)
+    assert active(calc) == 0 and rel(E_f, E_a) < 1e-10 and rel(F_f, F_a) < 1e-9
+    force_path(calc, 0)
     # the same list from the library's own neighbour list
     from admp_b200.neighbor import neighbor_list
     nbr = neighbor_list(s.box, rc).allocate(s.positions)

@@ -24,7 +24,7 @@ RTOL = 1e-6
 
 def rel(a, b):
     a = a.detach().cpu().double().numpy() if isinstance(a, torch.Tensor) else np.asarray(a, dtype=np.float64)
-    b = np.asarray(b, dtype=np.float64)
+    b = b.detach().cpu().double().numpy() if isinstance(b, torch.Tensor) else np.asarray(b, dtype=np.float64)
     scale = np.abs(b).max()
     return np.abs(a - b).max() / (scale if scale > 0 else 1.0)
 
