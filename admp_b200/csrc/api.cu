@@ -213,7 +213,7 @@ extern "C" int admp_ctx_destroy(admp_ctx* c) {
     free_recip(c);
     free_atoms(c);
     dfree(c->s_pairs); dfree(c->s_sidx); dfree(c->cw.ent_i); dfree(c->cw.ent_m); dfree(c->cw.state); dfree(c->box); dfree(c->scal); dfree(c->state); dfree(c->s_mS); dfree(c->s_pS); dfree(c->s_box);
-    dfree(c->nb.cell_of); dfree(c->nb.cell_count); dfree(c->nb.cell_start); dfree(c->nb.sorted); dfree(c->nb.nbr_count); dfree(c->nb.nbr_start);
+    dfree(c->nb.cell_of); dfree(c->nb.cell_count); dfree(c->nb.cell_start); dfree(c->nb.sorted); dfree(c->nb.nbr_count); dfree(c->nb.nbr_start); dfree(c->nb.geom); dfree(c->nb.scan_tmp);
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
     if (c->side_stream) cudaStreamDestroy(c->side_stream);
@@ -905,6 +905,7 @@ extern "C" int admp_pme_eval(admp_ctx* c, void* stream, const void* pos, const v
     if (polz && c->lmax < 1) return fail("admp_pme_eval: lpol with lmax = 0 is not supported (admp/pme.py:224-228 is broken upstream)");
     if ((flags & ADMP_WANT_GRAD) && (!dpos || !dQl)) return fail("admp_pme_eval: gradient outputs missing");
     if (!scalars) return fail("admp_pme_eval: scalars missing");
+    if (polz && (flags & ADMP_SCF) && maxiter < 1) return fail("admp_pme_eval: maxiter must be >= 1 (got %d)", maxiter);
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(c->device));
     const int n = c->n_atoms;
@@ -1030,6 +1031,9 @@ extern "C" int admp_tt_pair(admp_ctx* c, void* stream, const void* pos, const vo
     return 0;
 }
 
+static int nblist_build_impl(admp_ctx* c, cudaStream_t st, const void* pos, const void* box, const double* hb, int n, double rc,
+                             int32_t* pairs, int64_t capacity, int32_t* info);
+
 extern "C" int admp_nblist_build(admp_ctx* c, void* stream, const void* pos, const void* box, int n, double rc, int32_t* pairs,
                                  int64_t capacity, int32_t* info) {
     if (!c) return fail("null ctx");
@@ -1047,6 +1051,21 @@ extern "C" int admp_nblist_build(admp_ctx* c, void* stream, const void* pos, con
         for (int k = 0; k < 9; ++k) hb[k] = fb[k];
     }
     CK(cudaStreamSynchronize(st));
+    return nblist_build_impl(c, st, pos, box, hb, n, rc, pairs, capacity, info);
+}
+
+// same, with the caller's host copy of the box (9 doubles, row-major): no device-to-host read, no host synchronisation
+extern "C" int admp_nblist_build_hostbox(admp_ctx* c, void* stream, const void* pos, const void* box, const double* box_host, int n,
+                                         double rc, int32_t* pairs, int64_t capacity, int32_t* info) {
+    if (!c) return fail("null ctx");
+    if (!box_host) return fail("admp_nblist_build_hostbox: null host box");
+    if (n <= 0 || rc <= 0.0) return fail("admp_nblist_build: bad n_atoms / rc");
+    CK(cudaSetDevice(c->device));
+    return nblist_build_impl(c, (cudaStream_t)stream, pos, box, box_host, n, rc, pairs, capacity, info);
+}
+
+static int nblist_build_impl(admp_ctx* c, cudaStream_t st, const void* pos, const void* box, const double* hb, int n, double rc,
+                             int32_t* pairs, int64_t capacity, int32_t* info) {
     for (int a = 0; a < 3; ++a)
         for (int b = 0; b < 3; ++b)
             if (a != b && hb[3 * a + b] != 0.0) return fail("admp_nblist_build: orthorhombic boxes only");
@@ -1077,7 +1096,6 @@ extern "C" int admp_nblist_build(admp_ctx* c, void* stream, const void* pos, con
     }
     const int K1 = c->K[0] ? c->K[0] : 6, K2 = c->K[1] ? c->K[1] : 6, K3 = c->K[2] ? c->K[2] : 6;
     DISPATCH(c, launch_box_setup, st, box, c->box, K1, K2, K3);
-    launch_nblist(st, c->box, pos, c->dtype, n, rc, c->nb, nc[0], nc[1], nc[2], pairs, capacity, info);
-    CKLAUNCH();
+    CK(launch_nblist(st, c->box, pos, c->dtype, n, rc, c->nb, nc[0], nc[1], nc[2], pairs, capacity, info));
     return 0;
 }

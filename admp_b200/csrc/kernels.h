@@ -118,8 +118,11 @@ struct NbWork {
     int32_t* nbr_count;    // n+1
     int32_t* nbr_start;    // n+1
     int capacity_atoms, capacity_cells;
+    void* geom;            // NbGeom (device), per context
+    void* scan_tmp;        // CUB scan scratch, per context
+    size_t scan_tmp_bytes;
 };
-void launch_nblist(cudaStream_t st, const BoxInfo* B, const void* pos, int dtype, int n, double rc, NbWork& w, int ncx, int ncy,
+cudaError_t launch_nblist(cudaStream_t st, const BoxInfo* B, const void* pos, int dtype, int n, double rc, NbWork& w, int ncx, int ncy,
                    int ncz, int32_t* pairs, int64_t capacity, int32_t* info);
 
 }  // namespace admp

@@ -146,32 +146,37 @@ __global__ void nb_pad_kernel(int n, const int32_t* __restrict__ nbr_start, int3
     if (blockIdx.x == 0 && threadIdx.x == 0) { info[0] = (int32_t)total; info[1] = total > capacity ? 1 : 0; }
 }
 
-static void* g_scan_tmp = nullptr;
-static size_t g_scan_tmp_bytes = 0;
-static NbGeom* g_geom = nullptr;
-
-static cudaError_t exclusive_scan(cudaStream_t st, const int32_t* in, int32_t* out, int n) {
+// geometry block + CUB scratch live in the context's NbWork (one per admp_ctx: no sharing across contexts, streams or devices)
+static cudaError_t exclusive_scan(cudaStream_t st, NbWork& w, const int32_t* in, int32_t* out, int n) {
     size_t need = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, need, in, out, n, st);
-    if (need > g_scan_tmp_bytes) {
-        if (g_scan_tmp) cudaFree(g_scan_tmp);
-        cudaError_t e = cudaMalloc(&g_scan_tmp, need);
+    cudaError_t e = cub::DeviceScan::ExclusiveSum(nullptr, need, in, out, n, st);
+    if (e != cudaSuccess) return e;
+    if (need > w.scan_tmp_bytes) {
+        if (w.scan_tmp) cudaFree(w.scan_tmp);
+        w.scan_tmp = nullptr;
+        w.scan_tmp_bytes = 0;
+        e = cudaMalloc(&w.scan_tmp, need);
         if (e != cudaSuccess) return e;
-        g_scan_tmp_bytes = need;
+        w.scan_tmp_bytes = need;
     }
-    return cub::DeviceScan::ExclusiveSum(g_scan_tmp, need, in, out, n, st);
+    return cub::DeviceScan::ExclusiveSum(w.scan_tmp, need, in, out, n, st);
 }
 
-void launch_nblist(cudaStream_t st, const BoxInfo* B, const void* pos, int dtype, int n, double rc, NbWork& w, int ncx, int ncy,
-                   int ncz, int32_t* pairs, int64_t capacity, int32_t* info) {
-    if (g_geom == nullptr) cudaMalloc(&g_geom, sizeof(NbGeom));
+cudaError_t launch_nblist(cudaStream_t st, const BoxInfo* B, const void* pos, int dtype, int n, double rc, NbWork& w, int ncx, int ncy,
+                          int ncz, int32_t* pairs, int64_t capacity, int32_t* info) {
+    if (w.geom == nullptr) {
+        cudaError_t e = cudaMalloc(&w.geom, sizeof(NbGeom));
+        if (e != cudaSuccess) return e;
+    }
+    NbGeom* g_geom = static_cast<NbGeom*>(w.geom);
+    cudaError_t e;
     const int ncell = ncx * ncy * ncz;
     const int tb = 128, gb = (n + tb - 1) / tb;
     cudaMemsetAsync(w.cell_count, 0, sizeof(int32_t) * (ncell + 1), st);
     nb_geom_kernel<double><<<1, 32, 0, st>>>(B, rc, ncx, ncy, ncz, g_geom);
     if (dtype == ADMP_F64) nb_assign_kernel<double><<<gb, tb, 0, st>>>(n, g_geom, (const double*)pos, w.cell_of, w.cell_count);
     else nb_assign_kernel<float><<<gb, tb, 0, st>>>(n, g_geom, (const float*)pos, w.cell_of, w.cell_count);
-    exclusive_scan(st, w.cell_count, w.cell_start, ncell + 1);
+    if ((e = exclusive_scan(st, w, w.cell_count, w.cell_start, ncell + 1)) != cudaSuccess) return e;
     cudaMemsetAsync(w.cell_count, 0, sizeof(int32_t) * (ncell + 1), st);       // reused as the fill cursor
     nb_fill_kernel<<<gb, tb, 0, st>>>(n, w.cell_of, w.cell_start, w.cell_count, w.sorted);
     nb_sort_cells_kernel<<<(ncell + tb - 1) / tb, tb, 0, st>>>(ncell, w.cell_start, w.sorted);
@@ -180,12 +185,13 @@ void launch_nblist(cudaStream_t st, const BoxInfo* B, const void* pos, int dtype
         nb_pairs_kernel<double, false><<<gb, tb, 0, st>>>(n, g_geom, (const double*)pos, w.cell_start, w.sorted, w.nbr_count, nullptr, nullptr, 0);
     else
         nb_pairs_kernel<float, false><<<gb, tb, 0, st>>>(n, g_geom, (const float*)pos, w.cell_start, w.sorted, w.nbr_count, nullptr, nullptr, 0);
-    exclusive_scan(st, w.nbr_count, w.nbr_start, n + 1);
+    if ((e = exclusive_scan(st, w, w.nbr_count, w.nbr_start, n + 1)) != cudaSuccess) return e;
     if (dtype == ADMP_F64)
         nb_pairs_kernel<double, true><<<gb, tb, 0, st>>>(n, g_geom, (const double*)pos, w.cell_start, w.sorted, nullptr, w.nbr_start, pairs, capacity);
     else
         nb_pairs_kernel<float, true><<<gb, tb, 0, st>>>(n, g_geom, (const float*)pos, w.cell_start, w.sorted, nullptr, w.nbr_start, pairs, capacity);
     nb_pad_kernel<<<64, 256, 0, st>>>(n, w.nbr_start, pairs, capacity, info);
+    return cudaGetLastError();
 }
 
 }  // namespace admp

@@ -108,7 +108,8 @@ scf_field_kernel(int n, T kappa, const T* __restrict__ M, const T* __restrict__ 
             const double u = (double)U[3 * a + c];
             const double f = (double)F[3 * a + c] - 2 * D * f1 * ((double)M[(size_t)a * 10 + 1 + c] + u) + D * u / pt;
             F[3 * a + c] = (T)f;
-            if (p > 0.001) mx = fmax(mx, fabs(f));
+            // a NaN / Inf field must read as "not converged" (the reference's `NaN < thresh` is False): fmax would drop it
+            if (p > 0.001) mx = (f == f && fabs(f) <= 1.7e308) ? fmax(mx, fabs(f)) : 1.7976931348623157e308;
         }
     }
     mx = warp_max(mx);
@@ -134,10 +135,10 @@ __global__ void scf_decide_kernel(int32_t* __restrict__ state, double* __restric
         const int it = state[0];
         const double mx = __longlong_as_double((long long)reinterpret_cast<unsigned long long*>(scalars)[ADMP_S_MAXFIELD]);
         if (mx < thresh) {
-            state[1] = 0; state[3] = it; state[4] = (it == maxiter - 1) ? 0 : 1;
+            state[1] = 0; state[3] = it; state[4] = (it >= maxiter - 1) ? 0 : 1;
         } else {
             state[1] = 1;
-            if (it == maxiter - 1) {
+            if (it >= maxiter - 1) {
                 // last allowed cycle: U is still updated (pme.py:138), flag False. The mesh of the updated U is
                 // rebuilt by one more pass of the loop body, or by the caller's final (virial) pass.
                 state[3] = it; state[4] = 0;

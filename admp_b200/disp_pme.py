@@ -83,6 +83,8 @@ class ADMPDispPmeForce:
         n, dt, dev = self.n_atoms, self._dtype, c.device
         if positions.shape != (n, 3) or c_list.shape != (n, 3):
             raise ValueError('positions and c_list must be (%d, 3); c_list columns are C6, C8, C10' % n)
+        if tuple(box.shape) != (3, 3) or mScales.shape != (5,):
+            raise ValueError('box must be (3, 3) and mScales must hold exactly 5 entries')
         scal = torch.empty(_lib.S_COUNT, dtype=torch.float64, device=dev)
         dpos = torch.empty((n, 3), dtype=dt, device=dev) if flags & _lib.WANT_GRAD else None
         dc = torch.empty((n, 3), dtype=dt, device=dev) if flags & _lib.WANT_PGRAD else None
@@ -94,14 +96,27 @@ class ADMPDispPmeForce:
     def _prep(self, x):
         return to_dev(x, self._dtype, self._ctx.device)
 
+    def _prep_c(self, c_list):
+        """The reference's contract is Na x (pmax-4)/2 columns (admp/disp_pme.py:92); the kernels stride by 3. Narrower
+        inputs are zero-padded (differentiably: autograd slices the gradient back to the caller's width)."""
+        c = self._prep(c_list)
+        need = (int(self.pmax) - 4) // 2
+        if c.dim() != 2 or c.shape[0] != self.n_atoms or not (need <= c.shape[1] <= 3):
+            raise ValueError('c_list must be (%d, k) with %d <= k <= 3 for pmax = %d' % (self.n_atoms, need, self.pmax))
+        if c.shape[1] < 3:
+            c = torch.nn.functional.pad(c, (0, 3 - c.shape[1]))
+        return c.contiguous()
+
     def get_energy(self, positions, box, pairs, c_list, mScales):
         """admp/disp_pme.py:44-50"""
-        positions, box, c_list, mScales = map(self._prep, (positions, box, c_list, mScales))
+        positions, box, mScales = map(self._prep, (positions, box, mScales))
+        c_list = self._prep_c(c_list)
         return _DispFunction.apply(self, pairs_to_dev(pairs, self._ctx.device), positions, box, c_list, mScales)
 
     def get_forces(self, positions, box, pairs, c_list, mScales):
         """value_and_grad(get_energy): (E, +dE/dpositions)  (admp/disp_pme.py:76)"""
-        positions, box, c_list, mScales = (self._prep(x).detach() for x in (positions, box, c_list, mScales))
+        positions, box, mScales = (self._prep(x).detach() for x in (positions, box, mScales))
+        c_list = self._prep_c(c_list).detach()
         scal, dpos, _ = self._eval(positions, box, pairs_to_dev(pairs, self._ctx.device), c_list, mScales, _lib.WANT_GRAD)
         return (scal[_lib.S_E_REAL] + scal[_lib.S_E_RECIP] + scal[_lib.S_E_SELF]).to(self._dtype), dpos
 

@@ -8,6 +8,8 @@ format=OrderedSparse)`` call every reference script makes
 
 The pair SET is bit-exact w.r.t. oracle/pairlist.py (same float64 operation order).
 """
+import ctypes
+
 import numpy as np
 import torch
 
@@ -51,16 +53,20 @@ class NeighborListFn:
         self.dr_threshold = float(dr_threshold)
         self.capacity_multiplier = float(capacity_multiplier)
         self._ctx = Context()
+        # host and device copies of the box, made once: a build then needs no device-to-host read and no host sync
+        hb = box.detach().cpu().numpy() if isinstance(box, torch.Tensor) else np.asarray(box)
+        self._box_host = np.ascontiguousarray(hb, dtype=np.float64).reshape(3, 3)
+        self._box_dev = to_dev(self._box_host, self._ctx.dtype, self._ctx.device)
 
     def _build(self, positions, capacity):
         cx = self._ctx
         pos = to_dev(positions, cx.dtype, cx.device).detach()
-        box = to_dev(self.box, cx.dtype, cx.device).detach()
         n = int(pos.shape[0])
         pairs = torch.empty((capacity, 2), dtype=torch.int32, device=cx.device)
         info = torch.zeros(2, dtype=torch.int32, device=cx.device)
-        _lib.check(cx.lib.admp_nblist_build(cx.handle, _lib.stream_ptr(), _lib.ptr(pos), _lib.ptr(box), n,
-                                            self.rc + self.dr_threshold, _lib.ptr(pairs), int(capacity), _lib.ptr(info)))
+        _lib.check(cx.lib.admp_nblist_build_hostbox(cx.handle, _lib.stream_ptr(), _lib.ptr(pos), _lib.ptr(self._box_dev),
+                                                    self._box_host.ctypes.data_as(ctypes.c_void_p), n, self.rc + self.dr_threshold,
+                                                    _lib.ptr(pairs), int(capacity), _lib.ptr(info)))
         return NeighborList(self, pairs, info, pos)
 
     def allocate(self, positions, extra_capacity=0):

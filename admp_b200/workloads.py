@@ -94,8 +94,9 @@ def dense_water(n_side=64, spacing=3.104, seed=7, jitter=0.1, polarizable=True):
     density, random orientations from default_rng(seed) (SURVEY 8(d) "dense-256k" for n_side = 64)."""
     b = _base()
     rng = np.random.default_rng(seed)
-    nmol = n_side ** 3
-    g = np.stack(np.meshgrid(*[np.arange(n_side)] * 3, indexing='ij'), -1).reshape(-1, 3).astype(np.float64)
+    sides = (n_side,) * 3 if np.isscalar(n_side) else tuple(int(v) for v in n_side)      # cube, or (nx, ny, nz) molecules
+    nmol = sides[0] * sides[1] * sides[2]
+    g = np.stack(np.meshgrid(*[np.arange(v) for v in sides], indexing='ij'), -1).reshape(-1, 3).astype(np.float64)
     centres = (g + 0.5) * spacing + rng.normal(0.0, jitter, size=(nmol, 3))
     h = 104.52 * np.pi / 360.0
     local = np.array([[0.0, 0.0, 0.0], [0.9572 * np.sin(h), 0.0, 0.9572 * np.cos(h)], [-0.9572 * np.sin(h), 0.0, 0.9572 * np.cos(h)]])
@@ -106,6 +107,6 @@ def dense_water(n_side=64, spacing=3.104, seed=7, jitter=0.1, polarizable=True):
                   np.stack([2*(bq*c+a*d), a*a-bq*bq+c*c-d*d, 2*(c*d-a*bq)], 1),
                   np.stack([2*(bq*d-a*c), 2*(c*d+a*bq), a*a-bq*bq-c*c+d*d], 1)], 1)
     pos = (centres[:, None, :] + np.einsum('mab,kb->mka', R, local)).reshape(-1, 3)
-    w = _assemble(pos, np.full(3, n_side * spacing), b, polarizable)
+    w = _assemble(pos, np.array(sides, dtype=np.float64) * spacing, b, polarizable)
     w.K = None
     return w

@@ -220,6 +220,9 @@ int admp_tt_pair(admp_ctx* ctx, void* stream, const void* pos, const void* box,
  * info[0] = number of pairs found, info[1] = overflow flag (device int32[2]). */
 int admp_nblist_build(admp_ctx* ctx, void* stream, const void* pos, const void* box, int n_atoms,
                       double rc, int32_t* pairs, int64_t capacity, int32_t* info);
+/* same with the caller's host copy of the box (9 doubles): no device-to-host read of the box, no host synchronisation */
+int admp_nblist_build_hostbox(admp_ctx* ctx, void* stream, const void* pos, const void* box, const double* box_host,
+                              int n_atoms, double rc, int32_t* pairs, int64_t capacity, int32_t* info);
 
 /* ---- x-slab decomposition of reciprocal space over the GPUs of one NVLink domain (no reference counterpart;
  * north-star config "256k-water box at 1/2/4/8 B200"). Rank r owns the x planes [floor(r*K1/n), floor((r+1)*K1/n)) of the mesh
