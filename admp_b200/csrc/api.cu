@@ -1034,6 +1034,32 @@ extern "C" int admp_tt_pair(admp_ctx* c, void* stream, const void* pos, const vo
 static int nblist_build_impl(admp_ctx* c, cudaStream_t st, const void* pos, const void* box, const double* hb, int n, double rc,
                              int32_t* pairs, int64_t capacity, int32_t* info);
 
+extern "C" int admp_pair_geometry(admp_ctx* c, void* stream, const void* pos, const void* box, const int32_t* pairs, int64_t n_rows,
+                                  void* dr, int32_t* sidx) {
+    if (need(c, false, true)) return 1;
+    if (!dr || !sidx) return fail("admp_pair_geometry: outputs missing");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(c->device));
+    DISPATCH(c, launch_box_setup, st, box, c->box, c->K[0] ? c->K[0] : 6, c->K[1] ? c->K[1] : 6, c->K[2] ? c->K[2] : 6);
+    DISPATCH(c, launch_pair_geom, st, n_rows, c->n_atoms, c->box, pos, pairs, c->cov_off, c->cov_idx, c->cov_nb, dr, sidx);
+    CKLAUNCH();
+    return 0;
+}
+
+extern "C" int admp_pair_geometry_bwd(admp_ctx* c, void* stream, const void* pos, const void* box, const int32_t* pairs, int64_t n_rows,
+                                      const void* g_dr, uint32_t flags, void* dpos, double* scalars) {
+    if (need(c, false, true)) return 1;
+    if (!g_dr || !dpos || !scalars) return fail("admp_pair_geometry_bwd: arguments missing");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemsetAsync(scalars, 0, sizeof(double) * ADMP_S_COUNT, st));
+    CK(cudaMemsetAsync(dpos, 0, (size_t)c->n_atoms * 3 * c->w, st));
+    DISPATCH(c, launch_box_setup, st, box, c->box, c->K[0] ? c->K[0] : 6, c->K[1] ? c->K[1] : 6, c->K[2] ? c->K[2] : 6);
+    DISPATCH(c, launch_pair_geom_bwd, st, n_rows, c->n_atoms, c->box, pos, pairs, g_dr, flags, dpos, scalars);
+    CKLAUNCH();
+    return 0;
+}
+
 extern "C" int admp_nblist_build(admp_ctx* c, void* stream, const void* pos, const void* box, int n, double rc, int32_t* pairs,
                                  int64_t capacity, int32_t* info) {
     if (!c) return fail("null ctx");

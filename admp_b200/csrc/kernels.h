@@ -29,6 +29,14 @@ size_t pair_record_bytes(int dtype_bytes);        // per-atom record of the stag
 template <typename T>
 void launch_pair_pack(cudaStream_t st, int n, const void* pos, const void* M, const void* U, const void* pol, const void* tholes, void* rec);
 
+// pair_generic.cu - geometry + adjoint halves of the generic pair driver (any user kernel in between)
+template <typename T>
+void launch_pair_geom(cudaStream_t st, int64_t n_rows, int n_atoms, const BoxInfo* B, const void* pos, const int32_t* pairs,
+                      const int32_t* cov_off, const int32_t* cov_idx, const int8_t* cov_nb, void* dr, int32_t* sidx);
+template <typename T>
+void launch_pair_geom_bwd(cudaStream_t st, int64_t n_rows, int n_atoms, const BoxInfo* B, const void* pos, const int32_t* pairs,
+                          const void* gdr, uint32_t flags, void* dpos, double* scalars);
+
 // pair_cluster.cu - j-cluster x i-lane tiles built from the caller's pair rows (dense, (j, i)-sorted lists)
 struct ClusterWork {
     int32_t *cl_of, *cl_first, *cl_size;   // per atom / per cluster (host-built from the covalent map at set_topology)

@@ -28,6 +28,7 @@ class _RecipFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cx, kind, lmax, Kvec, positions, box, Q):
         n = ctx.needs_input_grad
+        ctx.kvec_ref = getattr(cx, 'kvec_ref', False)
         flags = 0
         if n[4] or n[5] or n[6]:
             flags |= _lib.WANT_GRAD
@@ -75,6 +76,8 @@ class _RecipFunction(torch.autograd.Function):
             W = scal[_lib.S_DNSTAR:_lib.S_DNSTAR + 9].reshape(3, 3)
             tk = scal[_lib.S_TK:_lib.S_TK + 6]
             T = torch.stack([tk[0], tk[1], tk[2], tk[1], tk[3], tk[4], tk[2], tk[4], tk[5]]).reshape(3, 3)
+            if ctx.kvec_ref:          # settings.KVEC_ORDER = 'reference': the reference's k table swaps mesh axes 0 and 1 (recip.py:339-341)
+                T = T[[1, 0, 2]][:, [1, 0, 2]]
             nstar = (ctx.Kvec[None, :] * inv).T
             dbox = -(inv.T @ (W.T @ nstar)) - 2 * T @ inv.T - scal[_lib.S_E_RECIP] * inv.T
             dbox = (g * dbox).to(dt)
@@ -94,6 +97,8 @@ def generate_pme_recip(Ck_fn, kappa, gamma, pme_order, K1, K2, K3, lmax):
         raise NotImplementedError('l > 2 (beyond quadrupole) not supported')
     cx = Context()
     cx.set_pme(kappa, K1, K2, K3, lmax)
+    from . import settings
+    cx.kvec_ref = settings.KVEC_ORDER == 'reference'
     state = {'n': 0}
     Kvec = torch.tensor([float(K1), float(K2), float(K3)], dtype=torch.float64, device=cx.device)
 

@@ -215,6 +215,16 @@ int admp_tt_pair(admp_ctx* ctx, void* stream, const void* pos, const void* box,
                  const void* b, const void* q, const void* c, uint32_t flags, double* scalars,
                  void* dpos, void* dparams);
 
+/* The generic half of generate_pairwise_interaction (admp/pairwise.py:57-77) for ANY user pair kernel: per row the
+ * minimum-image distance dr (1.0 on rows that are not evaluated) and the scale index covalent_map[i,j]-1 with 0 -> 4
+ * (-1 on rows that are not evaluated); and its adjoint: g_dr = dE/d(dr) per row -> dpos (n,3) (zeroed, then accumulated)
+ * and, with ADMP_WANT_VIRIAL, scalars[ADMP_S_DBOX..] (zeroed, then the image-shift term). The user kernel runs in between
+ * on device arrays (admp_b200/pairwise.py evaluates it with tensor operations; a JAX host would trace it). */
+int admp_pair_geometry(admp_ctx* ctx, void* stream, const void* pos, const void* box, const int32_t* pairs,
+                       int64_t n_rows, void* dr, int32_t* sidx);
+int admp_pair_geometry_bwd(admp_ctx* ctx, void* stream, const void* pos, const void* box, const int32_t* pairs,
+                           int64_t n_rows, const void* g_dr, uint32_t flags, void* dpos, double* scalars);
+
 /* jax_md.partition.neighbor_list(..., format=OrderedSparse) replacement (call sites:
  * examples/water_1024/run_admp.py:109-112). pairs (capacity,2) int32 padded with (N,N);
  * info[0] = number of pairs found, info[1] = overflow flag (device int32[2]). */
