@@ -26,7 +26,7 @@ EXPORTS = [
     'admp_frames_fwd', 'admp_frames_bwd', 'admp_rotate', 'admp_pme_real', 'admp_pme_recip', 'admp_pme_self',
     'admp_pme_spread', 'admp_pme_spread_only', 'admp_pme_fft', 'admp_pme_convolve', 'admp_pme_gather', 'admp_ctx_buffer', 'admp_ctx_buffer_io', 'admp_pme_fft_convolve', 'admp_pme_fft_pass', 'admp_set_box', 'admp_mesh_zero', 'admp_pme_spread_range',
     'admp_pme_gather_range', 'admp_pme_self_range', 'admp_frames_bwd_range', 'admp_scf_step', 'admp_virial_finalize', 'admp_ctx_fft_backend', 'admp_ctx_set_fft_backend',
-    'admp_pme_eval', 'admp_disp_eval', 'admp_tt_pair', 'admp_pair_geometry', 'admp_pair_geometry_bwd', 'admp_nblist_build', 'admp_nblist_build_hostbox', 'admp_fp_peak',
+    'admp_pme_eval', 'admp_disp_eval', 'admp_tt_pair', 'admp_tt_pair_c10', 'admp_pair_geometry', 'admp_pair_geometry_bwd', 'admp_nblist_build', 'admp_nblist_build_hostbox', 'admp_fp_peak',
     'admp_ipc_export', 'admp_ipc_open', 'admp_ipc_close', 'admp_ctx_set_peers', 'admp_slab_zero', 'admp_slab_spread', 'admp_slab_fft',
     'admp_slab_gather',
 ]
@@ -92,6 +92,7 @@ def load():
     lib.admp_pme_eval.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, u32, i32, dbl, vp, vp, vp, vp, vp, vp, vp]
     lib.admp_disp_eval.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp, i32, u32, vp, vp, vp]
     lib.admp_tt_pair.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, u32, vp, vp, vp]
+    lib.admp_tt_pair_c10.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, u32, vp, vp, vp]
     lib.admp_pair_geometry.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp]
     lib.admp_pair_geometry_bwd.argtypes = [vp, vp, vp, vp, vp, i64, vp, u32, vp, vp]
     lib.admp_nblist_build.argtypes = [vp, vp, vp, vp, i32, dbl, vp, i64, vp]

@@ -1011,9 +1011,9 @@ extern "C" int admp_disp_eval(admp_ctx* c, void* stream, const void* pos, const 
     return 0;
 }
 
-extern "C" int admp_tt_pair(admp_ctx* c, void* stream, const void* pos, const void* box, const int32_t* pairs, int64_t n_rows,
-                            const void* mScales, const void* a, const void* b, const void* q, const void* cc, uint32_t flags,
-                            double* scalars, void* dpos, void* dparams) {
+static int tt_pair_impl(admp_ctx* c, void* stream, const void* pos, const void* box, const int32_t* pairs, int64_t n_rows,
+                        const void* mScales, const void* a, const void* b, const void* q, const void* c6, const void* c8, const void* c10,
+                        int n_par, uint32_t flags, double* scalars, void* dpos, void* dparams) {
     if (need(c, false, true)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(c->device));
@@ -1021,14 +1021,27 @@ extern "C" int admp_tt_pair(admp_ctx* c, void* stream, const void* pos, const vo
     const size_t w = c->w;
     CK(cudaMemsetAsync(c->scal, 0, sizeof(double) * ADMP_S_COUNT, st));
     if (dpos) CK(cudaMemsetAsync(dpos, 0, (size_t)n * 3 * w, st));
-    if (dparams) CK(cudaMemsetAsync(dparams, 0, (size_t)n * 4 * w, st));
+    if (dparams) CK(cudaMemsetAsync(dparams, 0, (size_t)n * n_par * w, st));
     DISPATCH(c, launch_box_setup, st, box, c->box, c->K[0] ? c->K[0] : 6, c->K[1] ? c->K[1] : 6, c->K[2] ? c->K[2] : 6);
     const uint32_t f = flags & (ADMP_WANT_GRAD | ADMP_WANT_VIRIAL | ADMP_WANT_PGRAD);
-    DISPATCH(c, launch_tt_pair, st, n_rows, n, c->box, pos, pairs, c->cov_off, c->cov_idx, c->cov_nb, mScales, a, b, q, cc, f, dpos,
+    DISPATCH(c, launch_tt_pair, st, n_rows, n, c->box, pos, pairs, c->cov_off, c->cov_idx, c->cov_nb, mScales, a, b, q, c6, c8, c10, f, dpos,
              (f & ADMP_WANT_PGRAD) ? dparams : nullptr, c->scal);
     CKLAUNCH();
     CK(cudaMemcpyAsync(scalars, c->scal, sizeof(double) * ADMP_S_COUNT, cudaMemcpyDeviceToDevice, st));
     return 0;
+}
+
+extern "C" int admp_tt_pair(admp_ctx* c, void* stream, const void* pos, const void* box, const int32_t* pairs, int64_t n_rows,
+                            const void* mScales, const void* a, const void* b, const void* q, const void* cc, uint32_t flags,
+                            double* scalars, void* dpos, void* dparams) {
+    return tt_pair_impl(c, stream, pos, box, pairs, n_rows, mScales, a, b, q, cc, nullptr, nullptr, 4, flags, scalars, dpos, dparams);
+}
+
+extern "C" int admp_tt_pair_c10(admp_ctx* c, void* stream, const void* pos, const void* box, const int32_t* pairs, int64_t n_rows,
+                                const void* mScales, const void* a, const void* b, const void* q, const void* c6, const void* c8,
+                                const void* c10, uint32_t flags, double* scalars, void* dpos, void* dparams) {
+    if (!c6 || !c8 || !c10) return fail("admp_tt_pair_c10: c6, c8 and c10 are required");
+    return tt_pair_impl(c, stream, pos, box, pairs, n_rows, mScales, a, b, q, c6, c8, c10, 6, flags, scalars, dpos, dparams);
 }
 
 static int nblist_build_impl(admp_ctx* c, cudaStream_t st, const void* pos, const void* box, const double* hb, int n, double rc,

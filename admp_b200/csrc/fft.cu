@@ -361,7 +361,7 @@ struct FftDimCfg {
     FastOps ops;
 };
 
-static bool dim_cfg(int N, int tw_len, size_t esz, size_t smem_cap, int min_ls, bool zpass, bool allow_fast, FftDimCfg& c) {
+static bool dim_cfg(int N, int tw_len, size_t esz, size_t smem_cap, int min_ls, bool zpass, bool allow_fast, FftDimCfg& c, bool xpass = false) {
     if (!fft_factorize(N, c.P)) return false;
     c.LS = N | 1;
     if (c.LS < min_ls) c.LS = min_ls | 1;
@@ -376,7 +376,8 @@ static bool dim_cfg(int N, int tw_len, size_t esz, size_t smem_cap, int min_ls, 
         // two tile widths exist for the larger sizes: strided passes default to the wide tile (longer contiguous
         // global segments), the contiguous Z passes to the narrow one (more resident blocks); measured on B200
         const char* e = getenv("ADMP_FFT_WIDE");
-        const bool wide = e ? atoi(e) > 0 : !zpass;
+        bool wide = e ? atoi(e) > 0 : !zpass;
+        if (xpass) { const char* ex = getenv("ADMP_FFT_XWIDE"); if (ex) wide = atoi(ex) > 0; }
         c.fast = esz == 8 ? fast_lookup<double>(N, wide, c.ops) : fast_lookup<float>(N, wide, c.ops);
         if (c.fast) {
             c.ops.prepare(c.ops);
@@ -425,7 +426,7 @@ Fft3d* fft3d_create(int K1, int K2, int K3, int dtype, const char** why) {
     const char* env = getenv("ADMP_FFT");
     const bool allow_fast = !(env && strcmp(env, "generic") == 0);
     if (!dim_cfg(M, K3, f->esz, cap, M + 1, true, allow_fast, f->z) || !dim_cfg(K2, K2, f->esz, cap, 0, false, allow_fast, f->y) ||
-        !dim_cfg(K1, K1, f->esz, cap, 0, false, allow_fast, f->x)) {
+        !dim_cfg(K1, K1, f->esz, cap, 0, false, allow_fast, f->x, true)) {
         *why = msg_fac;
         delete f;
         return nullptr;

@@ -60,7 +60,8 @@ void launch_disp_pair(cudaStream_t st, int64_t n_rows, int n_atoms, const BoxInf
 template <typename T>
 void launch_tt_pair(cudaStream_t st, int64_t n_rows, int n_atoms, const BoxInfo* B, const void* pos, const int32_t* pairs,
                     const int32_t* cov_off, const int32_t* cov_idx, const int8_t* cov_nb, const void* mS, const void* a,
-                    const void* b, const void* q, const void* c, uint32_t flags, void* dpos, void* dparams, double* scalars);
+                    const void* b, const void* q, const void* c, const void* c8, const void* c10, uint32_t flags, void* dpos,
+                    void* dparams, double* scalars);
 
 // recip.cu
 template <typename T>

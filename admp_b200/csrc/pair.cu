@@ -503,14 +503,16 @@ disp_pair_kernel(int64_t n_rows, int n_atoms, const BoxInfo* __restrict__ Bp, T 
     if (want_pg) block_accumulate<5>(acc_ms, red, scalars + ADMP_S_DMSCALE);
 }
 
-// Tang-Toennies short-range kernel through the generic pair driver: admp/pairwise.py:45-113.
+// Tang-Toennies short-range kernel through the generic pair driver: admp/pairwise.py:45-113 (TT_damping_qq_c6_kernel), and
+// its extension to the C8 / C10 terms with their own Tang-Toennies damping (pc8 / pc10 non-null):
+//   f = 2625.5 a e^-br - 2625.5 e^-br (1 + br) q / br + sum_{n in 6[,8,10]} e^-br P_n(br) c_n,i c_n,j / r^n,  P_n = sum_{k<=n} x^k/k!
 template <typename T>
 __global__ void __launch_bounds__(128)
 tt_pair_kernel(int64_t n_rows, int n_atoms, const BoxInfo* __restrict__ Bp, const T* __restrict__ pos,
                const int32_t* __restrict__ pairs, const int32_t* __restrict__ cov_off, const int32_t* __restrict__ cov_idx,
                const int8_t* __restrict__ cov_nb, const T* __restrict__ mScales, const T* __restrict__ pa,
-               const T* __restrict__ pb, const T* __restrict__ pq, const T* __restrict__ pc, uint32_t flags,
-               T* __restrict__ dpos, T* __restrict__ dparams, double* __restrict__ scalars) {
+               const T* __restrict__ pb, const T* __restrict__ pq, const T* __restrict__ pc, const T* __restrict__ pc8,
+               const T* __restrict__ pc10, uint32_t flags, T* __restrict__ dpos, T* __restrict__ dparams, double* __restrict__ scalars) {
     __shared__ double red[10 * 4];
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double acc_e = 0.0, acc_box[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, acc_ms[5] = {0, 0, 0, 0, 0};
@@ -527,26 +529,45 @@ tt_pair_kernel(int64_t n_rows, int n_atoms, const BoxInfo* __restrict__ Bp, cons
         const T r = sqrt(r2);
         const int sidx = scale_index(cov_off, cov_idx, cov_nb, i, j);
         const T m = mScales[sidx];
-        const T ai = pa[i], aj = pa[j], bi = pb[i], bj = pb[j], qi = pq[i], qj = pq[j], ci = pc[i], cj = pc[j];
-        const T a = sqrt(ai * aj), b = sqrt(bi * bj), c = ci * cj, q = qi * qj;
+        const T ai = pa[i], aj = pa[j], bi = pb[i], bj = pb[j], qi = pq[i], qj = pq[j];
+        const T a = sqrt(ai * aj), b = sqrt(bi * bj), q = qi * qj;
         const T bohr = (T)1.889726878, ha = (T)2625.5;
         const T br = b * r * bohr, ex = exp(-br);
-        T poly = 1, term = 1, dpoly = 0;      // poly = sum_{k<=6} br^k/k!, dpoly = sum_{k<=5}
+        // P_n and x^n/n! for n = 6, 8, 10 (d/dx [e^-x P_n] = -e^-x x^n/n!)
+        T poly = 1, term = 1, P[3] = {0, 0, 0}, top[3] = {0, 0, 0};
 #pragma unroll
-        for (int k = 1; k <= 6; ++k) { dpoly = poly; term *= br / (T)k; poly += term; }
-        const T ir6 = (T)1 / (r2 * r2 * r2);
+        for (int k = 1; k <= 10; ++k) {
+            term *= br / (T)k;
+            poly += term;
+            if (k == 6) { P[0] = poly; top[0] = term; }
+            if (k == 8) { P[1] = poly; top[1] = term; }
+            if (k == 10) { P[2] = poly; top[2] = term; }
+        }
+        const T ir2 = (T)1 / r2, ir6 = ir2 * ir2 * ir2;
+        const T irn[3] = {ir6, ir6 * ir2, ir6 * ir2 * ir2};
+        const T* pcs[3] = {pc, pc8, pc10};
         const T f1 = ha * a * ex;
         const T f2 = -ha * ex * ((T)1 + br) * q / br;
-        const T f3 = ex * poly * c * ir6;
+        T f3 = 0, d3 = 0, nf3 = 0;          // dispersion energy, its d/d(br), sum n * term_n
+        T cn_i[3] = {0, 0, 0}, cn_j[3] = {0, 0, 0};
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            if (pcs[t] != nullptr) {
+                cn_i[t] = pcs[t][i]; cn_j[t] = pcs[t][j];
+                const T cc = cn_i[t] * cn_j[t];
+                const T e_t = ex * P[t] * cc * irn[t];
+                f3 += e_t;
+                d3 -= ex * top[t] * cc * irn[t];
+                nf3 += (T)(6 + 2 * t) * e_t;
+            }
+        }
         const T e = (f1 + f2 + f3) * m;
         acc_e = (double)e;
-        // d/d(br) of each term (r-dependence of 1/r^6 handled separately)
         const T d1 = -f1;
         // d/dbr [ -e^{-br}(1+br)/br ] = e^{-br} (1 + (1+br)/br^2)
         const T d2 = ha * ex * q * ((T)1 + ((T)1 + br) / (br * br));
-        const T d3 = ex * c * ir6 * (dpoly - poly);
         const T dE_dbr = (d1 + d2 + d3) * m;
-        const T dE_dr = dE_dbr * b * bohr - 6 * f3 * m / r;
+        const T dE_dr = dE_dbr * b * bohr - nf3 * m / r;
         if (want_grad) {
             T fv[3];
 #pragma unroll
@@ -573,8 +594,13 @@ tt_pair_kernel(int64_t n_rows, int n_atoms, const BoxInfo* __restrict__ Bp, cons
                 atomicAdd(dparams + n + i, eb * b / (2 * bi)); atomicAdd(dparams + n + j, eb * b / (2 * bj));
                 const T eq = m * (-ha * ex * ((T)1 + br) / br);
                 atomicAdd(dparams + 2 * n + i, eq * qj); atomicAdd(dparams + 2 * n + j, eq * qi);
-                const T ec = m * ex * poly * ir6;
-                atomicAdd(dparams + 3 * n + i, ec * cj); atomicAdd(dparams + 3 * n + j, ec * ci);
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    if (pcs[t] != nullptr) {
+                        const T ec = m * ex * P[t] * irn[t];
+                        atomicAdd(dparams + (3 + t) * n + i, ec * cn_j[t]); atomicAdd(dparams + (3 + t) * n + j, ec * cn_i[t]);
+                    }
+                }
             }
         }
     }
@@ -596,19 +622,20 @@ void launch_disp_pair(cudaStream_t st, int64_t n_rows, int n_atoms, const BoxInf
 template <typename T>
 void launch_tt_pair(cudaStream_t st, int64_t n_rows, int n_atoms, const BoxInfo* B, const void* pos, const int32_t* pairs,
                     const int32_t* cov_off, const int32_t* cov_idx, const int8_t* cov_nb, const void* mS, const void* a,
-                    const void* b, const void* q, const void* c, uint32_t flags, void* dpos, void* dparams, double* scalars) {
+                    const void* b, const void* q, const void* c, const void* c8, const void* c10, uint32_t flags, void* dpos,
+                    void* dparams, double* scalars) {
     if (n_rows <= 0) return;
     tt_pair_kernel<T><<<(unsigned)((n_rows + 127) / 128), 128, 0, st>>>(n_rows, n_atoms, B, (const T*)pos, pairs, cov_off, cov_idx, cov_nb,
                                                                        (const T*)mS, (const T*)a, (const T*)b, (const T*)q, (const T*)c,
-                                                                       flags, (T*)dpos, (T*)dparams, scalars);
+                                                                       (const T*)c8, (const T*)c10, flags, (T*)dpos, (T*)dparams, scalars);
 }
 template void launch_disp_pair<double>(cudaStream_t, int64_t, int, const BoxInfo*, double, int, const void*, const int32_t*, const int32_t*,
                                        const int32_t*, const int8_t*, const void*, const void*, uint32_t, void*, void*, double*);
 template void launch_disp_pair<float>(cudaStream_t, int64_t, int, const BoxInfo*, double, int, const void*, const int32_t*, const int32_t*,
                                       const int32_t*, const int8_t*, const void*, const void*, uint32_t, void*, void*, double*);
 template void launch_tt_pair<double>(cudaStream_t, int64_t, int, const BoxInfo*, const void*, const int32_t*, const int32_t*, const int32_t*,
-                                     const int8_t*, const void*, const void*, const void*, const void*, const void*, uint32_t, void*, void*, double*);
+                                     const int8_t*, const void*, const void*, const void*, const void*, const void*, const void*, const void*, uint32_t, void*, void*, double*);
 template void launch_tt_pair<float>(cudaStream_t, int64_t, int, const BoxInfo*, const void*, const int32_t*, const int32_t*, const int32_t*,
-                                    const int8_t*, const void*, const void*, const void*, const void*, const void*, uint32_t, void*, void*, double*);
+                                    const int8_t*, const void*, const void*, const void*, const void*, const void*, const void*, const void*, uint32_t, void*, void*, double*);
 
 }  // namespace admp

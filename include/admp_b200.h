@@ -214,6 +214,12 @@ int admp_tt_pair(admp_ctx* ctx, void* stream, const void* pos, const void* box,
                  const int32_t* pairs, int64_t n_rows, const void* mScales, const void* a,
                  const void* b, const void* q, const void* c, uint32_t flags, double* scalars,
                  void* dpos, void* dparams);
+/* the same pair pass with Tang-Toennies damped C8 and C10 terms added (sum_{n=6,8,10} e^-br P_n(br) c_n,i c_n,j / r^n; no
+ * reference counterpart: SURVEY 8(f) rank 3). params: a, b, q, c6, c8, c10; dparams (6, n). */
+int admp_tt_pair_c10(admp_ctx* ctx, void* stream, const void* pos, const void* box,
+                     const int32_t* pairs, int64_t n_rows, const void* mScales, const void* a,
+                     const void* b, const void* q, const void* c6, const void* c8, const void* c10,
+                     uint32_t flags, double* scalars, void* dpos, void* dparams);
 
 /* The generic half of generate_pairwise_interaction (admp/pairwise.py:57-77) for ANY user pair kernel: per row the
  * minimum-image distance dr (1.0 on rows that are not evaluated) and the scale index covalent_map[i,j]-1 with 0 -> 4
