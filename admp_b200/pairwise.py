@@ -188,6 +188,8 @@ def generate_pairwise_interaction(pair_int_kernel, covalent_map, static_args=Non
             if len(params) != pair_int_kernel.n_params:
                 raise TypeError('%s takes %d per-atom parameter arrays' % (pair_int_kernel.name, pair_int_kernel.n_params))
             return _FusedPairFunction.apply(holder, pair_int_kernel, pr, positions, box, mScales, *params)
+        if int(pr.shape[0]) == 0:
+            return positions.sum() * 0
         dr, sidx = _PairGeometry.apply(holder, pr, positions, box)
         live = sidx >= 0
         rows = torch.nonzero(live, as_tuple=False).squeeze(1)            # pairwise.py:60: only i < j rows are evaluated
