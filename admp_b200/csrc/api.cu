@@ -55,6 +55,9 @@ struct admp_ctx {
     BoxInfo* box = nullptr;
     // reciprocal space
     void *mesh = nullptr, *spec = nullptr, *fftwork = nullptr;
+    void* phi = nullptr;            // big meshes: the SCF body's inverse transform writes the potential here (see scf_body)
+    const void* phi_cur = nullptr;  // where the potential of the last reciprocal pass lives (mesh or phi)
+    cudaEvent_t ev_zfwd = nullptr;
     size_t mesh_bytes = 0, spec_bytes = 0, fftwork_bytes = 0;
     cufftHandle plan_fwd = 0, plan_inv = 0;
     bool plans = false;
@@ -160,6 +163,7 @@ extern "C" int admp_ctx_create(admp_ctx** out, int device, int dtype) {
     CK(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_zfwd, cudaEventDisableTiming));
     c->ws_bytes = sizeof(BoxInfo) + sizeof(double) * ADMP_S_COUNT + 256;
     *out = c;
     return 0;
@@ -167,8 +171,8 @@ extern "C" int admp_ctx_create(admp_ctx** out, int device, int dtype) {
 
 static void free_recip(admp_ctx* c) {
     if (c->plans) { cufftDestroy(c->plan_fwd); cufftDestroy(c->plan_inv); c->plans = false; }
-    c->ws_bytes -= c->mesh_bytes + c->spec_bytes + c->fftwork_bytes;
-    dfree(c->mesh); dfree(c->spec); dfree(c->fftwork);
+    c->ws_bytes -= c->mesh_bytes + c->spec_bytes + c->fftwork_bytes + (c->phi ? c->mesh_bytes : 0);
+    dfree(c->mesh); dfree(c->spec); dfree(c->fftwork); dfree(c->phi);
     c->mesh_bytes = c->spec_bytes = c->fftwork_bytes = 0;
     for (int d = 0; d < 3; ++d) dfree(c->bt[d]);
     dfree(c->ek); dfree(c->k2); dfree(c->ortho);
@@ -219,6 +223,7 @@ extern "C" int admp_ctx_destroy(admp_ctx* c) {
     if (c->side_stream) cudaStreamDestroy(c->side_stream);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ev_zfwd) cudaEventDestroy(c->ev_zfwd);
     if (c->slab_aux.ready) {
         for (int s = 0; s < SLAB_STREAMS; ++s) cudaStreamDestroy(c->slab_aux.copy_stream[s]);
         cudaEventDestroy(c->slab_aux.fork);
@@ -288,6 +293,16 @@ extern "C" int admp_ctx_set_pme(admp_ctx* c, double kappa, int K1, int K2, int K
     c->fft_note = c->fft ? "" : why;
     cudaGetLastError();
     c->ws_bytes += c->mesh_bytes + c->spec_bytes;
+    // second real buffer for the SCF body of meshes that do not fit in L2 (ADMP_TWO_MESH=0/1 overrides the size rule; on the
+    // L2-resident 154^3 mesh the larger working set costs more than the overlapped zero-fill saves: -8 % measured)
+    {
+        const char* e2 = getenv("ADMP_TWO_MESH");
+        const bool want = e2 ? atoi(e2) > 0 : (c->mesh_bytes > ((size_t)96 << 20));
+        if (want && c->use_custom_fft) {
+            if (cudaMalloc(&c->phi, c->mesh_bytes) == cudaSuccess) c->ws_bytes += c->mesh_bytes;
+            else { c->phi = nullptr; cudaGetLastError(); }
+        }
+    }
     if (!c->use_custom_fft && ensure_cufft(c)) return 1;
     return 0;
 }
@@ -421,6 +436,7 @@ static void conv_tables(admp_ctx* c, cudaStream_t st) {
 static int recip_field(admp_ctx* c, cudaStream_t st, const void* pos, const void* M, int cols, int stride, const void* U,
                        int kind, double* scalars, int want_vir, bool tables = true) {
     if (tables) conv_tables(c, st);
+    c->phi_cur = c->mesh;
     CK(cudaMemsetAsync(c->mesh, 0, c->mesh_bytes, st));
     DISPATCH(c, launch_spread, st, c->n_atoms, c->box, pos, M, cols, stride, U, c->mesh);
     CKLAUNCH();
@@ -813,9 +829,22 @@ static int scf_body(admp_ctx* c, cudaStream_t st, int maxiter, double thresh, ui
              c->cw.state);
     DISPATCH(c, launch_pme_cluster, c->side_stream, c->cw.n_clusters, c->box, c->kappa, c->cw, c->rec, c->s_U, c->s_mS, c->s_pS, 1, 0u, nullptr,
              nullptr, c->Fscf, nullptr, nullptr, c->scal);
-    CK(cudaEventRecord(c->ev_join, c->side_stream));
-    if (recip_field(c, st, c->s_pos, c->M, 10, 10, c->s_U, ADMP_CK_COULOMB, c->scal, 0, false)) return 1;
-    DISPATCH(c, launch_gather, st, c->n_atoms, c->box, c->s_pos, c->M, 10, 10, c->s_U, c->mesh, 1, 0u, nullptr, nullptr, 10, c->Fscf, c->scal);
+    if (c->phi != nullptr && c->use_custom_fft) {
+        // Big meshes (HBM-bound passes): the mesh is dead once the Z-forward pass has read it, so its zero-fill for the NEXT
+        // cycle runs on the side stream behind the pair kernel, concurrently with the Y / X / Y passes (which only touch the
+        // spectrum; the X pass is FP64-bound and leaves the memory system idle), and the inverse Z pass writes the potential
+        // to a second buffer. Entry invariant: c->mesh is zero (admp_pme_eval clears it before the loop).
+        DISPATCH(c, launch_spread, st, c->n_atoms, c->box, c->s_pos, c->M, 10, 10, c->s_U, c->mesh);
+        fft3d_convolve_roundtrip(c->fft, st, c->mesh, c->spec, c->box, c->kappa, ADMP_CK_COULOMB, c->tb, c->scal, 0, c->phi, c->ev_zfwd);
+        CK(cudaStreamWaitEvent(c->side_stream, c->ev_zfwd, 0));
+        CK(cudaMemsetAsync(c->mesh, 0, c->mesh_bytes, c->side_stream));
+        CK(cudaEventRecord(c->ev_join, c->side_stream));
+        DISPATCH(c, launch_gather, st, c->n_atoms, c->box, c->s_pos, c->M, 10, 10, c->s_U, c->phi, 1, 0u, nullptr, nullptr, 10, c->Fscf, c->scal);
+    } else {
+        CK(cudaEventRecord(c->ev_join, c->side_stream));
+        if (recip_field(c, st, c->s_pos, c->M, 10, 10, c->s_U, ADMP_CK_COULOMB, c->scal, 0, false)) return 1;
+        DISPATCH(c, launch_gather, st, c->n_atoms, c->box, c->s_pos, c->M, 10, 10, c->s_U, c->mesh, 1, 0u, nullptr, nullptr, 10, c->Fscf, c->scal);
+    }
     CK(cudaStreamWaitEvent(st, c->ev_join, 0));
     DISPATCH(c, launch_scf_field, st, c->n_atoms, c->kappa, c->M, c->s_U, c->s_pol, c->Fscf, c->scal);
     launch_scf_decide(st, c->state, c->scal, maxiter, thresh, refresh_in_loop, h, use_h);
@@ -941,7 +970,10 @@ extern "C" int admp_pme_eval(admp_ctx* c, void* stream, const void* pos, const v
         CK(cudaMemsetAsync(c->Fscf, 0, (size_t)n * 3 * w, st));
         // packed records of the cluster field kernel (it reads the current U from s_U, everything else from here)
         DISPATCH(c, launch_pair_pack, st, n, c->s_pos, c->M, c->s_U, c->s_pol, c->s_th, c->rec);
+        const bool two_mesh = c->phi != nullptr && c->use_custom_fft;
+        if (two_mesh) CK(cudaMemsetAsync(c->mesh, 0, c->mesh_bytes, st));
         if (run_scf(c, st, maxiter, thresh, flags)) return 1;
+        c->phi_cur = two_mesh ? c->phi : c->mesh;
         if (want_vir) {
             // final reciprocal pass on the converged / last-updated U with the k-space virial sums
             CK(cudaMemsetAsync(c->scal + ADMP_S_E_RECIP, 0, sizeof(double), st));
@@ -957,7 +989,7 @@ extern "C" int admp_pme_eval(admp_ctx* c, void* stream, const void* pos, const v
     const void* Uf = polz ? c->s_U : nullptr;
     const uint32_t f = flags & (ADMP_WANT_GRAD | ADMP_WANT_VIRIAL | ADMP_WANT_PGRAD);
     if (flags & ADMP_WANT_GRAD) {
-        DISPATCH(c, launch_gather, st, n, c->box, c->s_pos, c->M, 10, 10, Uf, c->mesh, 0, f, dpos, c->G, 10, polz ? F : nullptr, c->scal);
+        DISPATCH(c, launch_gather, st, n, c->box, c->s_pos, c->M, 10, 10, Uf, c->phi_cur, 0, f, dpos, c->G, 10, polz ? F : nullptr, c->scal);
     }
     DISPATCH(c, launch_pme_pair, st, c->pairs_cap, n, c->box, c->kappa, c->s_pos, c->s_pairs, c->s_sidx, c->cov_off, c->cov_idx, c->cov_nb, c->M, Uf,
              polz ? c->s_pol : nullptr, polz ? c->s_th : nullptr, c->s_mS, polz ? c->s_pS : nullptr, 0, f, dpos, c->G, F, dpol, dtholes, c->scal,

@@ -665,21 +665,26 @@ void fft3d_single_pass(Fft3d* p, cudaStream_t st, int which, void* mesh, void* s
 }
 
 // mesh -> phi = dE/dmesh in place of the mesh, energy (+virial sums) accumulated: 5 passes
+// mesh_out: where the inverse Z pass writes the potential (nullptr: over the input mesh); after_zfwd (optional): recorded
+// once the forward Z pass has consumed `mesh`, so the caller can recycle it while the spectrum passes run
 void fft3d_convolve_roundtrip(Fft3d* p, cudaStream_t st, void* mesh, void* spec, const BoxInfo* B, double kappa, int kind,
-                              const ConvTables& tb, double* scalars, int want_vir) {
+                              const ConvTables& tb, double* scalars, int want_vir, void* mesh_out, cudaEvent_t after_zfwd) {
     Fft3dImpl* f = reinterpret_cast<Fft3dImpl*>(p);
+    if (mesh_out == nullptr) mesh_out = mesh;
     if (f->esz == 8) {
         run_z<double>(f, st, mesh, spec, 1);
+        if (after_zfwd) cudaEventRecord(after_zfwd, st);
         run_strided<double>(f, st, spec, 1, 1);
         run_x_conv<double>(f, st, spec, B, kappa, kind, tb, scalars, want_vir);
         run_strided<double>(f, st, spec, 1, -1);
-        run_z<double>(f, st, mesh, spec, -1);
+        run_z<double>(f, st, mesh_out, spec, -1);
     } else {
         run_z<float>(f, st, mesh, spec, 1);
+        if (after_zfwd) cudaEventRecord(after_zfwd, st);
         run_strided<float>(f, st, spec, 1, 1);
         run_x_conv<float>(f, st, spec, B, kappa, kind, tb, scalars, want_vir);
         run_strided<float>(f, st, spec, 1, -1);
-        run_z<float>(f, st, mesh, spec, -1);
+        run_z<float>(f, st, mesh_out, spec, -1);
     }
 }
 

@@ -86,7 +86,8 @@ void fft3d_inverse(Fft3d* f, cudaStream_t st, void* spec, void* mesh);
 void fft3d_single_pass(Fft3d* f, cudaStream_t st, int which, void* mesh, void* spec, const BoxInfo* B, double kappa, int kind,
                        const ConvTables& tb, double* scalars);
 void fft3d_convolve_roundtrip(Fft3d* f, cudaStream_t st, void* mesh, void* spec, const BoxInfo* B, double kappa, int kind,
-                              const ConvTables& tb, double* scalars, int want_vir);
+                              const ConvTables& tb, double* scalars, int want_vir, void* mesh_out = nullptr,
+                              cudaEvent_t after_zfwd = nullptr);
 
 bool fft3d_slab_supported(const Fft3d* f);
 constexpr int SLAB_CHUNKS = 8;        // maximum pipeline depth of the pulled X pass (ADMP_SLAB_CHUNKS, default 4)

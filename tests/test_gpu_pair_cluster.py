@@ -194,3 +194,24 @@ def test_generic_pair_kernel_any_callable_and_fused_variants():
     padded = np.concatenate([c.pairs[:c.n_pairs], np.full((11, 2), s.n_atoms, dtype=c.pairs.dtype), c.pairs[:3, ::-1]])
     assert rel(fn(s.positions, s.box, padded, c.mScales_pert, s.tt_a, s.tt_b, s.tt_q), E_u) < 1e-12
     assert fn(s.positions, s.box, np.zeros((0, 2), dtype=np.int32), c.mScales_pert, s.tt_a, s.tt_b, s.tt_q).item() == 0.0
+
+
+def test_two_mesh_scf_body_matches_single_mesh(monkeypatch):
+    """Meshes beyond L2 run the SCF cycles with a second real buffer (zero-fill of the spread mesh overlapped with the
+    spectrum passes, api.cu scf_body); forced on here for a small mesh: same cycles, same result as the one-mesh body."""
+    from admp_b200.pme import ADMPPmeForce
+    c = refcases.get('lattice4')
+    g = np.load(os.path.join(GOLDEN, 'ref_lattice4.npz'))
+    s = c.s
+    args = (c.pairs, s.Q_local, s.pol, s.tholes, s.mScales, s.pScales, s.dScales)
+    out = {}
+    for mode in ('0', '1'):
+        monkeypatch.setenv('ADMP_TWO_MESH', mode)
+        calc = ADMPPmeForce(s.box, s.axis_type, s.axis_indices, s.covalent_map, c.rc, c.ethresh, 2, lpol=True)
+        E, F, V = calc.get_forces_and_virial(s.positions, s.box, *args)
+        E2, F2 = calc.get_forces(s.positions, s.box, *args)                 # no virial pass: the final gather reads the second buffer
+        assert calc.n_cycle == int(g['scf_n_cycle'])
+        assert rel(E, g['scf_E']) < 1e-6 and rel(F, g['scf_dpos']) < 1e-6 and rel(E2, g['scf_E']) < 1e-6 and rel(F2, g['scf_dpos']) < 1e-6
+        out[mode] = (E, F, V, calc.U_ind.clone())
+    for a, b in zip(out['0'], out['1']):
+        assert rel(a, b) < 1e-10
