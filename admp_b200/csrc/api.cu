@@ -293,11 +293,12 @@ extern "C" int admp_ctx_set_pme(admp_ctx* c, double kappa, int K1, int K2, int K
     c->fft_note = c->fft ? "" : why;
     cudaGetLastError();
     c->ws_bytes += c->mesh_bytes + c->spec_bytes;
-    // second real buffer for the SCF body of meshes that do not fit in L2 (ADMP_TWO_MESH=0/1 overrides the size rule; on the
-    // L2-resident 154^3 mesh the larger working set costs more than the overlapped zero-fill saves: -8 % measured)
+    // optional second real buffer for the SCF body (ADMP_TWO_MESH=1): measured and left off - on the L2-resident 154^3 mesh
+    // the larger working set costs 8 %, on 308x616x616 the overlapped zero-fill gains 1 % (97.2 vs 98.2 ms per evaluation:
+    // the memset kernel waits for SM slots behind the persistent X-pass blocks), not worth one more mesh of memory
     {
         const char* e2 = getenv("ADMP_TWO_MESH");
-        const bool want = e2 ? atoi(e2) > 0 : (c->mesh_bytes > ((size_t)96 << 20));
+        const bool want = e2 ? atoi(e2) > 0 : false;
         if (want && c->use_custom_fft) {
             if (cudaMalloc(&c->phi, c->mesh_bytes) == cudaSuccess) c->ws_bytes += c->mesh_bytes;
             else { c->phi = nullptr; cudaGetLastError(); }
