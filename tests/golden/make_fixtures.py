@@ -67,3 +67,16 @@ def main():
 
 if __name__ == '__main__':
     main()
+
+
+# ---- the reference's own force-field input of the api.py front end (a DATA file, 44 lines; examples/openmm_api/
+# forcefield.xml): committed verbatim so that the GPU box can parse exactly what a user of the reference passes to
+# Hamiltonian(...) (tests/test_api_parsing.py, tests/test_gpu_api.py). residues.xml is not needed: the <Residues> block
+# of forcefield.xml carries the bonds.
+def copy_forcefield_xml():
+    import shutil
+    shutil.copyfile(os.path.join(REF, 'examples', 'openmm_api', 'forcefield.xml'), os.path.join(HERE, 'openmm_api_forcefield.xml'))
+
+
+if __name__ == '__main__':
+    copy_forcefield_xml()

@@ -119,3 +119,51 @@ def test_hamiltonian_potentials_match_oracle(tmp_path):
     assert rel(disp_gen.params['mScales'].grad, gdo[0]) < RTOL
     assert rel(disp_gen.params['A'].grad, gdo[1]) < RTOL
     assert rel(disp_gen.params['C6'].grad, gdo[2]) < RTOL
+
+
+def test_reference_own_forcefield_xml_on_its_1024_water_box(tmp_path):
+    """The reference's own front-end input (examples/openmm_api/forcefield.xml + the topology / positions of its
+    water1024.pdb, run.py:15-45): both potentials against the oracle evaluated with the parameters of the XML."""
+    import os
+    from admp_b200.api import Hamiltonian, PDBFile
+    from admp_b200.multipole import convert_cart2harm, rot_ind_global2local
+    ff = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'openmm_api_forcefield.xml')
+    s = fixtures.water1024()
+    _, pdbfile = _write_inputs(tmp_path, s)
+    H = Hamiltonian(ff)
+    pdb = PDBFile(pdbfile)
+    disp_gen, pme_gen = H.getGenerators()
+    rc = 4.0
+    pot_disp, pot_pme = H.createPotential(pdb.topology, nonbondedCutoff=rc)
+    positions = pdb.positions
+    pairs, _ = pairlist.build_pairs(positions, s.box.numpy(), rc)
+    tp = torch.tensor(positions, dtype=torch.float64)
+    # parameters exactly as the XML states them (admp/api.py:319-338)
+    cart = np.array([[-1.0614, 0, 0, -0.023671684 * 10, 0.000150963 * 300, 0.00008707 * 300, -0.000238034 * 300, 0, 0, 0],
+                     [0.5307, 0, 0, 0, 0, 0, 0, 0, 0, 0]])
+    Ql = torch.tensor(np.asarray(convert_cart2harm(cart, 2)))[torch.tensor([0, 1, 1] * 1024)]
+    pol = torch.tensor(np.tile([1000 * float(np.float32(0.00088)), 0.0, 0.0], 1024))
+    th = torch.tensor(np.tile([8.0, 0.0, 0.0], 1024))
+    assert rel(pme_gen.params['Q_local'], Ql) < 1e-12 and rel(pme_gen.params['pol'], pol) < 1e-12
+    E = pot_pme(positions, s.box, pairs, pme_gen.params)
+    f = pme_gen.force
+    ref = orc.OraclePmeForce(s.box, s.axis_type, s.axis_indices, s.covalent_map, rc, 1e-5, 2, lpol=True)
+    assert (f.K1, f.K2, f.K3) == (ref.K1, ref.K2, ref.K3)
+    Eo = ref.get_energy(tp, s.box, pairs, Ql, pol, th, s.mScales, s.pScales, s.dScales)
+    assert f.n_cycle == ref.n_cycle and f.lconverg == ref.lconverg
+    assert abs(E.item() - Eo.item()) < RTOL * abs(Eo.item()), (E.item(), Eo.item())
+    Ed = pot_disp(positions, s.box, pairs, disp_gen.params)
+    idx = torch.as_tensor(disp_gen.map_atomtype)
+    raw = {k: torch.tensor([DISP[t][k] for t in ('380', '381')], dtype=torch.float64) for k in DISP['380']}     # DISP = the XML's block
+    a_l, b_l, q_l = raw['A'][idx] / 2625.5, raw['B'][idx] * 0.0529177249, raw['Q'][idx]
+    c = torch.stack([torch.sqrt(raw['C6'][idx] * 1e6), torch.sqrt(raw['C8'][idx] * 1e8), torch.sqrt(raw['C10'][idx] * 1e10)], 1)
+    kappa, K1, K2, K3 = orc.setup_ewald_parameters(rc, 1e-5, s.box)
+    Edo = o_pairwise(o_tt, s.covalent_map)(tp, s.box, pairs, s.mScales, a_l, b_l, q_l, c[:, 0]) \
+        - odisp.energy_disp_pme(tp, s.box, pairs, c, s.mScales, s.covalent_map, kappa, K1, K2, K3, 10)
+    assert abs(Ed.item() - Edo.item()) < RTOL * abs(Edo.item()), (Ed.item(), Edo.item())
+    # rot_ind_global2local (admp/multipole.py:80-89) on the device: R[zxy][:, zxy] . U
+    fr = f.construct_local_frames(positions, s.box)[:5].cpu()
+    U = torch.tensor(np.random.default_rng(0).normal(size=(5, 3)))
+    zxy = [2, 0, 1]
+    want = torch.stack([fr[k][zxy][:, zxy] @ U[k] for k in range(5)])
+    assert rel(rot_ind_global2local(U, fr), want) < 1e-12
