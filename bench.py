@@ -738,10 +738,12 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu, _, _ = cpu_oracle_evals(n_evals=4, budget_s=25.0)
-    # our kernels per evaluation: neighbour list 9, staging (pair scale, tile check/decide/rowstart/build, box, frames, tables,
-    # record pack) 9, per SCF body 13 (spread, 5 FFT passes, field gather, 2 pair traversals of which one is a no-op, field,
-    # decide, update + the mesh memset node is not a kernel), final pass 6 + 8 (gather, pack, 2 pair, self, frames adjoint, virial)
-    launches_per_eval = 9 + 9 + 13 * bodies + 14
+    # our kernels per evaluation, counted on the committed ncu launch list (profiles/r2_launch_summary.md: 390 admp:: launches
+    # between two frames_fwd_kernel launches): 12 per SCF cycle (spread, 5 FFT passes, field gather, the two pair traversals
+    # - one of them a no-op -, field, decide, update) + 6 for the final reciprocal pass with the virial sums + 8 (gather,
+    # 2 record packs, 2 pair traversals, self, frames adjoint, virial) + 9 staging (frames, tables, 2 box, pair scale, 4 tile
+    # kernels) + 7 neighbour list
+    launches_per_eval = 12 * (n_cycle + 1) + 30
     out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                ms_per_step=t_ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64' if esz == 8 else 'f32',
                data='synthetic',
