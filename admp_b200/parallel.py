@@ -516,8 +516,10 @@ class SlabPme:
                 with self._timed('pair'):
                     for wk in work:
                         if wk['nrows'] > 0:
+                            # one row slice per context: its scale indices / cluster tiles are built in cycle 0 and reused
+                            reuse = _lib.REUSE_PAIR_TILES if (len(work) == 1 and c_it > 0) else 0
                             _lib.check(lib.admp_pme_real(c.handle, sp(), p(pos), p(box_d), p(wk['pairs']), wk['nrows'], p(M), p(U), p(polt),
-                                                         p(th), p(mS), p(pS), 1, 0, None, None, p(F), None, None, p(scal)))
+                                                         p(th), p(mS), p(pS), 1, reuse, None, None, p(F), None, None, p(scal)))
                 with self._timed('allreduce_F'):
                     allreduce_sum_([F], self.group)      # also orders this cycle's gathers before the next slab_zero
                 with self._timed('scf_step'):
@@ -566,8 +568,9 @@ class SlabPme:
             if polz:
                 Fo.index_add_(0, wk['idx'], Fr)
             if wk['nrows'] > 0:
+                reuse = _lib.REUSE_PAIR_TILES if (len(work) == 1 and polz) else 0       # built by the SCF cycles
                 _lib.check(lib.admp_pme_real(c.handle, sp(), p(pos), p(box_d), p(wk['pairs']), wk['nrows'], p(M), p(U),
-                                             p(polt) if polz else None, p(th) if polz else None, p(mS), p(pS) if polz else None, 0, fl,
+                                             p(polt) if polz else None, p(th) if polz else None, p(mS), p(pS) if polz else None, 0, fl | reuse,
                                              p(dpos), p(G), p(Fo), None, None, p(scal)))
             _lib.check(lib.admp_pme_self_range(c.handle, sp(), p(M), p(U), p(polt) if polz else None, fl, p(G), p(Fo), None, p(scal),
                                                wk['a0'], wk['ac']))
