@@ -471,7 +471,11 @@ static StrideGeom geom_x(const Fft3dImpl* f, int TL) {
 // 154^3 mesh a pass is only 2-3 tiles per block, so an uneven deal costs a third of the pass)
 static int persistent_grid(const Fft3dImpl* f, int occ, int ntiles) {
     static const bool balanced = [] { const char* e = getenv("ADMP_FFT_BALANCED"); return e && atoi(e) > 0; }();
-    const long long cap = (long long)f->n_sm * (occ > 0 ? occ : 1);
+    // ADMP_FFT_GRID_DIV = d: a pass only asks for 1/d of the resident-block slots, so that the passes of d independent
+    // evaluations in flight on different streams run side by side instead of queueing behind each other's persistent blocks
+    static const int div = [] { const char* e = getenv("ADMP_FFT_GRID_DIV"); const int v = e ? atoi(e) : 1; return v > 0 ? v : 1; }();
+    long long cap = (long long)f->n_sm * (occ > 0 ? occ : 1) / div;
+    if (cap < 1) cap = 1;
     if (ntiles <= cap) return ntiles;
     if (!balanced) return (int)cap;
     const long long waves = (ntiles + cap - 1) / cap;

@@ -30,8 +30,7 @@ import time
 # frames in flight (config C4) use one lane stream + the SCF graph's capture / side streams per frame: with the default 8
 # hardware connections distinct streams share queues and some lane counts serialise (measured: 150-200 instead of 410 evals/s
 # at 3 lanes); harmless for the single-stream headline measurement. Must be set before CUDA initialises.
-if int(os.environ.get('WORLD_SIZE', '1')) == 1:          # the frames-in-flight measurement only runs on one GPU
-    os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
+os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -39,6 +38,10 @@ if ROOT not in sys.path:
 
 METRIC = 'force+energy evals/s (water_pol_1024, polarizable PME: SCF + E + dE/dr + dE/dbox + parameter gradients)'
 FRAMES_PER_STEP = int(os.environ.get('ADMP_BENCH_FRAMES', '32'))
+# frames of a step are independent: they are evaluated on LANES calculators (own context + CUDA stream + neighbour-list
+# workspace each) so that one frame's launch gaps and kernel tails are filled by the others (a 1024-water evaluation is a chain of
+# ~390 small dependent kernels); 1 = strictly one frame at a time
+LANES = max(1, int(os.environ.get('ADMP_BENCH_LANES', '4')))
 UNIT = 'evals/s'
 WORKLOAD = 'C2 examples/water_pol_1024: 1024 waters (3072 atoms), 50 A box, rc 4 A, K 154^3, lmax 2, SCF from U=0 (POL_CONV 10, MAX_N_POL 30)'
 
@@ -571,20 +574,52 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def eval_frame(pos):
+    from admp_b200.parallel import sibling_calculators
+    lanes = min(LANES, FR)
+    calcs = sibling_calculators(calc, lanes)
+    main_stream = torch.cuda.current_stream()
+    lane_nl = [nl] + [neighbor_list(w.box, w.rc) for _ in range(lanes - 1)]
+    lane_nbr0 = [nbr0] + [lane_nl[k].allocate(w.positions) for k in range(1, lanes)]
+    lane_stream = [main_stream] if lanes == 1 else [torch.cuda.Stream(device=dev) for _ in range(lanes)]
+    lane_gsum = [gsum] + [torch.zeros_like(gsum) for _ in range(lanes - 1)]
+    lane_over = [overflow] + [torch.zeros_like(overflow) for _ in range(lanes - 1)]
+
+    def eval_frame(pos, k=0):
         """one unit of work: neighbour list rebuilt on the GPU from this frame's positions, then the polarizable
         evaluation (SCF from U = 0; E, dE/dr, dE/dbox and all parameter gradients)"""
-        nb = nl.update(pos, nbr0)
-        overflow.add_(nb._info[1])
-        r = calc._eval(pos, box, nb.pairs, Ql, None, pol, th, mS, pS, flags, True, cache_scf=False)
-        gsum.add_(param_grad_vector(r, _lib))
+        nb = lane_nl[k].update(pos, lane_nbr0[k])
+        lane_over[k].add_(nb._info[1])
+        r = calcs[k]._eval(pos, box, nb.pairs, Ql, None, pol, th, mS, pS, flags, True, cache_scf=False)
+        lane_gsum[k].add_(param_grad_vector(r, _lib))
         return r
+
+    def fork():
+        if lanes > 1:
+            ev0 = torch.cuda.Event()
+            ev0.record(main_stream)
+            for st_ in lane_stream:
+                st_.wait_event(ev0)
+
+    def join():
+        if lanes > 1:
+            for st_ in lane_stream:
+                e1 = torch.cuda.Event()
+                e1.record(st_)
+                main_stream.wait_event(e1)
 
     def step(k):
         r = None
-        for pos in frames[k]:
-            r = eval_frame(pos)
+        fork()
+        for j, pos in enumerate(frames[k]):
+            with torch.cuda.stream(lane_stream[j % lanes]):
+                r = eval_frame(pos, j % lanes)
+        join()
         return r
+
+    def reduce_lanes():
+        for k in range(1, lanes):
+            gsum.add_(lane_gsum[k])
+            overflow.add_(lane_over[k])
 
     sampler = ClockSampler(local) if rank == 0 else None
     r = None
@@ -597,7 +632,8 @@ def run_ours(args):
     barrier()
     n_cycle, conv = [int(x) for x in r.scf.cpu()]
     bodies = n_cycle + 1 + (0 if conv or n_cycle < 29 else 1)
-    gsum.zero_()
+    for g_ in lane_gsum:
+        g_.zero_()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps + 1)]
     barrier()
     if sampler:
@@ -609,6 +645,7 @@ def run_ours(args):
         ev[k][1].record()
     # the one collective of the frame-sharded job: the frame-summed parameter gradients (inside the timed region)
     ev[-1][0].record()
+    reduce_lanes()
     if dist is not None:
         dist.all_reduce(gsum)
     ev[-1][1].record()
@@ -635,22 +672,32 @@ def run_ours(args):
     out_F = torch.empty((FR, n, 3), dtype=dt).pin_memory()
     out_V = torch.empty((FR, 3, 3), dtype=dt).pin_memory()
     out_G = torch.empty(gsum.shape, dtype=torch.float64).pin_memory()
-    leaves = [t.detach().clone().requires_grad_(True) for t in (Ql, pol, th, mS, pS)]
+
+    lane_leaves = [[t.detach().clone().requires_grad_(True) for t in (Ql, pol, th, mS, pS)] for _ in range(lanes)]
 
     def e2e_step(k):
-        acc = None
+        acc = [None] * lanes
+        fork()
         for j in range(FR):
-            pos = host_pos[k][j].to(dev, non_blocking=True).requires_grad_(True)
-            bx = host_box.to(dev, non_blocking=True).requires_grad_(True)
-            nb = nl.update(pos.detach(), nbr0)
-            E = calc.get_energy(pos, bx, nb.pairs, leaves[0], leaves[1], leaves[2], leaves[3], leaves[4], mS)
-            g = torch.autograd.grad(E, [pos, bx] + leaves)
-            out_E[j].copy_(E.detach(), non_blocking=True)
-            out_F[j].copy_(g[0], non_blocking=True)
-            out_V[j].copy_(g[1], non_blocking=True)
-            v = torch.cat([g[2].reshape(-1).double(), g[5].double(), g[6].double(), g[4].double(), g[3].double()])
-            acc = v if acc is None else acc + v
-        out_G.copy_(acc, non_blocking=True)
+            ln = j % lanes
+            lv = lane_leaves[ln]
+            with torch.cuda.stream(lane_stream[ln]):
+                pos = host_pos[k][j].to(dev, non_blocking=True).requires_grad_(True)
+                bx = host_box.to(dev, non_blocking=True).requires_grad_(True)
+                nb = lane_nl[ln].update(pos.detach(), lane_nbr0[ln])
+                E = calcs[ln].get_energy(pos, bx, nb.pairs, lv[0], lv[1], lv[2], lv[3], lv[4], mS)
+                g = torch.autograd.grad(E, [pos, bx] + lv)
+                out_E[j].copy_(E.detach(), non_blocking=True)
+                out_F[j].copy_(g[0], non_blocking=True)
+                out_V[j].copy_(g[1], non_blocking=True)
+                v = torch.cat([g[2].reshape(-1).double(), g[5].double(), g[6].double(), g[4].double(), g[3].double()])
+                acc[ln] = v if acc[ln] is None else acc[ln] + v
+        join()
+        tot = acc[0]
+        for a_ in acc[1:]:
+            if a_ is not None:
+                tot = tot + a_
+        out_G.copy_(tot, non_blocking=True)
 
     for k in range(max(1, min(args.warmup, 2))):
         e2e_step(k)
@@ -749,7 +796,7 @@ def run_ours(args):
     out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                ms_per_step=t_ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64' if esz == 8 else 'f32',
                data='synthetic',
-               config=dict(workload=WORKLOAD, frames_per_step=FR, evals_timed=n_evals,
+               config=dict(workload=WORKLOAD, frames_per_step=FR, frames_in_flight=lanes, evals_timed=n_evals,
                            unit_of_work='neighbour list (GPU) + SCF from U=0 + E + dE/dr + dE/dbox + dE/d(Q_local, mScales, pScales, tholes, pol) '
                                         'of one jittered frame (N(0, 0.02 A), default_rng(1000 + f)); parameter gradients summed over frames',
                            parallelism=('frames (rank r: frames r, r+N, ...), one all-reduce of the summed parameter gradients inside '
