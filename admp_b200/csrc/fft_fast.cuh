@@ -30,6 +30,40 @@ __device__ __forceinline__ void cp_async(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
+// ------------------------------------------------------------------------------------------ TMA bulk copies (sm_90+)
+// Tile loads of the float64 passes go through the TMA unit: `cp.async.bulk.shared.global` (SASS: UBLKCP) moves a whole
+// contiguous run - a 128-byte row of a strided tile, a full line of a Z tile - per instruction and signals an mbarrier with the
+// bytes it delivered; no per-thread 16-byte LDGSTS, no per-thread address arithmetic in registers, no cp.async group to drain.
+// One mbarrier per block (a single tile is in flight), phase parity flips per tile. The float passes keep cp.async (their
+// partial rows are not multiples of 16 bytes).
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem)),
+                 "l"(gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+// the generic-proxy reads of the tile buffer are ordered before the async-proxy writes that refill it
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned ok = 0;
+    for (unsigned spin = 0; !ok; ++spin) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (spin > (1u << 24)) __trap();          // a lost transaction must fail loudly, not hang the device
+    }
+}
+template <typename T> struct UseBulk { static constexpr bool value = sizeof(T) == 8; };
+// strided tiles are N rows of 128 bytes: as N separate bulk copies they lose (Y pass 0.467 -> 0.82 ms at 308x616x616, measured);
+// they keep 16-byte cp.async until the tile is ONE tensor-map copy. The contiguous Z lines (1.2-9.9 KB per copy) gain 2-4 %.
+template <typename T> struct UseBulkStrided { static constexpr bool value = false; };
+
 // Programmatic dependent launch (PDL): a kernel lets its successor in the stream start launching as soon as
 // all of its own blocks are resident (launch_dependents), and waits for its predecessor to complete and flush
 // before touching dependent data (wait). The successor's blocks fill the SM slots freed by the predecessor's
@@ -224,6 +258,20 @@ __device__ __forceinline__ void issue_tile(const StrideGeom& g, int tile, const 
     cp_async_commit();
 }
 
+// the same tile through the TMA unit: one bulk copy per position (nl consecutive lines = one contiguous run)
+template <typename T, int N, int TL>
+__device__ __forceinline__ void issue_tile_bulk(const StrideGeom& g, int tile, const cx<T>* __restrict__ spec, cx<T>* dst, int nthreads,
+                                                uint64_t* bar) {
+    const int o = tile / g.tiles, t = tile - o * g.tiles;
+    const int c0 = t * TL;
+    const int nl = min(TL, g.n_inner - c0);
+    const cx<T>* base = spec + (size_t)o * g.outer_stride + c0;
+    const unsigned bytes = (unsigned)(nl * sizeof(cx<T>));
+    fence_async_smem();
+    if (threadIdx.x == 0) mbar_expect_tx(bar, bytes * N);
+    for (int pos = threadIdx.x; pos < N; pos += nthreads) bulk_g2s(dst + pos * TL, base + (size_t)pos * g.line_stride, bytes, bar);
+}
+
 // X pass over an x-slab decomposed spectrum (PeerTab): point `pos` of every line lives in the buffer of rank
 // owner(pos); `sbase[pos]` (shared memory) holds that buffer's base pointer, element offsets are unchanged.
 template <typename T, int N, int TL, int JT>
@@ -246,16 +294,26 @@ fast_strided_kernel(StrideGeom g, int ntiles, cx<T>* __restrict__ spec, const cx
     cx<T>* A = I + TILE;
     cx<T>* tw2 = A + TILE;
     cx<T>* tw3 = tw2 + TwGeom<R1, R2, R3>::N2;
+    constexpr bool BULK = UseBulkStrided<T>::value;
+    __shared__ uint64_t bar;
+    unsigned parity = 0;
     const int l = threadIdx.x % TL, j = threadIdx.x / TL;
     int tile = blockIdx.x;
     pdl_launch_dependents();
+    if (BULK && threadIdx.x == 0) mbar_init(&bar, 1);
     build_twiddles<T, R1, R2, R3, 1>(tw2, tw3, gtw, NT);
+    if (BULK) __syncthreads();
     pdl_wait();
-    if (tile < ntiles) issue_tile<T, N, TL, JT>(g, tile, spec, I, l, j);
+    auto issue = [&](int t) {
+        if (BULK) issue_tile_bulk<T, N, TL>(g, t, spec, I, NT, &bar);
+        else issue_tile<T, N, TL, JT>(g, t, spec, I, l, j);
+    };
+    if (tile < ntiles) issue(tile);
     cx<T>* a = A + l;
     cx<T>* c = I + l;
     for (; tile < ntiles; tile += gridDim.x) {
-        cp_async_wait_all();
+        if (BULK) { mbar_wait(&bar, parity); parity ^= 1; }
+        else cp_async_wait_all();
         __syncthreads();                       // tile landed in I; A free (previous tile's last stage has read it)
         const int o = tile / g.tiles, t = tile - o * g.tiles;
         const int c0 = t * TL;
@@ -264,7 +322,7 @@ fast_strided_kernel(StrideGeom g, int ntiles, cx<T>* __restrict__ spec, const cx
         const size_t ls = g.line_stride;
         fft_head<T, R1, R2, R3, SIGN, JT>(j, live, [&](int pos) { return c[pos * TL]; }, [&](int pos, cx<T> v) { a[pos * TL] = v; });
         __syncthreads();                       // I consumed
-        if (tile + (int)gridDim.x < ntiles) issue_tile<T, N, TL, JT>(g, tile + gridDim.x, spec, I, l, j);
+        if (tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x);
         fft_tail<T, R1, R2, R3, SIGN, JT, false>(j, live, tw2, tw3, [&](int pos) { return a[pos * TL]; },
                                                  [&](int pos, cx<T> v) { a[pos * TL] = v; },
                                                  [&](int pos, cx<T> v) { out[(size_t)pos * ls] = v; });
@@ -316,11 +374,17 @@ fast_x_conv_kernel(StrideGeom g, int tile0, int ntiles, const BoxInfo* __restric
     double* sk2 = sek + N;                                                    // k1^2 (ortho) | signed index m1
     cx<T>** sbase = reinterpret_cast<cx<T>**>(sk2 + N);                       // PEER only: owner buffer of x plane pos
     const BoxInfo& B = *Bp;
+    constexpr bool BULK = UseBulkStrided<T>::value;
+    __shared__ uint64_t bar;
+    unsigned parity = 0;
+    const bool bulk = BULK && !(PEER && !local_reads);      // peer-memory loads keep cp.async
     const int l = threadIdx.x % TL, j = threadIdx.x / TL;
     int tile = tile0 + blockIdx.x;
     pdl_launch_dependents();
+    if (BULK && threadIdx.x == 0) mbar_init(&bar, 1);
     build_twiddles<T, R1, R2, R3, 1>(tw2, tw3, gtw, NT);
     build_twiddles<T, Q1, Q2, Q3, 1>(itw2, itw3, gtw, NT);
+    if (BULK) __syncthreads();
     if (PEER) {
         for (int i = threadIdx.x; i < N; i += NT) sbase[i] = reinterpret_cast<cx<T>*>(peers.base[peers.owner(i)]);
         __syncthreads();
@@ -330,6 +394,7 @@ fast_x_conv_kernel(StrideGeom g, int tile0, int ntiles, const BoxInfo* __restric
     // NVLink, pipelined by the host side): loads are local, only the stores go to the owners
     auto issue = [&](int t) {
         if (PEER && !local_reads) issue_tile_peer<T, N, TL, JT>(g, t, sbase, I, l, j);
+        else if (bulk) issue_tile_bulk<T, N, TL>(g, t, spec, I, NT, &bar);
         else issue_tile<T, N, TL, JT>(g, t, spec, I, l, j);
     };
     if (tile < ntiles) issue(tile);
@@ -353,7 +418,8 @@ fast_x_conv_kernel(StrideGeom g, int tile0, int ntiles, const BoxInfo* __restric
     // first inverse stage of the same radix, so the scaling and that inverse stage run in registers (no
     // exchange through shared memory, no barrier) and the inverse continues with the radices in reverse order.
     for (; tile < ntiles; tile += gridDim.x) {
-        cp_async_wait_all();
+        if (bulk) { mbar_wait(&bar, parity); parity ^= 1; }
+        else cp_async_wait_all();
         __syncthreads();
         const int c0 = tile * TL;
         const bool live = l < g.n_inner - c0;
@@ -453,26 +519,38 @@ fast_z_fwd_kernel(int nlines, int ntiles, const T* __restrict__ mesh, cx<T>* __r
     cx<T>* tw3 = tw2 + TwGeom<R1, R2, R3>::N2;
     cx<T>* zt = tw3 + TwGeom<R1, R2, R3>::N3;       // M+1 entries: exp(-2 pi i k / K3)
     const int j = threadIdx.x % JT, l = threadIdx.x / JT;
+    constexpr bool BULK = UseBulk<T>::value;
+    __shared__ uint64_t bar;
+    unsigned parity = 0;
     auto issue = [&](int tile) {
         const int L0 = tile * TL;
         const int nl = min(TL, nlines - L0);
         const cx<T>* src = reinterpret_cast<const cx<T>*>(mesh + (size_t)L0 * K3);
-        for (int e = threadIdx.x; e < nl * M; e += NT) {
-            const int ll = e / M, pos = e - ll * M;
-            cp_async<sizeof(cx<T>)>(I + ll * LS + pos, src + e);
+        if (BULK) {                                   // one bulk copy per line: K3 reals = M 16-byte units
+            fence_async_smem();
+            if (threadIdx.x == 0) mbar_expect_tx(&bar, (unsigned)(nl * M * sizeof(cx<T>)));
+            if (threadIdx.x < nl) bulk_g2s(I + threadIdx.x * LS, src + (size_t)threadIdx.x * M, (unsigned)(M * sizeof(cx<T>)), &bar);
+        } else {
+            for (int e = threadIdx.x; e < nl * M; e += NT) {
+                const int ll = e / M, pos = e - ll * M;
+                cp_async<sizeof(cx<T>)>(I + ll * LS + pos, src + e);
+            }
+            cp_async_commit();
         }
-        cp_async_commit();
     };
     int tile = blockIdx.x;
     pdl_launch_dependents();
+    if (BULK && threadIdx.x == 0) mbar_init(&bar, 1);
     build_twiddles<T, R1, R2, R3, 2>(tw2, tw3, gtw, NT);
     for (int i = threadIdx.x; i < K3h; i += NT) zt[i] = gtw[i];
+    if (BULK) __syncthreads();
     pdl_wait();
     if (tile < ntiles) issue(tile);
     cx<T>* a = A + l * LS;
     cx<T>* c = I + l * LS;
     for (; tile < ntiles; tile += gridDim.x) {
-        cp_async_wait_all();
+        if (BULK) { mbar_wait(&bar, parity); parity ^= 1; }
+        else cp_async_wait_all();
         __syncthreads();
         const int L0 = tile * TL;
         const int nl = min(TL, nlines - L0);
@@ -510,26 +588,38 @@ fast_z_inv_kernel(int nlines, int ntiles, const cx<T>* __restrict__ spec, T* __r
     cx<T>* tw3 = tw2 + TwGeom<R1, R2, R3>::N2;
     cx<T>* zt = tw3 + TwGeom<R1, R2, R3>::N3;
     const int j = threadIdx.x % JT, l = threadIdx.x / JT;
+    constexpr bool BULK = UseBulk<T>::value;
+    __shared__ uint64_t bar;
+    unsigned parity = 0;
     auto issue = [&](int tile) {
         const int L0 = tile * TL;
         const int nl = min(TL, nlines - L0);
         const cx<T>* src = spec + (size_t)L0 * K3h;
-        for (int e = threadIdx.x; e < nl * K3h; e += NT) {
-            const int ll = e / K3h, k = e - ll * K3h;
-            cp_async<sizeof(cx<T>)>(I + ll * LS + k, src + e);
+        if (BULK) {                                   // one bulk copy per line: K3/2 + 1 complex points
+            fence_async_smem();
+            if (threadIdx.x == 0) mbar_expect_tx(&bar, (unsigned)(nl * K3h * sizeof(cx<T>)));
+            if (threadIdx.x < nl) bulk_g2s(I + threadIdx.x * LS, src + (size_t)threadIdx.x * K3h, (unsigned)(K3h * sizeof(cx<T>)), &bar);
+        } else {
+            for (int e = threadIdx.x; e < nl * K3h; e += NT) {
+                const int ll = e / K3h, k = e - ll * K3h;
+                cp_async<sizeof(cx<T>)>(I + ll * LS + k, src + e);
+            }
+            cp_async_commit();
         }
-        cp_async_commit();
     };
     int tile = blockIdx.x;
     pdl_launch_dependents();
+    if (BULK && threadIdx.x == 0) mbar_init(&bar, 1);
     build_twiddles<T, R1, R2, R3, 2>(tw2, tw3, gtw, NT);
     for (int i = threadIdx.x; i < K3h; i += NT) zt[i] = gtw[i];
+    if (BULK) __syncthreads();
     pdl_wait();
     if (tile < ntiles) issue(tile);
     cx<T>* a = A + l * LS;
     cx<T>* c = I + l * LS;
     for (; tile < ntiles; tile += gridDim.x) {
-        cp_async_wait_all();
+        if (BULK) { mbar_wait(&bar, parity); parity ^= 1; }
+        else cp_async_wait_all();
         __syncthreads();
         const int L0 = tile * TL;
         const bool live = l < nlines - L0;
