@@ -22,6 +22,9 @@
 #include <cstring>
 #include <vector>
 
+#include <cuda.h>                 // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+#include <cudaTypedefs.h>
+
 #include "fft_trig.h"
 #include "influence.cuh"
 #include "kernels.h"
@@ -174,7 +177,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 fft_z_fwd_kernel(FftPlan P, int TL, int LS, int nlines, int K3, const T* __restrict__ mesh, cx<T>* __restrict__ spec,
                  const cx<T>* __restrict__ gtw) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     cx<T>* A = reinterpret_cast<cx<T>*>(smem_raw);
     cx<T>* Bf = A + TL * LS;
     cx<T>* stw = Bf + TL * LS;
@@ -207,7 +210,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 fft_z_inv_kernel(FftPlan P, int TL, int LS, int nlines, int K3, const cx<T>* __restrict__ spec, T* __restrict__ mesh,
                  const cx<T>* __restrict__ gtw) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     cx<T>* A = reinterpret_cast<cx<T>*>(smem_raw);
     cx<T>* Bf = A + TL * LS;
     cx<T>* stw = Bf + TL * LS;
@@ -268,7 +271,7 @@ __device__ __forceinline__ void store_tile(const cx<T>* A, cx<T>* __restrict__ g
 template <typename T, int SIGN>
 __global__ void __launch_bounds__(256)
 fft_strided_kernel(FftPlan P, int TL, int LS, StrideGeom g, cx<T>* __restrict__ spec, const cx<T>* __restrict__ gtw) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     cx<T>* A = reinterpret_cast<cx<T>*>(smem_raw);
     cx<T>* Bf = A + TL * LS;
     cx<T>* stw = Bf + TL * LS;
@@ -289,7 +292,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 fft_x_conv_kernel(FftPlan P, int TL, int LS, StrideGeom g, const BoxInfo* __restrict__ Bp, T kappa, int kind, ConvTables tb,
                   cx<T>* __restrict__ spec, const cx<T>* __restrict__ gtw, double* __restrict__ scalars, int want_vir) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double red[7 * 8];
     cx<T>* A = reinterpret_cast<cx<T>*>(smem_raw);
     cx<T>* Bf = A + TL * LS;
@@ -458,6 +461,34 @@ void fft3d_destroy(Fft3d* p) {
     delete f;
 }
 
+// ---- TMA tensor maps of the strided tiles (float64): dims {2*n_inner doubles, N positions, n_outer planes}, box
+// {2*TL, box_rows, 1}, no swizzle, out-of-range columns zero-filled. The encoder comes from the driver at run time
+// (cudaGetDriverEntryPoint: no link against libcuda); ADMP_FFT_TMA=0, a missing encoder or a failed encode select cp.async.
+static PFN_cuTensorMapEncodeTiled tmap_encoder() {
+    static PFN_cuTensorMapEncodeTiled fn = [] {
+        const char* e = getenv("ADMP_FFT_TMA");
+        if (e && atoi(e) == 0) return (PFN_cuTensorMapEncodeTiled) nullptr;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return (PFN_cuTensorMapEncodeTiled) nullptr;
+        }
+        return (PFN_cuTensorMapEncodeTiled)p;
+    }();
+    return fn;
+}
+static bool make_tmap(CUtensorMap* tm, void* base, const StrideGeom& g, int N, int TL, int box_rows) {
+    PFN_cuTensorMapEncodeTiled enc = tmap_encoder();
+    if (!enc) return false;
+    const cuuint64_t dims[3] = {2 * (cuuint64_t)g.n_inner, (cuuint64_t)N, (cuuint64_t)g.n_outer};
+    const cuuint64_t strides[2] = {(cuuint64_t)g.line_stride * 16, (cuuint64_t)(g.n_outer > 1 ? g.outer_stride : (size_t)N * g.line_stride) * 16};
+    const cuuint32_t box[3] = {(cuuint32_t)(2 * TL), (cuuint32_t)box_rows, 1};
+    const cuuint32_t es[3] = {1, 1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static StrideGeom geom_y(const Fft3dImpl* f, int TL) {
     const int K1 = f->K[0], K2 = f->K[1], K3h = f->K[2] / 2 + 1;
     return {K1, K3h, (size_t)K2 * K3h, (size_t)K3h, (K3h + TL - 1) / TL};
@@ -514,6 +545,11 @@ static void run_strided(Fft3dImpl* f, cudaStream_t st, void* spec, int dim, int 
             spec = (char*)spec + (size_t)x0 * g.outer_stride * sizeof(cx<T>);
         }
         const int ntiles = g.n_outer * g.tiles;
+        CUtensorMap tm;
+        if (sizeof(T) == 8 && c.ops.occ_tma[sign > 0 ? 0 : 1] > 0 && make_tmap(&tm, spec, g, c.ops.N, c.ops.TL, c.ops.box_rows)) {
+            c.ops.strided_tma(st, sign, g, ntiles, persistent_grid(f, c.ops.occ_tma[sign > 0 ? 0 : 1], ntiles), spec, tw, tm);
+            return;
+        }
         c.ops.strided(st, sign, g, ntiles, persistent_grid(f, c.ops.occ[sign > 0 ? 0 : 1], ntiles), spec, tw);
         return;
     }
@@ -530,7 +566,13 @@ static void run_x_conv(Fft3dImpl* f, cudaStream_t st, void* spec, const BoxInfo*
     const cx<T>* tw = (const cx<T>*)f->tw[0];
     if (c.fast) {
         const StrideGeom g = geom_x(f, c.ops.TL);
-        c.ops.xconv(st, g, 0, g.tiles, persistent_grid(f, c.ops.occ[(kind == ADMP_CK_COULOMB && !want_vir) ? 2 : 5], g.tiles), B, kappa, kind, tb, spec, tw, scalars, want_vir);
+        const bool quick = (kind == ADMP_CK_COULOMB && !want_vir);
+        CUtensorMap tm;
+        if (sizeof(T) == 8 && c.ops.occ_tma[quick ? 2 : 3] > 0 && make_tmap(&tm, spec, g, c.ops.N, c.ops.TL, c.ops.box_rows)) {
+            c.ops.xconv_tma(st, g, 0, g.tiles, persistent_grid(f, c.ops.occ_tma[quick ? 2 : 3], g.tiles), B, kappa, kind, tb, spec, tw, scalars, want_vir, tm);
+            return;
+        }
+        c.ops.xconv(st, g, 0, g.tiles, persistent_grid(f, c.ops.occ[quick ? 2 : 5], g.tiles), B, kappa, kind, tb, spec, tw, scalars, want_vir);
         return;
     }
     const StrideGeom g = geom_x(f, c.TL);

@@ -59,6 +59,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
         if (spin > (1u << 24)) __trap();          // a lost transaction must fail loudly, not hang the device
     }
 }
+// one 3-D tensor-map copy (SASS: UTMALDG): box {2*TL doubles, BOXN positions, 1 plane} of the spectrum -> shared memory
+__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem)),
+                 "l"(tm), "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+// rows of a strided tile per tensor-map box: the largest divisor of N that fits the 256-element box limit
+constexpr int tma_box_rows(int N) {
+    int b = 1;
+    for (int d = 1; d <= 256; ++d)
+        if (N % d == 0) b = d;
+    return b;
+}
 template <typename T> struct UseBulk { static constexpr bool value = sizeof(T) == 8; };
 // strided tiles are N rows of 128 bytes: as N separate bulk copies they lose (Y pass 0.467 -> 0.82 ms at 308x616x616, measured);
 // they keep 16-byte cp.async until the tile is ONE tensor-map copy. The contiguous Z lines (1.2-9.9 KB per copy) gain 2-4 %.
@@ -258,6 +272,21 @@ __device__ __forceinline__ void issue_tile(const StrideGeom& g, int tile, const 
     cp_async_commit();
 }
 
+// the tile as N / BOXN tensor-map copies issued by ONE thread: the TMA unit walks the rows (128 bytes each, any stride), the
+// other threads spend no instruction and no register on it; columns beyond the plane edge are zero-filled by the unit and the
+// full box is always accounted on the mbarrier
+template <typename T, int N, int TL>
+__device__ __forceinline__ void issue_tile_tma(const StrideGeom& g, int tile, const CUtensorMap* tm, cx<T>* dst, uint64_t* bar) {
+    constexpr int BOXN = tma_box_rows(N);
+    if (threadIdx.x == 0) {
+        const int o = tile / g.tiles, t = tile - o * g.tiles;
+        fence_async_smem();
+        mbar_expect_tx(bar, (unsigned)(N * TL * sizeof(cx<T>)));
+#pragma unroll
+        for (int b = 0; b < N / BOXN; ++b) tma_load_3d(dst + b * BOXN * TL, tm, 2 * t * TL, b * BOXN, o, bar);
+    }
+}
+
 // the same tile through the TMA unit: one bulk copy per position (nl consecutive lines = one contiguous run)
 template <typename T, int N, int TL>
 __device__ __forceinline__ void issue_tile_bulk(const StrideGeom& g, int tile, const cx<T>* __restrict__ spec, cx<T>* dst, int nthreads,
@@ -285,16 +314,16 @@ __device__ __forceinline__ void issue_tile_peer(const StrideGeom& g, int tile, c
     cp_async_commit();
 }
 
-template <typename T, int R1, int R2, int R3, int SIGN, int TL, int JT>
+template <typename T, int R1, int R2, int R3, int SIGN, int TL, int JT, bool TMA>
 __global__ void __launch_bounds__(TL* JT, MinBlocks<TL * JT, R3>::value)
-fast_strided_kernel(StrideGeom g, int ntiles, cx<T>* __restrict__ spec, const cx<T>* __restrict__ gtw) {
+fast_strided_kernel(StrideGeom g, int ntiles, cx<T>* __restrict__ spec, const cx<T>* __restrict__ gtw, const __grid_constant__ CUtensorMap tmap) {
     constexpr int N = R1 * R2 * R3, TILE = N * TL, NT = TL * JT;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     cx<T>* I = reinterpret_cast<cx<T>*>(smem_raw);
     cx<T>* A = I + TILE;
     cx<T>* tw2 = A + TILE;
     cx<T>* tw3 = tw2 + TwGeom<R1, R2, R3>::N2;
-    constexpr bool BULK = UseBulkStrided<T>::value;
+    constexpr bool BULK = TMA || UseBulkStrided<T>::value;
     __shared__ uint64_t bar;
     unsigned parity = 0;
     const int l = threadIdx.x % TL, j = threadIdx.x / TL;
@@ -305,7 +334,8 @@ fast_strided_kernel(StrideGeom g, int ntiles, cx<T>* __restrict__ spec, const cx
     if (BULK) __syncthreads();
     pdl_wait();
     auto issue = [&](int t) {
-        if (BULK) issue_tile_bulk<T, N, TL>(g, t, spec, I, NT, &bar);
+        if (TMA) issue_tile_tma<T, N, TL>(g, t, &tmap, I, &bar);
+        else if (BULK) issue_tile_bulk<T, N, TL>(g, t, spec, I, NT, &bar);
         else issue_tile<T, N, TL, JT>(g, t, spec, I, l, j);
     };
     if (tile < ntiles) issue(tile);
@@ -321,6 +351,7 @@ fast_strided_kernel(StrideGeom g, int ntiles, cx<T>* __restrict__ spec, const cx
         cx<T>* out = spec + (size_t)o * g.outer_stride + c0 + l;
         const size_t ls = g.line_stride;
         fft_head<T, R1, R2, R3, SIGN, JT>(j, live, [&](int pos) { return c[pos * TL]; }, [&](int pos, cx<T> v) { a[pos * TL] = v; });
+        if (BULK) fence_async_smem();
         __syncthreads();                       // I consumed
         if (tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x);
         fft_tail<T, R1, R2, R3, SIGN, JT, false>(j, live, tw2, tw3, [&](int pos) { return a[pos * TL]; },
@@ -354,13 +385,13 @@ __device__ __noinline__ double influence_general(const BoxInfo* Bp, const ConvTa
 // PEER: the spectrum is x-slab decomposed over the GPUs of the NVLink domain; this rank transforms the lines
 // of tiles [tile0, ntiles) by loading / storing every point from / to the rank that owns its x plane (cp.async
 // and stores on peer-mapped memory): the all-to-all transposes of a slab FFT are fused into the X pass.
-template <typename T, int R1, int R2, int R3, int TL, int JT, bool QUICK, bool PEER>
+template <typename T, int R1, int R2, int R3, int TL, int JT, bool QUICK, bool PEER, bool TMA = false>
 __global__ void __launch_bounds__(TL* JT, MinBlocks<TL * JT, R3>::value)
 fast_x_conv_kernel(StrideGeom g, int tile0, int ntiles, const BoxInfo* __restrict__ Bp, T kappa, int kind, ConvTables tb,
                    cx<T>* __restrict__ spec, const cx<T>* __restrict__ gtw, double* __restrict__ scalars, int want_vir, PeerTab peers,
-                   int local_reads) {
+                   int local_reads, const __grid_constant__ CUtensorMap tmap) {
     constexpr int N = R1 * R2 * R3, TILE = N * TL, NT = TL * JT;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double red[7 * ((NT + 31) / 32)];
     cx<T>* I = reinterpret_cast<cx<T>*>(smem_raw);
     cx<T>* A = I + TILE;
@@ -374,7 +405,7 @@ fast_x_conv_kernel(StrideGeom g, int tile0, int ntiles, const BoxInfo* __restric
     double* sk2 = sek + N;                                                    // k1^2 (ortho) | signed index m1
     cx<T>** sbase = reinterpret_cast<cx<T>**>(sk2 + N);                       // PEER only: owner buffer of x plane pos
     const BoxInfo& B = *Bp;
-    constexpr bool BULK = UseBulkStrided<T>::value;
+    constexpr bool BULK = TMA || UseBulkStrided<T>::value;
     __shared__ uint64_t bar;
     unsigned parity = 0;
     const bool bulk = BULK && !(PEER && !local_reads);      // peer-memory loads keep cp.async
@@ -394,6 +425,7 @@ fast_x_conv_kernel(StrideGeom g, int tile0, int ntiles, const BoxInfo* __restric
     // NVLink, pipelined by the host side): loads are local, only the stores go to the owners
     auto issue = [&](int t) {
         if (PEER && !local_reads) issue_tile_peer<T, N, TL, JT>(g, t, sbase, I, l, j);
+        else if (TMA) issue_tile_tma<T, N, TL>(g, t, &tmap, I, &bar);
         else if (bulk) issue_tile_bulk<T, N, TL>(g, t, spec, I, NT, &bar);
         else issue_tile<T, N, TL, JT>(g, t, spec, I, l, j);
     };
@@ -467,6 +499,7 @@ fast_x_conv_kernel(StrideGeom g, int tile0, int ntiles, const BoxInfo* __restric
         auto ldA = [&](int pos) { return a[pos * TL]; };
         auto stA = [&](int pos, cx<T> v) { a[pos * TL] = v; };
         fft_head<T, R1, R2, R3, 1, JT>(j, live, [&](int pos) { return c[pos * TL]; }, stA);
+        if (bulk) fence_async_smem();
         __syncthreads();                       // I consumed: fetch the next tile while this one is transformed
         if (tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x);
         if (R3 > 1) {                          // middle forward stage, in place in A
@@ -512,7 +545,7 @@ template <typename T, int R1, int R2, int R3, int TL, int JT>
 __global__ void __launch_bounds__(TL* JT, MinBlocks<TL * JT, R3>::value)
 fast_z_fwd_kernel(int nlines, int ntiles, const T* __restrict__ mesh, cx<T>* __restrict__ spec, const cx<T>* __restrict__ gtw) {
     constexpr int M = R1 * R2 * R3, K3 = 2 * M, K3h = M + 1, LS = ZGeom<M>::LS, TILE = TL * LS, NT = TL * JT;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     cx<T>* I = reinterpret_cast<cx<T>*>(smem_raw);
     cx<T>* A = I + TILE;
     cx<T>* tw2 = A + TILE;
@@ -581,7 +614,7 @@ template <typename T, int R1, int R2, int R3, int TL, int JT>
 __global__ void __launch_bounds__(TL* JT, MinBlocks<TL * JT, R3>::value)
 fast_z_inv_kernel(int nlines, int ntiles, const cx<T>* __restrict__ spec, T* __restrict__ mesh, const cx<T>* __restrict__ gtw) {
     constexpr int M = R1 * R2 * R3, K3 = 2 * M, K3h = M + 1, LS = ZGeom<M>::LS, TILE = TL * LS, NT = TL * JT;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     cx<T>* I = reinterpret_cast<cx<T>*>(smem_raw);
     cx<T>* A = I + TILE;
     cx<T>* tw2 = A + TILE;
@@ -662,6 +695,12 @@ struct FastOps {
     int occ[6];      // strided fwd, strided inv, x conv (quick), z fwd, z inv, x conv (general)
     void (*prepare)(FastOps&);
     void (*strided)(cudaStream_t, int sign, const StrideGeom&, int ntiles, int grid, void* spec, const void* tw);
+    // tensor-map variants (float64): tile loads are TMA tensor copies issued by one thread
+    void (*strided_tma)(cudaStream_t, int sign, const StrideGeom&, int ntiles, int grid, void* spec, const void* tw, const CUtensorMap&);
+    void (*xconv_tma)(cudaStream_t, const StrideGeom&, int tile0, int tile1, int grid, const BoxInfo*, double kappa, int kind,
+                      const ConvTables&, void* spec, const void* tw, double* scalars, int want_vir, const CUtensorMap&);
+    int occ_tma[4];   // strided fwd, strided inv, x conv quick, x conv general
+    int box_rows;
     void (*xconv)(cudaStream_t, const StrideGeom&, int tile0, int tile1, int grid, const BoxInfo*, double kappa, int kind,
                   const ConvTables&, void* spec, const void* tw, double* scalars, int want_vir);
     // x-slab decomposed spectrum: tiles [tile0, tile1) of the X pass on peer-mapped buffers
@@ -691,8 +730,14 @@ struct FastImpl {
                (peer ? N * sizeof(void*) : 0);
     }
     static void prepare(FastOps& o) {
-        o.occ[0] = prep_kernel(fast_strided_kernel<T, R1, R2, R3, 1, TL, JT>, o.threads, o.smem);
-        o.occ[1] = prep_kernel(fast_strided_kernel<T, R1, R2, R3, -1, TL, JT>, o.threads, o.smem);
+        o.occ[0] = prep_kernel(fast_strided_kernel<T, R1, R2, R3, 1, TL, JT, false>, o.threads, o.smem);
+        o.occ[1] = prep_kernel(fast_strided_kernel<T, R1, R2, R3, -1, TL, JT, false>, o.threads, o.smem);
+        if (sizeof(T) == 8) {
+            o.occ_tma[0] = prep_kernel(fast_strided_kernel<T, R1, R2, R3, 1, TL, JT, true>, o.threads, o.smem);
+            o.occ_tma[1] = prep_kernel(fast_strided_kernel<T, R1, R2, R3, -1, TL, JT, true>, o.threads, o.smem);
+            o.occ_tma[2] = prep_kernel(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, true, false, true>, o.threads, o.smem_x);
+            o.occ_tma[3] = prep_kernel(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, false, false, true>, o.threads, o.smem_x);
+        }
         o.occ[2] = prep_kernel(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, true, false>, o.threads, o.smem_x);
         o.occ[5] = prep_kernel(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, false, false>, o.threads, o.smem_x);
         o.occ_peer[0] = prep_kernel(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, true, true>, o.threads, o.smem_xp);
@@ -702,18 +747,34 @@ struct FastImpl {
     }
     static void strided(cudaStream_t st, int sign, const StrideGeom& g, int ntiles, int grid, void* spec, const void* tw) {
         const size_t smem = (size_t)(2 * N * TL + TwGeom<R1, R2, R3>::TOTAL) * sizeof(cx<T>);
-        if (sign > 0) launch_pdl(fast_strided_kernel<T, R1, R2, R3, 1, TL, JT>, grid, TL * JT, smem, st, g, ntiles, (cx<T>*)spec, (const cx<T>*)tw);
-        else launch_pdl(fast_strided_kernel<T, R1, R2, R3, -1, TL, JT>, grid, TL * JT, smem, st, g, ntiles, (cx<T>*)spec, (const cx<T>*)tw);
+        const CUtensorMap none = {};
+        if (sign > 0) launch_pdl(fast_strided_kernel<T, R1, R2, R3, 1, TL, JT, false>, grid, TL * JT, smem, st, g, ntiles, (cx<T>*)spec, (const cx<T>*)tw, none);
+        else launch_pdl(fast_strided_kernel<T, R1, R2, R3, -1, TL, JT, false>, grid, TL * JT, smem, st, g, ntiles, (cx<T>*)spec, (const cx<T>*)tw, none);
+    }
+    static void strided_tma(cudaStream_t st, int sign, const StrideGeom& g, int ntiles, int grid, void* spec, const void* tw, const CUtensorMap& tm) {
+        const size_t smem = (size_t)(2 * N * TL + TwGeom<R1, R2, R3>::TOTAL) * sizeof(cx<T>);
+        if (sign > 0) launch_pdl(fast_strided_kernel<T, R1, R2, R3, 1, TL, JT, true>, grid, TL * JT, smem, st, g, ntiles, (cx<T>*)spec, (const cx<T>*)tw, tm);
+        else launch_pdl(fast_strided_kernel<T, R1, R2, R3, -1, TL, JT, true>, grid, TL * JT, smem, st, g, ntiles, (cx<T>*)spec, (const cx<T>*)tw, tm);
+    }
+    static void xconv_tma(cudaStream_t st, const StrideGeom& g, int tile0, int ntiles, int grid, const BoxInfo* B, double kappa, int kind,
+                          const ConvTables& tb, void* spec, const void* tw, double* scalars, int want_vir, const CUtensorMap& tm) {
+        const size_t smem = smem_x_bytes();
+        if (kind == ADMP_CK_COULOMB && !want_vir)
+            launch_pdl(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, true, false, true>, grid, TL * JT, smem, st, g, tile0, ntiles, B, (T)kappa, kind, tb,
+                       (cx<T>*)spec, (const cx<T>*)tw, scalars, want_vir, PeerTab{}, 0, tm);
+        else
+            launch_pdl(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, false, false, true>, grid, TL * JT, smem, st, g, tile0, ntiles, B, (T)kappa, kind, tb,
+                       (cx<T>*)spec, (const cx<T>*)tw, scalars, want_vir, PeerTab{}, 0, tm);
     }
     static void xconv(cudaStream_t st, const StrideGeom& g, int tile0, int ntiles, int grid, const BoxInfo* B, double kappa, int kind,
                       const ConvTables& tb, void* spec, const void* tw, double* scalars, int want_vir) {
         const size_t smem = smem_x_bytes();
         if (kind == ADMP_CK_COULOMB && !want_vir)
             launch_pdl(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, true, false>, grid, TL * JT, smem, st, g, tile0, ntiles, B, (T)kappa, kind, tb,
-                       (cx<T>*)spec, (const cx<T>*)tw, scalars, want_vir, PeerTab{}, 0);
+                       (cx<T>*)spec, (const cx<T>*)tw, scalars, want_vir, PeerTab{}, 0, CUtensorMap{});
         else
             launch_pdl(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, false, false>, grid, TL * JT, smem, st, g, tile0, ntiles, B, (T)kappa, kind, tb,
-                       (cx<T>*)spec, (const cx<T>*)tw, scalars, want_vir, PeerTab{}, 0);
+                       (cx<T>*)spec, (const cx<T>*)tw, scalars, want_vir, PeerTab{}, 0, CUtensorMap{});
     }
     static void xconv_peer(cudaStream_t st, const StrideGeom& g, int tile0, int tile1, int grid, const BoxInfo* B, double kappa, int kind,
                            const ConvTables& tb, void* spec, const void* tw, double* scalars, int want_vir, const PeerTab& peers,
@@ -721,10 +782,12 @@ struct FastImpl {
         const size_t smem = smem_x_bytes(true);
         if (kind == ADMP_CK_COULOMB && !want_vir)
             fast_x_conv_kernel<T, R1, R2, R3, TL, JT, true, true><<<grid, TL * JT, smem, st>>>(g, tile0, tile1, B, (T)kappa, kind, tb, (cx<T>*)spec,
-                                                                                             (const cx<T>*)tw, scalars, want_vir, peers, local_reads);
+                                                                                             (const cx<T>*)tw, scalars, want_vir, peers, local_reads,
+                                                                                             CUtensorMap{});
         else
             fast_x_conv_kernel<T, R1, R2, R3, TL, JT, false, true><<<grid, TL * JT, smem, st>>>(g, tile0, tile1, B, (T)kappa, kind, tb, (cx<T>*)spec,
-                                                                                              (const cx<T>*)tw, scalars, want_vir, peers, local_reads);
+                                                                                              (const cx<T>*)tw, scalars, want_vir, peers, local_reads,
+                                                                                              CUtensorMap{});
     }
     static void zfwd(cudaStream_t st, int nlines, int ntiles, int grid, const void* mesh, void* spec, const void* tw) {
         const size_t smem = (size_t)(2 * ZTL * ZGeom<N>::LS + TwGeom<R1, R2, R3>::TOTAL + N + 1) * sizeof(cx<T>);
@@ -741,6 +804,8 @@ struct FastImpl {
         o.smem_x = smem_x_bytes();
         o.smem_xp = smem_x_bytes(true);
         o.zsmem = (size_t)(2 * ZTL * ZGeom<N>::LS + TwGeom<R1, R2, R3>::TOTAL + N + 1) * sizeof(cx<T>);
+        o.box_rows = tma_box_rows(N);
+        o.strided_tma = &strided_tma; o.xconv_tma = &xconv_tma;
         o.prepare = &prepare; o.strided = &strided; o.xconv = &xconv; o.xconv_peer = &xconv_peer; o.zfwd = &zfwd; o.zinv = &zinv;
         return o;
     }
