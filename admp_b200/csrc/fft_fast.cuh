@@ -66,11 +66,12 @@ __device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* tm, i
                  "l"(tm), "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
-// rows of a strided tile per tensor-map box: the largest divisor of N that fits the 256-element box limit
-constexpr int tma_box_rows(int N) {
-    int b = 1;
+// rows of a strided tile per tensor-map box: the largest divisor of N within the 256-element box limit whose boxes start
+// on 128-byte shared-memory boundaries (rows are TL complex doubles = TL*16 bytes); 0 = no such divisor (cp.async is used)
+constexpr int tma_box_rows(int N, int TL) {
+    int b = 0;
     for (int d = 1; d <= 256; ++d)
-        if (N % d == 0) b = d;
+        if (N % d == 0 && (d == N || (d * TL) % 8 == 0)) b = d;
     return b;
 }
 template <typename T> struct UseBulk { static constexpr bool value = sizeof(T) == 8; };
@@ -277,7 +278,7 @@ __device__ __forceinline__ void issue_tile(const StrideGeom& g, int tile, const 
 // full box is always accounted on the mbarrier
 template <typename T, int N, int TL>
 __device__ __forceinline__ void issue_tile_tma(const StrideGeom& g, int tile, const CUtensorMap* tm, cx<T>* dst, uint64_t* bar) {
-    constexpr int BOXN = tma_box_rows(N);
+    constexpr int BOXN = tma_box_rows(N, TL) > 0 ? tma_box_rows(N, TL) : N;
     if (threadIdx.x == 0) {
         const int o = tile / g.tiles, t = tile - o * g.tiles;
         fence_async_smem();
@@ -732,7 +733,7 @@ struct FastImpl {
     static void prepare(FastOps& o) {
         o.occ[0] = prep_kernel(fast_strided_kernel<T, R1, R2, R3, 1, TL, JT, false>, o.threads, o.smem);
         o.occ[1] = prep_kernel(fast_strided_kernel<T, R1, R2, R3, -1, TL, JT, false>, o.threads, o.smem);
-        if (sizeof(T) == 8) {
+        if (sizeof(T) == 8 && tma_box_rows(N, TL) > 0) {
             o.occ_tma[0] = prep_kernel(fast_strided_kernel<T, R1, R2, R3, 1, TL, JT, true>, o.threads, o.smem);
             o.occ_tma[1] = prep_kernel(fast_strided_kernel<T, R1, R2, R3, -1, TL, JT, true>, o.threads, o.smem);
             o.occ_tma[2] = prep_kernel(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, true, false, true>, o.threads, o.smem_x);
@@ -804,7 +805,7 @@ struct FastImpl {
         o.smem_x = smem_x_bytes();
         o.smem_xp = smem_x_bytes(true);
         o.zsmem = (size_t)(2 * ZTL * ZGeom<N>::LS + TwGeom<R1, R2, R3>::TOTAL + N + 1) * sizeof(cx<T>);
-        o.box_rows = tma_box_rows(N);
+        o.box_rows = tma_box_rows(N, TL);
         o.strided_tma = &strided_tma; o.xconv_tma = &xconv_tma;
         o.prepare = &prepare; o.strided = &strided; o.xconv = &xconv; o.xconv_peer = &xconv_peer; o.zfwd = &zfwd; o.zinv = &zinv;
         return o;

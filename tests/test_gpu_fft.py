@@ -103,3 +103,39 @@ def test_full_evaluation_identical_on_both_backends():
     assert abs(res[0][0] - res[1][0]) < 1e-9 * abs(res[0][0])
     assert (res[0][1] - res[1][1]).abs().max().item() < 1e-9 * res[0][1].abs().max().item()
     assert (res[0][2] - res[1][2]).abs().max().item() < 1e-8 * res[0][2].abs().max().item()
+
+
+@pytest.mark.parametrize('env', [{'ADMP_FFT_WIDE': '0'}, {'ADMP_FFT_WIDE': '1'}, {'ADMP_FFT_TMA': '0'}, {'ADMP_FFT_XWIDE': '0'}])
+@pytest.mark.parametrize('K', [(308, 616, 154), (616, 154, 308), (154, 1232, 616)])
+def test_tile_width_and_tma_switches_give_the_same_round_trip(K, env, monkeypatch):
+    """Every tile-load path of the float64 passes (TMA tensor-map copies, TMA bulk copies, cp.async; wide and narrow tiles,
+    whose tensor-map boxes must start on 128-byte shared-memory boundaries) against the cuFFT + convolve_kernel round trip."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    cx = _ctx(K)
+    cx.set_topology(4, None, None, None)
+    sp, p = _lib.stream_ptr, _lib.ptr
+    box = torch.diag(torch.tensor([31.0, 29.0, 37.0], dtype=torch.float64, device='cuda'))
+    pos = torch.rand((4, 3), dtype=torch.float64, device='cuda') * 20
+    Q = torch.rand((4, 1), dtype=torch.float64, device='cuda')
+    g = torch.Generator(device='cuda').manual_seed(5)
+    mesh = torch.randn(K, dtype=torch.float64, device='cuda', generator=g)
+    out = {}
+    for backend in (1, 0):
+        _lib.check(cx.lib.admp_ctx_set_fft_backend(cx.handle, backend))
+        _lib.check(cx.lib.admp_pme_spread(cx.handle, sp(), p(pos), p(box), p(Q), 1, 1, None))
+        _lib.check(cx.lib.admp_ctx_buffer_io(cx.handle, sp(), 0, p(mesh), mesh.numel() * 8, 1))
+        scal = torch.zeros(_lib.S_COUNT, dtype=torch.float64, device='cuda')
+        if backend == 1:
+            _lib.check(cx.lib.admp_pme_fft_convolve(cx.handle, sp(), _lib.CK_COULOMB, 0, p(scal)))
+        else:
+            _lib.check(cx.lib.admp_pme_fft(cx.handle, sp(), 0))
+            _lib.check(cx.lib.admp_pme_convolve(cx.handle, sp(), _lib.CK_COULOMB, 0, p(scal)))
+            _lib.check(cx.lib.admp_pme_fft(cx.handle, sp(), 1))
+        phi = torch.empty_like(mesh)
+        _lib.check(cx.lib.admp_ctx_buffer_io(cx.handle, sp(), 0, p(phi), phi.numel() * 8, 0))
+        torch.cuda.synchronize()
+        out[backend] = (phi, scal.clone())
+    a, b = out[1], out[0]
+    assert (a[0] - b[0]).abs().max().item() < 1e-11 * b[0].abs().max().item()
+    assert abs(a[1][_lib.S_E_RECIP].item() - b[1][_lib.S_E_RECIP].item()) < 1e-11 * abs(b[1][_lib.S_E_RECIP].item())
