@@ -95,6 +95,9 @@ struct admp_ctx {
     // cluster pair tiles (pair_cluster.cu)
     ClusterWork cw = {};
     int cluster_force = 0;          // ADMP_PAIR_CLUSTER: 0 auto, 1 always (when the row order allows), -1 never
+    // brick-staged spread (spread_brick.cu): atom bins per evaluation
+    BrickWork bw = {};
+    int spread_mode = 0;            // admp_ctx_set_spread: 0 one warp per atom (+ zero-fill; the faster one, see spread_brick.cu), 1 bricks
     size_t ws_bytes = 0;
 };
 
@@ -155,6 +158,7 @@ extern "C" int admp_ctx_create(admp_ctx** out, int device, int dtype) {
     c->cw.min_rows_per_cluster = 96;
     if (const char* e = getenv("ADMP_PAIR_CLUSTER")) c->cluster_force = atoi(e) > 0 ? 1 : (atoi(e) < 0 || e[0] == '0' ? -1 : 0);
     if (const char* e = getenv("ADMP_PAIR_CLUSTER_MINROWS")) c->cw.min_rows_per_cluster = atoi(e);
+    if (const char* e = getenv("ADMP_SPREAD")) c->spread_mode = strcmp(e, "bricks") == 0 ? 1 : 0;
     CK(cudaMalloc(&c->s_mS, 8 * 8));
     CK(cudaMalloc(&c->s_pS, 8 * 8));
     CK(cudaMalloc(&c->s_box, 9 * 8));
@@ -179,6 +183,8 @@ static void free_recip(admp_ctx* c) {
     if (c->fft) { fft3d_destroy(c->fft); c->fft = nullptr; }
     c->use_custom_fft = false;
     c->peer_n = 0;
+    c->ws_bytes -= brick_bytes(c->bw);
+    brick_free(c->bw);
 }
 
 // cuFFT plans + work area of the library backend: created on first use (the hand-written passes need none of it;
@@ -208,6 +214,8 @@ static void free_atoms(admp_ctx* c) {
     dfree(c->axis_type); dfree(c->axis_idx); dfree(c->cov_off); dfree(c->cov_idx); dfree(c->cov_nb);
     dfree(c->cw.cl_of); dfree(c->cw.cl_first); dfree(c->cw.cl_size); dfree(c->cw.row_start); dfree(c->cw.cl_extra);
     c->cw.n_clusters = 0;
+    c->ws_bytes -= brick_bytes(c->bw);
+    brick_free(c->bw);
 }
 
 extern "C" int admp_ctx_destroy(admp_ctx* c) {
@@ -251,6 +259,25 @@ static std::vector<double> theta_inv2(int K, int count) {
     }
     return out;
 }
+
+// atom bins of the brick-staged spread: need both the mesh and the atom count (whichever of set_pme / set_topology comes second)
+static int ensure_bricks(admp_ctx* c) {
+    if (c->bw.ready || !c->mesh || c->n_atoms <= 0) return 0;
+    if (c->spread_mode == 0) return 0;                 // allocated only when the brick variant is asked for
+    CK(brick_alloc(c->bw, c->n_atoms, c->K, c->n_sm, c->w));
+    c->ws_bytes += brick_bytes(c->bw);
+    return 0;
+}
+static inline bool use_bricks(const admp_ctx* c) { return c->bw.ready && c->spread_mode == 1; }
+
+extern "C" int admp_ctx_set_spread(admp_ctx* c, int bricks) {
+    if (!c) return fail("admp_ctx_set_spread: null context");
+    CK(cudaSetDevice(c->device));
+    c->spread_mode = bricks ? 1 : 0;
+    drop_graph(c);
+    return ensure_bricks(c);
+}
+extern "C" int admp_ctx_spread_bricks(const admp_ctx* c) { return (c && use_bricks(c)) ? c->bw.geom.bz : 0; }
 
 extern "C" int admp_ctx_set_pme(admp_ctx* c, double kappa, int K1, int K2, int K3, int lmax) {
     if (!c) return fail("admp_ctx_set_pme: null ctx");
@@ -305,7 +332,7 @@ extern "C" int admp_ctx_set_pme(admp_ctx* c, double kappa, int K1, int K2, int K
         }
     }
     if (!c->use_custom_fft && ensure_cufft(c)) return 1;
-    return 0;
+    return ensure_bricks(c);
 }
 
 /* 1: hand-written fused FFT, 0: cuFFT + separate convolution kernel */
@@ -395,7 +422,7 @@ extern "C" int admp_ctx_set_topology(admp_ctx* c, int n, const int32_t* axis_typ
         CK(cudaMemcpy(c->cw.cl_first, cl_first.data(), sizeof(int32_t) * nc, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c->cw.cl_size, cl_size.data(), sizeof(int32_t) * nc, cudaMemcpyHostToDevice));
     }
-    return 0;
+    return ensure_bricks(c);
 }
 
 // ------------------------------------------------------------------------------------------ helpers
@@ -433,14 +460,31 @@ static void conv_tables(admp_ctx* c, cudaStream_t st) {
     launch_conv_tables(st, c->box, c->kappa, c->bt[0], c->bt[1], c->bt[2], c->ek, c->k2, c->ortho, maxK);
 }
 
-// `tables`: rebuild the separable influence tables first (needed once per box, i.e. per evaluation)
+// once per evaluation (positions / box changed): bin the atoms by mesh brick
+static void spread_prepare(admp_ctx* c, cudaStream_t st, const void* pos) {
+    if (use_bricks(c)) DISPATCH(c, launch_brick_sort, st, c->bw, c->box, pos);
+}
+// the whole spread: mesh = sum of the atoms' stencils (bricks: one coalesced write; otherwise zero-fill + per-atom scatter)
+static int spread_all(admp_ctx* c, cudaStream_t st, const void* pos, const void* M, int cols, int stride, const void* U) {
+    if (use_bricks(c)) {
+        DISPATCH(c, launch_spread_brick, st, c->bw, c->box, pos, M, cols, stride, U, c->mesh);
+    } else {
+        CK(cudaMemsetAsync(c->mesh, 0, c->mesh_bytes, st));
+        DISPATCH(c, launch_spread, st, c->n_atoms, c->box, pos, M, cols, stride, U, c->mesh);
+    }
+    CKLAUNCH();
+    return 0;
+}
+
+// `tables`: rebuild the separable influence tables and the atom bins first (needed once per box / positions, i.e. per evaluation)
 static int recip_field(admp_ctx* c, cudaStream_t st, const void* pos, const void* M, int cols, int stride, const void* U,
                        int kind, double* scalars, int want_vir, bool tables = true) {
-    if (tables) conv_tables(c, st);
+    if (tables) {
+        conv_tables(c, st);
+        spread_prepare(c, st, pos);
+    }
     c->phi_cur = c->mesh;
-    CK(cudaMemsetAsync(c->mesh, 0, c->mesh_bytes, st));
-    DISPATCH(c, launch_spread, st, c->n_atoms, c->box, pos, M, cols, stride, U, c->mesh);
-    CKLAUNCH();
+    if (spread_all(c, st, pos, M, cols, stride, U)) return 1;
     if (c->use_custom_fft) {
         fft3d_convolve_roundtrip(c->fft, st, c->mesh, c->spec, c->box, c->kappa, kind, c->tb, scalars, want_vir);
         CKLAUNCH();
@@ -542,14 +586,16 @@ extern "C" int admp_pme_spread(admp_ctx* c, void* stream, const void* pos, const
     cudaStream_t st = (cudaStream_t)stream;
     CK(cudaSetDevice(c->device));
     DISPATCH(c, launch_box_setup, st, box, c->box, c->K[0], c->K[1], c->K[2]);
-    CK(cudaMemsetAsync(c->mesh, 0, c->mesh_bytes, st));
-    DISPATCH(c, launch_spread, st, c->n_atoms, c->box, pos, M, M_cols, M_stride, U, c->mesh);
-    CKLAUNCH();
-    return 0;
+    spread_prepare(c, st, pos);
+    return spread_all(c, st, pos, M, M_cols, M_stride, U);
 }
 extern "C" int admp_pme_spread_only(admp_ctx* c, void* stream, const void* pos, const void* M, int M_cols, int M_stride, const void* U) {
-    if (need(c, true, true)) return 1;     // no zero-fill, no box set-up: the bare scatter kernel
-    DISPATCH(c, launch_spread, (cudaStream_t)stream, c->n_atoms, c->box, pos, M, M_cols, M_stride, U, c->mesh);
+    if (need(c, true, true)) return 1;     // no box set-up, no binning: the spread kernel alone on the state admp_pme_spread left
+    if (use_bricks(c)) {                   // (bricks: writes the whole mesh; per-atom path: the bare scatter without the zero-fill)
+        DISPATCH(c, launch_spread_brick, (cudaStream_t)stream, c->bw, c->box, pos, M, M_cols, M_stride, U, c->mesh);
+    } else {
+        DISPATCH(c, launch_spread, (cudaStream_t)stream, c->n_atoms, c->box, pos, M, M_cols, M_stride, U, c->mesh);
+    }
     CKLAUNCH();
     return 0;
 }
@@ -965,6 +1011,7 @@ extern "C" int admp_pme_eval(admp_ctx* c, void* stream, const void* pos, const v
     DISPATCH(c, launch_box_setup, st, c->s_box, c->box, c->K[0], c->K[1], c->K[2]);
     DISPATCH(c, launch_frames_fwd, st, n, c->lmax, c->box, c->s_pos, c->axis_type, c->axis_idx, Ql, c->M, nullptr, nullptr);
     conv_tables(c, st);
+    spread_prepare(c, st, c->s_pos);
     CKLAUNCH();
     const int want_vir = (flags & ADMP_WANT_VIRIAL) ? 1 : 0;
     if (polz && (flags & ADMP_SCF)) {
@@ -984,7 +1031,7 @@ extern "C" int admp_pme_eval(admp_ctx* c, void* stream, const void* pos, const v
         if (scf_out) CK(cudaMemcpyAsync(scf_out, c->state + 3, sizeof(int32_t) * 2, cudaMemcpyDeviceToDevice, st));
         CK(cudaMemcpyAsync(U_io, c->s_U, (size_t)n * 3 * w, cudaMemcpyDeviceToDevice, st));
     } else {
-        if (recip_field(c, st, c->s_pos, c->M, 10, 10, polz ? c->s_U : nullptr, ADMP_CK_COULOMB, c->scal, want_vir)) return 1;
+        if (recip_field(c, st, c->s_pos, c->M, 10, 10, polz ? c->s_U : nullptr, ADMP_CK_COULOMB, c->scal, want_vir, false)) return 1;
     }
     // final evaluation at fixed U (Hellmann-Feynman, pme.py:83-85): phi of the last pass is still in c->mesh
     const void* Uf = polz ? c->s_U : nullptr;

@@ -77,6 +77,28 @@ void launch_gather(cudaStream_t st, int n, const BoxInfo* B, const void* pos, co
                    const void* phi, int mode, uint32_t flags, void* dpos, void* G, int g_stride, void* F, double* scalars,
                    const PeerTab* peers = nullptr);
 
+// spread_brick.cu - brick-staged spread (mesh written once, zero-fill included); atoms binned by home brick per evaluation
+struct BrickGeom { int nb[3]; int bz; };       // bricks per dimension (16 x 16 x bz points each)
+struct BrickWork {
+    int32_t* count = nullptr;      // n_bricks + 1: histogram, then fill cursors
+    int32_t* start = nullptr;      // n_bricks + 1: first sorted slot of every brick
+    int4* tmp = nullptr;           // n_atoms: (i0, j0, k0, home brick) in atom order
+    int4* anchor = nullptr;        // n_atoms: (i0, j0, k0, atom) sorted by home brick
+    void* rec = nullptr;           // n_atoms x 72 reals: per-atom spline / coefficient records of the current spread (sorted order)
+    size_t rec_bytes = 0;
+    BrickGeom geom = {};
+    int n_bricks = 0, n_atoms = 0;
+    bool ready = false;
+};
+bool brick_supported(const int K[3]);
+cudaError_t brick_alloc(BrickWork& w, int n_atoms, const int K[3], int n_sm, size_t elem_bytes);
+void brick_free(BrickWork& w);
+size_t brick_bytes(const BrickWork& w);
+template <typename T> void launch_brick_sort(cudaStream_t st, const BrickWork& w, const BoxInfo* B, const void* pos);
+template <typename T>
+void launch_spread_brick(cudaStream_t st, const BrickWork& w, const BoxInfo* B, const void* pos, const void* M, int m_cols,
+                         int m_stride, const void* U, void* mesh);
+
 // fft.cu - hand-written 3-D real FFT fused with the influence-function convolution
 struct Fft3d;
 Fft3d* fft3d_create(int K1, int K2, int K3, int dtype, const char** why);     // nullptr when the sizes are unsupported

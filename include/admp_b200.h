@@ -97,6 +97,16 @@ int admp_ctx_set_kvec_order(admp_ctx* ctx, int reference);
  * admp_ctx_pair_cluster_active reads back which one the last evaluation used (1 cluster, 0 flat; synchronises - tests only). */
 int admp_ctx_set_pair_cluster(admp_ctx* ctx, int force, int min_rows_per_cluster);
 int admp_ctx_pair_cluster_active(admp_ctx* ctx);
+/* B-spline spread of admp_pme_eval / admp_pme_recip / admp_pme_spread (replaces admp/recip.py:313-392). Two kernels, same
+ * result to rounding. bricks = 0 (default): zero-fill + one warp per atom with global atomics. bricks = 1: brick-staged - atoms
+ * binned by 16 x 16 x 16|32 mesh bricks once per evaluation, one block accumulates a brick in shared memory (no atomics) and
+ * writes it once with coalesced stores (the zero-fill is part of the write); needs >= 3 bricks per mesh dimension, not
+ * available for x-slab decomposed meshes / atom sub-ranges. Measured slower on B200 on every workload (each atom is visited
+ * by ~2 bricks and the kernel is instruction-bound; DESIGN.md section 5, profiles/r2i_brick_spread.md), hence opt-in.
+ * admp_ctx_spread_bricks returns the brick depth in z (16 / 32) when the brick path is active, 0 otherwise.
+ * Environment: ADMP_SPREAD=bricks selects it at context creation, ADMP_BRICK_Z=16|32 forces the depth. */
+int admp_ctx_set_spread(admp_ctx* ctx, int bricks);
+int admp_ctx_spread_bricks(const admp_ctx* ctx);
 int64_t admp_ctx_workspace_bytes(const admp_ctx* ctx);
 /* 1 when optimize_Uind runs as the device-resident CUDA-graph WHILE loop, 0 when the
  * host-synchronised loop is in use (ADMP_SCF_HOSTSYNC or graph construction failed). */
