@@ -259,6 +259,125 @@ __device__ __forceinline__ void fft_head(int j, bool live, Ld ld, St st) {
         s.put(j, st);
     }
 }
+// ------------------------------------------------------------------------------------------ prime-factor (Good-Thomas) stages
+// All sizes of the mesh family but 1232 = 11*14*8 factor into PAIRWISE COPRIME radices (77 = 11*7, 154 = 11*14, 308 = 11*7*4,
+// 616 = 11*7*8), so the line FFT of the strided passes is a pure R1 x R2 x R3 multi-dimensional DFT - no twiddle factors:
+//   input   n = (n1 S1 + n2 S2 + n3 S3) mod N,  S_d = N / R_d                       (Good's map, natural order in)
+//   output  k = (k1 T1 + k2 T2 + k3 T3) mod N,  T_d = S_d * (S_d^-1 mod R_d)         (CRT map, natural order out)
+//   W_N^(n k) = prod_d W_Rd^(n_d k_d)           (cross terms S_d T_e are multiples of N, S_d T_d = 1 mod R_d)
+// The work buffer holds the multi-index array row-major, w(i1, i2, i3) at i1 + R1 (i2 + R2 i3). The first dimension gathers
+// its inputs from the natural-order tile through Good's map, the middle dimension works IN PLACE (every butterfly reads and
+// writes the same positions: no barrier between its loads and stores), the last dimension scatters through the CRT map. In
+// the fused X pass the frequency side never needs natural order: the influence tables are permuted once per block, and the
+// inverse runs the dimensions backwards and leaves through Good's map again. Versus the Stockham stages above: no twiddle
+// tables / complex multiplies (16 % of the FP64 instructions of a 308-point X pass), 5 instead of 9 barriers per X tile.
+#ifndef ADMP_FFT_PFA
+#define ADMP_FFT_PFA 1
+#endif
+constexpr int pfa_gcd(int a, int b) { return b == 0 ? a : pfa_gcd(b, a % b); }
+constexpr int pfa_inv(int a, int m) {
+    int r = 0;
+    for (int x = 1; x < m; ++x)
+        if ((a % m) * x % m == 1) r = x;
+    return r;
+}
+template <int R1, int R2, int R3> struct Pfa {
+    static constexpr int N = R1 * R2 * R3;
+    static constexpr bool value = ADMP_FFT_PFA && pfa_gcd(R1, R2) == 1 && pfa_gcd(R1, R3) == 1 && pfa_gcd(R2, R3) == 1;
+    // stand-alone Y passes: measured on B200 against the Stockham stages - 154 points 18.3 -> 17.2 us, 616 points 0.444 -> 0.456 ms
+    // (HBM-bound either way), so only the two-factor sizes use it there; the fused X pass gains at every size (308: 0.919 -> 0.747 ms)
+    static constexpr bool strided = value && R3 == 1;
+    static constexpr int S1 = N / R1, S2 = N / R2, S3 = N / R3;
+    static constexpr int T1 = (S1 * pfa_inv(S1, R1)) % N, T2 = (S2 * pfa_inv(S2, R2)) % N, T3 = R3 > 1 ? (S3 * pfa_inv(S3, R3)) % N : 0;
+    // butterflies of dimension 1: b = i2 + R2 i3
+    static __device__ __forceinline__ int rm1(int b) { return R1 * b; }
+    static __device__ __forceinline__ int rm1_off(int bs, int t) { return bs + t; }
+    static __device__ __forceinline__ int good1(int b) {
+        const int i3 = b / R2, i2 = b - i3 * R2;
+        int x = i2 * S2 + (R3 > 1 ? i3 * S3 : 0);
+        return x >= N ? x - N : x;
+    }
+    static __device__ __forceinline__ int good1_off(int bs, int t) {
+        const int p = bs + t * S1;
+        return p >= N ? p - N : p;
+    }
+    // butterflies of dimension 2 (three factors: middle dimension): b = i1 + R1 i3
+    static __device__ __forceinline__ int rm2(int b) {
+        const int i3 = b / R1;
+        return b + (R2 - 1) * R1 * i3;
+    }
+    static __device__ __forceinline__ int rm2_off(int bs, int t) { return bs + t * R1; }
+    // last dimension (3 when R3 > 1, else 2): b = row-major index of the other dimensions, stride = their product
+    static constexpr int RL = R3 > 1 ? R3 : R2, SL = N / RL, TLAST = R3 > 1 ? T3 : T2;
+    static __device__ __forceinline__ int rml(int b) { return b; }
+    static __device__ __forceinline__ int rml_off(int bs, int t) { return bs + t * SL; }
+    static __device__ __forceinline__ int crtl(int b) {
+        if (R3 > 1) {
+            const int i2 = b / R1, i1 = b - i2 * R1;
+            return (i1 * T1 + i2 * T2) % N;
+        }
+        return (b * T1) % N;
+    }
+    static __device__ __forceinline__ int crtl_off(int bs, int t) {
+        const int p = bs + (t * TLAST) % N;
+        return p >= N ? p - N : p;
+    }
+    // frequency of row-major position p (set-up of the permuted influence tables)
+    static __device__ __forceinline__ int freq(int p) {
+        const int i1 = p % R1, r = p / R1, i2 = r % R2, i3 = r / R2;
+        return (i1 * T1 + i2 * T2 + i3 * T3) % N;
+    }
+};
+
+// one dimension of the multi-dimensional DFT: butterflies b = j, j + JT, ... < NB of radix R; `base(b)` / `off(base, t)` give the
+// position of point t of butterfly b in the buffer behind `in` / `out`
+template <typename T, int R, int SIGN, int NB, int JT>
+struct PStage {
+    static constexpr int iters = (NB + JT - 1) / JT;
+    cx<T> v[iters][R];
+    template <typename Base, typename Off, typename In>
+    __device__ __forceinline__ void run(int j, Base base, Off off, In in) {
+#pragma unroll
+        for (int it = 0; it < iters; ++it) {
+            const int b = j + it * JT;
+            if ((it + 1) * JT <= NB || b < NB) {
+                const int bs = base(b);
+#pragma unroll
+                for (int t = 0; t < R; ++t) v[it][t] = in(off(bs, t));
+                Dft<T, R, SIGN>::run(v[it]);
+            }
+            if (it + 1 < iters) asm volatile("" ::: "memory");       // one butterfly's loads at a time (registers)
+        }
+    }
+    // v <- f(position, v), then the DFT of the opposite sign on the same points (frequency-side scaling between a forward
+    // and an inverse transform, in registers)
+    template <typename Base, typename Off, typename Scale>
+    __device__ __forceinline__ void scale_inverse(int j, Base base, Off off, Scale f) {
+#pragma unroll
+        for (int it = 0; it < iters; ++it) {
+            const int b = j + it * JT;
+            if ((it + 1) * JT <= NB || b < NB) {
+                const int bs = base(b);
+#pragma unroll
+                for (int t = 0; t < R; ++t) v[it][t] = f(off(bs, t), v[it][t]);
+                Dft<T, R, -SIGN>::run(v[it]);
+            }
+        }
+    }
+    template <typename Base, typename Off, typename Out>
+    __device__ __forceinline__ void put(int j, Base base, Off off, Out out) const {
+#pragma unroll
+        for (int it = 0; it < iters; ++it) {
+            const int b = j + it * JT;
+            if ((it + 1) * JT <= NB || b < NB) {
+                const int bs = base(b);
+#pragma unroll
+                for (int t = 0; t < R; ++t) out(off(bs, t), v[it][t]);
+            }
+        }
+    }
+};
+
 // ------------------------------------------------------------------------------------------ strided passes (Y, X)
 template <typename T, int N, int TL, int JT>
 __device__ __forceinline__ void issue_tile(const StrideGeom& g, int tile, const cx<T>* __restrict__ spec, cx<T>* dst, int l, int j) {
@@ -331,7 +450,7 @@ fast_strided_kernel(StrideGeom g, int ntiles, cx<T>* __restrict__ spec, const cx
     int tile = blockIdx.x;
     pdl_launch_dependents();
     if (BULK && threadIdx.x == 0) mbar_init(&bar, 1);
-    build_twiddles<T, R1, R2, R3, 1>(tw2, tw3, gtw, NT);
+    if (!Pfa<R1, R2, R3>::strided) build_twiddles<T, R1, R2, R3, 1>(tw2, tw3, gtw, NT);
     if (BULK) __syncthreads();
     pdl_wait();
     auto issue = [&](int t) {
@@ -351,6 +470,34 @@ fast_strided_kernel(StrideGeom g, int ntiles, cx<T>* __restrict__ spec, const cx
         const bool live = l < g.n_inner - c0;
         cx<T>* out = spec + (size_t)o * g.outer_stride + c0 + l;
         const size_t ls = g.line_stride;
+        if (Pfa<R1, R2, R3>::strided) {
+            using P = Pfa<R1, R2, R3>;
+            auto ldI = [&](int pos) { return c[pos * TL]; };
+            auto ldA = [&](int pos) { return a[pos * TL]; };
+            auto stA = [&](int pos, cx<T> v) { a[pos * TL] = v; };
+            if (live) {                        // dimension 1: natural-order tile (Good's map) -> row-major work buffer
+                PStage<T, R1, SIGN, N / R1, JT> s;
+                s.run(j, P::good1, P::good1_off, ldI);
+                s.put(j, P::rm1, P::rm1_off, stA);
+            }
+            if (BULK) fence_async_smem();
+            __syncthreads();                   // I consumed
+            if (tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x);
+            if (R3 > 1) {                      // middle dimension, in place (no barrier between its loads and stores)
+                if (live) {
+                    PStage<T, R2, SIGN, N / R2, JT> s;
+                    s.run(j, P::rm2, P::rm2_off, ldA);
+                    s.put(j, P::rm2, P::rm2_off, stA);
+                }
+                __syncthreads();
+            }
+            if (live) {                        // last dimension: results leave through the CRT map, in natural order
+                PStage<T, P::RL, SIGN, N / P::RL, JT> s;
+                s.run(j, P::rml, P::rml_off, ldA);
+                s.put(j, P::crtl, P::crtl_off, [&](int pos, cx<T> v) { out[(size_t)pos * ls] = v; });
+            }
+            continue;
+        }
         fft_head<T, R1, R2, R3, SIGN, JT>(j, live, [&](int pos) { return c[pos * TL]; }, [&](int pos, cx<T> v) { a[pos * TL] = v; });
         if (BULK) fence_async_smem();
         __syncthreads();                       // I consumed
@@ -414,8 +561,15 @@ fast_x_conv_kernel(StrideGeom g, int tile0, int ntiles, const BoxInfo* __restric
     int tile = tile0 + blockIdx.x;
     pdl_launch_dependents();
     if (BULK && threadIdx.x == 0) mbar_init(&bar, 1);
-    build_twiddles<T, R1, R2, R3, 1>(tw2, tw3, gtw, NT);
-    build_twiddles<T, Q1, Q2, Q3, 1>(itw2, itw3, gtw, NT);
+    constexpr bool PFA = Pfa<R1, R2, R3>::value;
+    using P = Pfa<R1, R2, R3>;
+    int* sfreq = reinterpret_cast<int*>(tw2);                 // PFA: frequency of row-major position p (the twiddle tables are unused)
+    if (!PFA) {
+        build_twiddles<T, R1, R2, R3, 1>(tw2, tw3, gtw, NT);
+        build_twiddles<T, Q1, Q2, Q3, 1>(itw2, itw3, gtw, NT);
+    } else {
+        for (int i = threadIdx.x; i < N; i += NT) sfreq[i] = P::freq(i);
+    }
     if (BULK) __syncthreads();
     if (PEER) {
         for (int i = threadIdx.x; i < N; i += NT) sbase[i] = reinterpret_cast<cx<T>*>(peers.base[peers.owner(i)]);
@@ -432,10 +586,11 @@ fast_x_conv_kernel(StrideGeom g, int tile0, int ntiles, const BoxInfo* __restric
     };
     if (tile < ntiles) issue(tile);
     const bool ortho = (*tb.ortho != 0);
-    if (QUICK) {
+    if (QUICK) {                                              // PFA: tables in the order of the work buffer (row-major multi-index)
         for (int i = threadIdx.x; i < N; i += NT) {
-            sek[i] = ortho ? tb.ek[0][i] : tb.bt[0][i];
-            sk2[i] = ortho ? tb.k2[0][i] : (double)kint(i, N);
+            const int f = PFA ? P::freq(i) : i;
+            sek[i] = ortho ? tb.ek[0][f] : tb.bt[0][f];
+            sk2[i] = ortho ? tb.k2[0][f] : (double)kint(f, N);
         }
     }
     const int K2 = B.K[1], K3 = B.K[2], K3h = K3 / 2 + 1;
@@ -491,7 +646,7 @@ fast_x_conv_kernel(StrideGeom g, int tile0, int ntiles, const BoxInfo* __restric
                 }
                 if (origin_line && i1 == 0) gg = 0.0;         // gamma point dropped (recip.py:416)
             } else {
-                gg = 2.0 * scale * influence_general(Bp, &tb, kind, kap, i1, i2, i3, s2 * scale, want_vir, acc_t);
+                gg = 2.0 * scale * influence_general(Bp, &tb, kind, kap, PFA ? sfreq[i1] : i1, i2, i3, s2 * scale, want_vir, acc_t);
             }
             acc_line = fma(gg, s2, acc_line);
             const T gt = (T)gg;
@@ -499,6 +654,54 @@ fast_x_conv_kernel(StrideGeom g, int tile0, int ntiles, const BoxInfo* __restric
         };
         auto ldA = [&](int pos) { return a[pos * TL]; };
         auto stA = [&](int pos, cx<T> v) { a[pos * TL] = v; };
+        if (PFA) {
+            // forward: dimension 1 (natural tile -> row-major), [2 in place], last dimension + scaling + its inverse in
+            // registers; inverse: [2 in place], dimension 1 leaves through Good's map in natural order. `scale_point` sees
+            // row-major positions: its tables were permuted at set-up (position 0 is frequency 0).
+            if (live) {
+                PStage<T, R1, 1, N / R1, JT> s;
+                s.run(j, P::good1, P::good1_off, [&](int pos) { return c[pos * TL]; });
+                s.put(j, P::rm1, P::rm1_off, stA);
+            }
+            if (bulk) fence_async_smem();
+            __syncthreads();                   // I consumed: fetch the next tile while this one is transformed
+            if (tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x);
+            if (R3 > 1) {
+                if (live) {
+                    PStage<T, R2, 1, N / R2, JT> s;
+                    s.run(j, P::rm2, P::rm2_off, ldA);
+                    s.put(j, P::rm2, P::rm2_off, stA);
+                }
+                __syncthreads();
+            }
+            if (live) {
+                PStage<T, P::RL, 1, N / P::RL, JT> s;
+                s.run(j, P::rml, P::rml_off, ldA);
+                s.scale_inverse(j, P::rml, P::rml_off, scale_point);
+                s.put(j, P::rml, P::rml_off, stA);
+            }
+            __syncthreads();
+            acc_e = fma(0.5 * wgt, acc_line, acc_e);
+            if (R3 > 1) {
+                if (live) {
+                    PStage<T, R2, -1, N / R2, JT> s;
+                    s.run(j, P::rm2, P::rm2_off, ldA);
+                    s.put(j, P::rm2, P::rm2_off, stA);
+                }
+                __syncthreads();
+            }
+            if (live) {
+                PStage<T, R1, -1, N / R1, JT> s;
+                s.run(j, P::rm1, P::rm1_off, ldA);
+                if (PEER) {
+                    const size_t col = (size_t)c0 + l;
+                    s.put(j, P::good1, P::good1_off, [&](int pos, cx<T> v) { sbase[pos][(size_t)pos * ls + col] = v; });
+                } else {
+                    s.put(j, P::good1, P::good1_off, [&](int pos, cx<T> v) { out[(size_t)pos * ls] = v; });
+                }
+            }
+            continue;
+        }
         fft_head<T, R1, R2, R3, 1, JT>(j, live, [&](int pos) { return c[pos * TL]; }, stA);
         if (bulk) fence_async_smem();
         __syncthreads();                       // I consumed: fetch the next tile while this one is transformed
