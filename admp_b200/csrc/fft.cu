@@ -381,7 +381,9 @@ static bool dim_cfg(int N, int tw_len, size_t esz, size_t smem_cap, int min_ls, 
         const char* e = getenv("ADMP_FFT_WIDE");
         bool wide = e ? atoi(e) > 0 : !zpass;
         if (xpass) { const char* ex = getenv("ADMP_FFT_XWIDE"); if (ex) wide = atoi(ex) > 0; }
-        c.fast = esz == 8 ? fast_lookup<double>(N, wide, c.ops) : fast_lookup<float>(N, wide, c.ops);
+        int force = -1;
+        if (!zpass) { const char* ef = getenv(xpass ? "ADMP_FFT_XCFG" : "ADMP_FFT_YCFG"); if (ef) force = atoi(ef); }
+        c.fast = esz == 8 ? fast_lookup<double>(N, wide, c.ops, force) : fast_lookup<float>(N, wide, c.ops, force);
         if (c.fast) {
             c.ops.prepare(c.ops);
             const bool usable = zpass ? (c.ops.occ[3] > 0 && c.ops.occ[4] > 0) : (c.ops.occ[0] > 0 && c.ops.occ[1] > 0 && c.ops.occ[2] > 0 && c.ops.occ[5] > 0);

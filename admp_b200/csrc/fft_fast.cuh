@@ -123,7 +123,10 @@ __device__ __forceinline__ double fast_rcp(double x) {
 // outputs in registers across a barrier)
 template <int NT, int R3 = 1> struct MinBlocks {
     static constexpr int budget = R3 == 1 ? 512 : 384;      // threads per SM at 128 / 168 registers per thread
-    static constexpr int value = (budget / ((NT + 31) / 32 * 32)) > 0 ? (budget / ((NT + 31) / 32 * 32)) : 1;
+    static constexpr int NTr = (NT + 31) / 32 * 32;
+    // three-stage transforms in 128-thread blocks (fewer threads per line, several butterflies per thread): two blocks per SM at
+    // up to 255 registers - two independent barrier domains instead of one 224-thread block
+    static constexpr int value = (R3 > 1 && NTr == 128 && NT == 128) ? 2 : ((budget / NTr) > 0 ? (budget / NTr) : 1);
 };
 
 // ------------------------------------------------------------------------------------------ one Stockham stage
@@ -330,50 +333,42 @@ template <int R1, int R2, int R3> struct Pfa {
 };
 
 // one dimension of the multi-dimensional DFT: butterflies b = j, j + JT, ... < NB of radix R; `base(b)` / `off(base, t)` give the
-// position of point t of butterfly b in the buffer behind `in` / `out`
+// position of point t of butterfly b behind `in` / `out`. Every butterfly is loaded, transformed and stored on its own (in place or
+// into another buffer: no butterfly reads what another one writes within a dimension), so a thread holds ONE butterfly in registers
+// however many it processes.
 template <typename T, int R, int SIGN, int NB, int JT>
 struct PStage {
     static constexpr int iters = (NB + JT - 1) / JT;
-    cx<T> v[iters][R];
-    template <typename Base, typename Off, typename In>
-    __device__ __forceinline__ void run(int j, Base base, Off off, In in) {
+    template <typename BaseI, typename OffI, typename In, typename BaseO, typename OffO, typename Out>
+    static __device__ __forceinline__ void run(int j, BaseI basei, OffI offi, In in, BaseO baseo, OffO offo, Out out) {
+#pragma unroll 1
+        for (int b = j; b < NB; b += JT) {                           // rolled: one butterfly's registers and code, whatever NB / JT
+            cx<T> v[R];
+            const int bi = basei(b);
 #pragma unroll
-        for (int it = 0; it < iters; ++it) {
-            const int b = j + it * JT;
-            if ((it + 1) * JT <= NB || b < NB) {
-                const int bs = base(b);
+            for (int t = 0; t < R; ++t) v[t] = in(offi(bi, t));
+            Dft<T, R, SIGN>::run(v);
+            const int bo = baseo(b);
 #pragma unroll
-                for (int t = 0; t < R; ++t) v[it][t] = in(off(bs, t));
-                Dft<T, R, SIGN>::run(v[it]);
-            }
-            if (it + 1 < iters) asm volatile("" ::: "memory");       // one butterfly's loads at a time (registers)
+            for (int t = 0; t < R; ++t) out(offo(bo, t), v[t]);
         }
     }
-    // v <- f(position, v), then the DFT of the opposite sign on the same points (frequency-side scaling between a forward
-    // and an inverse transform, in registers)
-    template <typename Base, typename Off, typename Scale>
-    __device__ __forceinline__ void scale_inverse(int j, Base base, Off off, Scale f) {
+    // forward DFT, v <- f(position, v), inverse DFT, back to the same positions (frequency-side scaling between a forward and an
+    // inverse transform, in registers)
+    template <typename Base, typename Off, typename In, typename Scale, typename Out>
+    static __device__ __forceinline__ void run_scaled(int j, Base base, Off off, In in, Scale f, Out out) {
+#pragma unroll 1
+        for (int b = j; b < NB; b += JT) {
+            cx<T> v[R];
+            const int bs = base(b);
 #pragma unroll
-        for (int it = 0; it < iters; ++it) {
-            const int b = j + it * JT;
-            if ((it + 1) * JT <= NB || b < NB) {
-                const int bs = base(b);
+            for (int t = 0; t < R; ++t) v[t] = in(off(bs, t));
+            Dft<T, R, SIGN>::run(v);
 #pragma unroll
-                for (int t = 0; t < R; ++t) v[it][t] = f(off(bs, t), v[it][t]);
-                Dft<T, R, -SIGN>::run(v[it]);
-            }
-        }
-    }
-    template <typename Base, typename Off, typename Out>
-    __device__ __forceinline__ void put(int j, Base base, Off off, Out out) const {
+            for (int t = 0; t < R; ++t) v[t] = f(off(bs, t), v[t]);
+            Dft<T, R, -SIGN>::run(v);
 #pragma unroll
-        for (int it = 0; it < iters; ++it) {
-            const int b = j + it * JT;
-            if ((it + 1) * JT <= NB || b < NB) {
-                const int bs = base(b);
-#pragma unroll
-                for (int t = 0; t < R; ++t) out(off(bs, t), v[it][t]);
-            }
+            for (int t = 0; t < R; ++t) out(off(bs, t), v[t]);
         }
     }
 };
@@ -475,27 +470,19 @@ fast_strided_kernel(StrideGeom g, int ntiles, cx<T>* __restrict__ spec, const cx
             auto ldI = [&](int pos) { return c[pos * TL]; };
             auto ldA = [&](int pos) { return a[pos * TL]; };
             auto stA = [&](int pos, cx<T> v) { a[pos * TL] = v; };
-            if (live) {                        // dimension 1: natural-order tile (Good's map) -> row-major work buffer
-                PStage<T, R1, SIGN, N / R1, JT> s;
-                s.run(j, P::good1, P::good1_off, ldI);
-                s.put(j, P::rm1, P::rm1_off, stA);
-            }
+            // dimension 1: natural-order tile (Good's map) -> row-major work buffer
+            if (live) PStage<T, R1, SIGN, N / R1, JT>::run(j, P::good1, P::good1_off, ldI, P::rm1, P::rm1_off, stA);
             if (BULK) fence_async_smem();
             __syncthreads();                   // I consumed
             if (tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x);
             if (R3 > 1) {                      // middle dimension, in place (no barrier between its loads and stores)
-                if (live) {
-                    PStage<T, R2, SIGN, N / R2, JT> s;
-                    s.run(j, P::rm2, P::rm2_off, ldA);
-                    s.put(j, P::rm2, P::rm2_off, stA);
-                }
+                if (live) PStage<T, R2, SIGN, N / R2, JT>::run(j, P::rm2, P::rm2_off, ldA, P::rm2, P::rm2_off, stA);
                 __syncthreads();
             }
-            if (live) {                        // last dimension: results leave through the CRT map, in natural order
-                PStage<T, P::RL, SIGN, N / P::RL, JT> s;
-                s.run(j, P::rml, P::rml_off, ldA);
-                s.put(j, P::crtl, P::crtl_off, [&](int pos, cx<T> v) { out[(size_t)pos * ls] = v; });
-            }
+            // last dimension: results leave through the CRT map, in natural order
+            if (live)
+                PStage<T, P::RL, SIGN, N / P::RL, JT>::run(j, P::rml, P::rml_off, ldA, P::crtl, P::crtl_off,
+                                                           [&](int pos, cx<T> v) { out[(size_t)pos * ls] = v; });
             continue;
         }
         fft_head<T, R1, R2, R3, SIGN, JT>(j, live, [&](int pos) { return c[pos * TL]; }, [&](int pos, cx<T> v) { a[pos * TL] = v; });
@@ -533,8 +520,17 @@ __device__ __noinline__ double influence_general(const BoxInfo* Bp, const ConvTa
 // PEER: the spectrum is x-slab decomposed over the GPUs of the NVLink domain; this rank transforms the lines
 // of tiles [tile0, ntiles) by loading / storing every point from / to the rank that owns its x plane (cp.async
 // and stores on peer-mapped memory): the all-to-all transposes of a slab FFT are fused into the X pass.
+// resident blocks of the fused X pass: the prime-factor stages hold one butterfly per thread (~150 registers at radix 11), so two
+// blocks of a three-stage transform fit (shared memory - two tiles per block - allows no more at 8 lines of 308 points)
+#ifndef ADMP_X_MINBLOCKS
+#define ADMP_X_MINBLOCKS 2
+#endif
+template <int NT, int R1, int R2, int R3> struct XMinBlocks {
+    static constexpr int base = MinBlocks<NT, R3>::value;
+    static constexpr int value = (Pfa<R1, R2, R3>::value && R3 > 1 && base < ADMP_X_MINBLOCKS) ? ADMP_X_MINBLOCKS : base;
+};
 template <typename T, int R1, int R2, int R3, int TL, int JT, bool QUICK, bool PEER, bool TMA = false>
-__global__ void __launch_bounds__(TL* JT, MinBlocks<TL * JT, R3>::value)
+__global__ void __launch_bounds__(TL* JT, XMinBlocks<TL * JT, R1, R2, R3>::value)
 fast_x_conv_kernel(StrideGeom g, int tile0, int ntiles, const BoxInfo* __restrict__ Bp, T kappa, int kind, ConvTables tb,
                    cx<T>* __restrict__ spec, const cx<T>* __restrict__ gtw, double* __restrict__ scalars, int want_vir, PeerTab peers,
                    int local_reads, const __grid_constant__ CUtensorMap tmap) {
@@ -658,46 +654,29 @@ fast_x_conv_kernel(StrideGeom g, int tile0, int ntiles, const BoxInfo* __restric
             // forward: dimension 1 (natural tile -> row-major), [2 in place], last dimension + scaling + its inverse in
             // registers; inverse: [2 in place], dimension 1 leaves through Good's map in natural order. `scale_point` sees
             // row-major positions: its tables were permuted at set-up (position 0 is frequency 0).
-            if (live) {
-                PStage<T, R1, 1, N / R1, JT> s;
-                s.run(j, P::good1, P::good1_off, [&](int pos) { return c[pos * TL]; });
-                s.put(j, P::rm1, P::rm1_off, stA);
-            }
+            if (live) PStage<T, R1, 1, N / R1, JT>::run(j, P::good1, P::good1_off, [&](int pos) { return c[pos * TL]; }, P::rm1, P::rm1_off, stA);
             if (bulk) fence_async_smem();
             __syncthreads();                   // I consumed: fetch the next tile while this one is transformed
             if (tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x);
             if (R3 > 1) {
-                if (live) {
-                    PStage<T, R2, 1, N / R2, JT> s;
-                    s.run(j, P::rm2, P::rm2_off, ldA);
-                    s.put(j, P::rm2, P::rm2_off, stA);
-                }
+                if (live) PStage<T, R2, 1, N / R2, JT>::run(j, P::rm2, P::rm2_off, ldA, P::rm2, P::rm2_off, stA);
                 __syncthreads();
             }
-            if (live) {
-                PStage<T, P::RL, 1, N / P::RL, JT> s;
-                s.run(j, P::rml, P::rml_off, ldA);
-                s.scale_inverse(j, P::rml, P::rml_off, scale_point);
-                s.put(j, P::rml, P::rml_off, stA);
-            }
+            if (live) PStage<T, P::RL, 1, N / P::RL, JT>::run_scaled(j, P::rml, P::rml_off, ldA, scale_point, stA);
             __syncthreads();
             acc_e = fma(0.5 * wgt, acc_line, acc_e);
             if (R3 > 1) {
-                if (live) {
-                    PStage<T, R2, -1, N / R2, JT> s;
-                    s.run(j, P::rm2, P::rm2_off, ldA);
-                    s.put(j, P::rm2, P::rm2_off, stA);
-                }
+                if (live) PStage<T, R2, -1, N / R2, JT>::run(j, P::rm2, P::rm2_off, ldA, P::rm2, P::rm2_off, stA);
                 __syncthreads();
             }
             if (live) {
-                PStage<T, R1, -1, N / R1, JT> s;
-                s.run(j, P::rm1, P::rm1_off, ldA);
                 if (PEER) {
                     const size_t col = (size_t)c0 + l;
-                    s.put(j, P::good1, P::good1_off, [&](int pos, cx<T> v) { sbase[pos][(size_t)pos * ls + col] = v; });
+                    PStage<T, R1, -1, N / R1, JT>::run(j, P::rm1, P::rm1_off, ldA, P::good1, P::good1_off,
+                                                       [&](int pos, cx<T> v) { sbase[pos][(size_t)pos * ls + col] = v; });
                 } else {
-                    s.put(j, P::good1, P::good1_off, [&](int pos, cx<T> v) { out[(size_t)pos * ls] = v; });
+                    PStage<T, R1, -1, N / R1, JT>::run(j, P::rm1, P::rm1_off, ldA, P::good1, P::good1_off,
+                                                       [&](int pos, cx<T> v) { out[(size_t)pos * ls] = v; });
                 }
             }
             continue;
@@ -891,7 +870,9 @@ fast_z_inv_kernel(int nlines, int ntiles, const cx<T>* __restrict__ spec, T* __r
     X(3, 11, 7, 4, 8, 28, 8, 28)     \
     X(4, 11, 7, 8, 2, 56, 2, 56)     \
     X(5, 11, 7, 8, 4, 56, 4, 56)     \
-    X(6, 11, 14, 8, 2, 112, 2, 112)
+    X(6, 11, 14, 8, 2, 112, 2, 112)  \
+    X(7, 11, 7, 4, 8, 16, 8, 28)     \
+    X(8, 11, 7, 8, 4, 32, 4, 56)
 
 struct FastOps {
     int N, TL, threads, zTL, zthreads;
@@ -1016,11 +997,16 @@ struct FastImpl {
 };
 
 // the table entries for (size N, element size); wide = prefer the wider tile when two are listed
+// entries 7, 8 (128-thread blocks) are only taken when asked for by id (ADMP_FFT_XCFG / ADMP_FFT_YCFG)
 template <typename T>
-static bool fast_lookup(int N, bool wide, FastOps& out) {
+static bool fast_lookup(int N, bool wide, FastOps& out, int force_id = -1) {
     bool found = false;
 #define X(id, a, b, c, tl, jt, ztl, zjt)                                                   \
-    if (N == (a) * (b) * (c) && (!found || wide)) { out = FastImpl<T, a, b, c, tl, jt, ztl, zjt>::ops(); found = true; }
+    if (N == (a) * (b) * (c) && force_id == (id)) { out = FastImpl<T, a, b, c, tl, jt, ztl, zjt>::ops(); return true; }
+    ADMP_FAST_LIST(X)
+#undef X
+#define X(id, a, b, c, tl, jt, ztl, zjt)                                                   \
+    if ((id) < 7 && N == (a) * (b) * (c) && (!found || wide)) { out = FastImpl<T, a, b, c, tl, jt, ztl, zjt>::ops(); found = true; }
     ADMP_FAST_LIST(X)
 #undef X
     return found;
