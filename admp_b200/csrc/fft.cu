@@ -96,6 +96,34 @@ template <typename T, int SIGN> struct Dft<T, 8, SIGN> {
         v[3] = e[3] + o3;   v[7] = e[3] - o3;
     }
 };
+// 16 = 4 x 4 (Cooley-Tukey inside the registers): n = 4 n1 + n2, k = k1 + 4 k2, twiddles W16^(n2 k1)
+template <typename T, int SIGN> struct Dft<T, 16, SIGN> {
+    static __device__ __forceinline__ cx<T> tw(cx<T> v, int m) {        // v * W16^m, m in {1, 2, 3, 4, 6, 9}
+        constexpr double C[10] = {1.0, 0.92387953251128674, 0.70710678118654752, 0.38268343236508977, 0.0,
+                                  -0.38268343236508977, -0.70710678118654752, -0.92387953251128674, -1.0, -0.92387953251128674};
+        constexpr double S[10] = {0.0, 0.38268343236508977, 0.70710678118654752, 0.92387953251128674, 1.0,
+                                  0.92387953251128674, 0.70710678118654752, 0.38268343236508977, 0.0, -0.38268343236508977};
+        const T wr = (T)C[m], wi = (T)(-(double)SIGN * S[m]);           // W = cos - i SIGN sin
+        return {v.x * wr - v.y * wi, v.x * wi + v.y * wr};
+    }
+    static __device__ __forceinline__ void run(cx<T> (&v)[16]) {
+        cx<T> y[4][4];
+#pragma unroll
+        for (int n2 = 0; n2 < 4; ++n2) {
+            cx<T> c[4] = {v[n2], v[4 + n2], v[8 + n2], v[12 + n2]};
+            Dft<T, 4, SIGN>::run(c);
+#pragma unroll
+            for (int k1 = 0; k1 < 4; ++k1) y[n2][k1] = (n2 * k1 == 0) ? c[k1] : tw(c[k1], n2 * k1);
+        }
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1) {
+            cx<T> c[4] = {y[0][k1], y[1][k1], y[2][k1], y[3][k1]};
+            Dft<T, 4, SIGN>::run(c);
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2) v[k1 + 4 * k2] = c[k2];
+        }
+    }
+};
 // 14 = 2 x 7 by the prime-factor (Good-Thomas) map: no internal twiddles.
 //   input  n = (7 n1 + 2 n2) mod 14 ; output k = (7 k1 + 8 k2) mod 14
 template <typename T, int SIGN> struct Dft<T, 14, SIGN> {
@@ -382,6 +410,7 @@ static bool dim_cfg(int N, int tw_len, size_t esz, size_t smem_cap, int min_ls, 
         bool wide = e ? atoi(e) > 0 : !zpass;
         if (xpass) { const char* ex = getenv("ADMP_FFT_XWIDE"); if (ex) wide = atoi(ex) > 0; }
         int force = -1;
+        if (xpass && N == 616) force = 9;          // X pass of 616 points: one 448-thread block on 8-line tiles (6.73 -> 6.13 ms at 616x1232x1232)
         if (!zpass) { const char* ef = getenv(xpass ? "ADMP_FFT_XCFG" : "ADMP_FFT_YCFG"); if (ef) force = atoi(ef); }
         c.fast = esz == 8 ? fast_lookup<double>(N, wide, c.ops, force) : fast_lookup<float>(N, wide, c.ops, force);
         if (c.fast) {

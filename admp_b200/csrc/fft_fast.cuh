@@ -263,8 +263,8 @@ __device__ __forceinline__ void fft_head(int j, bool live, Ld ld, St st) {
     }
 }
 // ------------------------------------------------------------------------------------------ prime-factor (Good-Thomas) stages
-// All sizes of the mesh family but 1232 = 11*14*8 factor into PAIRWISE COPRIME radices (77 = 11*7, 154 = 11*14, 308 = 11*7*4,
-// 616 = 11*7*8), so the line FFT of the strided passes is a pure R1 x R2 x R3 multi-dimensional DFT - no twiddle factors:
+// All sizes of the mesh family factor into PAIRWISE COPRIME radices (77 = 11*7, 154 = 11*14, 308 = 11*7*4, 616 = 11*7*8,
+// 1232 = 11*7*16), so the line FFT of the strided passes is a pure R1 x R2 x R3 multi-dimensional DFT - no twiddle factors:
 //   input   n = (n1 S1 + n2 S2 + n3 S3) mod N,  S_d = N / R_d                       (Good's map, natural order in)
 //   output  k = (k1 T1 + k2 T2 + k3 T3) mod N,  T_d = S_d * (S_d^-1 mod R_d)         (CRT map, natural order out)
 //   W_N^(n k) = prod_d W_Rd^(n_d k_d)           (cross terms S_d T_e are multiples of N, S_d T_d = 1 mod R_d)
@@ -289,7 +289,10 @@ template <int R1, int R2, int R3> struct Pfa {
     static constexpr bool value = ADMP_FFT_PFA && pfa_gcd(R1, R2) == 1 && pfa_gcd(R1, R3) == 1 && pfa_gcd(R2, R3) == 1;
     // stand-alone Y passes: measured on B200 against the Stockham stages - 154 points 18.3 -> 17.2 us, 616 points 0.444 -> 0.456 ms
     // (HBM-bound either way), so only the two-factor sizes use it there; the fused X pass gains at every size (308: 0.919 -> 0.747 ms)
-    static constexpr bool strided = value && R3 == 1;
+#ifndef ADMP_Y_PFA3
+#define ADMP_Y_PFA3 1
+#endif
+    static constexpr bool strided = value && (R3 == 1 || ADMP_Y_PFA3);
     static constexpr int S1 = N / R1, S2 = N / R2, S3 = N / R3;
     static constexpr int T1 = (S1 * pfa_inv(S1, R1)) % N, T2 = (S2 * pfa_inv(S2, R2)) % N, T3 = R3 > 1 ? (S3 * pfa_inv(S3, R3)) % N : 0;
     // butterflies of dimension 1: b = i2 + R2 i3
@@ -304,6 +307,21 @@ template <int R1, int R2, int R3> struct Pfa {
         const int p = bs + t * S1;
         return p >= N ? p - N : p;
     }
+    // the same dimension for line-major tiles (Z passes: lanes = consecutive butterflies of ONE line): b = i3 + R3 i2, so that
+    // consecutive lanes are S3 = R1 R2 (odd) points apart on both sides - no shared-memory bank conflicts
+    static __device__ __forceinline__ int rm1z(int b) {
+        if (R3 == 1) return R1 * b;
+        const int i2 = b / R3, i3 = b - i2 * R3;
+        return R1 * (i2 + R2 * i3);
+    }
+    static __device__ __forceinline__ int good1z(int b) {
+        if (R3 == 1) return b * S2;
+        const int i2 = b / R3, i3 = b - i2 * R3;
+        const int x = i2 * S2 + i3 * S3;
+        return x >= N ? x - N : x;
+    }
+    // row-major position of frequency k (k = k_d mod R_d)
+    static __device__ __forceinline__ int pos_of_freq(int k) { return k % R1 + R1 * (k % R2 + R2 * (R3 > 1 ? k % R3 : 0)); }
     // butterflies of dimension 2 (three factors: middle dimension): b = i1 + R1 i3
     static __device__ __forceinline__ int rm2(int b) {
         const int i3 = b / R1;
@@ -429,8 +447,17 @@ __device__ __forceinline__ void issue_tile_peer(const StrideGeom& g, int tile, c
     cp_async_commit();
 }
 
+// resident blocks of the prime-factor passes: the stages hold one butterfly per thread (~150 registers at radix 11), so two
+// blocks of a three-stage transform fit (shared memory - two tiles per block - allows no more at 8 lines of 308 points)
+#ifndef ADMP_X_MINBLOCKS
+#define ADMP_X_MINBLOCKS 2
+#endif
+template <int NT, int R1, int R2, int R3> struct XMinBlocks {
+    static constexpr int base = MinBlocks<NT, R3>::value;
+    static constexpr int value = (Pfa<R1, R2, R3>::value && R3 > 1 && NT <= 256 && base < ADMP_X_MINBLOCKS) ? ADMP_X_MINBLOCKS : base;
+};
 template <typename T, int R1, int R2, int R3, int SIGN, int TL, int JT, bool TMA>
-__global__ void __launch_bounds__(TL* JT, MinBlocks<TL * JT, R3>::value)
+__global__ void __launch_bounds__(TL* JT, (Pfa<R1, R2, R3>::strided ? XMinBlocks<TL * JT, R1, R2, R3>::value : MinBlocks<TL * JT, R3>::value))
 fast_strided_kernel(StrideGeom g, int ntiles, cx<T>* __restrict__ spec, const cx<T>* __restrict__ gtw, const __grid_constant__ CUtensorMap tmap) {
     constexpr int N = R1 * R2 * R3, TILE = N * TL, NT = TL * JT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -520,15 +547,6 @@ __device__ __noinline__ double influence_general(const BoxInfo* Bp, const ConvTa
 // PEER: the spectrum is x-slab decomposed over the GPUs of the NVLink domain; this rank transforms the lines
 // of tiles [tile0, ntiles) by loading / storing every point from / to the rank that owns its x plane (cp.async
 // and stores on peer-mapped memory): the all-to-all transposes of a slab FFT are fused into the X pass.
-// resident blocks of the fused X pass: the prime-factor stages hold one butterfly per thread (~150 registers at radix 11), so two
-// blocks of a three-stage transform fit (shared memory - two tiles per block - allows no more at 8 lines of 308 points)
-#ifndef ADMP_X_MINBLOCKS
-#define ADMP_X_MINBLOCKS 2
-#endif
-template <int NT, int R1, int R2, int R3> struct XMinBlocks {
-    static constexpr int base = MinBlocks<NT, R3>::value;
-    static constexpr int value = (Pfa<R1, R2, R3>::value && R3 > 1 && base < ADMP_X_MINBLOCKS) ? ADMP_X_MINBLOCKS : base;
-};
 template <typename T, int R1, int R2, int R3, int TL, int JT, bool QUICK, bool PEER, bool TMA = false>
 __global__ void __launch_bounds__(TL* JT, XMinBlocks<TL * JT, R1, R2, R3>::value)
 fast_x_conv_kernel(StrideGeom g, int tile0, int ntiles, const BoxInfo* __restrict__ Bp, T kappa, int kind, ConvTables tb,
@@ -725,7 +743,7 @@ template <int M> struct ZGeom {
 
 // forward: K3 reals per line -> K3/2+1 complex (packed real FFT, tools/fft_model.py r2c)
 template <typename T, int R1, int R2, int R3, int TL, int JT>
-__global__ void __launch_bounds__(TL* JT, MinBlocks<TL * JT, R3>::value)
+__global__ void __launch_bounds__(TL* JT, XMinBlocks<TL * JT, R1, R2, R3>::value)
 fast_z_fwd_kernel(int nlines, int ntiles, const T* __restrict__ mesh, cx<T>* __restrict__ spec, const cx<T>* __restrict__ gtw) {
     constexpr int M = R1 * R2 * R3, K3 = 2 * M, K3h = M + 1, LS = ZGeom<M>::LS, TILE = TL * LS, NT = TL * JT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -757,7 +775,19 @@ fast_z_fwd_kernel(int nlines, int ntiles, const T* __restrict__ mesh, cx<T>* __r
     int tile = blockIdx.x;
     pdl_launch_dependents();
     if (BULK && threadIdx.x == 0) mbar_init(&bar, 1);
-    build_twiddles<T, R1, R2, R3, 2>(tw2, tw3, gtw, NT);
+    // (three-factor sizes only: with two factors consecutive k sit 1 + R1 = 12 points apart in the work buffer - 4-way bank conflicts
+    // in the post-processing reads; measured 23.1 -> 25.0 us at 154^3 against 4.83 -> 3.55 ms at 616x1232x1232 for three factors)
+    constexpr bool PFA = Pfa<R1, R2, R3>::value && R3 > 1;
+    using P = Pfa<R1, R2, R3>;
+    // PFA: the transformed line stays in the row-major multi-index order of the work buffer; the real-FFT post-processing looks
+    // the positions of k and M - k up (table in the unused twiddle space; M + 1 <= its size for every size of the family)
+    static_assert(!PFA || (TwGeom<R1, R2, R3>::TOTAL * sizeof(cx<T>) >= (M + 1) * sizeof(int)), "position table does not fit");
+    int* kpos = reinterpret_cast<int*>(tw2);
+    if (PFA) {
+        for (int i = threadIdx.x; i <= M; i += NT) kpos[i] = P::pos_of_freq(i == M ? 0 : i);
+    } else {
+        build_twiddles<T, R1, R2, R3, 2>(tw2, tw3, gtw, NT);
+    }
     for (int i = threadIdx.x; i < K3h; i += NT) zt[i] = gtw[i];
     if (BULK) __syncthreads();
     pdl_wait();
@@ -771,18 +801,29 @@ fast_z_fwd_kernel(int nlines, int ntiles, const T* __restrict__ mesh, cx<T>* __r
         const int L0 = tile * TL;
         const int nl = min(TL, nlines - L0);
         const bool live = l < nl;
-        fft_head<T, R1, R2, R3, 1, JT>(j, live, [&](int pos) { return c[pos]; }, [&](int pos, cx<T> v) { a[pos] = v; });
-        __syncthreads();
-        if (tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x);
         auto ldA = [&](int pos) { return a[pos]; };
         auto stA = [&](int pos, cx<T> v) { a[pos] = v; };
-        fft_tail<T, R1, R2, R3, 1, JT, true>(j, live, tw2, tw3, ldA, stA, stA);
+        if (PFA) {
+            if (live) PStage<T, R1, 1, M / R1, JT>::run(j, P::good1z, P::good1_off, [&](int pos) { return c[pos]; }, P::rm1z, P::rm1_off, stA);
+            __syncthreads();
+            if (tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x);
+            if (R3 > 1) {
+                if (live) PStage<T, R2, 1, M / R2, JT>::run(j, P::rm2, P::rm2_off, ldA, P::rm2, P::rm2_off, stA);
+                __syncthreads();
+            }
+            if (live) PStage<T, P::RL, 1, M / P::RL, JT>::run(j, P::rml, P::rml_off, ldA, P::rml, P::rml_off, stA);
+        } else {
+            fft_head<T, R1, R2, R3, 1, JT>(j, live, [&](int pos) { return c[pos]; }, stA);
+            __syncthreads();
+            if (tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x);
+            fft_tail<T, R1, R2, R3, 1, JT, true>(j, live, tw2, tw3, ldA, stA, stA);
+        }
         __syncthreads();
         cx<T>* dst = spec + (size_t)L0 * K3h;
         for (int e = threadIdx.x; e < nl * K3h; e += NT) {
             const int ll = e / K3h, k = e - ll * K3h;
-            const cx<T> zk = A[ll * LS + (k == M ? 0 : k)];
-            cx<T> zc = A[ll * LS + ((k == 0 || k == M) ? 0 : M - k)];
+            const cx<T> zk = A[ll * LS + (PFA ? kpos[k] : (k == M ? 0 : k))];
+            cx<T> zc = A[ll * LS + (PFA ? kpos[M - k] : ((k == 0 || k == M) ? 0 : M - k))];
             zc.y = -zc.y;
             const cx<T> s = {(T)0.5 * (zk.x + zc.x), (T)0.5 * (zk.y + zc.y)}, d = {(T)0.5 * (zk.x - zc.x), (T)0.5 * (zk.y - zc.y)};
             const cx<T> tw = zt[k];                                   // (cos phi, -sin phi), phi = 2 pi k / K3
@@ -872,7 +913,9 @@ fast_z_inv_kernel(int nlines, int ntiles, const cx<T>* __restrict__ spec, T* __r
     X(5, 11, 7, 8, 4, 56, 4, 56)     \
     X(6, 11, 14, 8, 2, 112, 2, 112)  \
     X(7, 11, 7, 4, 8, 16, 8, 28)     \
-    X(8, 11, 7, 8, 4, 32, 4, 56)
+    X(8, 11, 7, 8, 4, 32, 4, 56)     \
+    X(9, 11, 7, 8, 8, 56, 4, 56)     \
+    X(10, 11, 7, 16, 4, 112, 2, 112)
 
 struct FastOps {
     int N, TL, threads, zTL, zthreads;
@@ -997,7 +1040,8 @@ struct FastImpl {
 };
 
 // the table entries for (size N, element size); wide = prefer the wider tile when two are listed
-// entries 7, 8 (128-thread blocks) are only taken when asked for by id (ADMP_FFT_XCFG / ADMP_FFT_YCFG)
+// entries 7 and 9 are only taken when asked for by id (ADMP_FFT_XCFG / ADMP_FFT_YCFG); 8 (616 points in 128-thread blocks, two
+// per SM) is the wide default of its size: Y pass 0.380 -> 0.362 ms at 308x616x616, X pass 7.04 -> 6.74 ms at 616x1232x1232
 template <typename T>
 static bool fast_lookup(int N, bool wide, FastOps& out, int force_id = -1) {
     bool found = false;
@@ -1006,7 +1050,7 @@ static bool fast_lookup(int N, bool wide, FastOps& out, int force_id = -1) {
     ADMP_FAST_LIST(X)
 #undef X
 #define X(id, a, b, c, tl, jt, ztl, zjt)                                                   \
-    if ((id) < 7 && N == (a) * (b) * (c) && (!found || wide)) { out = FastImpl<T, a, b, c, tl, jt, ztl, zjt>::ops(); found = true; }
+    if (((id) < 7 || (id) == 8 || (id) == 10) && N == (a) * (b) * (c) && (!found || wide)) { out = FastImpl<T, a, b, c, tl, jt, ztl, zjt>::ops(); found = true; }
     ADMP_FAST_LIST(X)
 #undef X
     return found;
