@@ -36,6 +36,52 @@ template <typename T> __device__ __forceinline__ cx<T> operator+(cx<T> a, cx<T> 
 template <typename T> __device__ __forceinline__ cx<T> operator-(cx<T> a, cx<T> b) { return {a.x - b.x, a.y - b.y}; }
 template <typename T> __device__ __forceinline__ cx<T> cmul(cx<T> a, cx<T> b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
 
+// Butterfly constants live in constant memory: a float64 literal whose low word is not zero cannot be an immediate of DFMA, so
+// as a literal every use costs two UMOV (9 % of the instructions of the 308-point X pass, ncu r2i); as a constant-bank operand
+// (DFMA R, R, c[3][..], R) it costs nothing. One table per radix and precision, entry m = cos / sin(2 pi m / R).
+#define ADMP_TRIG_TABLE(R)                                                                                                        \
+    __constant__ double g_cos##R##_d[R] = {}; __constant__ double g_sin##R##_d[R] = {};                                           \
+    __constant__ float g_cos##R##_f[R] = {};  __constant__ float g_sin##R##_f[R] = {};
+ADMP_TRIG_TABLE(3) ADMP_TRIG_TABLE(5) ADMP_TRIG_TABLE(7) ADMP_TRIG_TABLE(11) ADMP_TRIG_TABLE(13) ADMP_TRIG_TABLE(16)
+#undef ADMP_TRIG_TABLE
+template <typename T, int R> __device__ __forceinline__ T ktrig_cos(int m) {
+    if constexpr (sizeof(T) == 8) {
+        if constexpr (R == 3) return g_cos3_d[m]; else if constexpr (R == 5) return g_cos5_d[m]; else if constexpr (R == 7) return g_cos7_d[m];
+        else if constexpr (R == 11) return g_cos11_d[m]; else if constexpr (R == 13) return g_cos13_d[m]; else return g_cos16_d[m];
+    } else {
+        if constexpr (R == 3) return g_cos3_f[m]; else if constexpr (R == 5) return g_cos5_f[m]; else if constexpr (R == 7) return g_cos7_f[m];
+        else if constexpr (R == 11) return g_cos11_f[m]; else if constexpr (R == 13) return g_cos13_f[m]; else return g_cos16_f[m];
+    }
+}
+template <typename T, int R> __device__ __forceinline__ T ktrig_sin(int m) {
+    if constexpr (sizeof(T) == 8) {
+        if constexpr (R == 3) return g_sin3_d[m]; else if constexpr (R == 5) return g_sin5_d[m]; else if constexpr (R == 7) return g_sin7_d[m];
+        else if constexpr (R == 11) return g_sin11_d[m]; else if constexpr (R == 13) return g_sin13_d[m]; else return g_sin16_d[m];
+    } else {
+        if constexpr (R == 3) return g_sin3_f[m]; else if constexpr (R == 5) return g_sin5_f[m]; else if constexpr (R == 7) return g_sin7_f[m];
+        else if constexpr (R == 11) return g_sin11_f[m]; else if constexpr (R == 13) return g_sin13_f[m]; else return g_sin16_f[m];
+    }
+}
+// filled once per process and device by fft3d_create (host-computed in long double)
+static cudaError_t upload_trig_tables() {
+    cudaError_t e = cudaSuccess;
+#define ADMP_UP(R)                                                                                             \
+    {                                                                                                          \
+        double c[R], s[R]; float cf[R], sf[R];                                                                 \
+        for (int m = 0; m < R; ++m) {                                                                          \
+            const long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)m / (long double)R; \
+            c[m] = (double)cosl(a); s[m] = (double)sinl(a); cf[m] = (float)c[m]; sf[m] = (float)s[m];          \
+        }                                                                                                      \
+        if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_cos##R##_d, c, sizeof(c));                              \
+        if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_sin##R##_d, s, sizeof(s));                              \
+        if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_cos##R##_f, cf, sizeof(cf));                            \
+        if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_sin##R##_f, sf, sizeof(sf));                            \
+    }
+    ADMP_UP(3) ADMP_UP(5) ADMP_UP(7) ADMP_UP(11) ADMP_UP(13) ADMP_UP(16)
+#undef ADMP_UP
+    return e;
+}
+
 // r-point DFT, SIGN = +1: e^{-i..} (forward), -1: e^{+i..} (inverse)
 template <typename T, int R, int SIGN> struct Dft;
 
@@ -69,7 +115,7 @@ template <typename T, int R, int SIGN> struct Dft {
             T rc = x0.x, ic = x0.y, rs = 0, is = 0;
 #pragma unroll
             for (int j = 1; j <= H; ++j) {
-                const T c = (T)trig_cos<R>((j * k) % R), s = (T)trig_sin<R>((j * k) % R);
+                const T c = ktrig_cos<T, R>((j * k) % R), s = ktrig_sin<T, R>((j * k) % R);
                 rc += a[j - 1].x * c; ic += a[j - 1].y * c;
                 rs += b[j - 1].x * s; is += b[j - 1].y * s;
             }
@@ -85,7 +131,7 @@ template <typename T, int SIGN> struct Dft<T, 8, SIGN> {
         cx<T> e[4] = {v[0], v[2], v[4], v[6]}, o[4] = {v[1], v[3], v[5], v[7]};
         Dft<T, 4, SIGN>::run(e);
         Dft<T, 4, SIGN>::run(o);
-        const T h = (T)0.70710678118654752440;
+        const T h = ktrig_cos<T, 16>(2);          // sqrt(1/2)
         // W8^1 = (1 - i s)/sqrt2, W8^2 = -i s, W8^3 = (-1 - i s)/sqrt2   with s = SIGN
         const cx<T> o1 = {h * (o[1].x + (T)SIGN * o[1].y), h * (o[1].y - (T)SIGN * o[1].x)};
         const cx<T> o2 = {(T)SIGN * o[2].y, -(T)SIGN * o[2].x};
@@ -99,12 +145,10 @@ template <typename T, int SIGN> struct Dft<T, 8, SIGN> {
 // 16 = 4 x 4 (Cooley-Tukey inside the registers): n = 4 n1 + n2, k = k1 + 4 k2, twiddles W16^(n2 k1)
 template <typename T, int SIGN> struct Dft<T, 16, SIGN> {
     static __device__ __forceinline__ cx<T> tw(cx<T> v, int m) {        // v * W16^m, m in {1, 2, 3, 4, 6, 9}
-        constexpr double C[10] = {1.0, 0.92387953251128674, 0.70710678118654752, 0.38268343236508977, 0.0,
-                                  -0.38268343236508977, -0.70710678118654752, -0.92387953251128674, -1.0, -0.92387953251128674};
-        constexpr double S[10] = {0.0, 0.38268343236508977, 0.70710678118654752, 0.92387953251128674, 1.0,
-                                  0.92387953251128674, 0.70710678118654752, 0.38268343236508977, 0.0, -0.38268343236508977};
-        const T wr = (T)C[m], wi = (T)(-(double)SIGN * S[m]);           // W = cos - i SIGN sin
-        return {v.x * wr - v.y * wi, v.x * wi + v.y * wr};
+        if (m == 4) return {(T)SIGN * v.y, -(T)SIGN * v.x};            // W16^4 = -i SIGN
+        const T wr = ktrig_cos<T, 16>(m), ws = ktrig_sin<T, 16>(m);      // W = cos - i SIGN sin
+        if (SIGN > 0) return {v.x * wr + v.y * ws, v.y * wr - v.x * ws};
+        return {v.x * wr - v.y * ws, v.y * wr + v.x * ws};
     }
     static __device__ __forceinline__ void run(cx<T> (&v)[16]) {
         cx<T> y[4][4];
@@ -455,6 +499,7 @@ Fft3d* fft3d_create(int K1, int K2, int K3, int dtype, const char** why) {
     cudaGetDevice(&dev);
     f->n_sm = 148;
     cudaDeviceGetAttribute(&f->n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (upload_trig_tables() != cudaSuccess) { cudaGetLastError(); *why = msg_cuda; delete f; return nullptr; }
     const size_t cap = 200 * 1024;
     const int M = K3 / 2;
     const char* env = getenv("ADMP_FFT");
