@@ -7,6 +7,9 @@
 //   s = r*(1/L) ; t = (s_i - s_j) + 0.5 ; ds = (t - floor(t)) - 0.5 ; d = ds*L
 //   d2 = (dx*dx + dy*dy) + dz*dz ; keep iff d2 < rc*rc
 // Orthorhombic boxes (the scope of the reference's examples). HBM-bound: Na*3*w read, Np*8 written.
+#include <cstdlib>
+#include <cstring>
+
 #include <cub/device/device_scan.cuh>
 
 #include "kernels.h"
@@ -136,6 +139,96 @@ nb_pairs_kernel(int n, const NbGeom* __restrict__ gp, const T* __restrict__ pos,
     }
 }
 
+// The same two passes with ONE WARP PER ATOM (the per-thread walk above is a serial chain of ~27 cells x dependent loads: 85 us
+// per pass for 3 072 atoms): lanes = the <= 27 neighbour cells (start / count, warp scan), then the candidates 32 at a time
+// (cell by binary search in the prefix, float64 predicate per lane, ballot -> running count). EMIT writes the hits unsorted
+// into column 0 of the atom's rows, ranks every hit among the row segment (ascending j, the order jax_md's OrderedSparse emits
+// and the cluster pair kernel needs) and writes (i, j) - the pair SET and the row order are exactly those of nb_pairs_kernel.
+constexpr int NBW_WARPS = 4;
+template <typename T, bool EMIT>
+__global__ void __launch_bounds__(NBW_WARPS * 32)
+nb_pairs_warp_kernel(int n, const NbGeom* __restrict__ gp, const T* __restrict__ pos, const int32_t* __restrict__ cell_start,
+                     const int32_t* __restrict__ sorted, int32_t* __restrict__ nbr_count, const int32_t* __restrict__ nbr_start,
+                     int32_t* pairs, int64_t capacity) {
+    __shared__ int s_lo[NBW_WARPS][32], s_pref[NBW_WARPS][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * NBW_WARPS + warp;
+    if (i >= n) return;                                   // whole warps leave together
+    const NbGeom& g = *gp;
+    double si[3];
+    load_s(g, pos, i, si);
+    int ci[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) ci[k] = cell_coord(si[k], g.nc[k]);
+    const int nx = g.nc[0] < 3 ? g.nc[0] : 3, ny = g.nc[1] < 3 ? g.nc[1] : 3, nz = g.nc[2] < 3 ? g.nc[2] : 3;
+    const int ncell = nx * ny * nz;
+    int lo = 0, cnt = 0;
+    if (lane < ncell) {
+        const int oz = lane % nz, oy = (lane / nz) % ny, ox = lane / (nz * ny);
+        const int cx = g.nc[0] < 3 ? ox : (ci[0] + ox - 1 + g.nc[0]) % g.nc[0];
+        const int cy = g.nc[1] < 3 ? oy : (ci[1] + oy - 1 + g.nc[1]) % g.nc[1];
+        const int cz = g.nc[2] < 3 ? oz : (ci[2] + oz - 1 + g.nc[2]) % g.nc[2];
+        const int c = (cx * g.nc[1] + cy) * g.nc[2] + cz;
+        lo = cell_start[c];
+        cnt = cell_start[c + 1] - lo;
+    }
+    int pre = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, pre, o);
+        if (lane >= o) pre += y;
+    }
+    const int total = __shfl_sync(0xffffffffu, pre, 31);
+    s_lo[warp][lane] = lo;
+    s_pref[warp][lane] = pre - cnt;                       // exclusive prefix (lanes >= ncell: total)
+    __syncwarp();
+    const int64_t base = EMIT ? (int64_t)nbr_start[i] : 0;
+    const unsigned lt = (1u << lane) - 1u;
+    int m = 0;
+    for (int q0 = 0; q0 < total; q0 += 32) {
+        const int q = q0 + lane;
+        bool ok = false;
+        int j = -1;
+        if (q < total) {
+            int c = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1)
+                if (c + step < ncell && s_pref[warp][c + step] <= q) c += step;
+            j = sorted[s_lo[warp][c] + (q - s_pref[warp][c])];
+            if (j > i) {
+                double sj[3];
+                load_s(g, pos, j, sj);
+                ok = pair_within(g, si, sj);
+            }
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, ok);
+        if (EMIT && ok) {
+            const int64_t row = base + m + __popc(mask & lt);
+            if (row < capacity) pairs[2 * row] = j;       // column 0 = scratch until the ranks are known
+        }
+        m += __popc(mask);
+    }
+    if (!EMIT) {
+        if (lane == 0) nbr_count[i] = m;
+        return;
+    }
+    int64_t mm = m;
+    if (base + mm > capacity) mm = capacity > base ? capacity - base : 0;
+    __syncwarp();
+    // rank of every hit among the row segment (all j distinct) -> ascending j in column 1; then column 0 = i
+    for (int64_t a0 = 0; a0 < mm; a0 += 32) {
+        const int64_t a = a0 + lane;
+        if (a < mm) {
+            const int v = __ldcg(pairs + 2 * (base + a));
+            int rank = 0;
+            for (int64_t b = 0; b < mm; ++b) rank += (__ldcg(pairs + 2 * (base + b)) < v) ? 1 : 0;
+            pairs[2 * (base + rank) + 1] = v;
+        }
+    }
+    __syncwarp();
+    for (int64_t a = lane; a < mm; a += 32) pairs[2 * (base + a)] = i;
+}
+
 __global__ void nb_pad_kernel(int n, const int32_t* __restrict__ nbr_start, int32_t* __restrict__ pairs, int64_t capacity,
                               int32_t* __restrict__ info) {
     const int64_t total = nbr_start[n];
@@ -179,17 +272,34 @@ cudaError_t launch_nblist(cudaStream_t st, const BoxInfo* B, const void* pos, in
     if ((e = exclusive_scan(st, w, w.cell_count, w.cell_start, ncell + 1)) != cudaSuccess) return e;
     cudaMemsetAsync(w.cell_count, 0, sizeof(int32_t) * (ncell + 1), st);       // reused as the fill cursor
     nb_fill_kernel<<<gb, tb, 0, st>>>(n, w.cell_of, w.cell_start, w.cell_count, w.sorted);
-    nb_sort_cells_kernel<<<(ncell + tb - 1) / tb, tb, 0, st>>>(ncell, w.cell_start, w.sorted);
+    // one warp per atom up to 2^18 atoms (3 072 atoms: 209 -> 92 us per list; 98 304 atoms at liquid density, rc 8 A: 3.9 -> 1.5 ms);
+    // beyond that one thread per atom already fills the GPU and wins (786 432 gas-like atoms: 0.80 vs 1.11 ms). ADMP_NBLIST=thread|warp
+    static const int forced = [] { const char* e = getenv("ADMP_NBLIST"); return !e ? 0 : (strcmp(e, "thread") == 0 ? 1 : (strcmp(e, "warp") == 0 ? 2 : 0)); }();
+    const bool per_thread = forced == 1 || (forced == 0 && n > (1 << 18));
     cudaMemsetAsync(w.nbr_count, 0, sizeof(int32_t) * (n + 1), st);
-    if (dtype == ADMP_F64)
-        nb_pairs_kernel<double, false><<<gb, tb, 0, st>>>(n, g_geom, (const double*)pos, w.cell_start, w.sorted, w.nbr_count, nullptr, nullptr, 0);
-    else
-        nb_pairs_kernel<float, false><<<gb, tb, 0, st>>>(n, g_geom, (const float*)pos, w.cell_start, w.sorted, w.nbr_count, nullptr, nullptr, 0);
-    if ((e = exclusive_scan(st, w, w.nbr_count, w.nbr_start, n + 1)) != cudaSuccess) return e;
-    if (dtype == ADMP_F64)
-        nb_pairs_kernel<double, true><<<gb, tb, 0, st>>>(n, g_geom, (const double*)pos, w.cell_start, w.sorted, nullptr, w.nbr_start, pairs, capacity);
-    else
-        nb_pairs_kernel<float, true><<<gb, tb, 0, st>>>(n, g_geom, (const float*)pos, w.cell_start, w.sorted, nullptr, w.nbr_start, pairs, capacity);
+    if (per_thread) {
+        nb_sort_cells_kernel<<<(ncell + tb - 1) / tb, tb, 0, st>>>(ncell, w.cell_start, w.sorted);
+        if (dtype == ADMP_F64)
+            nb_pairs_kernel<double, false><<<gb, tb, 0, st>>>(n, g_geom, (const double*)pos, w.cell_start, w.sorted, w.nbr_count, nullptr, nullptr, 0);
+        else
+            nb_pairs_kernel<float, false><<<gb, tb, 0, st>>>(n, g_geom, (const float*)pos, w.cell_start, w.sorted, w.nbr_count, nullptr, nullptr, 0);
+        if ((e = exclusive_scan(st, w, w.nbr_count, w.nbr_start, n + 1)) != cudaSuccess) return e;
+        if (dtype == ADMP_F64)
+            nb_pairs_kernel<double, true><<<gb, tb, 0, st>>>(n, g_geom, (const double*)pos, w.cell_start, w.sorted, nullptr, w.nbr_start, pairs, capacity);
+        else
+            nb_pairs_kernel<float, true><<<gb, tb, 0, st>>>(n, g_geom, (const float*)pos, w.cell_start, w.sorted, nullptr, w.nbr_start, pairs, capacity);
+    } else {
+        const int gw = (n + NBW_WARPS - 1) / NBW_WARPS, tw = NBW_WARPS * 32;
+        if (dtype == ADMP_F64)
+            nb_pairs_warp_kernel<double, false><<<gw, tw, 0, st>>>(n, g_geom, (const double*)pos, w.cell_start, w.sorted, w.nbr_count, nullptr, nullptr, 0);
+        else
+            nb_pairs_warp_kernel<float, false><<<gw, tw, 0, st>>>(n, g_geom, (const float*)pos, w.cell_start, w.sorted, w.nbr_count, nullptr, nullptr, 0);
+        if ((e = exclusive_scan(st, w, w.nbr_count, w.nbr_start, n + 1)) != cudaSuccess) return e;
+        if (dtype == ADMP_F64)
+            nb_pairs_warp_kernel<double, true><<<gw, tw, 0, st>>>(n, g_geom, (const double*)pos, w.cell_start, w.sorted, nullptr, w.nbr_start, pairs, capacity);
+        else
+            nb_pairs_warp_kernel<float, true><<<gw, tw, 0, st>>>(n, g_geom, (const float*)pos, w.cell_start, w.sorted, nullptr, w.nbr_start, pairs, capacity);
+    }
     nb_pad_kernel<<<64, 256, 0, st>>>(n, w.nbr_start, pairs, capacity, info);
     return cudaGetLastError();
 }
