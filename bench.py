@@ -220,7 +220,7 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------- GPU arm
-def kernel_rooflines(torch, _lib, reps, peak, flush, n_launch=10):
+def kernel_rooflines(torch, _lib, reps, peak, flush, n_launch=10, with_library=True):
     """Times spread / convolve / gather alone (CUDA events on the launch stream, L2 flushed before each
     launch) on the mesh of water_box(reps); returns {name: roofline dict}.  Algorithmic bytes are the
     SURVEY 8(d) figures: spread w*G (zero-fill, separate memset) + 216*2*w*Na scatter RMW;
@@ -287,6 +287,7 @@ def kernel_rooflines(torch, _lib, reps, peak, flush, n_launch=10):
         out['fused_roundtrip_5_passes'] = dict(bound='hbm', achieved=round(nb / (ms * 1e-3) / 1e9, 1), peak=peak, unit='GB/s',
                                                frac=round(nb / (ms * 1e-3) / 1e9 / peak, 4), traffic=None, ms=round(ms, 4),
                                                algorithmic_bytes=nb, mesh='%dx%dx%d' % w.K)
+    if custom and with_library:
         # the library alternative on the same mesh, for the share table only
         _lib.check(cx.lib.admp_ctx_set_fft_backend(cx.handle, 0))
         ms = time_stage(lambda: cx.lib.admp_pme_fft(cx.handle, sp(), 0)) + time_stage(lambda: cx.lib.admp_pme_fft(cx.handle, sp(), 1)) \
@@ -737,9 +738,11 @@ def run_ours(args):
     peak, peak_src = measured_peaks()
     roof_small = kernel_rooflines(torch, _lib, (1, 1, 1), peak, flush)
     roof_large = None if args.no_large else kernel_rooflines(torch, _lib, (2, 4, 4), peak, flush, n_launch=5)
+    # the 256k-water mesh of config C5 (616x1232x1232, 7.5 GB + 7.5 GB): the same per-kernel table, single GPU only
+    roof_c5 = None if (args.no_large or world > 1) else kernel_rooflines(torch, _lib, (4, 8, 8), peak, flush, n_launch=3, with_library=False)
     dominant = next((k for k in roof_small if k.startswith('fft_x_conv')), 'convolve_kernel')
     traffic = ncu_traffic()
-    for tab in (roof_small, roof_large or {}):
+    for tab in (roof_small, roof_large or {}, roof_c5 or {}):
         for name, d in tab.items():
             t = traffic.get(name, {}).get(d.get('mesh'))
             if t is not None:
@@ -791,8 +794,8 @@ def run_ours(args):
     # between two frames_fwd_kernel launches): 12 per SCF cycle (spread, 5 FFT passes, field gather, the two pair traversals
     # - one of them a no-op -, field, decide, update) + 6 for the final reciprocal pass with the virial sums + 8 (gather,
     # 2 record packs, 2 pair traversals, self, frames adjoint, virial) + 9 staging (frames, tables, 2 box, pair scale, 4 tile
-    # kernels) + 7 neighbour list
-    launches_per_eval = 12 * (n_cycle + 1) + 30
+    # kernels) + 6 neighbour list (the per-cell sort went away with the warp-per-atom list kernels, which rank the hits themselves)
+    launches_per_eval = 12 * (n_cycle + 1) + 29
     out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                ms_per_step=t_ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64' if esz == 8 else 'f32',
                data='synthetic',
@@ -809,7 +812,7 @@ def run_ours(args):
                e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                         api='torch.autograd.grad(ADMPPmeForce.get_energy(...), [positions, box, Q_local, pol, tholes, mScales, pScales]) per frame'),
                gpu_launches=args.steps * FR * launches_per_eval, clocks=clocks, roofline=roofline,
-               kernels=dict(C2=roof_small, C3=roof_large, dense=roof_dense), cpu_baseline=cpu)
+               kernels=dict(C2=roof_small, C3=roof_large, C5=roof_c5, dense=roof_dense), cpu_baseline=cpu)
     out.update(extras)
     out.update(slab)
     print(json.dumps(out))
