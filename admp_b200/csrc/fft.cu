@@ -643,12 +643,15 @@ static void run_x_conv(Fft3dImpl* f, cudaStream_t st, void* spec, const BoxInfo*
     if (c.fast) {
         const StrideGeom g = geom_x(f, c.ops.TL);
         const bool quick = (kind == ADMP_CK_COULOMB && !want_vir);
+        const bool qv = (kind == ADMP_CK_COULOMB && want_vir);        // quick + virial variant when it fits (occ_qv > 0)
+        const int occ_t = (qv && c.ops.occ_qv[1] > 0) ? c.ops.occ_qv[1] : c.ops.occ_tma[quick ? 2 : 3];
+        const int occ_c = (qv && c.ops.occ_qv[0] > 0) ? c.ops.occ_qv[0] : c.ops.occ[quick ? 2 : 5];
         CUtensorMap tm;
-        if (sizeof(T) == 8 && c.ops.occ_tma[quick ? 2 : 3] > 0 && make_tmap(&tm, spec, g, c.ops.N, c.ops.TL, c.ops.box_rows)) {
-            c.ops.xconv_tma(st, g, 0, g.tiles, persistent_grid(f, c.ops.occ_tma[quick ? 2 : 3], g.tiles), B, kappa, kind, tb, spec, tw, scalars, want_vir, tm);
+        if (sizeof(T) == 8 && occ_t > 0 && c.ops.occ_tma[3] > 0 && make_tmap(&tm, spec, g, c.ops.N, c.ops.TL, c.ops.box_rows)) {
+            c.ops.xconv_tma(st, g, 0, g.tiles, persistent_grid(f, occ_t, g.tiles), B, kappa, kind, tb, spec, tw, scalars, want_vir, tm);
             return;
         }
-        c.ops.xconv(st, g, 0, g.tiles, persistent_grid(f, c.ops.occ[quick ? 2 : 5], g.tiles), B, kappa, kind, tb, spec, tw, scalars, want_vir);
+        c.ops.xconv(st, g, 0, g.tiles, persistent_grid(f, occ_c, g.tiles), B, kappa, kind, tb, spec, tw, scalars, want_vir);
         return;
     }
     const StrideGeom g = geom_x(f, c.TL);

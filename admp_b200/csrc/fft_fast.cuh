@@ -547,7 +547,20 @@ __device__ __noinline__ double influence_general(const BoxInfo* Bp, const ConvTa
 // PEER: the spectrum is x-slab decomposed over the GPUs of the NVLink domain; this rank transforms the lines
 // of tiles [tile0, ntiles) by loading / storing every point from / to the rank that owns its x plane (cp.async
 // and stores on peer-mapped memory): the all-to-all transposes of a slab FFT are fused into the X pass.
-template <typename T, int R1, int R2, int R3, int TL, int JT, bool QUICK, bool PEER, bool TMA = false>
+// per-line virial sums -> the six T_ab accumulators (xx, xy, xz, yy, yz, zz)
+__device__ __forceinline__ void fold_virial(double (&acc_t)[6], double Sxx, double Sxy, double Sxz, double Sb, double ky, double kz,
+                                            double pw, double p1) {
+    acc_t[0] += (1.0 + pw) * Sxx;
+    acc_t[1] += Sxy;
+    acc_t[2] += Sxz;
+    acc_t[3] += (1.0 + pw) * ky * ky * Sb;
+    acc_t[4] += (1.0 - pw * p1) * ky * kz * Sb;
+    acc_t[5] += (1.0 + pw) * kz * kz * Sb;
+}
+// VIR (QUICK only): the Coulomb pass that also accumulates the k-space virial sums T_ab = sum_k w dC/dk^2 |S|^2 / theta^2 k_a k_b
+// (the one pass after the SCF loop), from the same separable tables on an orthorhombic cell: ~11 more FP64 operations per point
+// instead of the general influence function (exp, divisions, a call per point: 3x the time of the SCF-cycle pass).
+template <typename T, int R1, int R2, int R3, int TL, int JT, bool QUICK, bool PEER, bool TMA = false, bool VIR = false>
 __global__ void __launch_bounds__(TL* JT, XMinBlocks<TL * JT, R1, R2, R3>::value)
 fast_x_conv_kernel(StrideGeom g, int tile0, int ntiles, const BoxInfo* __restrict__ Bp, T kappa, int kind, ConvTables tb,
                    cx<T>* __restrict__ spec, const cx<T>* __restrict__ gtw, double* __restrict__ scalars, int want_vir, PeerTab peers,
@@ -566,6 +579,8 @@ fast_x_conv_kernel(StrideGeom g, int tile0, int ntiles, const BoxInfo* __restric
     double* sek = reinterpret_cast<double*>(itw3 + TwGeom<Q1, Q2, Q3>::N3);    // exp(-k1^2/4kappa^2)/theta_1^2  (ortho) | 1/theta_1^2
     double* sk2 = sek + N;                                                    // k1^2 (ortho) | signed index m1
     cx<T>** sbase = reinterpret_cast<cx<T>**>(sk2 + N);                       // PEER only: owner buffer of x plane pos
+    double* skx = sk2 + N;                                                    // VIR only (never with PEER): signed k1, Nyquist parity p0
+    double* sp0 = skx + N;
     const BoxInfo& B = *Bp;
     constexpr bool BULK = TMA || UseBulkStrided<T>::value;
     __shared__ uint64_t bar;
@@ -605,6 +620,10 @@ fast_x_conv_kernel(StrideGeom g, int tile0, int ntiles, const BoxInfo* __restric
             const int f = PFA ? P::freq(i) : i;
             sek[i] = ortho ? tb.ek[0][f] : tb.bt[0][f];
             sk2[i] = ortho ? tb.k2[0][f] : (double)kint(f, N);
+            if (VIR) {
+                skx[i] = 6.283185307179586 * (double)kint(f, N) * B.inv[0];
+                sp0[i] = (2 * f == N) ? 1.0 : -1.0;
+            }
         }
     }
     const int K2 = B.K[1], K3 = B.K[2], K3h = K3 / 2 + 1;
@@ -643,6 +662,17 @@ fast_x_conv_kernel(StrideGeom g, int tile0, int ntiles, const BoxInfo* __restric
             }
         }
         double acc_line = 0.0;
+        // VIR: per-line factors of the virial products (influence.cuh virial_terms on an orthorhombic cell: k = (kx, ky, kz), Hermitian
+        // partner (p0 kx, p1 ky, -kz) for weight-2 points) and the per-line sums
+        double vky = 0.0, vkz = 0.0, vxyB = 0.0, vxzB = 0.0, Sxx = 0.0, Sxy = 0.0, Sxz = 0.0, Sb = 0.0;
+        const double pw = (wgt == 2.0) ? 1.0 : 0.0;
+        const double p1 = (2 * i2 == K2) ? 1.0 : -1.0;
+        if (VIR) {
+            vky = 6.283185307179586 * (double)kint(i2, K2) * B.inv[4];
+            vkz = 6.283185307179586 * (double)i3 * B.inv[8];
+            vxyB = vky * pw * p1;
+            vxzB = -vkz * pw;
+        }
         cx<T>* out = spec + c0 + l;
         const size_t ls = g.line_stride;
         auto scale_point = [&](int i1, cx<T> s) -> cx<T> {
@@ -650,7 +680,18 @@ fast_x_conv_kernel(StrideGeom g, int tile0, int ntiles, const BoxInfo* __restric
             double gg;                                        // 2*scale*C_k/theta_k^2
             if (QUICK) {
                 if (ortho) {
-                    gg = e23 * sek[i1] * fast_rcp(sk2[i1] + k23);
+                    const double rk = fast_rcp(sk2[i1] + k23);
+                    gg = e23 * sek[i1] * rk;
+                    if (VIR && !(origin_line && i1 == 0)) {
+                        // b = scale * dC/dk^2 / theta^2 * |S|^2 = -gg/2 (1/k^2 + 1/4kappa^2) |S|^2
+                        const double b = -0.5 * gg * (rk - q4k) * s2, bx = b * skx[i1];
+                        Sxx = fma(bx, skx[i1], Sxx);
+                        Sxy = fma(bx, fma(vxyB, sp0[i1], vky), Sxy);
+                        Sxz = fma(bx, fma(vxzB, sp0[i1], vkz), Sxz);
+                        Sb += b;
+                    }
+                } else if (VIR) {
+                    gg = 2.0 * scale * influence_general(Bp, &tb, kind, kap, PFA ? sfreq[i1] : i1, i2, i3, s2 * scale, want_vir, acc_t);
                 } else {
                     const double m1 = sk2[i1];
                     const double kx = kb[0] + 6.283185307179586 * m1 * B.inv[0], ky = kb[1] + 6.283185307179586 * m1 * B.inv[1],
@@ -683,6 +724,7 @@ fast_x_conv_kernel(StrideGeom g, int tile0, int ntiles, const BoxInfo* __restric
             if (live) PStage<T, P::RL, 1, N / P::RL, JT>::run_scaled(j, P::rml, P::rml_off, ldA, scale_point, stA);
             __syncthreads();
             acc_e = fma(0.5 * wgt, acc_line, acc_e);
+            if (VIR) fold_virial(acc_t, Sxx, Sxy, Sxz, Sb, vky, vkz, pw, p1);
             if (R3 > 1) {
                 if (live) PStage<T, R2, -1, N / R2, JT>::run(j, P::rm2, P::rm2_off, ldA, P::rm2, P::rm2_off, stA);
                 __syncthreads();
@@ -722,6 +764,7 @@ fast_x_conv_kernel(StrideGeom g, int tile0, int ntiles, const BoxInfo* __restric
             __syncthreads();
         }
         acc_e = fma(0.5 * wgt, acc_line, acc_e);              // E = scale * sum wgt g |S|^2 = sum wgt/2 * gg |S|^2
+        if (VIR) fold_virial(acc_t, Sxx, Sxy, Sxz, Sb, vky, vkz, pw, p1);
         if (PEER) {
             const size_t col = (size_t)c0 + l;
             fft_tail<T, Q1, Q2, Q3, -1, JT, false>(j, live, itw2, itw3, ldA, stA,
@@ -732,7 +775,7 @@ fast_x_conv_kernel(StrideGeom g, int tile0, int ntiles, const BoxInfo* __restric
     }
     double e1[1] = {acc_e};
     block_accumulate<1>(e1, red, scalars + ADMP_S_E_RECIP);
-    if (!QUICK && want_vir) block_accumulate<6>(acc_t, red, scalars + ADMP_S_TK);
+    if ((!QUICK || VIR) && want_vir) block_accumulate<6>(acc_t, red, scalars + ADMP_S_TK);
 }
 
 // ------------------------------------------------------------------------------------------ Z passes (contiguous lines)
@@ -936,6 +979,8 @@ struct FastOps {
                        const ConvTables&, void* spec, const void* tw, double* scalars, int want_vir, const PeerTab&, int local_reads);
     size_t smem_xp;
     int occ_peer[2];  // x conv on peers: quick, general
+    size_t smem_xv;   // quick + virial variant (two more N-entry tables)
+    int occ_qv[2];    // its resident blocks: cp.async tiles, TMA tiles (0: does not fit -> the general kernel runs the virial pass)
     void (*zfwd)(cudaStream_t, int nlines, int ntiles, int grid, const void* mesh, void* spec, const void* tw);
     void (*zinv)(cudaStream_t, int nlines, int ntiles, int grid, const void* spec, void* mesh, const void* tw);
 };
@@ -952,10 +997,14 @@ template <typename T, int R1, int R2, int R3, int TLd, int JT, int ZTLd, int ZJT
 struct FastImpl {
     static constexpr int N = R1 * R2 * R3;
     static constexpr int TL = TLd * (sizeof(T) == 4 ? 2 : 1), ZTL = ZTLd * (sizeof(T) == 4 ? 2 : 1);
-    static size_t smem_x_bytes(bool peer = false) {
+    static size_t smem_x_bytes(bool peer = false, bool vir = false) {
         constexpr int Q1 = R3 > 1 ? R3 : R2, Q2 = R3 > 1 ? R2 : R1, Q3 = R3 > 1 ? R1 : 1;
         return (size_t)(2 * N * TL + TwGeom<R1, R2, R3>::TOTAL + TwGeom<Q1, Q2, Q3>::TOTAL) * sizeof(cx<T>) + 2 * N * sizeof(double) +
-               (peer ? N * sizeof(void*) : 0);
+               (peer ? N * sizeof(void*) : 0) + (vir ? 2 * N * sizeof(double) : 0);
+    }
+    static bool& quick_vir_ok(bool tma) {          // set by prepare(): the quick + virial instantiation fits on this device
+        static bool ok[2] = {false, false};
+        return ok[tma ? 1 : 0];
     }
     static void prepare(FastOps& o) {
         o.occ[0] = prep_kernel(fast_strided_kernel<T, R1, R2, R3, 1, TL, JT, false>, o.threads, o.smem);
@@ -965,6 +1014,17 @@ struct FastImpl {
             o.occ_tma[1] = prep_kernel(fast_strided_kernel<T, R1, R2, R3, -1, TL, JT, true>, o.threads, o.smem);
             o.occ_tma[2] = prep_kernel(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, true, false, true>, o.threads, o.smem_x);
             o.occ_tma[3] = prep_kernel(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, false, false, true>, o.threads, o.smem_x);
+        }
+        o.occ_qv[0] = prep_kernel(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, true, false, false, true>, o.threads, o.smem_xv);
+        o.occ_qv[1] = 0;
+        if (sizeof(T) == 8 && tma_box_rows(N, TL) > 0)
+            o.occ_qv[1] = prep_kernel(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, true, false, true, true>, o.threads, o.smem_xv);
+        {
+            const char* e = getenv("ADMP_FFT_QUICKVIR");
+            const bool allow = !(e && atoi(e) == 0);
+            quick_vir_ok(false) = allow && o.occ_qv[0] > 0;
+            quick_vir_ok(true) = allow && o.occ_qv[1] > 0;
+            if (!allow) o.occ_qv[0] = o.occ_qv[1] = 0;
         }
         o.occ[2] = prep_kernel(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, true, false>, o.threads, o.smem_x);
         o.occ[5] = prep_kernel(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, false, false>, o.threads, o.smem_x);
@@ -990,6 +1050,9 @@ struct FastImpl {
         if (kind == ADMP_CK_COULOMB && !want_vir)
             launch_pdl(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, true, false, true>, grid, TL * JT, smem, st, g, tile0, ntiles, B, (T)kappa, kind, tb,
                        (cx<T>*)spec, (const cx<T>*)tw, scalars, want_vir, PeerTab{}, 0, tm);
+        else if (kind == ADMP_CK_COULOMB && quick_vir_ok(true))
+            launch_pdl(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, true, false, true, true>, grid, TL * JT, smem_x_bytes(false, true), st, g, tile0, ntiles, B,
+                       (T)kappa, kind, tb, (cx<T>*)spec, (const cx<T>*)tw, scalars, want_vir, PeerTab{}, 0, tm);
         else
             launch_pdl(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, false, false, true>, grid, TL * JT, smem, st, g, tile0, ntiles, B, (T)kappa, kind, tb,
                        (cx<T>*)spec, (const cx<T>*)tw, scalars, want_vir, PeerTab{}, 0, tm);
@@ -1000,6 +1063,9 @@ struct FastImpl {
         if (kind == ADMP_CK_COULOMB && !want_vir)
             launch_pdl(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, true, false>, grid, TL * JT, smem, st, g, tile0, ntiles, B, (T)kappa, kind, tb,
                        (cx<T>*)spec, (const cx<T>*)tw, scalars, want_vir, PeerTab{}, 0, CUtensorMap{});
+        else if (kind == ADMP_CK_COULOMB && quick_vir_ok(false))
+            launch_pdl(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, true, false, false, true>, grid, TL * JT, smem_x_bytes(false, true), st, g, tile0, ntiles, B,
+                       (T)kappa, kind, tb, (cx<T>*)spec, (const cx<T>*)tw, scalars, want_vir, PeerTab{}, 0, CUtensorMap{});
         else
             launch_pdl(fast_x_conv_kernel<T, R1, R2, R3, TL, JT, false, false>, grid, TL * JT, smem, st, g, tile0, ntiles, B, (T)kappa, kind, tb,
                        (cx<T>*)spec, (const cx<T>*)tw, scalars, want_vir, PeerTab{}, 0, CUtensorMap{});
@@ -1031,6 +1097,7 @@ struct FastImpl {
         o.smem = (size_t)(2 * N * TL + TwGeom<R1, R2, R3>::TOTAL) * sizeof(cx<T>);
         o.smem_x = smem_x_bytes();
         o.smem_xp = smem_x_bytes(true);
+        o.smem_xv = smem_x_bytes(false, true);
         o.zsmem = (size_t)(2 * ZTL * ZGeom<N>::LS + TwGeom<R1, R2, R3>::TOTAL + N + 1) * sizeof(cx<T>);
         o.box_rows = tma_box_rows(N, TL);
         o.strided_tma = &strided_tma; o.xconv_tma = &xconv_tma;

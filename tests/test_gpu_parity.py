@@ -277,6 +277,20 @@ def test_scf_graph_loop_equals_host_synchronised_loop_and_handles_non_convergenc
     assert abs(a.energy.item() - b.energy.item()) < 1e-10 * abs(b.energy.item())
 
 
+@pytest.mark.parametrize('sides, rc', [((8, 8, 8), 8.0), ((6, 7, 12), 7.5), ((3, 3, 20), 4.6)])
+def test_neighbor_list_liquid_density_many_neighbours_per_atom(sides, rc):
+    """Warp-per-atom list kernels on boxes where an atom has ~100 listed partners (several 32-candidate rounds, rank sort of a long
+    row segment) and where a dimension holds exactly 3 or only 2 cells: pair array identical to the oracle's, row for row."""
+    from admp_b200 import workloads
+    from admp_b200.neighbor import neighbor_list
+    w = workloads.dense_water(sides)
+    po, no = pairlist.build_pairs(np.asarray(w.positions), np.asarray(w.box), rc)
+    nbr = neighbor_list(w.box, rc).allocate(w.positions)
+    assert nbr.n_pairs == no and not nbr.did_buffer_overflow
+    assert np.array_equal(nbr.pairs[:no].cpu().numpy(), po[:no])
+    assert 2.0 * no / w.n_atoms > 30
+
+
 def test_reference_example_water_1024_nonpol():
     """Config C1: examples/water_1024 (3072 atoms, rc 4, kappa 0.657065221219616, K 154^3)."""
     from admp_b200.pme import ADMPPmeForce
