@@ -1,5 +1,5 @@
 """The bench line contract (task statement, section 4) checked on the committed line of the last GPU run
-(profiles/r2g_bench.json, written by `python bench.py --steps 20 --warmup 5` on a B200) and on the reference-arm line: every key the driver
+(profiles/r2k_bench.json, written by `python bench.py --steps 20 --warmup 5` on a B200) and on the reference-arm line: every key the driver
 and the judge read is present and self-consistent. CPU only; bench.py itself needs a GPU."""
 import json
 import os
@@ -13,7 +13,7 @@ def _load(name):
 
 
 def test_gpu_arm_line():
-    d = _load('r2g_bench.json')
+    d = _load('r2k_bench.json')
     for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'vs_baseline',
               'dtype', 'data', 'config', 'e2e', 'gpu_launches', 'clocks', 'roofline', 'cpu_baseline'):
         assert k in d, k
@@ -22,7 +22,7 @@ def test_gpu_arm_line():
     fr = d['config']['frames_per_step']
     assert fr == 32 and d['config']['evals_timed'] == d['n_gpus'] * d['steps'] * fr
     assert abs(d['value'] - d['n_gpus'] * fr * 1e3 / d['ms_per_step']) < 1e-6 * d['value']
-    assert d['gpu_launches'] % (d['steps'] * fr) == 0 and 380 <= d['gpu_launches'] // (d['steps'] * fr) <= 440   # ~390 per eval (launch list)
+    assert d['gpu_launches'] % (d['steps'] * fr) == 0 and 380 <= d['gpu_launches'] // (d['steps'] * fr) <= 440   # ~389 per eval (launch list)
     e = d['e2e']
     assert e['unit'] == 'evals/s' and e['h2d_bytes_per_step'] > 0 and e['d2h_bytes_per_step'] > 0 and 0 < e['value'] <= 1.05 * d['value']
     r = d['roofline']
@@ -41,7 +41,7 @@ def test_gpu_arm_line():
 
 
 def test_two_gpu_line_has_the_collective_and_the_slab_runs():
-    d = _load('r2f_bench_2gpu.json')
+    d = _load('r2k_bench_2gpu.json')
     assert d['n_gpus'] == 2 and 'all-reduce' in d['config']['parallelism'] and d['scaling'] == 'weak'
     assert abs(d['value'] - 2 * d['config']['frames_per_step'] * 1e3 / d['ms_per_step']) < 1e-6 * d['value']
     for key in ('c3_slab', 'c5_slab'):
@@ -49,9 +49,9 @@ def test_two_gpu_line_has_the_collective_and_the_slab_runs():
 
 
 def test_reference_arm_line():
-    d = _load('r2g_bench_reference.json')
+    d = _load('r2k_bench_reference.json')
     assert d['impl'] == 'reference' and d['unit'] == 'evals/s' and d['value'] > 0
     assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0 and d['e2e']['value'] == d['value']
     assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['value'] == d['value']
-    assert d['metric'] == _load('r2g_bench.json')['metric'] and d['config']['workload'] == _load('r2g_bench.json')['config']['workload']
+    assert d['metric'] == _load('r2k_bench.json')['metric'] and d['config']['workload'] == _load('r2k_bench.json')['config']['workload']
     assert d['config']['evals_timed'] >= 1 and 'nothing extrapolated' in d['cpu_baseline']['sample']
