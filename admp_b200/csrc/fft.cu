@@ -436,7 +436,10 @@ struct FftDimCfg {
     FastOps ops;
 };
 
-static bool dim_cfg(int N, int tw_len, size_t esz, size_t smem_cap, int min_ls, bool zpass, bool allow_fast, FftDimCfg& c, bool xpass = false) {
+// zfwd: configuration of the FORWARD Z pass alone - it wants 8-line tiles (line-fastest thread mapping, fft_fast.cuh), the inverse Z
+// pass the narrow ones; only the forward kernel of the entry has to fit
+static bool dim_cfg(int N, int tw_len, size_t esz, size_t smem_cap, int min_ls, bool zpass, bool allow_fast, FftDimCfg& c, bool xpass = false,
+                    bool zfwd = false) {
     if (!fft_factorize(N, c.P)) return false;
     c.LS = N | 1;
     if (c.LS < min_ls) c.LS = min_ls | 1;
@@ -451,15 +454,20 @@ static bool dim_cfg(int N, int tw_len, size_t esz, size_t smem_cap, int min_ls, 
         // two tile widths exist for the larger sizes: strided passes default to the wide tile (longer contiguous
         // global segments), the contiguous Z passes to the narrow one (more resident blocks); measured on B200
         const char* e = getenv("ADMP_FFT_WIDE");
-        bool wide = e ? atoi(e) > 0 : !zpass;
+        bool wide = e ? atoi(e) > 0 : (!zpass || zfwd);
         if (xpass) { const char* ex = getenv("ADMP_FFT_XWIDE"); if (ex) wide = atoi(ex) > 0; }
         int force = -1;
         if (xpass && N == 616) force = 9;          // X pass of 616 points: one 448-thread block on 8-line tiles (6.73 -> 6.13 ms at 616x1232x1232)
         if (!zpass) { const char* ef = getenv(xpass ? "ADMP_FFT_XCFG" : "ADMP_FFT_YCFG"); if (ef) force = atoi(ef); }
+        if (zfwd) {
+            if (N == 616) force = 11;              // 8-line tiles in one 448-thread block
+            const char* ef = getenv("ADMP_FFT_ZFCFG");
+            if (ef) force = atoi(ef);
+        }
         c.fast = esz == 8 ? fast_lookup<double>(N, wide, c.ops, force) : fast_lookup<float>(N, wide, c.ops, force);
         if (c.fast) {
             c.ops.prepare(c.ops);
-            const bool usable = zpass ? (c.ops.occ[3] > 0 && c.ops.occ[4] > 0) : (c.ops.occ[0] > 0 && c.ops.occ[1] > 0 && c.ops.occ[2] > 0 && c.ops.occ[5] > 0);
+            const bool usable = zfwd ? (c.ops.occ[3] > 0) : zpass ? (c.ops.occ[3] > 0 && c.ops.occ[4] > 0) : (c.ops.occ[0] > 0 && c.ops.occ[1] > 0 && c.ops.occ[2] > 0 && c.ops.occ[5] > 0);
             if (!usable) c.fast = false;
         }
     }
@@ -471,6 +479,7 @@ struct Fft3dImpl {
     size_t esz;
     int n_sm;
     FftDimCfg z, y, x;
+    FftDimCfg zf;    // forward Z pass (8-line tiles where they exist); z serves the inverse pass and the generic fallback
     void* tw[3];     // device twiddle tables: exp(-2 pi i m / K_d), m < K_d
 };
 
@@ -509,6 +518,11 @@ Fft3d* fft3d_create(int K1, int K2, int K3, int dtype, const char** why) {
         *why = msg_fac;
         delete f;
         return nullptr;
+    }
+    f->zf = f->z;
+    if (f->z.fast) {
+        FftDimCfg zf;
+        if (dim_cfg(M, K3, f->esz, cap, M + 1, true, allow_fast, zf, false, true) && zf.fast) f->zf = zf;
     }
     cudaError_t e = dtype == ADMP_F64 ? set_smem_attr<double>(f) : set_smem_attr<float>(f);
     if (e != cudaSuccess) { *why = msg_cuda; delete f; return nullptr; }
@@ -597,7 +611,7 @@ static void run_z(Fft3dImpl* f, cudaStream_t st, void* mesh, void* spec, int sig
     const int nlines = nx * f->K[1];
     mesh = (char*)mesh + (size_t)x0 * f->K[1] * K3 * sizeof(T);
     spec = (char*)spec + (size_t)x0 * f->K[1] * (K3 / 2 + 1) * sizeof(cx<T>);
-    const FftDimCfg& c = f->z;
+    const FftDimCfg& c = (sign > 0) ? f->zf : f->z;
     const cx<T>* tw = (const cx<T>*)f->tw[2];
     if (c.fast) {
         const int ntiles = (nlines + c.ops.zTL - 1) / c.ops.zTL;

@@ -795,7 +795,13 @@ fast_z_fwd_kernel(int nlines, int ntiles, const T* __restrict__ mesh, cx<T>* __r
     cx<T>* tw2 = A + TILE;
     cx<T>* tw3 = tw2 + TwGeom<R1, R2, R3>::N2;
     cx<T>* zt = tw3 + TwGeom<R1, R2, R3>::N3;       // M+1 entries: exp(-2 pi i k / K3)
-    const int j = threadIdx.x % JT, l = threadIdx.x / JT;
+    // Tiles whose TL lines fill a 128-byte bank row (8 lines of float64): thread = (line fastest, butterfly) - the lanes of a quarter
+    // warp work on the SAME butterfly of 8 different lines, LS (odd) apart in shared memory: 8 distinct 16-byte bank groups whatever the
+    // position pattern of the stage (Good gather, row-major, Stockham strides). With the butterfly index fastest this pass spent 50 %
+    // of its stall samples on shared memory (ncu r2k: short scoreboard 34 %, MIO 16 %). Narrower tiles keep the butterfly index
+    // fastest (line-fastest halves of two butterflies collide: measured 0.494 -> 0.553 ms with 4-line tiles at 308x616x616).
+    constexpr bool LINE_FASTEST = TL * sizeof(cx<T>) >= 128;
+    const int j = LINE_FASTEST ? threadIdx.x / TL : threadIdx.x % JT, l = LINE_FASTEST ? threadIdx.x % TL : threadIdx.x / JT;
     constexpr bool BULK = UseBulk<T>::value;
     __shared__ uint64_t bar;
     unsigned parity = 0;
@@ -958,7 +964,8 @@ fast_z_inv_kernel(int nlines, int ntiles, const cx<T>* __restrict__ spec, T* __r
     X(7, 11, 7, 4, 8, 16, 8, 28)     \
     X(8, 11, 7, 8, 4, 32, 4, 56)     \
     X(9, 11, 7, 8, 8, 56, 4, 56)     \
-    X(10, 11, 7, 16, 4, 112, 2, 112)
+    X(10, 11, 7, 16, 4, 112, 2, 112) \
+    X(11, 11, 7, 8, 8, 56, 8, 56)
 
 struct FastOps {
     int N, TL, threads, zTL, zthreads;
@@ -1107,7 +1114,7 @@ struct FastImpl {
 };
 
 // the table entries for (size N, element size); wide = prefer the wider tile when two are listed
-// entries 7 and 9 are only taken when asked for by id (ADMP_FFT_XCFG / ADMP_FFT_YCFG); 8 (616 points in 128-thread blocks, two
+// entries 7, 9 and 11 (11: 8-line Z tiles of 616 points for the forward Z pass) are only taken when asked for by id (ADMP_FFT_XCFG / YCFG / ZFCFG); 8 (616 points in 128-thread blocks, two
 // per SM) is the wide default of its size: Y pass 0.380 -> 0.362 ms at 308x616x616, X pass 7.04 -> 6.74 ms at 616x1232x1232
 template <typename T>
 static bool fast_lookup(int N, bool wide, FastOps& out, int force_id = -1) {
