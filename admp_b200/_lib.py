@@ -18,6 +18,7 @@ S_E_REAL, S_E_RECIP, S_E_SELF, S_E_PEN = 0, 1, 2, 3
 S_DBOX, S_DNSTAR, S_TK, S_DMSCALE, S_DPSCALE, S_MAXFIELD, S_COUNT = 4, 13, 22, 28, 33, 38, 48
 
 WANT_GRAD, WANT_VIRIAL, WANT_PGRAD, SCF, SCF_HOSTSYNC = 1, 2, 4, 8, 16
+SCF_CG = 32                 # beyond the reference: conjugate-gradient SCF (include/admp_b200.h)
 REUSE_PAIR_TILES = 0x20000000
 
 EXPORTS = [

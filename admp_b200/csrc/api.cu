@@ -70,6 +70,7 @@ struct admp_ctx {
     std::string fft_note;
     // per-atom workspaces and staged inputs of admp_pme_eval
     void *M = nullptr, *G = nullptr, *Fscf = nullptr, *rec = nullptr;
+    double* cg = nullptr;           // conjugate-gradient work vectors [U | r | p] + rz (allocated on first use, ADMP_SCF_CG)
     void *s_pos = nullptr, *s_U = nullptr, *s_pol = nullptr, *s_th = nullptr, *s_mS = nullptr, *s_pS = nullptr, *s_box = nullptr;
     int32_t* s_pairs = nullptr;
     int8_t* s_sidx = nullptr;       // scale index per staged pair row (-1: row not evaluated)
@@ -210,7 +211,7 @@ static int ensure_cufft(admp_ctx* c) {
 }
 
 static void free_atoms(admp_ctx* c) {
-    dfree(c->M); dfree(c->G); dfree(c->Fscf); dfree(c->rec); dfree(c->s_pos); dfree(c->s_U); dfree(c->s_pol); dfree(c->s_th);
+    dfree(c->M); dfree(c->G); dfree(c->Fscf); dfree(c->rec); dfree(c->cg); dfree(c->s_pos); dfree(c->s_U); dfree(c->s_pol); dfree(c->s_th);
     dfree(c->axis_type); dfree(c->axis_idx); dfree(c->cov_off); dfree(c->cov_idx); dfree(c->cov_nb);
     dfree(c->cw.cl_of); dfree(c->cw.cl_first); dfree(c->cw.cl_size); dfree(c->cw.row_start); dfree(c->cw.cl_extra);
     c->cw.n_clusters = 0;
@@ -894,8 +895,14 @@ static int scf_body(admp_ctx* c, cudaStream_t st, int maxiter, double thresh, ui
     }
     CK(cudaStreamWaitEvent(st, c->ev_join, 0));
     DISPATCH(c, launch_scf_field, st, c->n_atoms, c->kappa, c->M, c->s_U, c->s_pol, c->Fscf, c->scal);
-    launch_scf_decide(st, c->state, c->scal, maxiter, thresh, refresh_in_loop, h, use_h);
-    DISPATCH(c, launch_scf_update, st, c->n_atoms, c->state, c->Fscf, c->s_pol, c->s_U, 1);
+    if (flags & ADMP_SCF_CG) {
+        // beyond the reference: conjugate gradients on the same body (site.cu scf_cg_kernel). Its last pass is always a field
+        // evaluation on the final U, so the mesh / reciprocal energy need no refresh whatever the caller does afterwards.
+        DISPATCH(c, launch_scf_cg, st, c->n_atoms, c->state, c->scal, c->Fscf, c->s_pol, c->s_U, c->cg, maxiter, thresh, h, use_h);
+    } else {
+        launch_scf_decide(st, c->state, c->scal, maxiter, thresh, refresh_in_loop, h, use_h);
+        DISPATCH(c, launch_scf_update, st, c->n_atoms, c->state, c->Fscf, c->s_pol, c->s_U, 1);
+    }
     CKLAUNCH();
     return 0;
 }
@@ -929,7 +936,11 @@ static int build_scf_graph(admp_ctx* c, int maxiter, double thresh, uint32_t fla
 
 static int run_scf(admp_ctx* c, cudaStream_t st, int maxiter, double thresh, uint32_t flags) {
     CK(cudaMemsetAsync(c->state, 0, sizeof(int32_t) * 8, st));
-    const uint32_t gkey = flags & ADMP_WANT_VIRIAL;
+    const uint32_t gkey = flags & (ADMP_WANT_VIRIAL | ADMP_SCF_CG);
+    if ((flags & ADMP_SCF_CG) && !c->cg) {
+        drop_graph(c);
+        CK(cudaMalloc((void**)&c->cg, sizeof(double) * ((size_t)9 * c->n_atoms + 1)));
+    }
     if (!(flags & ADMP_SCF_HOSTSYNC) && !c->graph_failed) {
         if (!c->gexec || c->g_maxiter != maxiter || c->g_thresh != thresh || c->g_flags != gkey) {
             if (build_scf_graph(c, maxiter, thresh, gkey)) {
@@ -946,7 +957,8 @@ static int run_scf(admp_ctx* c, cudaStream_t st, int maxiter, double thresh, uin
     // debug / fallback: same kernels, loop condition read back every iteration
     cudaGraphConditionalHandle none;
     memset(&none, 0, sizeof(none));
-    for (int it = 0; it <= maxiter; ++it) {
+    const int max_pass = (flags & ADMP_SCF_CG) ? 2 * maxiter + 3 : maxiter;     // CG: restarts re-evaluate the true residual
+    for (int it = 0; it <= max_pass; ++it) {
         if (scf_body(c, st, maxiter, thresh, gkey, none, 0)) return 1;
         CK(cudaMemcpyAsync(c->h_state, c->state, sizeof(int32_t) * 8, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));

@@ -139,6 +139,10 @@ void launch_scf_decide(cudaStream_t st, int32_t* state, double* scalars, int max
                        cudaGraphConditionalHandle handle, int use_handle);
 template <typename T>
 void launch_scf_update(cudaStream_t st, int n, const int32_t* state, void* F, const void* pol, void* U, int zero_F);
+// preconditioned conjugate gradients on the Jacobi fixed point (beyond the reference): replaces decide + update
+template <typename T>
+void launch_scf_cg(cudaStream_t st, int n, int32_t* state, double* scalars, void* F, const void* pol, void* Us, double* cg, int maxiter,
+                   double thresh, cudaGraphConditionalHandle handle, int use_handle);
 void launch_virial_finalize(cudaStream_t st, const BoxInfo* B, double* scalars, int kvec_ref);
 
 // nblist.cu

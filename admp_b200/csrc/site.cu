@@ -175,6 +175,125 @@ scf_update_kernel(int n, const int32_t* __restrict__ state, T* __restrict__ F, c
     }
 }
 
+// ---- beyond the reference: conjugate gradients on the same fixed point, preconditioned with the
+// Jacobi scaling pol / DIEL.  The loop body is the Jacobi one (pair field + reciprocal field + scf_field_kernel, all
+// evaluated on the dipoles in `Us`); this kernel replaces decide + update.  One block: the dot products and the maximum
+// are block reductions in a fixed order, so a run is reproducible bit for bit.
+//   phase 0 (state[6] = 0): F = field(U), Us = U.  max|F| (scalars[ADMP_S_MAXFIELD], sites with pol > 0.001) < thresh
+//            -> converged, stop: the mesh and the reciprocal energy of this pass belong to the final U.  Else
+//            r = -F, z = M r, p = z, Us = U + p.
+//   phase 1 (state[6] = 1): F = field(U + p), so A p = F + r;  alpha = rz / pAp;  U += alpha p;  r -= alpha A p;
+//            max|r| < thresh or the iteration budget is spent -> Us = U, back to phase 0 (the TRUE residual decides);
+//            else z = M r, beta = rz' / rz, p = z + beta p, Us = U + p.
+//            pAp <= 0 (A not positive definite along p): Us = U, one refresh pass, stop with flag 0.
+// cg = [U | r | p] (3n doubles each) + 1 double (rz).  state as in scf_decide_kernel; [0] counts CG iterations.
+__device__ __forceinline__ double cg_block_sum(double v, double* red) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    return s;
+}
+__device__ __forceinline__ double cg_block_max(double v, double* red) {
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s = fmax(s, red[w]);
+    return s;
+}
+template <typename T>
+__global__ void __launch_bounds__(1024)
+scf_cg_kernel(int n, int32_t* __restrict__ state, double* __restrict__ scalars, T* __restrict__ F, const T* __restrict__ pol,
+              T* __restrict__ Us, double* __restrict__ cg, int maxiter, double thresh, cudaGraphConditionalHandle handle, int use_handle) {
+    __shared__ double red[32];
+    const int n3 = 3 * n;
+    double* U = cg;
+    double* r = cg + n3;
+    double* p = cg + 2 * (size_t)n3;
+    double* rzp = cg + 3 * (size_t)n3;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const double invD = 1.0 / ADMP_DIEL;
+    auto finish = [&](int cond) {           // every thread calls it (uniform `cond`)
+        for (int e = tid; e < n3; e += nt) F[e] = (T)0;          // the next pass accumulates its field with atomics
+        if (tid == 0) {
+            state[5] = cond;
+            if (!cond) state[7] = 1;
+            if (cond) {
+                scalars[ADMP_S_MAXFIELD] = 0.0;
+                scalars[ADMP_S_E_RECIP] = 0.0;
+            }
+            if (use_handle) cudaGraphSetConditional(handle, cond);
+        }
+    };
+    if (state[7]) { finish(0); return; }     // the loop has ended (speculative extra pass): leave everything alone
+    if (state[2]) { finish(0); return; }     // this pass only refreshed the mesh / field on the final U
+    const int it = state[0];
+    if (state[6] == 0) {
+        const double mx = __longlong_as_double((long long)reinterpret_cast<unsigned long long*>(scalars)[ADMP_S_MAXFIELD]);
+        if (mx < thresh || it >= maxiter) {
+            if (tid == 0) { state[3] = it; state[4] = (mx < thresh) ? 1 : 0; }
+            finish(0);
+            return;
+        }
+        double acc = 0.0;
+        for (int e = tid; e < n3; e += nt) {
+            const double u = (double)Us[e], rr = -(double)F[e], z = (double)pol[e / 3] * invD * rr;
+            U[e] = u; r[e] = rr; p[e] = z;
+            Us[e] = (T)(u + z);
+            acc = fma(rr, z, acc);
+        }
+        const double rz = cg_block_sum(acc, red);
+        if (tid == 0) { *rzp = rz; state[6] = 1; }
+        finish(1);
+        return;
+    }
+    // phase 1
+    double acc = 0.0;
+    for (int e = tid; e < n3; e += nt) acc = fma(p[e], (double)F[e] + r[e], acc);
+    const double pAp = cg_block_sum(acc, red);
+    const double rz = *rzp;
+    if (!(pAp > 0.0) || !(rz == rz)) {       // indefinite direction (or NaN): stop on the current U, flag 0
+        for (int e = tid; e < n3; e += nt) Us[e] = (T)U[e];
+        __syncthreads();
+        if (tid == 0) { state[3] = it; state[4] = 0; state[2] = 1; state[6] = 0; }
+        finish(1);
+        return;
+    }
+    const double alpha = rz / pAp;
+    double mx = 0.0;
+    acc = 0.0;
+    for (int e = tid; e < n3; e += nt) {
+        const double pe = p[e], pl = (double)pol[e / 3];
+        const double rr = r[e] - alpha * ((double)F[e] + r[e]);
+        U[e] += alpha * pe;
+        r[e] = rr;
+        if (pl > 0.001) mx = (rr == rr && fabs(rr) <= 1.7e308) ? fmax(mx, fabs(rr)) : 1.7976931348623157e308;
+        acc = fma(rr, pl * invD * rr, acc);
+    }
+    const double rz_new = cg_block_sum(acc, red);
+    mx = cg_block_max(mx, red);
+    if (mx < thresh || it + 1 >= maxiter) {
+        for (int e = tid; e < n3; e += nt) Us[e] = (T)U[e];
+        __syncthreads();
+        if (tid == 0) { state[0] = it + 1; state[6] = 0; }
+        finish(1);
+        return;
+    }
+    const double beta = rz_new / rz;
+    for (int e = tid; e < n3; e += nt) {
+        const double pe = (double)pol[e / 3] * invD * r[e] + beta * p[e];
+        p[e] = pe;
+        Us[e] = (T)(U[e] + pe);
+    }
+    __syncthreads();
+    if (tid == 0) { state[0] = it + 1; *rzp = rz_new; }
+    finish(1);
+}
+
 // dE/dbox (3x3, row-major) += reciprocal-space part assembled from the accumulators:
 //   -inv^T (W^T Nstar)  [spread/gather, W = dE/dNstar]  - 2 T inv^T - E_recip inv^T  [k^2 and V in C_k]
 __global__ void virial_finalize_kernel(const BoxInfo* __restrict__ B, double* __restrict__ s, int kvec_ref) {
@@ -230,6 +349,11 @@ void launch_scf_decide(cudaStream_t st, int32_t* state, double* scalars, int max
     scf_decide_kernel<<<1, 32, 0, st>>>(state, scalars, maxiter, thresh, handle, use_handle, refresh_in_loop);
 }
 template <typename T>
+void launch_scf_cg(cudaStream_t st, int n, int32_t* state, double* scalars, void* F, const void* pol, void* Us, double* cg, int maxiter,
+                   double thresh, cudaGraphConditionalHandle handle, int use_handle) {
+    scf_cg_kernel<T><<<1, 1024, 0, st>>>(n, state, scalars, (T*)F, (const T*)pol, (T*)Us, cg, maxiter, thresh, handle, use_handle);
+}
+template <typename T>
 void launch_scf_update(cudaStream_t st, int n, const int32_t* state, void* F, const void* pol, void* U, int zero_F) {
     scf_update_kernel<T><<<(n + 127) / 128, 128, 0, st>>>(n, state, (T*)F, (const T*)pol, (T*)U, zero_F);
 }
@@ -240,7 +364,9 @@ void launch_scf_update(cudaStream_t st, int n, const int32_t* state, void* F, co
                                  void*, double*);                                                                            \
     template void launch_disp_self<T>(cudaStream_t, int, double, int, const void*, uint32_t, void*, double*);                \
     template void launch_scf_field<T>(cudaStream_t, int, double, const void*, const void*, const void*, void*, double*);     \
-    template void launch_scf_update<T>(cudaStream_t, int, const int32_t*, void*, const void*, void*, int);
+    template void launch_scf_update<T>(cudaStream_t, int, const int32_t*, void*, const void*, void*, int);                   \
+    template void launch_scf_cg<T>(cudaStream_t, int, int32_t*, double*, void*, const void*, void*, double*, int, double,   \
+                                   cudaGraphConditionalHandle, int);
 ADMP_INST(double)
 ADMP_INST(float)
 #undef ADMP_INST

@@ -166,7 +166,7 @@ class ADMPPmeForce:
         return None if x is None else to_dev(x, self._dtype, self._ctx.device)
 
     def _eval(self, positions, box, pairs, Q_local, U, pol, tholes, mScales, pScales, flags, do_scf,
-              maxiter=None, thresh=None, hostsync=False, cache_scf=True):
+              maxiter=None, thresh=None, hostsync=False, cache_scf=True, solver=None):
         """One admp_pme_eval launch on the current stream. All tensors already on device.
         Paths that run the SCF cache U_ind / status on self, as the reference's get_energy does
         (admp/pme.py:82)."""
@@ -207,6 +207,11 @@ class ADMPPmeForce:
         # ADMP_SCF_HOSTSYNC=1 selects the host-synchronised loop (same kernels; used under profilers)
         hostsync = hostsync or os.environ.get('ADMP_SCF_HOSTSYNC', '0') == '1'
         f = flags | (_lib.SCF if (polz and do_scf) else 0) | (_lib.SCF_HOSTSYNC if hostsync else 0)
+        solver = settings.SCF_SOLVER if solver is None else solver
+        if solver not in ('jacobi', 'pcg'):
+            raise ValueError("SCF_SOLVER must be 'jacobi' (the reference's iteration) or 'pcg', got %r" % (solver,))
+        if solver == 'pcg':
+            f |= _lib.SCF_CG
         p = _lib.ptr
         _lib.check(c.lib.admp_pme_eval(
             c.handle, _lib.stream_ptr(), p(positions), p(box), p(pairs), int(pairs.shape[0]), p(Q_local), p(r.U),
@@ -255,15 +260,17 @@ class ADMPPmeForce:
         return r.dpos
 
     def optimize_Uind(self, positions, box, pairs, Q_local, pol, tholes, mScales, pScales, dScales,
-                      U_init=None, maxiter=None, thresh=None):
+                      U_init=None, maxiter=None, thresh=None, solver=None):
         '''Converges the induced dipoles with the reference's Jacobi iteration and stopping rule
         (admp/pme.py:111-143), as device-resident iterations (CUDA-graph WHILE loop).
-        Returns (U, flag, i) like the reference; reading flag / i synchronises the host.'''
+        Returns (U, flag, i) like the reference; reading flag / i synchronises the host.
+        solver (default settings.SCF_SOLVER = 'jacobi'): 'pcg' converges the same fixed point with preconditioned
+        conjugate gradients (beyond the reference; i = CG iterations, flag = max|field(U)| < thresh on the final U).'''
         args = [self._prep(x).detach() for x in (positions, box, Q_local, pol, tholes, mScales, pScales)]
         pairs = pairs_to_dev(pairs, self._ctx.device)
         U0 = None if U_init is None else self._prep(U_init).detach()
         r = self._eval(args[0], args[1], pairs, args[2], U0, args[3], args[4], args[5], args[6], 0, True,
-                       maxiter=maxiter, thresh=thresh, cache_scf=False)
+                       maxiter=maxiter, thresh=thresh, cache_scf=False, solver=solver)
         scf = r.scf.cpu()
         return r.U, bool(scf[1].item()), int(scf[0].item())
 

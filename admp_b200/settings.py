@@ -12,6 +12,13 @@ POL_CONV = 10.0   # gradient convergence thresh for induced dipoles
 MAX_N_POL = 30    # maximum number of cycles for optimizing induced dipoles
 
 
+# Induced-dipole solver (no counterpart in admp/settings.py). 'jacobi': the reference's iteration, cycle for cycle
+# (admp/pme.py:132-138) - the default, and the only setting under which n_cycle / lconverg / U_ind reproduce the reference.
+# 'pcg': conjugate gradients preconditioned with pol / DIELECTRIC on the same linear fixed point: same
+# stopping rule (max|dE/dU| < POL_CONV over pol > 0.001, tested on the final U), MAX_N_POL bounds the CG iterations; it
+# converges in fewer field evaluations and wherever the matrix is positive definite, also where the Jacobi iteration diverges.
+SCF_SOLVER = 'jacobi'
+
 # Convention of the k-space part of dE/dbox (no counterpart in admp/settings.py). 'natural': component i of a k-vector
 # belongs to mesh axis i - the chain-rule-correct virial. 'reference': the reference's k table (admp/recip.py:339-341,
 # meshgrid(kz, kx, ky)), which exchanges axes 0 and 1 in dk^2/dbox; on cubic cells with K1=K2=K3 this reproduces the

@@ -62,6 +62,9 @@ extern "C" {
 #define ADMP_WANT_PGRAD 4u    /* dE/dmScales, dE/dpScales, dE/dtholes, dE/dpol */
 #define ADMP_SCF 8u           /* run optimize_Uind before the final evaluation */
 #define ADMP_SCF_HOSTSYNC 16u /* debug: host-synchronised SCF loop instead of the device-resident graph */
+#define ADMP_SCF_CG 32u       /* beyond the reference: converge U with conjugate gradients preconditioned by pol/DIELECTRIC instead of
+                               * the Jacobi iteration of admp/pme.py:132-138 (same fixed point and stopping rule, evaluated on the
+                               * final U; scf_out[0] = CG iterations). Default off: the reference's iteration, cycle for cycle. */
 /* admp_pme_real only: the pair rows, topology and scales index are those of the previous admp_pme_real call on this
  * context - reuse its per-row scale indices and cluster tiles (what admp_pme_eval does for the 31 pair passes of one
  * polarizable evaluation) instead of rebuilding them */
