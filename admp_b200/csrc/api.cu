@@ -70,6 +70,8 @@ struct admp_ctx {
     std::string fft_note;
     // per-atom workspaces and staged inputs of admp_pme_eval
     void *M = nullptr, *G = nullptr, *Fscf = nullptr, *rec = nullptr;
+    int phi_zld = 0;                // reals per line of phi_cur (0: K3)
+    bool inplace_ok = false;        // the real mesh of the fused evaluations may live in the spectrum buffer (set_pme / ADMP_MESH_INPLACE)
     double* cg = nullptr;           // conjugate-gradient work vectors [U | r | p] + rz (allocated on first use, ADMP_SCF_CG)
     void *s_pos = nullptr, *s_U = nullptr, *s_pol = nullptr, *s_th = nullptr, *s_mS = nullptr, *s_pS = nullptr, *s_box = nullptr;
     int32_t* s_pairs = nullptr;
@@ -319,6 +321,10 @@ extern "C" int admp_ctx_set_pme(admp_ctx* c, double kappa, int K1, int K2, int K
     c->fft = fft3d_create(K1, K2, K3, c->dtype, &why);
     c->use_custom_fft = (c->fft != nullptr) && !(env && strcmp(env, "cufft") == 0);
     c->fft_note = c->fft ? "" : why;
+    {
+        const char* e3 = getenv("ADMP_MESH_INPLACE");
+        c->inplace_ok = c->fft != nullptr && fft3d_inplace_supported(c->fft) && !(e3 && atoi(e3) == 0);
+    }
     cudaGetLastError();
     c->ws_bytes += c->mesh_bytes + c->spec_bytes;
     // optional second real buffer for the SCF body (ADMP_TWO_MESH=1): measured and left off - on the L2-resident 154^3 mesh
@@ -466,9 +472,27 @@ static void spread_prepare(admp_ctx* c, cudaStream_t st, const void* pos) {
     if (use_bricks(c)) DISPATCH(c, launch_brick_sort, st, c->bw, c->box, pos);
 }
 // the whole spread: mesh = sum of the atoms' stencils (bricks: one coalesced write; otherwise zero-fill + per-atom scatter)
-static int spread_all(admp_ctx* c, cudaStream_t st, const void* pos, const void* M, int cols, int stride, const void* U) {
+// In-place mesh of the fused evaluations (admp_pme_eval, admp_disp_eval, admp_pme_recip): the real mesh occupies the spectrum
+// buffer, line l of K3 reals at the start of spectrum line l (the layout of an in-place real-to-complex transform), so one
+// reciprocal round trip touches 16 (K3/2 + 1) K1 K2 bytes instead of twice that - on the 154^3 mesh of the reference's examples four
+// evaluations in flight then fit the 126 MB L2. Needs the tile-pipelined Z passes (they hold a whole tile in shared memory before
+// they write it); per-atom spread only; off for the stand-alone stage entry points, the slab / atom-block decompositions and the
+// two-buffer SCF body, which keep the separate mesh. ADMP_MESH_INPLACE=0 switches it off.
+static bool mesh_inplace(const admp_ctx* c) {
+    return c->inplace_ok && c->use_custom_fft && c->fft && c->phi == nullptr && !use_bricks(c) && c->spec_peers.n <= 1;
+}
+static void* mesh_buf(admp_ctx* c) { return mesh_inplace(c) ? c->spec : c->mesh; }
+static int mesh_zld(const admp_ctx* c) { return mesh_inplace(c) ? 2 * (c->K[2] / 2 + 1) : 0; }
+static size_t mesh_fill_bytes(const admp_ctx* c) { return mesh_inplace(c) ? c->spec_bytes : c->mesh_bytes; }
+
+// fused: part of a self-contained spread -> transform -> gather chain (may use the in-place mesh); the stand-alone stage entry
+// points always work on the separate mesh buffer
+static int spread_all(admp_ctx* c, cudaStream_t st, const void* pos, const void* M, int cols, int stride, const void* U, bool fused) {
     if (use_bricks(c)) {
         DISPATCH(c, launch_spread_brick, st, c->bw, c->box, pos, M, cols, stride, U, c->mesh);
+    } else if (fused) {
+        CK(cudaMemsetAsync(mesh_buf(c), 0, mesh_fill_bytes(c), st));
+        DISPATCH(c, launch_spread, st, c->n_atoms, c->box, pos, M, cols, stride, U, mesh_buf(c), nullptr, mesh_zld(c));
     } else {
         CK(cudaMemsetAsync(c->mesh, 0, c->mesh_bytes, st));
         DISPATCH(c, launch_spread, st, c->n_atoms, c->box, pos, M, cols, stride, U, c->mesh);
@@ -484,10 +508,11 @@ static int recip_field(admp_ctx* c, cudaStream_t st, const void* pos, const void
         conv_tables(c, st);
         spread_prepare(c, st, pos);
     }
-    c->phi_cur = c->mesh;
-    if (spread_all(c, st, pos, M, cols, stride, U)) return 1;
+    c->phi_cur = mesh_buf(c);
+    c->phi_zld = mesh_zld(c);
+    if (spread_all(c, st, pos, M, cols, stride, U, true)) return 1;
     if (c->use_custom_fft) {
-        fft3d_convolve_roundtrip(c->fft, st, c->mesh, c->spec, c->box, c->kappa, kind, c->tb, scalars, want_vir);
+        fft3d_convolve_roundtrip(c->fft, st, mesh_buf(c), c->spec, c->box, c->kappa, kind, c->tb, scalars, want_vir, nullptr, nullptr, mesh_zld(c));
         CKLAUNCH();
         return 0;
     }
@@ -573,7 +598,8 @@ extern "C" int admp_pme_recip(admp_ctx* c, void* stream, const void* pos, const 
     DISPATCH(c, launch_box_setup, st, box, c->box, c->K[0], c->K[1], c->K[2]);
     if (recip_field(c, st, pos, M, M_cols, M_stride, U, kind, scalars, (flags & ADMP_WANT_VIRIAL) ? 1 : 0)) return 1;
     if (mode == 1 || (flags & ADMP_WANT_GRAD)) {
-        DISPATCH(c, launch_gather, st, c->n_atoms, c->box, pos, M, M_cols, M_stride, U, c->mesh, mode, flags, dpos, G, G_stride, F, scalars);
+        DISPATCH(c, launch_gather, st, c->n_atoms, c->box, pos, M, M_cols, M_stride, U, c->phi_cur, mode, flags, dpos, G, G_stride, F, scalars,
+                 nullptr, c->phi_zld);
         CKLAUNCH();
     }
     return 0;
@@ -588,7 +614,7 @@ extern "C" int admp_pme_spread(admp_ctx* c, void* stream, const void* pos, const
     CK(cudaSetDevice(c->device));
     DISPATCH(c, launch_box_setup, st, box, c->box, c->K[0], c->K[1], c->K[2]);
     spread_prepare(c, st, pos);
-    return spread_all(c, st, pos, M, M_cols, M_stride, U);
+    return spread_all(c, st, pos, M, M_cols, M_stride, U, false);
 }
 extern "C" int admp_pme_spread_only(admp_ctx* c, void* stream, const void* pos, const void* M, int M_cols, int M_stride, const void* U) {
     if (need(c, true, true)) return 1;     // no box set-up, no binning: the spread kernel alone on the state admp_pme_spread left
@@ -792,6 +818,7 @@ extern "C" int admp_ctx_set_peers(admp_ctx* c, int rank, int nranks, void* const
     c->mesh_peers.n = c->spec_peers.n = nranks;
     c->peer_rank = rank;
     c->peer_n = nranks;
+    drop_graph(c);              // a captured SCF body may address the in-place mesh, which a decomposed context does not use
     return 0;
 }
 static int need_peers(admp_ctx* c) {
@@ -891,7 +918,8 @@ static int scf_body(admp_ctx* c, cudaStream_t st, int maxiter, double thresh, ui
     } else {
         CK(cudaEventRecord(c->ev_join, c->side_stream));
         if (recip_field(c, st, c->s_pos, c->M, 10, 10, c->s_U, ADMP_CK_COULOMB, c->scal, 0, false)) return 1;
-        DISPATCH(c, launch_gather, st, c->n_atoms, c->box, c->s_pos, c->M, 10, 10, c->s_U, c->mesh, 1, 0u, nullptr, nullptr, 10, c->Fscf, c->scal);
+        DISPATCH(c, launch_gather, st, c->n_atoms, c->box, c->s_pos, c->M, 10, 10, c->s_U, c->phi_cur, 1, 0u, nullptr, nullptr, 10, c->Fscf, c->scal,
+                 nullptr, c->phi_zld);
     }
     CK(cudaStreamWaitEvent(st, c->ev_join, 0));
     DISPATCH(c, launch_scf_field, st, c->n_atoms, c->kappa, c->M, c->s_U, c->s_pol, c->Fscf, c->scal);
@@ -1033,7 +1061,8 @@ extern "C" int admp_pme_eval(admp_ctx* c, void* stream, const void* pos, const v
         const bool two_mesh = c->phi != nullptr && c->use_custom_fft;
         if (two_mesh) CK(cudaMemsetAsync(c->mesh, 0, c->mesh_bytes, st));
         if (run_scf(c, st, maxiter, thresh, flags)) return 1;
-        c->phi_cur = two_mesh ? c->phi : c->mesh;
+        c->phi_cur = two_mesh ? c->phi : mesh_buf(c);
+        c->phi_zld = two_mesh ? 0 : mesh_zld(c);
         if (want_vir) {
             // final reciprocal pass on the converged / last-updated U with the k-space virial sums
             CK(cudaMemsetAsync(c->scal + ADMP_S_E_RECIP, 0, sizeof(double), st));
@@ -1049,7 +1078,8 @@ extern "C" int admp_pme_eval(admp_ctx* c, void* stream, const void* pos, const v
     const void* Uf = polz ? c->s_U : nullptr;
     const uint32_t f = flags & (ADMP_WANT_GRAD | ADMP_WANT_VIRIAL | ADMP_WANT_PGRAD);
     if (flags & ADMP_WANT_GRAD) {
-        DISPATCH(c, launch_gather, st, n, c->box, c->s_pos, c->M, 10, 10, Uf, c->phi_cur, 0, f, dpos, c->G, 10, polz ? F : nullptr, c->scal);
+        DISPATCH(c, launch_gather, st, n, c->box, c->s_pos, c->M, 10, 10, Uf, c->phi_cur, 0, f, dpos, c->G, 10, polz ? F : nullptr, c->scal, nullptr,
+                 c->phi_zld);
     }
     DISPATCH(c, launch_pme_pair, st, c->pairs_cap, n, c->box, c->kappa, c->s_pos, c->s_pairs, c->s_sidx, c->cov_off, c->cov_idx, c->cov_nb, c->M, Uf,
              polz ? c->s_pol : nullptr, polz ? c->s_th : nullptr, c->s_mS, polz ? c->s_pS : nullptr, 0, f, dpos, c->G, F, dpol, dtholes, c->scal,
@@ -1091,8 +1121,8 @@ extern "C" int admp_disp_eval(admp_ctx* c, void* stream, const void* pos, const 
         if (recip_field(c, st, pos, col, 1, 3, nullptr, kinds[p], c->scal, (f & ADMP_WANT_VIRIAL) ? 1 : 0)) return 1;
         if (f & (ADMP_WANT_GRAD | ADMP_WANT_PGRAD)) {
             void* g = ((f & ADMP_WANT_PGRAD) && dc) ? (void*)((char*)dc + p * w) : nullptr;
-            DISPATCH(c, launch_gather, st, n, c->box, pos, col, 1, 3, nullptr, c->mesh, 0, f, (f & ADMP_WANT_GRAD) ? dpos : nullptr, g, 3,
-                     nullptr, c->scal);
+            DISPATCH(c, launch_gather, st, n, c->box, pos, col, 1, 3, nullptr, c->phi_cur, 0, f, (f & ADMP_WANT_GRAD) ? dpos : nullptr, g, 3,
+                     nullptr, c->scal, nullptr, c->phi_zld);
             CKLAUNCH();
         }
     }

@@ -605,18 +605,19 @@ static int persistent_grid(const Fft3dImpl* f, int occ, int ntiles) {
 
 // x0 / nx: restrict the pass to the planes [x0, x0 + nx) of the buffers (x-slab decomposition); nx < 0 = all
 template <typename T>
-static void run_z(Fft3dImpl* f, cudaStream_t st, void* mesh, void* spec, int sign, int x0 = 0, int nx = -1) {
+static void run_z(Fft3dImpl* f, cudaStream_t st, void* mesh, void* spec, int sign, int x0 = 0, int nx = -1, int zld = 0) {
     const int K3 = f->K[2];
     if (nx < 0) nx = f->K[0];
     const int nlines = nx * f->K[1];
-    mesh = (char*)mesh + (size_t)x0 * f->K[1] * K3 * sizeof(T);
+    if (zld <= 0) zld = K3;                   // reals per mesh line: K3, or 2 (K3/2 + 1) when the mesh lives in the spectrum buffer
+    mesh = (char*)mesh + (size_t)x0 * f->K[1] * zld * sizeof(T);
     spec = (char*)spec + (size_t)x0 * f->K[1] * (K3 / 2 + 1) * sizeof(cx<T>);
     const FftDimCfg& c = (sign > 0) ? f->zf : f->z;
     const cx<T>* tw = (const cx<T>*)f->tw[2];
     if (c.fast) {
         const int ntiles = (nlines + c.ops.zTL - 1) / c.ops.zTL;
-        if (sign > 0) c.ops.zfwd(st, nlines, ntiles, persistent_grid(f, c.ops.occ[3], ntiles), mesh, spec, tw);
-        else c.ops.zinv(st, nlines, ntiles, persistent_grid(f, c.ops.occ[4], ntiles), spec, mesh, tw);
+        if (sign > 0) c.ops.zfwd(st, nlines, ntiles, persistent_grid(f, c.ops.occ[3], ntiles), mesh, spec, tw, zld / 2);
+        else c.ops.zinv(st, nlines, ntiles, persistent_grid(f, c.ops.occ[4], ntiles), spec, mesh, tw, zld / 2);
         return;
     }
     const int grid = (nlines + c.TL - 1) / c.TL;
@@ -807,24 +808,31 @@ void fft3d_single_pass(Fft3d* p, cudaStream_t st, int which, void* mesh, void* s
 // mesh_out: where the inverse Z pass writes the potential (nullptr: over the input mesh); after_zfwd (optional): recorded
 // once the forward Z pass has consumed `mesh`, so the caller can recycle it while the spectrum passes run
 void fft3d_convolve_roundtrip(Fft3d* p, cudaStream_t st, void* mesh, void* spec, const BoxInfo* B, double kappa, int kind,
-                              const ConvTables& tb, double* scalars, int want_vir, void* mesh_out, cudaEvent_t after_zfwd) {
+                              const ConvTables& tb, double* scalars, int want_vir, void* mesh_out, cudaEvent_t after_zfwd, int zld) {
     Fft3dImpl* f = reinterpret_cast<Fft3dImpl*>(p);
     if (mesh_out == nullptr) mesh_out = mesh;
     if (f->esz == 8) {
-        run_z<double>(f, st, mesh, spec, 1);
+        run_z<double>(f, st, mesh, spec, 1, 0, -1, zld);
         run_strided<double>(f, st, spec, 1, 1);
         if (after_zfwd) cudaEventRecord(after_zfwd, st);      // recorded in front of the X pass: FP64-bound, leaves DRAM idle
         run_x_conv<double>(f, st, spec, B, kappa, kind, tb, scalars, want_vir);
         run_strided<double>(f, st, spec, 1, -1);
-        run_z<double>(f, st, mesh_out, spec, -1);
+        run_z<double>(f, st, mesh_out, spec, -1, 0, -1, zld);
     } else {
-        run_z<float>(f, st, mesh, spec, 1);
+        run_z<float>(f, st, mesh, spec, 1, 0, -1, zld);
         run_strided<float>(f, st, spec, 1, 1);
         if (after_zfwd) cudaEventRecord(after_zfwd, st);
         run_x_conv<float>(f, st, spec, B, kappa, kind, tb, scalars, want_vir);
         run_strided<float>(f, st, spec, 1, -1);
-        run_z<float>(f, st, mesh_out, spec, -1);
+        run_z<float>(f, st, mesh_out, spec, -1, 0, -1, zld);
     }
+}
+
+// the real mesh may live in the spectrum buffer (line l of K3 reals at the start of spectrum line l, zld = 2 (K3/2 + 1)): only the
+// tile-pipelined Z passes read a whole tile into shared memory before they write it
+bool fft3d_inplace_supported(const Fft3d* p) {
+    const Fft3dImpl* f = reinterpret_cast<const Fft3dImpl*>(p);
+    return f->zf.fast && f->z.fast;
 }
 
 }  // namespace admp

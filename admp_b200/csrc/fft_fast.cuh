@@ -787,8 +787,10 @@ template <int M> struct ZGeom {
 // forward: K3 reals per line -> K3/2+1 complex (packed real FFT, tools/fft_model.py r2c)
 template <typename T, int R1, int R2, int R3, int TL, int JT>
 __global__ void __launch_bounds__(TL* JT, XMinBlocks<TL * JT, R1, R2, R3>::value)
-fast_z_fwd_kernel(int nlines, int ntiles, const T* __restrict__ mesh, cx<T>* __restrict__ spec, const cx<T>* __restrict__ gtw) {
-    constexpr int M = R1 * R2 * R3, K3 = 2 * M, K3h = M + 1, LS = ZGeom<M>::LS, TILE = TL * LS, NT = TL * JT;
+fast_z_fwd_kernel(int nlines, int ntiles, const T* __restrict__ mesh, cx<T>* __restrict__ spec, const cx<T>* __restrict__ gtw, int zlc) {
+    // zlc: 16-byte units per REAL line (M: the mesh has its own buffer; M + 1: the mesh lives in the spectrum buffer, line by line in
+    // place - a tile is complete in shared memory before its spectrum lines are written, and no other block touches those lines)
+    constexpr int M = R1 * R2 * R3, K3h = M + 1, LS = ZGeom<M>::LS, TILE = TL * LS, NT = TL * JT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cx<T>* I = reinterpret_cast<cx<T>*>(smem_raw);
     cx<T>* A = I + TILE;
@@ -808,15 +810,15 @@ fast_z_fwd_kernel(int nlines, int ntiles, const T* __restrict__ mesh, cx<T>* __r
     auto issue = [&](int tile) {
         const int L0 = tile * TL;
         const int nl = min(TL, nlines - L0);
-        const cx<T>* src = reinterpret_cast<const cx<T>*>(mesh + (size_t)L0 * K3);
+        const cx<T>* src = reinterpret_cast<const cx<T>*>(mesh) + (size_t)L0 * zlc;
         if (BULK) {                                   // one bulk copy per line: K3 reals = M 16-byte units
             fence_async_smem();
             if (threadIdx.x == 0) mbar_expect_tx(&bar, (unsigned)(nl * M * sizeof(cx<T>)));
-            if (threadIdx.x < nl) bulk_g2s(I + threadIdx.x * LS, src + (size_t)threadIdx.x * M, (unsigned)(M * sizeof(cx<T>)), &bar);
+            if (threadIdx.x < nl) bulk_g2s(I + threadIdx.x * LS, src + (size_t)threadIdx.x * zlc, (unsigned)(M * sizeof(cx<T>)), &bar);
         } else {
             for (int e = threadIdx.x; e < nl * M; e += NT) {
                 const int ll = e / M, pos = e - ll * M;
-                cp_async<sizeof(cx<T>)>(I + ll * LS + pos, src + e);
+                cp_async<sizeof(cx<T>)>(I + ll * LS + pos, src + (size_t)ll * zlc + pos);
             }
             cp_async_commit();
         }
@@ -885,8 +887,8 @@ fast_z_fwd_kernel(int nlines, int ntiles, const T* __restrict__ mesh, cx<T>* __r
 // inverse: K3/2+1 complex -> K3 reals, unnormalised (tools/fft_model.py c2r)
 template <typename T, int R1, int R2, int R3, int TL, int JT>
 __global__ void __launch_bounds__(TL* JT, MinBlocks<TL * JT, R3>::value)
-fast_z_inv_kernel(int nlines, int ntiles, const cx<T>* __restrict__ spec, T* __restrict__ mesh, const cx<T>* __restrict__ gtw) {
-    constexpr int M = R1 * R2 * R3, K3 = 2 * M, K3h = M + 1, LS = ZGeom<M>::LS, TILE = TL * LS, NT = TL * JT;
+fast_z_inv_kernel(int nlines, int ntiles, const cx<T>* __restrict__ spec, T* __restrict__ mesh, const cx<T>* __restrict__ gtw, int zlc) {
+    constexpr int M = R1 * R2 * R3, K3h = M + 1, LS = ZGeom<M>::LS, TILE = TL * LS, NT = TL * JT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cx<T>* I = reinterpret_cast<cx<T>*>(smem_raw);
     cx<T>* A = I + TILE;
@@ -933,7 +935,7 @@ fast_z_inv_kernel(int nlines, int ntiles, const cx<T>* __restrict__ spec, T* __r
         __syncthreads();
         const int L0 = tile * TL;
         const bool live = l < nlines - L0;
-        cx<T>* line = reinterpret_cast<cx<T>*>(mesh + (size_t)(L0 + l) * K3);
+        cx<T>* line = reinterpret_cast<cx<T>*>(mesh) + (size_t)(L0 + l) * zlc;
         auto untangle = [&](cx<T> xk, cx<T> xc, cx<T> tw) {           // half-complex -> packed complex: Z = s + (-sin phi + i cos phi) d
             xc.y = -xc.y;
             const cx<T> s = xk + xc, d = xk - xc;
@@ -952,10 +954,10 @@ fast_z_inv_kernel(int nlines, int ntiles, const cx<T>* __restrict__ spec, T* __r
             fft_tail<T, R1, R2, R3, -1, JT, true>(j, live, tw2, tw3, ldA, stA, stA);
             __syncthreads();
             const int nl = min(TL, nlines - L0);
-            cx<T>* dst = reinterpret_cast<cx<T>*>(mesh + (size_t)L0 * K3);
+            cx<T>* dst = reinterpret_cast<cx<T>*>(mesh) + (size_t)L0 * zlc;
             for (int e = threadIdx.x; e < nl * M; e += NT) {
                 const int ll = e / M, k = e - ll * M;
-                dst[e] = A[ll * LS + k];
+                dst[(size_t)ll * zlc + k] = A[ll * LS + k];
             }
         } else {
             fft_tail<T, R1, R2, R3, -1, JT, false>(j, live, tw2, tw3, [&](int pos) { return a[pos]; }, [&](int pos, cx<T> v) { a[pos] = v; },
@@ -1003,8 +1005,8 @@ struct FastOps {
     int occ_peer[2];  // x conv on peers: quick, general
     size_t smem_xv;   // quick + virial variant (two more N-entry tables)
     int occ_qv[2];    // its resident blocks: cp.async tiles, TMA tiles (0: does not fit -> the general kernel runs the virial pass)
-    void (*zfwd)(cudaStream_t, int nlines, int ntiles, int grid, const void* mesh, void* spec, const void* tw);
-    void (*zinv)(cudaStream_t, int nlines, int ntiles, int grid, const void* spec, void* mesh, const void* tw);
+    void (*zfwd)(cudaStream_t, int nlines, int ntiles, int grid, const void* mesh, void* spec, const void* tw, int zlc);
+    void (*zinv)(cudaStream_t, int nlines, int ntiles, int grid, const void* spec, void* mesh, const void* tw, int zlc);
 };
 
 template <typename K>
@@ -1105,13 +1107,13 @@ struct FastImpl {
                                                                                               (const cx<T>*)tw, scalars, want_vir, peers, local_reads,
                                                                                               CUtensorMap{});
     }
-    static void zfwd(cudaStream_t st, int nlines, int ntiles, int grid, const void* mesh, void* spec, const void* tw) {
+    static void zfwd(cudaStream_t st, int nlines, int ntiles, int grid, const void* mesh, void* spec, const void* tw, int zlc) {
         const size_t smem = (size_t)(2 * ZTL * ZGeom<N>::LS + TwGeom<R1, R2, R3>::TOTAL + N + 1) * sizeof(cx<T>);
-        launch_pdl(fast_z_fwd_kernel<T, R1, R2, R3, ZTL, ZJT>, grid, ZTL * ZJT, smem, st, nlines, ntiles, (const T*)mesh, (cx<T>*)spec, (const cx<T>*)tw);
+        launch_pdl(fast_z_fwd_kernel<T, R1, R2, R3, ZTL, ZJT>, grid, ZTL * ZJT, smem, st, nlines, ntiles, (const T*)mesh, (cx<T>*)spec, (const cx<T>*)tw, zlc);
     }
-    static void zinv(cudaStream_t st, int nlines, int ntiles, int grid, const void* spec, void* mesh, const void* tw) {
+    static void zinv(cudaStream_t st, int nlines, int ntiles, int grid, const void* spec, void* mesh, const void* tw, int zlc) {
         const size_t smem = (size_t)(2 * ZTL * ZGeom<N>::LS + TwGeom<R1, R2, R3>::TOTAL + N + 1) * sizeof(cx<T>);
-        launch_pdl(fast_z_inv_kernel<T, R1, R2, R3, ZTL, ZJT>, grid, ZTL * ZJT, smem, st, nlines, ntiles, (const cx<T>*)spec, (T*)mesh, (const cx<T>*)tw);
+        launch_pdl(fast_z_inv_kernel<T, R1, R2, R3, ZTL, ZJT>, grid, ZTL * ZJT, smem, st, nlines, ntiles, (const cx<T>*)spec, (T*)mesh, (const cx<T>*)tw, zlc);
     }
     static FastOps ops() {
         FastOps o = {};

@@ -66,7 +66,7 @@ void launch_tt_pair(cudaStream_t st, int64_t n_rows, int n_atoms, const BoxInfo*
 // recip.cu
 template <typename T>
 void launch_spread(cudaStream_t st, int n, const BoxInfo* B, const void* pos, const void* M, int m_cols, int m_stride,
-                   const void* U, void* mesh, const PeerTab* peers = nullptr);
+                   const void* U, void* mesh, const PeerTab* peers = nullptr, int zld = 0);   // zld: reals per mesh line (0: K3)
 template <typename T>
 void launch_convolve(cudaStream_t st, const BoxInfo* B, size_t n_half, int n_sm, double kappa, int kind, const ConvTables& tb,
                      void* S, double* scalars, int want_vir);
@@ -75,7 +75,7 @@ void launch_conv_tables(cudaStream_t st, const BoxInfo* B, double kappa, const d
 template <typename T>
 void launch_gather(cudaStream_t st, int n, const BoxInfo* B, const void* pos, const void* M, int m_cols, int m_stride, const void* U,
                    const void* phi, int mode, uint32_t flags, void* dpos, void* G, int g_stride, void* F, double* scalars,
-                   const PeerTab* peers = nullptr);
+                   const PeerTab* peers = nullptr, int zld = 0);
 
 // spread_brick.cu - brick-staged spread (mesh written once, zero-fill included); atoms binned by home brick per evaluation
 struct BrickGeom { int nb[3]; int bz; };       // bricks per dimension (16 x 16 x bz points each)
@@ -109,7 +109,9 @@ void fft3d_single_pass(Fft3d* f, cudaStream_t st, int which, void* mesh, void* s
                        const ConvTables& tb, double* scalars);
 void fft3d_convolve_roundtrip(Fft3d* f, cudaStream_t st, void* mesh, void* spec, const BoxInfo* B, double kappa, int kind,
                               const ConvTables& tb, double* scalars, int want_vir, void* mesh_out = nullptr,
-                              cudaEvent_t after_zfwd = nullptr);
+                              cudaEvent_t after_zfwd = nullptr, int zld = 0);
+// mesh == spec (in place, line by line; zld = 2 (K3/2 + 1) reals per mesh line) is allowed when this returns true
+bool fft3d_inplace_supported(const Fft3d* f);
 
 bool fft3d_slab_supported(const Fft3d* f);
 constexpr int SLAB_CHUNKS = 8;        // maximum pipeline depth of the pulled X pass (ADMP_SLAB_CHUNKS, default 4)

@@ -28,7 +28,7 @@ constexpr int SPREAD_WARPS = 4;
 template <typename T, bool MULTIPOLE, bool PEER>
 __global__ void __launch_bounds__(SPREAD_WARPS * 32)
 spread_kernel(int n, const BoxInfo* __restrict__ Bp, const T* __restrict__ pos, const T* __restrict__ M, int m_stride,
-              const T* __restrict__ U, T* __restrict__ mesh, PeerTab peers) {
+              const T* __restrict__ U, T* __restrict__ mesh, PeerTab peers, int zld) {
     __shared__ T sw[SPREAD_WARPS][3][18];
     __shared__ int si[SPREAD_WARPS][3];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -67,6 +67,7 @@ spread_kernel(int n, const BoxInfo* __restrict__ Bp, const T* __restrict__ pos, 
     const T* w1 = sw[warp][1];
     const T* w2 = sw[warp][2];
     const int K1 = B.K[0], K2 = B.K[1], K3 = B.K[2];
+    const int zl = zld > 0 ? zld : K3;          // reals per mesh line (2 (K3/2 + 1) when the mesh lives in the spectrum buffer)
     const int i0 = si[warp][0], j0 = si[warp][1], k0 = si[warp][2];
     for (int pt = lane; pt < 216; pt += 32) {
         const int ia = pt / 36, ib = (pt / 6) % 6, ic = pt % 6;
@@ -86,7 +87,7 @@ spread_kernel(int n, const BoxInfo* __restrict__ Bp, const T* __restrict__ pos, 
         int gj = j0 + ib; if (gj >= K2) gj -= K2;
         int gk = k0 + ic; if (gk >= K3) gk -= K3;
         T* base = PEER ? reinterpret_cast<T*>(peers.base[peers.owner(gi)]) : mesh;
-        atomicAdd(base + ((size_t)gi * K2 + gj) * K3 + gk, val);
+        atomicAdd(base + ((size_t)gi * K2 + gj) * zl + gk, val);
     }
 }
 
@@ -181,7 +182,7 @@ template <typename T, bool MULTIPOLE, int MODE, bool PEER, int LPA>
 __global__ void __launch_bounds__(128)
 gather_kernel(int n, const BoxInfo* __restrict__ Bp, const T* __restrict__ pos, const T* __restrict__ M, int m_stride,
               const T* __restrict__ U, const T* __restrict__ phi, uint32_t flags, T* __restrict__ dpos, T* __restrict__ G,
-              int g_stride, T* __restrict__ F, double* __restrict__ scalars, PeerTab peers) {
+              int g_stride, T* __restrict__ F, double* __restrict__ scalars, PeerTab peers, int zld) {
     constexpr int NP = (MODE == 1) ? 2 : (MULTIPOLE ? 4 : 2);
     constexpr int GATHER_LPA = LPA, GATHER_APB = 128 / LPA;
     __shared__ T sw[GATHER_APB][3][6 * NP];
@@ -214,6 +215,7 @@ gather_kernel(int n, const BoxInfo* __restrict__ Bp, const T* __restrict__ pos, 
         const int K1 = B.K[0], K2 = B.K[1], K3 = B.K[2];
         const int i0 = si[slot][0], j0 = si[slot][1], k0 = si[slot][2];
         const bool wrap = k0 + 5 >= K3;
+        const int zl = zld > 0 ? zld : K3;
 #pragma unroll
         for (int c = 0; c < (36 + GATHER_LPA - 1) / GATHER_LPA; ++c) {
             const int col = sub + GATHER_LPA * c;
@@ -221,7 +223,7 @@ gather_kernel(int n, const BoxInfo* __restrict__ Bp, const T* __restrict__ pos, 
             const int ia = col / 6, ib = col - 6 * ia;
             int gi = i0 + ia; if (gi >= K1) gi -= K1;
             int gj = j0 + ib; if (gj >= K2) gj -= K2;
-            const T* line = (PEER ? reinterpret_cast<const T*>(peers.base[peers.owner(gi)]) : phi) + ((size_t)gi * K2 + gj) * K3;
+            const T* line = (PEER ? reinterpret_cast<const T*>(peers.base[peers.owner(gi)]) : phi) + ((size_t)gi * K2 + gj) * zl;
             T ph[6];
             if (!wrap) {
 #pragma unroll
@@ -364,11 +366,11 @@ gather_kernel(int n, const BoxInfo* __restrict__ Bp, const T* __restrict__ pos, 
 // ---------------------------------------------------------------------------- launchers
 template <typename T>
 void launch_spread(cudaStream_t st, int n, const BoxInfo* B, const void* pos, const void* M, int m_cols, int m_stride,
-                   const void* U, void* mesh, const PeerTab* peers) {
+                   const void* U, void* mesh, const PeerTab* peers, int zld) {
     if (n <= 0) return;
     const unsigned grid = (n + SPREAD_WARPS - 1) / SPREAD_WARPS;
     const PeerTab pt = peers ? *peers : PeerTab{};
-#define ADMP_S_ARGS(u) n, B, (const T*)pos, (const T*)M, m_stride, u, (T*)mesh, pt
+#define ADMP_S_ARGS(u) n, B, (const T*)pos, (const T*)M, m_stride, u, (T*)mesh, pt, zld
     if (peers) {
         if (m_cols >= 10) spread_kernel<T, true, true><<<grid, SPREAD_WARPS * 32, 0, st>>>(ADMP_S_ARGS((const T*)U));
         else spread_kernel<T, false, true><<<grid, SPREAD_WARPS * 32, 0, st>>>(ADMP_S_ARGS(nullptr));
@@ -393,14 +395,14 @@ void launch_conv_tables(cudaStream_t st, const BoxInfo* B, double kappa, const d
 template <typename T>
 void launch_gather(cudaStream_t st, int n, const BoxInfo* B, const void* pos, const void* M, int m_cols, int m_stride, const void* U,
                    const void* phi, int mode, uint32_t flags, void* dpos, void* G, int g_stride, void* F, double* scalars,
-                   const PeerTab* peers) {
+                   const PeerTab* peers, int zld) {
     if (n <= 0) return;
     static const int force_lpa = [] { const char* e = getenv("ADMP_GATHER_LPA"); return e ? atoi(e) : 0; }();
     const bool wide = force_lpa ? force_lpa == 16 : n < GATHER_SMALL_N;
     const int apb = 128 / (wide ? 16 : 4);
     const unsigned grid = (n + apb - 1) / apb;
     const PeerTab pt = peers ? *peers : PeerTab{};
-#define ADMP_G_ARGS n, B, (const T*)pos, (const T*)M, m_stride, (const T*)U, (const T*)phi, flags, (T*)dpos, (T*)G, g_stride, (T*)F, scalars, pt
+#define ADMP_G_ARGS n, B, (const T*)pos, (const T*)M, m_stride, (const T*)U, (const T*)phi, flags, (T*)dpos, (T*)G, g_stride, (T*)F, scalars, pt, zld
 #define ADMP_G_LAUNCH(PEER, LPA)                                                                         \
     do {                                                                                                 \
         if (mode == 1) gather_kernel<T, true, 1, PEER, LPA><<<grid, 128, 0, st>>>(ADMP_G_ARGS);          \
@@ -417,11 +419,11 @@ void launch_gather(cudaStream_t st, int n, const BoxInfo* B, const void* pos, co
 }
 #define ADMP_INST(T)                                                                                                              \
     template void launch_spread<T>(cudaStream_t, int, const BoxInfo*, const void*, const void*, int, int, const void*, void*,     \
-                                   const PeerTab*);                                                                               \
+                                   const PeerTab*, int);                                                                          \
     template void launch_convolve<T>(cudaStream_t, const BoxInfo*, size_t, int, double, int, const ConvTables&, void*, double*,   \
                                      int);                                                                                        \
     template void launch_gather<T>(cudaStream_t, int, const BoxInfo*, const void*, const void*, int, int, const void*, const void*, \
-                                   int, uint32_t, void*, void*, int, void*, double*, const PeerTab*);
+                                   int, uint32_t, void*, void*, int, void*, double*, const PeerTab*, int);
 ADMP_INST(double)
 ADMP_INST(float)
 #undef ADMP_INST

@@ -139,3 +139,32 @@ def test_tile_width_and_tma_switches_give_the_same_round_trip(K, env, monkeypatc
     a, b = out[1], out[0]
     assert (a[0] - b[0]).abs().max().item() < 1e-11 * b[0].abs().max().item()
     assert abs(a[1][_lib.S_E_RECIP].item() - b[1][_lib.S_E_RECIP].item()) < 1e-11 * abs(b[1][_lib.S_E_RECIP].item())
+
+
+def test_in_place_mesh_equals_separate_mesh(monkeypatch):
+    """The fused evaluations keep the real mesh in the spectrum buffer (line by line in place, ADMP_MESH_INPLACE, default on);
+    ADMP_MESH_INPLACE=0 selects the separate mesh buffer: same energies, gradients, dipoles and SCF cycle counts (the two differ
+    only in the order of the spread atomics), polarizable and dispersion, on a mesh with three different fast sizes."""
+    from oracle import fixtures, pairlist
+    from admp_b200.pme import ADMPPmeForce
+    from admp_b200.disp_pme import ADMPDispPmeForce
+    s = fixtures.lattice_water(4, 3.15, seed=5)
+    pairs, _ = pairlist.build_pairs(s.positions.numpy(), s.box.numpy(), 5.0)
+    out = {}
+    for mode in ('1', '0'):
+        monkeypatch.setenv('ADMP_MESH_INPLACE', mode)
+        calc = ADMPPmeForce(s.box, s.axis_type, s.axis_indices, s.covalent_map, 5.0, 1e-4, 2, lpol=True)
+        calc.update_env('K1', 154); calc.update_env('K2', 308); calc.update_env('K3', 154)
+        E, g, vir = calc.get_forces_and_virial(s.positions, s.box, pairs, s.Q_local, s.pol, s.tholes, s.mScales, s.pScales, s.dScales)
+        E1 = calc.get_energy(s.positions, s.box, pairs, s.Q_local, s.pol, s.tholes, s.mScales, s.pScales, s.dScales)
+        disp = ADMPDispPmeForce(s.box, s.covalent_map, 5.0, 1e-4, 10)
+        disp.update_env('K1', 154); disp.update_env('K2', 154); disp.update_env('K3', 308)
+        c_list = torch.as_tensor(np.tile(np.array([[37.2, 85.3, 134.4], [7.6, 11.9, 15.1], [7.6, 11.9, 15.1]]), (s.n_atoms // 3, 1)))
+        Ed, gd = disp.get_forces(s.positions, s.box, pairs, c_list, s.mScales)
+        out[mode] = (E.item(), g.cpu(), vir.cpu(), calc.U_ind.cpu(), calc.n_cycle, E1.item(), Ed.item(), gd.cpu())
+    a, b = out['1'], out['0']
+    assert a[4] == b[4]
+    for k in (0, 5, 6):
+        assert abs(a[k] - b[k]) <= 1e-11 * abs(b[k])
+    for k in (1, 2, 3, 7):
+        assert (a[k] - b[k]).abs().max().item() <= 1e-10 * b[k].abs().max().item()
