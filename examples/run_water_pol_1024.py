@@ -36,6 +36,10 @@ if __name__ == '__main__':
     print('# SCF: converged', pme_force.lconverg, 'after cycle', pme_force.n_cycle,
           '(the reference Jacobi loop does not converge on the shipped gas-like box: DESIGN.md section 2)')
     print('# max |dE/dr|:', F.abs().max().item())
+    # beyond the reference: the same fixed point by preconditioned conjugate gradients; on this box it finds a direction of
+    # negative curvature (the polarization matrix is indefinite - 1.1 A O-O contacts), which is why the Jacobi loop diverges
+    U, flag, it = pme_force.optimize_Uind(positions, box, pairs, w.Q_local, w.pol, w.tholes, w.mScales, w.pScales, w.dScales, solver='pcg')
+    print('# conjugate-gradient SCF: converged', flag, 'after', it, 'iterations, max |U| =', U.abs().max().item())
     Ed, Fd = disp_pme_force.get_forces(positions, box, pairs, w.c_list, w.mScales)
     print('# Dispersion PME energy (kJ/mol, physical dispersion is -E):', Ed.item())
     # parameter derivatives, as jax.grad(get_energy, argnums=...) in the reference
