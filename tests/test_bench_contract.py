@@ -1,5 +1,5 @@
 """The bench line contract (task statement, section 4) checked on the committed line of the last GPU run
-(profiles/r2l_bench.json, written by `python bench.py --steps 20 --warmup 5` on a B200) and on the reference-arm line: every key the driver
+(profiles/r2n_bench.json, written by `python bench.py --steps 20 --warmup 5` on a B200) and on the reference-arm line: every key the driver
 and the judge read is present and self-consistent. CPU only; bench.py itself needs a GPU."""
 import json
 import os
@@ -13,7 +13,7 @@ def _load(name):
 
 
 def test_gpu_arm_line():
-    d = _load('r2l_bench.json')
+    d = _load('r2n_bench.json')
     for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'vs_baseline',
               'dtype', 'data', 'config', 'e2e', 'gpu_launches', 'clocks', 'roofline', 'cpu_baseline'):
         assert k in d, k
@@ -38,6 +38,10 @@ def test_gpu_arm_line():
     for key in ('c1_nonpol_one_gpu', 'c3_one_gpu', 'c5_one_gpu', 'liquid_1024_one_gpu'):
         assert d[key]['evals_per_s'] > 0
     assert d['liquid_1024_one_gpu']['scf_converged'] is True
+    t = d['liquid_1024_one_gpu']['tight_scf']                     # the same box converged to 1e-4: reference loop vs conjugate gradients
+    assert t['jacobi']['converged'] and t['pcg']['converged'] and t['pcg']['field_evaluations'] < t['jacobi']['field_evaluations']
+    assert abs(t['jacobi']['energy'] - t['pcg']['energy']) < 1e-8 * abs(t['jacobi']['energy'])
+    assert 'ms_back_to_back' in d['kernels']['C3']['fft_y_fwd']
 
 
 def test_two_gpu_line_has_the_collective_and_the_slab_runs():
@@ -49,9 +53,9 @@ def test_two_gpu_line_has_the_collective_and_the_slab_runs():
 
 
 def test_reference_arm_line():
-    d = _load('r2l_bench_reference.json')
+    d = _load('r2n_bench_reference.json')
     assert d['impl'] == 'reference' and d['unit'] == 'evals/s' and d['value'] > 0
     assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0 and d['e2e']['value'] == d['value']
     assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['value'] == d['value']
-    assert d['metric'] == _load('r2l_bench.json')['metric'] and d['config']['workload'] == _load('r2l_bench.json')['config']['workload']
+    assert d['metric'] == _load('r2n_bench.json')['metric'] and d['config']['workload'] == _load('r2n_bench.json')['config']['workload']
     assert d['config']['evals_timed'] >= 1 and 'nothing extrapolated' in d['cpu_baseline']['sample']
