@@ -45,7 +45,7 @@ def test_gpu_arm_line():
 
 
 def test_two_gpu_line_has_the_collective_and_the_slab_runs():
-    d = _load('r2k_bench_2gpu.json')
+    d = _load('r2n_bench_2gpu.json')
     assert d['n_gpus'] == 2 and 'all-reduce' in d['config']['parallelism'] and d['scaling'] == 'weak'
     assert abs(d['value'] - 2 * d['config']['frames_per_step'] * 1e3 / d['ms_per_step']) < 1e-6 * d['value']
     for key in ('c3_slab', 'c5_slab'):
