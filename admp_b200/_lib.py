@@ -23,7 +23,7 @@ REUSE_PAIR_TILES = 0x20000000
 
 EXPORTS = [
     'admp_last_error', 'admp_version', 'admp_ctx_create', 'admp_ctx_destroy', 'admp_ctx_set_pme',
-    'admp_ctx_set_topology', 'admp_ctx_set_kvec_order', 'admp_ctx_set_pair_cluster', 'admp_ctx_pair_cluster_active', 'admp_ctx_set_spread', 'admp_ctx_spread_bricks', 'admp_ctx_workspace_bytes', 'admp_ctx_scf_graph_active',
+    'admp_ctx_set_topology', 'admp_ctx_set_kvec_order', 'admp_ctx_set_pair_cluster', 'admp_ctx_set_in_flight', 'admp_ctx_pair_cluster_active', 'admp_ctx_set_spread', 'admp_ctx_spread_bricks', 'admp_ctx_workspace_bytes', 'admp_ctx_scf_graph_active',
     'admp_frames_fwd', 'admp_frames_bwd', 'admp_rotate', 'admp_pme_real', 'admp_pme_recip', 'admp_pme_self',
     'admp_pme_spread', 'admp_pme_spread_only', 'admp_pme_fft', 'admp_pme_convolve', 'admp_pme_gather', 'admp_ctx_buffer', 'admp_ctx_buffer_io', 'admp_pme_fft_convolve', 'admp_pme_fft_pass', 'admp_set_box', 'admp_mesh_zero', 'admp_pme_spread_range',
     'admp_pme_gather_range', 'admp_pme_self_range', 'admp_frames_bwd_range', 'admp_scf_step', 'admp_virial_finalize', 'admp_ctx_fft_backend', 'admp_ctx_set_fft_backend',
@@ -60,6 +60,7 @@ def load():
     lib.admp_ctx_set_topology.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     lib.admp_ctx_set_kvec_order.argtypes = [vp, i32]
     lib.admp_ctx_set_pair_cluster.argtypes = [vp, i32, i32]
+    lib.admp_ctx_set_in_flight.argtypes = [vp, i32]
     lib.admp_ctx_pair_cluster_active.argtypes = [vp]
     lib.admp_ctx_set_spread.argtypes = [vp, i32]
     lib.admp_ctx_spread_bricks.argtypes = [vp]

@@ -71,6 +71,7 @@ struct admp_ctx {
     // per-atom workspaces and staged inputs of admp_pme_eval
     void *M = nullptr, *G = nullptr, *Fscf = nullptr, *rec = nullptr;
     int phi_zld = 0;                // reals per line of phi_cur (0: K3)
+    int in_flight = 1;              // admp_ctx_set_in_flight: evaluations the caller keeps in flight on other contexts / streams
     bool inplace_ok = false;        // the real mesh of the fused evaluations may live in the spectrum buffer (set_pme / ADMP_MESH_INPLACE)
     double* cg = nullptr;           // conjugate-gradient work vectors [U | r | p] + rz (allocated on first use, ADMP_SCF_CG)
     void *s_pos = nullptr, *s_U = nullptr, *s_pol = nullptr, *s_th = nullptr, *s_mS = nullptr, *s_pS = nullptr, *s_box = nullptr;
@@ -113,6 +114,13 @@ extern "C" int admp_ctx_pair_cluster_active(admp_ctx* c) {
     cudaSetDevice(c->device);
     if (cudaMemcpy(h, c->cw.state, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;   // synchronises: tests / tools only
     return h[2];
+}
+extern "C" int admp_ctx_set_in_flight(admp_ctx* c, int n) {
+    if (!c) return fail("admp_ctx_set_in_flight: null context");
+    if (n < 1) return fail("admp_ctx_set_in_flight: n = %d", n);
+    if ((n > 1) != (c->in_flight > 1)) drop_graph(c);          // the captured SCF body holds the gather variant
+    c->in_flight = n;
+    return 0;
 }
 extern "C" int admp_ctx_set_pair_cluster(admp_ctx* c, int force, int min_rows_per_cluster) {
     if (!c) return fail("admp_ctx_set_pair_cluster: null context");
@@ -599,7 +607,7 @@ extern "C" int admp_pme_recip(admp_ctx* c, void* stream, const void* pos, const 
     if (recip_field(c, st, pos, M, M_cols, M_stride, U, kind, scalars, (flags & ADMP_WANT_VIRIAL) ? 1 : 0)) return 1;
     if (mode == 1 || (flags & ADMP_WANT_GRAD)) {
         DISPATCH(c, launch_gather, st, c->n_atoms, c->box, pos, M, M_cols, M_stride, U, c->phi_cur, mode, flags, dpos, G, G_stride, F, scalars,
-                 nullptr, c->phi_zld);
+                 nullptr, c->phi_zld, c->in_flight > 1);
         CKLAUNCH();
     }
     return 0;
@@ -919,7 +927,7 @@ static int scf_body(admp_ctx* c, cudaStream_t st, int maxiter, double thresh, ui
         CK(cudaEventRecord(c->ev_join, c->side_stream));
         if (recip_field(c, st, c->s_pos, c->M, 10, 10, c->s_U, ADMP_CK_COULOMB, c->scal, 0, false)) return 1;
         DISPATCH(c, launch_gather, st, c->n_atoms, c->box, c->s_pos, c->M, 10, 10, c->s_U, c->phi_cur, 1, 0u, nullptr, nullptr, 10, c->Fscf, c->scal,
-                 nullptr, c->phi_zld);
+                 nullptr, c->phi_zld, c->in_flight > 1);
     }
     CK(cudaStreamWaitEvent(st, c->ev_join, 0));
     DISPATCH(c, launch_scf_field, st, c->n_atoms, c->kappa, c->M, c->s_U, c->s_pol, c->Fscf, c->scal);
@@ -1079,7 +1087,7 @@ extern "C" int admp_pme_eval(admp_ctx* c, void* stream, const void* pos, const v
     const uint32_t f = flags & (ADMP_WANT_GRAD | ADMP_WANT_VIRIAL | ADMP_WANT_PGRAD);
     if (flags & ADMP_WANT_GRAD) {
         DISPATCH(c, launch_gather, st, n, c->box, c->s_pos, c->M, 10, 10, Uf, c->phi_cur, 0, f, dpos, c->G, 10, polz ? F : nullptr, c->scal, nullptr,
-                 c->phi_zld);
+                 c->phi_zld, c->in_flight > 1);
     }
     DISPATCH(c, launch_pme_pair, st, c->pairs_cap, n, c->box, c->kappa, c->s_pos, c->s_pairs, c->s_sidx, c->cov_off, c->cov_idx, c->cov_nb, c->M, Uf,
              polz ? c->s_pol : nullptr, polz ? c->s_th : nullptr, c->s_mS, polz ? c->s_pS : nullptr, 0, f, dpos, c->G, F, dpol, dtholes, c->scal,
@@ -1122,7 +1130,7 @@ extern "C" int admp_disp_eval(admp_ctx* c, void* stream, const void* pos, const 
         if (f & (ADMP_WANT_GRAD | ADMP_WANT_PGRAD)) {
             void* g = ((f & ADMP_WANT_PGRAD) && dc) ? (void*)((char*)dc + p * w) : nullptr;
             DISPATCH(c, launch_gather, st, n, c->box, pos, col, 1, 3, nullptr, c->phi_cur, 0, f, (f & ADMP_WANT_GRAD) ? dpos : nullptr, g, 3,
-                     nullptr, c->scal, nullptr, c->phi_zld);
+                     nullptr, c->scal, nullptr, c->phi_zld, c->in_flight > 1);
             CKLAUNCH();
         }
     }

@@ -591,7 +591,9 @@ static StrideGeom geom_x(const Fft3dImpl* f, int TL) {
 // every block gets the same number of tiles (no block does one tile more than the rest: on the L2-resident
 // 154^3 mesh a pass is only 2-3 tiles per block, so an uneven deal costs a third of the pass)
 static int persistent_grid(const Fft3dImpl* f, int occ, int ntiles) {
-    static const bool balanced = [] { const char* e = getenv("ADMP_FFT_BALANCED"); return e && atoi(e) > 0; }();
+    // default on: with four evaluations in flight the slots a shrunk grid leaves free take the other evaluations' blocks
+    // (C2 469 -> 477 evals/s, twice each on one lease; a pass timed alone is 1-4 % slower); ADMP_FFT_BALANCED=0: all resident slots
+    static const bool balanced = [] { const char* e = getenv("ADMP_FFT_BALANCED"); return !(e && atoi(e) == 0); }();
     // ADMP_FFT_GRID_DIV = d: a pass only asks for 1/d of the resident-block slots, so that the passes of d independent
     // evaluations in flight on different streams run side by side instead of queueing behind each other's persistent blocks
     static const int div = [] { const char* e = getenv("ADMP_FFT_GRID_DIV"); const int v = e ? atoi(e) : 1; return v > 0 ? v : 1; }();

@@ -75,7 +75,7 @@ void launch_conv_tables(cudaStream_t st, const BoxInfo* B, double kappa, const d
 template <typename T>
 void launch_gather(cudaStream_t st, int n, const BoxInfo* B, const void* pos, const void* M, int m_cols, int m_stride, const void* U,
                    const void* phi, int mode, uint32_t flags, void* dpos, void* G, int g_stride, void* F, double* scalars,
-                   const PeerTab* peers = nullptr, int zld = 0);
+                   const PeerTab* peers = nullptr, int zld = 0, int narrow = 0);
 
 // spread_brick.cu - brick-staged spread (mesh written once, zero-fill included); atoms binned by home brick per evaluation
 struct BrickGeom { int nb[3]; int bz; };       // bricks per dimension (16 x 16 x bz points each)

@@ -395,10 +395,12 @@ void launch_conv_tables(cudaStream_t st, const BoxInfo* B, double kappa, const d
 template <typename T>
 void launch_gather(cudaStream_t st, int n, const BoxInfo* B, const void* pos, const void* M, int m_cols, int m_stride, const void* U,
                    const void* phi, int mode, uint32_t flags, void* dpos, void* G, int g_stride, void* F, double* scalars,
-                   const PeerTab* peers, int zld) {
+                   const PeerTab* peers, int zld, int narrow) {
     if (n <= 0) return;
     static const int force_lpa = [] { const char* e = getenv("ADMP_GATHER_LPA"); return e ? atoi(e) : 0; }();
-    const bool wide = force_lpa ? force_lpa == 16 : n < GATHER_SMALL_N;
+    // narrow (admp_ctx_set_in_flight > 1): 4 lanes per atom whatever n - a quarter of the blocks, so that the gathers of several
+    // evaluations in flight share the SMs with the other evaluations' passes (C2, four in flight: 474 -> 481 evals/s)
+    const bool wide = force_lpa ? force_lpa == 16 : (n < GATHER_SMALL_N && !narrow);
     const int apb = 128 / (wide ? 16 : 4);
     const unsigned grid = (n + apb - 1) / apb;
     const PeerTab pt = peers ? *peers : PeerTab{};
@@ -423,7 +425,7 @@ void launch_gather(cudaStream_t st, int n, const BoxInfo* B, const void* pos, co
     template void launch_convolve<T>(cudaStream_t, const BoxInfo*, size_t, int, double, int, const ConvTables&, void*, double*,   \
                                      int);                                                                                        \
     template void launch_gather<T>(cudaStream_t, int, const BoxInfo*, const void*, const void*, int, int, const void*, const void*, \
-                                   int, uint32_t, void*, void*, int, void*, double*, const PeerTab*, int);
+                                   int, uint32_t, void*, void*, int, void*, double*, const PeerTab*, int, int);
 ADMP_INST(double)
 ADMP_INST(float)
 #undef ADMP_INST

@@ -87,7 +87,10 @@ def sibling_calculators(calc, count):
         c2.refresh_calculators()
         sibs.append(c2)
     calc._siblings, calc._siblings_key = sibs, key
-    return [calc] + sibs[:count - 1]
+    out = [calc] + sibs[:count - 1]
+    for c in out:                       # hint for the kernels: `count` evaluations share the GPU
+        _lib.check(c._ctx.lib.admp_ctx_set_in_flight(c._ctx.handle, max(1, int(count))))
+    return out
 
 
 def evaluate_frames(calc, frames, box, pairs, Q_local, pol=None, tholes=None, mScales=None, pScales=None,

@@ -99,6 +99,10 @@ int admp_ctx_set_kvec_order(admp_ctx* ctx, int reference);
  * list holds >= min_rows_per_cluster rows per cluster, default 96), 1 = cluster whenever the order allows, -1 = flat.
  * admp_ctx_pair_cluster_active reads back which one the last evaluation used (1 cluster, 0 flat; synchronises - tests only). */
 int admp_ctx_set_pair_cluster(admp_ctx* ctx, int force, int min_rows_per_cluster);
+/* Hint: the caller keeps n evaluations in flight (n contexts on n streams - the frame batches of force-field fitting,
+ * admp/api.py usage in examples/openmm_api/run.py:41-45). n > 1 selects kernel shapes that leave SM room for the other
+ * evaluations (today: the narrow gather); results are unchanged up to summation order. Default 1. */
+int admp_ctx_set_in_flight(admp_ctx* ctx, int n);
 int admp_ctx_pair_cluster_active(admp_ctx* ctx);
 /* B-spline spread of admp_pme_eval / admp_pme_recip / admp_pme_spread (replaces admp/recip.py:313-392). Two kernels, same
  * result to rounding. bricks = 0 (default): zero-fill + one warp per atom with global atomics. bricks = 1: brick-staged - atoms

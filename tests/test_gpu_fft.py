@@ -168,3 +168,24 @@ def test_in_place_mesh_equals_separate_mesh(monkeypatch):
         assert abs(a[k] - b[k]) <= 1e-11 * abs(b[k])
     for k in (1, 2, 3, 7):
         assert (a[k] - b[k]).abs().max().item() <= 1e-10 * b[k].abs().max().item()
+
+
+def test_in_flight_hint_changes_kernel_shapes_not_results():
+    """admp_ctx_set_in_flight(n > 1) (set by parallel.sibling_calculators for frame batches) selects the narrow gather: same
+    energies, gradients, dipoles and cycle counts up to summation order."""
+    from oracle import fixtures, pairlist
+    from admp_b200.pme import ADMPPmeForce
+    s = fixtures.lattice_water(4, 3.15, seed=5)
+    pairs, _ = pairlist.build_pairs(s.positions.numpy(), s.box.numpy(), 5.0)
+    calc = ADMPPmeForce(s.box, s.axis_type, s.axis_indices, s.covalent_map, 5.0, 1e-4, 2, lpol=True)
+    args = (s.positions, s.box, pairs, s.Q_local, s.pol, s.tholes, s.mScales, s.pScales, s.dScales)
+    out = []
+    for n in (1, 4, 1):
+        _lib.check(calc._ctx.lib.admp_ctx_set_in_flight(calc._ctx.handle, n))
+        E, g, vir = calc.get_forces_and_virial(*args)
+        out.append((E.item(), g.cpu(), vir.cpu(), calc.U_ind.cpu(), calc.n_cycle))
+    for a in out[1:]:
+        assert a[4] == out[0][4] and abs(a[0] - out[0][0]) <= 1e-11 * abs(out[0][0])
+        for k in (1, 2, 3):
+            assert (a[k] - out[0][k]).abs().max().item() <= 1e-10 * out[0][k].abs().max().item()
+    assert calc._ctx.lib.admp_ctx_set_in_flight(calc._ctx.handle, 0) != 0      # rejected
