@@ -176,7 +176,11 @@ int admp_pme_fft_pass(admp_ctx* ctx, void* stream, int which, int kind, double* 
 int admp_pme_gather(admp_ctx* ctx, void* stream, const void* pos, const void* M, int M_cols,
                     int M_stride, const void* U, int mode, uint32_t flags, void* dpos, void* G,
                     int G_stride, void* F, double* scalars);
-/* which: 0 = real mesh (K1*K2*K3 reals), 1 = half spectrum (K1*K2*(K3/2+1) complex) */
+/* which: 0 = real mesh (K1*K2*K3 reals), 1 = half spectrum (K1*K2*(K3/2+1) complex)
+ * Buffer 0 is the mesh of the stage entry points above and of the decompositions. The fused evaluations (admp_pme_eval,
+ * admp_disp_eval, admp_pme_recip) keep their real mesh INSIDE buffer 1 (line l of K3 reals at the start of spectrum line l, the layout
+ * of an in-place real-to-complex transform) whenever the tile-pipelined Z passes serve the mesh size; ADMP_MESH_INPLACE=0 makes them
+ * use buffer 0. Neither buffer holds anything a caller may rely on after a fused evaluation. */
 void* admp_ctx_buffer(admp_ctx* ctx, int which);
 /* device-to-device copy between a caller buffer and the context's mesh / spectrum (tests, tools) */
 int admp_ctx_buffer_io(admp_ctx* ctx, void* stream, int which, void* user, int64_t nbytes, int to_ctx);
